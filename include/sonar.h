@@ -1,0 +1,431 @@
+/*
+ * sonar.h — C ABI of the B200-native fingerprint + alignment hot path.
+ *
+ * This is the drop-in boundary for RyanBlaney/sonido-sonar's data-parallel hot
+ * path.  The reference is pure Go and has no FFI today; its
+ * only plugin point is the Go interface `extractors.FeatureExtractor`
+ * (fingerprint/extractors/feature_extractor.go:10-15).  A cgo shim (see
+ * INTEGRATION.md and go/) binds exactly the entry points declared here.  Every
+ * entry point names the reference function(s) it replaces (file:line relative
+ * to the reference repository root).
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch / CUDA types in any signature;
+ *   - every function returns a sonar_status; on error a human readable message
+ *     (using the reference's own error text where it has one) is available from
+ *     sonar_last_error() on the calling thread;
+ *   - `_f64` entry points take HOST pointers (Go `[]float64` backing arrays,
+ *     flattened row-major for `[][]float64`), copy to the device, run the CUDA
+ *     kernels and copy the results back into caller-allocated buffers;
+ *   - `_dev` entry points take DEVICE pointers (allocated with
+ *     sonar_dev_alloc or by the caller, e.g. a torch tensor's data_ptr) and do
+ *     not touch the host: they are what a device-resident chain (§8 f3) and the
+ *     bench's `value` leg use;
+ *   - the library is re-entrant: no global mutable state except a
+ *     mutex-guarded plan cache inside the context;
+ *   - there is NO CPU fallback: with no usable CUDA device sonar_init fails.
+ *
+ * The same header is implemented a second time by the CPU oracle
+ * (oracle/sonar_oracle.cpp -> oracle/libsonar_oracle.so), which is test
+ * infrastructure only.
+ */
+#ifndef SONAR_H_
+#define SONAR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SONAR_ABI_VERSION 1
+
+typedef struct sonar_ctx sonar_ctx;
+
+typedef enum sonar_status {
+  SONAR_OK = 0,
+  SONAR_ERR_INVALID = 1,     /* nil / non-positive argument                       */
+  SONAR_ERR_EMPTY = 2,       /* "empty signal", "empty signals provided", ...     */
+  SONAR_ERR_TOO_SHORT = 3,   /* "signal too short for given window size and hop size" */
+  SONAR_ERR_CUDA = 4,        /* CUDA runtime failure (message carries cudaGetErrorString) */
+  SONAR_ERR_NOMEM = 5,       /* device / pinned allocation failed or would exceed the limit */
+  SONAR_ERR_UNSUPPORTED = 6  /* valid in the reference but outside this path's scope */
+} sonar_status;
+
+/* analyzers.WindowType (fingerprint/analyzers/windowing.go:12-24) */
+typedef enum sonar_window {
+  SONAR_WINDOW_HANN = 0,
+  SONAR_WINDOW_HAMMING = 1,
+  SONAR_WINDOW_BLACKMAN = 2,
+  SONAR_WINDOW_BLACKMAN_HARRIS = 3,
+  SONAR_WINDOW_KAISER = 4,
+  SONAR_WINDOW_TUKEY = 5,
+  SONAR_WINDOW_RECTANGULAR = 6,
+  SONAR_WINDOW_BARTLETT = 7,
+  SONAR_WINDOW_WELCH = 8
+} sonar_window;
+
+/* config.FeatureConfig.Enable* as the speech extractor actually reads them
+ * (fingerprint/extractors/speech.go:168,179,201).  Spectral, energy and
+ * harmonic groups are unconditional in the reference (speech.go:193,215,224). */
+#define SONAR_FP_ENABLE_MFCC      0x1u
+#define SONAR_FP_ENABLE_TEMPORAL  0x2u   /* speech.go:370-408            */
+#define SONAR_FP_ENABLE_SPEECH    0x4u   /* speech.go:271-317 — out of scope: UNSUPPORTED */
+
+/* ------------------------------------------------------------------------- */
+/* context                                                                    */
+/* ------------------------------------------------------------------------- */
+
+/* Creates a context bound to `n_devices` CUDA devices (device_ids == NULL:
+ * devices 0..n_devices-1; n_devices <= 0: the current device only).
+ * Fails with SONAR_ERR_CUDA when no CUDA device is usable. */
+int sonar_init(int n_devices, const int* device_ids, sonar_ctx** out);
+void sonar_destroy(sonar_ctx* ctx);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* sonar_last_error(void);
+int sonar_abi_version(void);
+/* "cuda-sm100a" for the product library, "cpu-oracle" for the oracle. */
+const char* sonar_backend(void);
+
+/* Pinned host memory for callers that want full PCIe rate (optional). */
+int sonar_host_alloc(sonar_ctx* ctx, uint64_t bytes, void** out);
+int sonar_host_free(sonar_ctx* ctx, void* p);
+/* Device memory on the context's first device (for `_dev` entry points). */
+int sonar_dev_alloc(sonar_ctx* ctx, uint64_t bytes, void** out);
+int sonar_dev_free(sonar_ctx* ctx, void* p);
+int sonar_memcpy_h2d(sonar_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);
+int sonar_memcpy_d2h(sonar_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
+int sonar_synchronize(sonar_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench claim). */
+uint64_t sonar_kernel_launches(sonar_ctx* ctx);
+
+/* ------------------------------------------------------------------------- */
+/* windows                                                                    */
+/* ------------------------------------------------------------------------- */
+
+/* analyzers.WindowGenerator.Generate (fingerprint/analyzers/windowing.go:77-136,
+ * 246-371, 427-437) and the un-normalised algorithms/windowing structs
+ * (algorithms/windowing/hann.go:16-37 ...).  Host-side table generator; the
+ * device kernels consume these tables. `beta` = Kaiser, `alpha` = Tukey. */
+int sonar_window_f64(int window_type, int size, int symmetric, int normalize,
+                     double beta, double alpha, double* out);
+
+/* ------------------------------------------------------------------------- */
+/* fingerprint (GenerateFingerprint)                                          */
+/* ------------------------------------------------------------------------- */
+
+/* Exactly what the reference's algorithm objects were constructed with
+ * (SURVEY §0 F2-F4). Zero-initialise, then sonar_fp_params_default(). */
+typedef struct sonar_fp_params {
+  int32_t window_size;       /* FingerprintConfig.WindowSize  (fingerprint.go:177)            */
+  int32_t hop_size;          /* FingerprintConfig.HopSize     (fingerprint.go:180)            */
+  int32_t window_type;       /* FeatureConfig.WindowType      (fingerprint.go:182)            */
+  int32_t algo_sample_rate;  /* extractor's config.SampleRate (speech.go:70-96). Stock
+                                GenerateFingerprint passes 0 (content_config.go:87-103, F2).  */
+  int32_t call_sample_rate;  /* audioData.SampleRate handed to ExtractFeatures (fingerprint.go:207) */
+  int32_t energy_frame;      /* FeatureConfig.WindowSize seen by temporal.NewEnergy (speech.go:85, F4) */
+  int32_t energy_hop;        /* FeatureConfig.HopSize    seen by temporal.NewEnergy               */
+  int32_t n_mfcc;            /* FeatureConfig.MFCCCoefficients (<=0 -> 13, mfcc.go:59)           */
+  int32_t n_mel;             /* MFCCParams.NumMelFilters       (<=0 -> 26, mfcc.go:62)           */
+  int32_t use_liftering;     /* MFCCParams.UseLiftering (NewMFCC: true, mfcc.go:50)              */
+  uint32_t enable;           /* SONAR_FP_ENABLE_*                                                */
+  int32_t reserved0;
+  double low_hz;             /* MFCCParams.LowFreq  (0)                                          */
+  double high_hz;            /* MFCCParams.HighFreq (<=0 -> algo_sample_rate/2, mfcc.go:65)      */
+  double lifter;             /* MFCCParams.LifterCoeff (<=0 -> 22, mfcc.go:68)                   */
+  double pre_emph_alpha;     /* filters.NewPreEmphasisForContent("speech") = 0.97 (pre_emphasis.go:114) */
+} sonar_fp_params;
+
+/* Output sizes, computable up front so the Go shim can allocate flat slices. */
+typedef struct sonar_fp_sizes_t {
+  int64_t n_frames;          /* T  = (N-W)/H+1                     (analyzers/spectral.go:409)  */
+  int64_t n_bins;            /* B  = W/2+1                         (analyzers/spectral.go:428)  */
+  int64_t n_flux;            /* T-1 if T>1 else 0                  (speech.go:361)              */
+  int64_t n_energy_frames;   /* Te = (N-Fe)/He+1 or 0              (temporal/energy.go:26-30)   */
+  int64_t n_pitch_frames;    /* Tp = (N-1024)/512+1                (speech.go:468-470)          */
+  int64_t n_mfcc;            /* effective coefficient count                                     */
+  int64_t n_envelope;        /* (N-512)/256+1 or 0                 (speech.go:751-761)          */
+} sonar_fp_sizes_t;
+
+/* Caller-allocated flat outputs; any pointer may be NULL (skipped).  Layout
+ * mirrors extractors.ExtractedFeatures (fingerprint/extractors/features.go:5-124). */
+typedef struct sonar_fp_out {
+  /* MFCC [T][n_mfcc] row-major                        (features.go:11, mfcc.go:167)       */
+  double* mfcc;
+  /* SpectralFeatures, each [T] (flux: [T-1])          (features.go:30-40, speech.go:320-367) */
+  double* spectral_centroid;
+  double* spectral_rolloff;
+  double* spectral_bandwidth;
+  double* spectral_flatness;
+  double* spectral_crest;
+  double* spectral_slope;
+  double* spectral_flux;
+  double* zero_crossing_rate;
+  /* EnergyFeatures, each [Te]                         (features.go:97-110, speech.go:411-461) */
+  double* short_time_energy;
+  double* energy_entropy;
+  double* low_energy_ratio;
+  double* high_energy_ratio;
+  /* HarmonicFeatures, each [Tp]                       (features.go:115-124, speech.go:464-509) */
+  double* pitch_estimate;
+  double* pitch_confidence;
+  double* voicing_strength;
+  double* harmonic_ratio;
+  double* inharmonicity_ratio;
+  double* tonal_centroid;
+  /* TemporalFeatures (only with SONAR_FP_ENABLE_TEMPORAL; features.go:70-92, speech.go:370-408) */
+  double* rms_energy;        /* [Te]                                                         */
+  double* envelope_shape;    /* [n_envelope]                                                 */
+  double* attack_time;       /* [attack_time_cap]; n_attack_time entries written              */
+  int64_t attack_time_cap;
+  /* scalars, written by the call */
+  double energy_variance;    /* speech.go:418 */
+  double loudness_range;     /* speech.go:421 */
+  double dynamic_range;      /* speech.go:377 */
+  double silence_ratio;      /* speech.go:380 */
+  double peak_amplitude;     /* speech.go:384-392 */
+  double average_amplitude;  /* speech.go:393-395 */
+  double onset_density;      /* speech.go:398-399 */
+  int64_t n_attack_time;     /* number of onsets (speech.go:402) */
+} sonar_fp_out;
+
+void sonar_fp_params_default(sonar_fp_params* p);
+
+/* Replaces the size arithmetic of ComputeSTFTWithWindow / ComputeShortTimeEnergy
+ * / extractHarmonicFeatures (see sonar_fp_sizes_t). Returns the reference's
+ * errors for n_samples == 0, W <= 0, H <= 0, T <= 0. */
+int sonar_fp_sizes(const sonar_fp_params* p, int64_t n_samples, sonar_fp_sizes_t* out);
+
+/* Replaces FingerprintGenerator.GenerateFingerprint's compute
+ * (fingerprint/fingerprint.go:190-207): ComputeSTFTWithWindow
+ * (analyzers/spectral.go:385-545) fused with SpeechFeatureExtractor.
+ * ExtractFeatures (extractors/speech.go:135-243) — the spectrogram is never
+ * materialised. `pcm` is a host pointer to n float64 samples. */
+int sonar_fingerprint_f64(sonar_ctx* ctx, const double* pcm, int64_t n,
+                          const sonar_fp_params* p, sonar_fp_out* out);
+
+/* Batch form (the analogue of ComputeSTFTBatch, analyzers/spectral.go:234-285,
+ * applied to whole fingerprints): n_streams host buffers, one sonar_fp_out
+ * each.  Streams are sharded round-robin over the context's devices and
+ * pipelined (pinned double-buffered H2D) on each. */
+int sonar_fingerprint_batch_f64(sonar_ctx* ctx, const double* const* pcm, const int64_t* n,
+                                int n_streams, const sonar_fp_params* p, sonar_fp_out* outs);
+
+/* Device-resident batch: `pcm_dev` holds n_streams streams of `n` samples
+ * each, stream s starting at pcm_dev + s*stride (stride >= n, in samples,
+ * even).  `feat_dev` receives the features of stream s at feat_dev +
+ * s*sonar_fp_dev_stride(p, n) doubles, in the layout described by
+ * sonar_fp_dev_layout().  Asynchronous on the context's compute stream;
+ * call sonar_synchronize() before reading. */
+int sonar_fingerprint_batch_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n, int64_t stride,
+                                int n_streams, const sonar_fp_params* p, double* feat_dev);
+
+/* Offsets (in doubles, relative to the stream's feature block) of each array
+ * in the device layout; total = block size. Arrays are in sonar_fp_out order. */
+typedef struct sonar_fp_dev_layout_t {
+  int64_t mfcc, spectral_centroid, spectral_rolloff, spectral_bandwidth, spectral_flatness,
+      spectral_crest, spectral_slope, spectral_flux, zero_crossing_rate, short_time_energy,
+      energy_entropy, low_energy_ratio, high_energy_ratio, pitch_estimate, pitch_confidence,
+      voicing_strength, harmonic_ratio, inharmonicity_ratio, tonal_centroid, scalars, total;
+} sonar_fp_dev_layout_t;
+int sonar_fp_dev_layout(const sonar_fp_params* p, int64_t n_samples, sonar_fp_dev_layout_t* out);
+
+/* SpectralAnalyzer.ComputeSTFTWithWindow as a materialising call
+ * (analyzers/spectral.go:385-545): mag [T][B] required; phase [T][B] and cplx
+ * [T][B][2] (re,im) optional (NULL = skipped). */
+int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int hop, int window_type,
+                   double* mag, double* phase, double* cplx);
+
+/* ------------------------------------------------------------------------- */
+/* alignment: cross-correlation                                               */
+/* ------------------------------------------------------------------------- */
+
+/* stats.CorrelationResult without the arrays (algorithms/stats/correlation.go:44-71) */
+typedef struct sonar_xcorr_summary {
+  double peak_correlation;   /* correlation.go:526-544 (max |c|, first index wins) */
+  double p_value;            /* correlation.go:547-569 */
+  double snr;                /* correlation.go:572-601 (+Inf possible) */
+  double sharpness;          /* correlation.go:611-619 */
+  double second_peak;        /* correlation.go:622-636 */
+  double peak_to_sidelobe;   /* correlation.go:639-661 (+Inf possible) */
+  int32_t peak_lag;
+  int32_t peak_index;
+  int32_t actual_max_lag;    /* correlation.go:452-461 */
+  int32_t overlap_length;    /* correlation.go:664-667 */
+  int32_t is_significant;    /* p < 1-0.95, correlation.go:168 */
+  int32_t n_candidates;      /* lags re-evaluated in reference summation order (diagnostic) */
+} sonar_xcorr_summary;
+
+/* CrossCorrelation.Compute as configured by stats.NewAlignmentAnalyzer
+ * (algorithms/stats/alignment.go:60-81): TimeDomain, NormalizedCrossCorrelation,
+ * normalizeInputs=true -> correlation.go:131-228,373-409,421-501,526-667.
+ * corr receives 2*actual_max_lag+1 values (caller allocates 2*max_lag+1; NULL =
+ * not wanted); lag of corr[i] is i-actual_max_lag. */
+int sonar_xcorr_ncc_f64(sonar_ctx* ctx, const double* a, int64_t na, const double* b, int64_t nb,
+                        int max_lag, double* corr, sonar_xcorr_summary* out);
+
+/* Batch of independent pairs (BASELINE config 5): pair p uses a[p][0..na[p]),
+ * b[p][0..nb[p]); corr[p] may be NULL. Sharded by pair over the devices. */
+int sonar_xcorr_batch_f64(sonar_ctx* ctx, const double* const* a, const int64_t* na,
+                          const double* const* b, const int64_t* nb, int n_pairs, int max_lag,
+                          double* const* corr, sonar_xcorr_summary* outs);
+
+/* Device-resident uniform batch (bench `value` leg): a_dev/b_dev hold n_pairs
+ * sequences of na / nb doubles back to back; corr_dev (nullable) receives
+ * n_pairs*(2*max_lag+1) values; summ_host receives the summaries after an
+ * internal synchronise. */
+int sonar_xcorr_batch_dev(sonar_ctx* ctx, const double* a_dev, int64_t na, const double* b_dev,
+                          int64_t nb, int n_pairs, int max_lag, double* corr_dev,
+                          sonar_xcorr_summary* summ_host);
+
+/* Lag-range shard of ONE correlation: evaluates only the lag
+ * indices [idx_lo, idx_hi) of the 2L+1 and returns this shard's partials.
+ * The ranks exchange `sonar_xcorr_shard_peak` (16 B) with an all-gather, pick
+ * the global peak with sonar_xcorr_merge_peaks, then call
+ * sonar_xcorr_shard_metrics for the peak-relative partial sums, all-gather
+ * those, and finish with sonar_xcorr_merge_metrics. */
+typedef struct sonar_xcorr_shard_peak {
+  double abs_peak;           /* max |c| in the shard, after the exact re-check     */
+  int64_t index;             /* global lag index of its first occurrence; -1 = empty shard */
+} sonar_xcorr_shard_peak;
+typedef struct sonar_xcorr_shard_metrics {
+  double noise_sum;          /* sum c^2 over |i-peak|>5 in the shard  */
+  double noise_count;
+  double max_sidelobe;       /* max |c| over |i-peak|>10 in the shard */
+  double second_abs;         /* max |c| over i != peak in the shard   */
+  double second_val;         /* signed value of its first occurrence  */
+  double second_index;       /* its global index (-1 = none)          */
+  double c_peak, c_prev, c_next;   /* c[peak], c[peak-1], c[peak+1] when owned, else NaN */
+} sonar_xcorr_shard_metrics;
+typedef struct sonar_xcorr_shard sonar_xcorr_shard;   /* opaque: device state of one shard */
+int sonar_xcorr_shard_open(sonar_ctx* ctx, const double* a, int64_t na, const double* b,
+                           int64_t nb, int max_lag, int64_t idx_lo, int64_t idx_hi,
+                           sonar_xcorr_shard** out, sonar_xcorr_shard_peak* peak);
+int sonar_xcorr_shard_metrics_f64(sonar_xcorr_shard* sh, int64_t global_peak_index,
+                                  sonar_xcorr_shard_metrics* out);
+/* copies this shard's correlations (idx_hi-idx_lo doubles) to the host */
+int sonar_xcorr_shard_corr(sonar_xcorr_shard* sh, double* corr);
+void sonar_xcorr_shard_close(sonar_xcorr_shard* sh);
+/* pure host arithmetic over the gathered partials (same tie rules as findPeak) */
+int sonar_xcorr_merge_peaks(const sonar_xcorr_shard_peak* peaks, int n, int64_t* global_index);
+int sonar_xcorr_merge_metrics(const sonar_xcorr_shard_metrics* parts, int n, int64_t na,
+                              int64_t nb, int max_lag, int64_t global_peak_index,
+                              sonar_xcorr_summary* out);
+
+/* stats.AlignmentResult scalars (algorithms/stats/alignment.go:34-58) */
+typedef struct sonar_align_result {
+  int32_t method;            /* stats.AlignmentMethod: 0 DTW, 1 cross-correlation, 3 hybrid */
+  int32_t offset;            /* alignment.go:164 / :140 (samples)                  */
+  double offset_seconds;     /* alignment.go:165 / :141                            */
+  double confidence;         /* alignment.go:183-243 / :420-452                    */
+  double similarity;         /* alignment.go:171-174 / :380-405                    */
+  double alignment_quality;  /* alignment.go:245-305 / :543-566                    */
+  double noise_level;        /* alignment.go:178 (can be -Inf)                     */
+  double stability;          /* alignment.go:618-643 (DTW only)                    */
+  int32_t query_length;
+  int32_t reference_length;
+  int32_t sample_rate;
+  int32_t reserved0;
+} sonar_align_result;
+
+/* AlignmentAnalyzer.AlignFeatures with method = AlignmentCrossCorrelation on
+ * the first feature component (alignment.go:84-106,151-181,363-378) — the call
+ * extractors.alignWithFeatures makes for "corr_energy"
+ * (fingerprint/extractors/alignment.go:323-332,357-409), including its
+ * max-lag clamp min(maxLagFrames, minFrames-1) (:372-374). */
+int sonar_align_xcorr_f64(sonar_ctx* ctx, const double* query, int64_t nq, const double* reference,
+                          int64_t nr, int max_lag_frames, int hop_size, int sample_rate,
+                          double* corr, sonar_xcorr_summary* xc, sonar_align_result* out);
+
+/* ------------------------------------------------------------------------- */
+/* alignment: DTW                                                             */
+/* ------------------------------------------------------------------------- */
+
+typedef enum sonar_step_pattern {
+  SONAR_STEP_SYMMETRIC2 = 0, /* dtw.go:140-142 (unweighted 3-way min) */
+  SONAR_STEP_ASYMMETRIC = 1, /* dtw.go:144-146 */
+  SONAR_STEP_SYMMETRIC1 = 2  /* dtw.go:148-157 */
+} sonar_step_pattern;
+
+typedef enum sonar_metric {
+  SONAR_METRIC_EUCLIDEAN = 0 /* distance.go:29-36; others UNSUPPORTED on this path */
+} sonar_metric;
+
+/* stats.DTWResult (algorithms/stats/dtw.go:18-34). Caller allocates path_*
+ * with capacity n+m; cost_matrix (nullable) is the full [n][m+1] matrix the
+ * reference returns as CostMatrix (dtw.go:96) — opt-in, SURVEY F7. */
+typedef struct sonar_dtw_out {
+  int32_t* path_query;       /* AlignPoint.QueryIndex (can be -1, dtw.go:169-197) */
+  int32_t* path_ref;         /* AlignPoint.RefIndex                               */
+  double* path_cost;         /* AlignPoint.Cost = C[i][j]-C[i-1][j-1] (dtw.go:171-174) */
+  int64_t path_cap;
+  int64_t path_len;          /* written                                           */
+  double distance;           /* C[n][m]/len(path)      (dtw.go:88-91)             */
+  double total_cost;         /* C[n][m]                                           */
+  double* cost_matrix;       /* optional [n][m+1]                                 */
+} sonar_dtw_out;
+
+/* DTWAlignment.Align (algorithms/stats/dtw.go:55-217): q [n][dim], r [m][dim]
+ * row-major; band <= 0 = unconstrained (dtw.go:115). */
+int sonar_dtw_f64(sonar_ctx* ctx, const double* q, int n, const double* r, int m, int dim,
+                  int band, int step_pattern, int metric, sonar_dtw_out* out);
+
+/* Batch of independent pairs of identical shape (replicas). */
+int sonar_dtw_batch_f64(sonar_ctx* ctx, const double* const* q, const double* const* r,
+                        int n_pairs, int n, int m, int dim, int band, int step_pattern, int metric,
+                        sonar_dtw_out* outs);
+
+/* AlignmentAnalyzer.alignWithDTW's scalars from a finished path
+ * (algorithms/stats/alignment.go:129-148,380-643). Host arithmetic. */
+int sonar_align_dtw_scalars(const sonar_dtw_out* dtw, int n, int m, int sample_rate,
+                            sonar_align_result* out);
+
+/* ------------------------------------------------------------------------- */
+/* comparison                                                                 */
+/* ------------------------------------------------------------------------- */
+
+/* extractMFCCStatistics x2 + cosineSimilarity (fingerprint/comparison.go:
+ * 774-800,858-873): per column gonum mean and unbiased variance over the
+ * frames, 2*dim statistics per side, cosine of the two vectors.
+ * dim == 1 gives compareSequenceStats (comparison.go:827-842). */
+int sonar_colstats_cosine_f64(sonar_ctx* ctx, const double* x, int64_t tx, const double* y,
+                              int64_t ty, int dim, double* sim);
+
+/* Column mean / unbiased std only (2*dim doubles: means then stds). */
+int sonar_colstats_f64(sonar_ctx* ctx, const double* x, int64_t t, int dim, double* stats);
+
+/* One side of FingerprintComparator.Compare: the feature arrays Compare reads
+ * (comparison.go:266-341,646-771). NULL / zero-length = feature absent. */
+typedef struct sonar_cmp_features {
+  const double* mfcc; int64_t mfcc_frames; int32_t mfcc_dim; int32_t content_type;
+  const double* spectral_centroid; int64_t n_centroid;
+  const double* spectral_rolloff; int64_t n_rolloff;
+  const double* spectral_flux; int64_t n_flux;
+  int32_t has_spectral; int32_t has_harmonic;
+  const double* harmonic_ratio; int64_t n_harmonic_ratio;
+  const double* pitch_estimate; int64_t n_pitch;
+  const double* rms_energy; int64_t n_rms;       /* temporal (comparison.go:688-718) */
+  int32_t has_temporal; int32_t reserved0;
+  double dynamic_range, silence_ratio, onset_density;
+} sonar_cmp_features;
+
+/* feature weights in the order mfcc, spectral, chroma, temporal, speech,
+ * harmonic, energy (comparison.go:1055-1104; fp1.Metadata["feature_weights"]) */
+typedef struct sonar_cmp_weights { double w[7]; } sonar_cmp_weights;
+
+/* SimilarityResult scalars (comparison.go:28-39) */
+typedef struct sonar_cmp_result {
+  double overall_similarity, feature_similarity, confidence;
+  double dist_mfcc, dist_spectral, dist_temporal, dist_harmonic;   /* NaN = feature not compared */
+  int32_t content_type_match; int32_t n_features;
+} sonar_cmp_result;
+
+/* FingerprintComparator.Compare (comparison.go:133-194) on flattened features. */
+int sonar_compare_f64(sonar_ctx* ctx, const sonar_cmp_features* f1, const sonar_cmp_features* f2,
+                      const sonar_cmp_weights* weights, int enable_content_filter,
+                      sonar_cmp_result* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONAR_H_ */
