@@ -1,0 +1,198 @@
+// Internal declarations shared by the CUDA library sources (libsonar.so).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sonar.h"
+
+namespace sonar {
+
+// ---- errors ----------------------------------------------------------------
+int set_error(int code, const std::string& msg);
+int cuda_error(cudaError_t e, const char* what);
+const std::string& last_error_string();
+#define SONAR_CUDA(call)                                   \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) return ::sonar::cuda_error(e__, #call); \
+  } while (0)
+
+// ---- host-side table construction (host_tables.cpp) ------------------------
+// All tables are built in float64 exactly as the reference's constructors do
+// and rounded to float32 once.
+int host_window(int type, int n, bool symmetric, bool normalize, double beta, double alpha,
+                double* w);
+// mel_scale.go:29-86 bin points; returns false when a non-empty segment would
+// index a negative bin (the reference would panic).
+bool host_mel_bins(int n_mel, int fft_size, int sample_rate, double low, double high,
+                   std::vector<int64_t>& bins);
+void resolve_mfcc(const sonar_fp_params* p, int* n_mfcc, int* n_mel, double* high, double* lifter);
+int host_fp_sizes(const sonar_fp_params* p, int64_t n, sonar_fp_sizes_t* out);
+int host_fp_layout(const sonar_fp_params* p, int64_t n, sonar_fp_dev_layout_t* out);
+int actual_max_lag(int max_lag, int64_t l1, int64_t l2);
+int64_t overlap_len(int64_t l1, int64_t l2, int64_t lag);
+void xcorr_derive(sonar_xcorr_summary* s, int64_t na, int64_t nb);  // p-value, overlap, significance
+double corr_confidence(const sonar_xcorr_summary* c);
+double corr_quality(const sonar_xcorr_summary* c, int max_lag);
+int host_align_dtw_scalars(const sonar_dtw_out* d, int n, int m, int sr, sonar_align_result* out);
+
+// ---- fused STFT + feature kernel (stft_features.cu) ------------------------
+struct MelRegion {  // bins [prev next_b, next_b): fall=(bhi-k)*inv_f -> acc[r-1], rise=(k-blo)*inv_r -> acc[r]
+  int next_b;
+  float blo, bhi, inv_f, inv_r;
+};
+
+constexpr int kMaxMel = 64;
+constexpr int kMaxMfcc = 32;
+
+struct FpPlan {  // immutable once built; cached per context keyed by the parameters
+  int R1 = 0, R2 = 0, N = 0, hop = 0, B = 0;
+  int n_mfcc = 0, n_mel = 0, n_regions = 0;
+  int algo_sr = 0, split = 0, slope_on = 0;
+  double freq_scale = 0;  // sr / N
+  double slope_ntot = 0, slope_xxtot = 0;
+  // one device blob; offsets in bytes
+  void* d_blob = nullptr;
+  size_t blob_bytes = 0;
+  size_t off_win2 = 0, off_tw1 = 0, off_wn = 0, off_xtab = 0, off_dct = 0, off_lift = 0, off_regions = 0,
+         off_chunk_region = 0, off_hann = 0;
+  ~FpPlan();
+};
+
+struct StftArgs {
+  const double* pcm;
+  int64_t n, stride;
+  int n_streams;
+  int64_t T, Te;
+  int hop;
+  int runs_per_stream;
+  int64_t total_runs;
+  // tables
+  const float2* win2;
+  const float2* tw1;
+  const float2* wn;
+  const float* xtab;
+  const float* dct;
+  const float* lift;
+  const MelRegion* regions;
+  const int* chunk_region;
+  int n_regions, n_mel, n_mfcc, split, slope_on, mfcc_on;
+  double freq_scale, slope_ntot, slope_xxtot;
+  // features mode outputs (device layout, per-stream stride in doubles)
+  double* feat;
+  int64_t feat_stride;
+  int64_t o_mfcc, o_centroid, o_rolloff, o_bandwidth, o_flatness, o_crest, o_slope, o_flux, o_low, o_high;
+  // spectrum mode outputs (single stream)
+  double* mag;
+  double* phase;
+  double* cplx;
+};
+
+int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out);
+int launch_stft_features(const FpPlan& plan, StftArgs& a, bool spectrum_mode, cudaStream_t st);
+bool stft_supported(int window_size);
+
+// ---- exact FP64 time-domain kernels (timedomain.cu) -------------------------
+// o_* are offsets (doubles) into each stream's output block; < 0 = not wanted.
+int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int frame,
+                      int hop, int64_t Tn, int sr, double* out, int64_t out_stride, int64_t o_energy,
+                      int64_t o_entropy, int64_t o_zcr, cudaStream_t st);
+int launch_variance(const double* x, int64_t n, int64_t stride, int n_streams, double* out, int64_t out_stride,
+                    cudaStream_t st);
+int launch_rms_windows(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int win,
+                       int hop, int64_t nw, double* out, int64_t out_stride, cudaStream_t st);
+int launch_loudness_range(const double* rms, int64_t nw, int64_t in_stride, int n_streams, double* out,
+                          int64_t out_stride, cudaStream_t st);
+int launch_fill(double* p, int64_t n, double v, cudaStream_t st);
+int launch_fill_strided(double* p, int64_t count, int64_t stride, int n_streams, double v, cudaStream_t st);
+
+// ---- YIN (yin.cu) ------------------------------------------------------------
+// scratch: per stream 2*Tp doubles, scratch_stride apart; hann_dev: un-normalised symmetric Hann(1024)
+int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, int sr, int64_t Tp,
+               const double* hann_dev, double* feat, int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
+               int64_t o_voicing, int64_t o_hratio, int64_t o_inharm, int64_t o_tonal, double* scratch,
+               int64_t scratch_stride, cudaStream_t st);
+
+// ---- cross-correlation (xcorr.cu) ------------------------------------------
+// z-score `count` sequences (population sigma, reference summation order): in[s*in_stride .. +n)
+int launch_znorm(const double* x, int64_t n, int64_t in_stride, int count, double* z, int64_t out_stride,
+                 cudaStream_t st);
+struct XcorrPairOut {  // device result of one pair (or one lag shard of a pair)
+  double peak;            // exact c[peak_index]
+  double noise_sum, noise_cnt, max_sidelobe;
+  double second_abs, second_val;
+  double c_prev, c_next;  // NaN when not inside [idx_lo, idx_hi)
+  int64_t peak_index;     // global lag index, -1 = empty shard
+  int64_t second_index;   // -1 = none
+  int32_t n_candidates, pad;
+};
+size_t xcorr_scratch_bytes(int64_t na, int64_t nb, int n_pairs, int64_t n_lags);
+// corr: n_pairs * corr_stride doubles (lag indices idx_lo..idx_hi-1 of each pair at corr + p*corr_stride)
+int launch_xcorr(const double* za, int64_t na, int64_t sa, const double* zb, int64_t nb, int64_t sb, int n_pairs,
+                 int aml, int64_t idx_lo, int64_t idx_hi, double* corr, int64_t corr_stride, void* scratch,
+                 XcorrPairOut* out, cudaStream_t st);
+int launch_xcorr_metrics(const double* corr, int64_t corr_stride, int n_pairs, int64_t idx_lo, int64_t idx_hi,
+                         const XcorrPairOut* peaks_dev, int64_t peak_override, XcorrPairOut* out,
+                         cudaStream_t st);
+
+// ---- DTW (dtw.cu) -------------------------------------------------------------
+struct DtwGeom {
+  int n, m, band;   // band <= 0: unconstrained
+  int64_t W;        // cells per stored row
+  int64_t cells;    // cells per pair ((n+1) rows)
+  int max_diag;     // max cells on one anti-diagonal
+};
+int dtw_geometry(int n, int m, int band, DtwGeom* g);
+struct DtwPairOut {
+  double total_cost;
+  int64_t path_len;
+};
+int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, int dim, int step, double* cells,
+               int32_t* path_q, int32_t* path_r, double* path_c, int64_t path_cap, DtwPairOut* out,
+               cudaStream_t st);
+int launch_dtw_expand(const double* cells, const DtwGeom& g, double* full, cudaStream_t st);
+
+// ---- column statistics (colstats.cu) ----------------------------------------
+int launch_colstats(const double* x, int64_t t, int dim, double* stats, cudaStream_t st);
+
+// ---- context ------------------------------------------------------------------
+struct Buf {  // growable allocation (device or pinned host)
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+struct Slot {  // one in-flight unit of work on a device: its stream and buffers
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;
+  Buf d_in, d_out, d_tmp, h_in, h_out;
+};
+struct DevCtx {
+  int device = 0;
+  Slot slot[2];
+  int ensure_dev(Buf& b, size_t bytes);
+  int ensure_host(Buf& b, size_t bytes);
+};
+
+}  // namespace sonar
+
+struct sonar_ctx {
+  std::vector<sonar::DevCtx> devs;
+  std::mutex mu;       // guards the plan cache
+  std::mutex call_mu;  // one in-flight call per context (slots and their buffers are per context)
+  std::map<std::string, std::shared_ptr<sonar::FpPlan>> plans;
+  std::atomic<uint64_t> launches{0};
+};
+
+namespace sonar {
+void count_launch(int n = 1);  // adds to the calling thread's current context counter
+void set_current_ctx(sonar_ctx* c);
+// speech.go:370-408 temporal block (temporal.cu)
+int fingerprint_temporal_tail(sonar_ctx* ctx, const double* const* pcm, const int64_t* n, int n_streams,
+                              const sonar_fp_params* p, sonar_fp_out* outs);
+}  // namespace sonar

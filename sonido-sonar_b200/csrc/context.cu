@@ -1,0 +1,237 @@
+// Context, error plumbing, memory helpers and the host-arithmetic entry points of
+// the C ABI (include/sonar.h).  No kernels live here.
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <sstream>
+
+#include "common.h"
+
+namespace sonar {
+
+namespace {
+thread_local std::string g_err;
+thread_local sonar_ctx* g_cur = nullptr;
+}  // namespace
+
+int set_error(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_error(cudaError_t e, const char* what) {
+  std::ostringstream os;
+  os << "CUDA error: " << cudaGetErrorString(e) << " (" << what << ")";
+  g_err = os.str();
+  return e == cudaErrorMemoryAllocation ? SONAR_ERR_NOMEM : SONAR_ERR_CUDA;
+}
+const std::string& last_error_string() { return g_err; }
+void count_launch(int n) {
+  if (g_cur) g_cur->launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+}
+void set_current_ctx(sonar_ctx* c) { g_cur = c; }
+
+int DevCtx::ensure_dev(Buf& b, size_t bytes) {
+  if (bytes <= b.bytes) return SONAR_OK;
+  if (b.p) {
+    SONAR_CUDA(cudaDeviceSynchronize());
+    SONAR_CUDA(cudaFree(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  const size_t want = bytes + bytes / 8 + 256;  // head-room against ping-pong regrowth
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    cudaGetLastError();
+    std::ostringstream os;
+    os << "device allocation of " << want << " bytes failed: " << cudaGetErrorString(e);
+    return set_error(SONAR_ERR_NOMEM, os.str());
+  }
+  b.bytes = want;
+  return SONAR_OK;
+}
+
+int DevCtx::ensure_host(Buf& b, size_t bytes) {
+  if (bytes <= b.bytes) return SONAR_OK;
+  if (b.p) {
+    SONAR_CUDA(cudaDeviceSynchronize());
+    SONAR_CUDA(cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  const size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMallocHost(&b.p, want);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    cudaGetLastError();
+    std::ostringstream os;
+    os << "pinned host allocation of " << want << " bytes failed: " << cudaGetErrorString(e);
+    return set_error(SONAR_ERR_NOMEM, os.str());
+  }
+  b.bytes = want;
+  return SONAR_OK;
+}
+
+}  // namespace sonar
+
+using namespace sonar;
+
+extern "C" {
+
+int sonar_init(int n_devices, const int* device_ids, sonar_ctx** out) {
+  if (!out) return set_error(SONAR_ERR_INVALID, "nil argument");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return set_error(SONAR_ERR_CUDA,
+                     std::string("no usable CUDA device (there is no CPU fallback): ") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  }
+  std::vector<int> ids;
+  if (n_devices <= 0) {
+    int cur = 0;
+    SONAR_CUDA(cudaGetDevice(&cur));
+    ids.push_back(cur);
+  } else {
+    for (int i = 0; i < n_devices; i++) ids.push_back(device_ids ? device_ids[i] : i);
+  }
+  for (int id : ids)
+    if (id < 0 || id >= count) return set_error(SONAR_ERR_INVALID, "device id out of range");
+  int restore = 0;
+  cudaGetDevice(&restore);
+  auto* ctx = new sonar_ctx();
+  ctx->devs.resize(ids.size());
+  for (size_t i = 0; i < ids.size(); i++) {
+    DevCtx& d = ctx->devs[i];
+    d.device = ids[i];
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(d.device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, d.device)) != cudaSuccess) {
+      delete ctx;
+      return cuda_error(e, "cudaSetDevice");
+    }
+    if (prop.major < 10) {
+      delete ctx;
+      return set_error(SONAR_ERR_CUDA, "libsonar.so is built for sm_100a (B200) only; device is older");
+    }
+    for (auto& s : d.slot) {
+      if ((e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) {
+        delete ctx;
+        return cuda_error(e, "cudaStreamCreate");
+      }
+    }
+  }
+  cudaSetDevice(restore);
+  *out = ctx;
+  return SONAR_OK;
+}
+
+void sonar_destroy(sonar_ctx* ctx) {
+  if (!ctx) return;
+  int restore = 0;
+  cudaGetDevice(&restore);
+  for (auto& d : ctx->devs) {
+    cudaSetDevice(d.device);
+    cudaDeviceSynchronize();
+    for (auto& s : d.slot) {
+      if (s.d_in.p) cudaFree(s.d_in.p);
+      if (s.d_out.p) cudaFree(s.d_out.p);
+      if (s.d_tmp.p) cudaFree(s.d_tmp.p);
+      if (s.h_in.p) cudaFreeHost(s.h_in.p);
+      if (s.h_out.p) cudaFreeHost(s.h_out.p);
+      if (s.done) cudaEventDestroy(s.done);
+      if (s.st) cudaStreamDestroy(s.st);
+    }
+  }
+  if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].device);
+  ctx->plans.clear();
+  cudaSetDevice(restore);
+  delete ctx;
+}
+
+const char* sonar_last_error(void) { return last_error_string().c_str(); }
+int sonar_abi_version(void) { return SONAR_ABI_VERSION; }
+const char* sonar_backend(void) { return "cuda-sm100a"; }
+
+int sonar_host_alloc(sonar_ctx* ctx, uint64_t bytes, void** out) {
+  if (!ctx || !out) return set_error(SONAR_ERR_INVALID, "nil argument");
+  SONAR_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+  return SONAR_OK;
+}
+int sonar_host_free(sonar_ctx*, void* p) {
+  if (p) SONAR_CUDA(cudaFreeHost(p));
+  return SONAR_OK;
+}
+int sonar_dev_alloc(sonar_ctx* ctx, uint64_t bytes, void** out) {
+  if (!ctx || !out) return set_error(SONAR_ERR_INVALID, "nil argument");
+  SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
+  SONAR_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  return SONAR_OK;
+}
+int sonar_dev_free(sonar_ctx* ctx, void* p) {
+  if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
+  if (p) SONAR_CUDA(cudaFree(p));
+  return SONAR_OK;
+}
+int sonar_memcpy_h2d(sonar_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
+  SONAR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->devs[0].slot[0].st));
+  SONAR_CUDA(cudaStreamSynchronize(ctx->devs[0].slot[0].st));
+  return SONAR_OK;
+}
+int sonar_memcpy_d2h(sonar_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
+  SONAR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->devs[0].slot[0].st));
+  SONAR_CUDA(cudaStreamSynchronize(ctx->devs[0].slot[0].st));
+  return SONAR_OK;
+}
+int sonar_synchronize(sonar_ctx* ctx) {
+  if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  for (auto& d : ctx->devs) {
+    SONAR_CUDA(cudaSetDevice(d.device));
+    for (auto& s : d.slot) SONAR_CUDA(cudaStreamSynchronize(s.st));
+  }
+  SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
+  return SONAR_OK;
+}
+uint64_t sonar_kernel_launches(sonar_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int sonar_window_f64(int type, int size, int symmetric, int normalize, double beta, double alpha, double* out) {
+  if (!out) return set_error(SONAR_ERR_INVALID, "nil argument");
+  return host_window(type, size, symmetric != 0, normalize != 0, beta, alpha, out);
+}
+
+void sonar_fp_params_default(sonar_fp_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->window_size = 1024;
+  p->hop_size = 256;
+  p->window_type = SONAR_WINDOW_HANN;
+  p->algo_sample_rate = 0;  // what stock GenerateFingerprint passes (content_config.go:87-103)
+  p->call_sample_rate = 44100;
+  p->energy_frame = 1024;
+  p->energy_hop = 256;
+  p->n_mfcc = 13;
+  p->n_mel = 26;
+  p->use_liftering = 1;
+  p->enable = SONAR_FP_ENABLE_MFCC;
+  p->lifter = 22.0;
+  p->pre_emph_alpha = 0.97;
+}
+
+int sonar_fp_sizes(const sonar_fp_params* p, int64_t n, sonar_fp_sizes_t* out) { return host_fp_sizes(p, n, out); }
+
+int sonar_fp_dev_layout(const sonar_fp_params* p, int64_t n, sonar_fp_dev_layout_t* out) {
+  if (!p || !out) return set_error(SONAR_ERR_INVALID, "nil argument");
+  return host_fp_layout(p, n, out);
+}
+
+int sonar_align_dtw_scalars(const sonar_dtw_out* d, int n, int m, int sr, sonar_align_result* out) {
+  return host_align_dtw_scalars(d, n, m, sr, out);
+}
+
+}  // extern "C"

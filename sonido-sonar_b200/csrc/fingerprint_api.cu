@@ -1,0 +1,437 @@
+// C-ABI entry points of the fingerprint path: kernel sequencing, H2D/D2H staging,
+// multi-device sharding of stream batches.  The arithmetic lives in
+// stft_features.cu / timedomain.cu / yin.cu.
+//
+//   GenerateFingerprint            fingerprint/fingerprint.go:137-236
+//   SpeechFeatureExtractor         fingerprint/extractors/speech.go:135-243
+//   ComputeSTFTWithWindow          fingerprint/analyzers/spectral.go:385-545
+//   ComputeSTFTBatch (batch form)  fingerprint/analyzers/spectral.go:234-285
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+#include <thread>
+
+#include "common.h"
+
+namespace sonar {
+
+namespace {
+
+int64_t go_int(double x) {
+  if (!(x > -9.2e18 && x < 9.2e18)) return INT64_MIN;
+  return (int64_t)x;
+}
+
+std::string plan_key(int device, const sonar_fp_params* p) {
+  std::ostringstream os;
+  os.precision(17);
+  os << device << '/' << p->window_size << '/' << p->hop_size << '/' << p->window_type << '/'
+     << p->algo_sample_rate << '/' << p->n_mfcc << '/' << p->n_mel << '/' << p->use_liftering << '/' << p->low_hz
+     << '/' << p->high_hz << '/' << p->lifter;
+  return os.str();
+}
+
+int get_plan(sonar_ctx* ctx, int device, const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  const std::string key = plan_key(device, p);
+  auto it = ctx->plans.find(key);
+  if (it != ctx->plans.end()) {
+    *out = it->second;
+    return SONAR_OK;
+  }
+  std::shared_ptr<FpPlan> plan;
+  int rc = build_fp_plan(p, &plan);  // allocates on the current device
+  if (rc) return rc;
+  ctx->plans[key] = plan;
+  *out = plan;
+  return SONAR_OK;
+}
+
+int validate(const sonar_fp_params* p) {
+  if (p->call_sample_rate <= 0) return set_error(SONAR_ERR_INVALID, "sample rate must be positive");  // speech.go:143
+  if (p->enable & SONAR_FP_ENABLE_SPEECH)
+    return set_error(SONAR_ERR_UNSUPPORTED, "speech feature group is outside this path's scope");
+  if (!stft_supported(p->window_size))
+    return set_error(SONAR_ERR_UNSUPPORTED, "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
+  return SONAR_OK;
+}
+
+struct FpShape {
+  sonar_fp_sizes_t sz;
+  sonar_fp_dev_layout_t L;
+  int64_t lr_win = 0, lr_hop = 0, lr_nw = 0;  // loudness-range windows (energy.go:157-179)
+  size_t tmp_doubles_per_stream = 0;
+};
+
+int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s) {
+  int rc = host_fp_sizes(p, n, &s->sz);
+  if (rc) return rc;
+  rc = host_fp_layout(p, n, &s->L);
+  if (rc) return rc;
+  s->lr_win = s->lr_hop = s->lr_nw = 0;
+  if (p->algo_sample_rate > 0) {
+    s->lr_win = go_int(0.4 * (double)p->algo_sample_rate);
+    s->lr_hop = s->lr_win / 4;
+    if (s->lr_hop <= 0) s->lr_hop = 1;
+    s->lr_nw = (n < s->lr_win || s->lr_win <= 0) ? 0 : (n - s->lr_win) / s->lr_hop + 1;
+  }
+  s->tmp_doubles_per_stream = (size_t)(2 * s->sz.n_pitch_frames + s->lr_nw + 2);
+  return SONAR_OK;
+}
+
+// Enqueues every kernel of one uniform batch on `st`.  pcm_dev: ns streams of n samples,
+// `stride` apart; feat_dev: ns feature blocks of sh.L.total doubles; tmp_dev: ns *
+// sh.tmp_doubles_per_stream doubles.
+int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, const FpShape& sh,
+                        const double* pcm_dev, int64_t n, int64_t stride, int ns, double* feat_dev,
+                        double* tmp_dev, cudaStream_t st) {
+  std::shared_ptr<FpPlan> plan;
+  int rc = get_plan(ctx, device, p, &plan);
+  if (rc) return rc;
+  const auto& L = sh.L;
+  const int64_t T = sh.sz.n_frames, Te = sh.sz.n_energy_frames, Tp = sh.sz.n_pitch_frames;
+  const unsigned char* blob = static_cast<const unsigned char*>(plan->d_blob);
+
+  StftArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.pcm = pcm_dev;
+  a.n = n;
+  a.stride = stride;
+  a.n_streams = ns;
+  a.T = T;
+  a.Te = Te;
+  a.hop = p->hop_size;
+  a.win2 = reinterpret_cast<const float2*>(blob + plan->off_win2);
+  a.tw1 = reinterpret_cast<const float2*>(blob + plan->off_tw1);
+  a.wn = reinterpret_cast<const float2*>(blob + plan->off_wn);
+  a.xtab = reinterpret_cast<const float*>(blob + plan->off_xtab);
+  a.dct = reinterpret_cast<const float*>(blob + plan->off_dct);
+  a.lift = reinterpret_cast<const float*>(blob + plan->off_lift);
+  a.regions = reinterpret_cast<const MelRegion*>(blob + plan->off_regions);
+  a.chunk_region = reinterpret_cast<const int*>(blob + plan->off_chunk_region);
+  a.n_regions = plan->n_regions;
+  a.n_mel = plan->n_mel;
+  a.n_mfcc = plan->n_mfcc;
+  a.split = plan->split;
+  a.slope_on = plan->slope_on;
+  a.mfcc_on = (p->enable & SONAR_FP_ENABLE_MFCC) ? 1 : 0;
+  a.freq_scale = plan->freq_scale;
+  a.slope_ntot = plan->slope_ntot;
+  a.slope_xxtot = plan->slope_xxtot;
+  a.feat = feat_dev;
+  a.feat_stride = L.total;
+  a.o_mfcc = L.mfcc;
+  a.o_centroid = L.spectral_centroid;
+  a.o_rolloff = L.spectral_rolloff;
+  a.o_bandwidth = L.spectral_bandwidth;
+  a.o_flatness = L.spectral_flatness;
+  a.o_crest = L.spectral_crest;
+  a.o_slope = L.spectral_slope;
+  a.o_flux = L.spectral_flux;
+  a.o_low = L.low_energy_ratio;
+  a.o_high = L.high_energy_ratio;
+  rc = launch_stft_features(*plan, a, false, st);
+  if (rc) return rc;
+  if (!a.mfcc_on) {
+    rc = launch_fill_strided(feat_dev + L.mfcc, T * sh.sz.n_mfcc, L.total, ns, 0.0, st);
+    if (rc) return rc;
+  }
+
+  // exact FP64 walks over the pre-emphasised PCM: short-time energy (+entropy) and ZCR
+  const bool same_grid = (Te == T) && p->energy_frame == p->window_size && p->energy_hop == p->hop_size;
+  if (same_grid) {
+    rc = launch_frame_walk(pcm_dev, n, stride, ns, p->pre_emph_alpha, p->window_size, p->hop_size, T,
+                           p->algo_sample_rate, feat_dev, L.total, L.short_time_energy, L.energy_entropy,
+                           L.zero_crossing_rate, st);
+    if (rc) return rc;
+  } else {
+    if (Te > 0) {
+      rc = launch_frame_walk(pcm_dev, n, stride, ns, p->pre_emph_alpha, p->energy_frame, p->energy_hop, Te,
+                             p->algo_sample_rate, feat_dev, L.total, L.short_time_energy, L.energy_entropy, -1,
+                             st);
+      if (rc) return rc;
+    }
+    rc = launch_frame_walk(pcm_dev, n, stride, ns, p->pre_emph_alpha, p->window_size, p->hop_size, T,
+                           p->algo_sample_rate, feat_dev, L.total, -1, -1, L.zero_crossing_rate, st);
+    if (rc) return rc;
+  }
+  if (Te > T) {  // band ratios only exist where a magnitude frame does (speech.go:436-456)
+    rc = launch_fill_strided(feat_dev + L.low_energy_ratio + T, Te - T, L.total, ns, 0.0, st);
+    if (rc) return rc;
+    rc = launch_fill_strided(feat_dev + L.high_energy_ratio + T, Te - T, L.total, ns, 0.0, st);
+    if (rc) return rc;
+  }
+
+  // scalars: [0] energy variance (energy.go:97-118), [1] loudness range (energy.go:157-225)
+  rc = launch_fill_strided(feat_dev + L.scalars, L.total - L.scalars, L.total, ns, 0.0, st);
+  if (rc) return rc;
+  if (Te >= 2) {
+    rc = launch_variance(feat_dev + L.short_time_energy, Te, L.total, ns, feat_dev + L.scalars, L.total, st);
+    if (rc) return rc;
+  }
+  const int64_t tstride = (int64_t)sh.tmp_doubles_per_stream;
+  if (sh.lr_nw > 0) {
+    double* rms = tmp_dev + 2 * Tp;
+    rc = launch_rms_windows(pcm_dev, n, stride, ns, p->pre_emph_alpha, (int)sh.lr_win, (int)sh.lr_hop, sh.lr_nw,
+                            rms, tstride, st);
+    if (rc) return rc;
+    rc = launch_loudness_range(rms, sh.lr_nw, tstride, ns, feat_dev + L.scalars + 1, L.total, st);
+    if (rc) return rc;
+  }
+
+  // harmonic block (speech.go:464-509)
+  const double* hann = reinterpret_cast<const double*>(blob + plan->off_hann);
+  rc = launch_yin(pcm_dev, stride, ns, p->pre_emph_alpha, p->algo_sample_rate, Tp, hann, feat_dev, L.total,
+                  L.pitch_estimate, L.pitch_confidence, L.voicing_strength, L.harmonic_ratio,
+                  L.inharmonicity_ratio, L.tonal_centroid, tmp_dev, tstride, st);
+  return rc;
+}
+
+void scatter_block(const double* f, const FpShape& sh, sonar_fp_out* o) {
+  const auto& L = sh.L;
+  const int64_t T = sh.sz.n_frames, Te = sh.sz.n_energy_frames, Tp = sh.sz.n_pitch_frames;
+  auto cp = [&](double* dst, int64_t off, int64_t cnt) {
+    if (dst && cnt > 0) std::memcpy(dst, f + off, sizeof(double) * (size_t)cnt);
+  };
+  cp(o->mfcc, L.mfcc, T * sh.sz.n_mfcc);
+  cp(o->spectral_centroid, L.spectral_centroid, T);
+  cp(o->spectral_rolloff, L.spectral_rolloff, T);
+  cp(o->spectral_bandwidth, L.spectral_bandwidth, T);
+  cp(o->spectral_flatness, L.spectral_flatness, T);
+  cp(o->spectral_crest, L.spectral_crest, T);
+  cp(o->spectral_slope, L.spectral_slope, T);
+  cp(o->spectral_flux, L.spectral_flux, sh.sz.n_flux);
+  cp(o->zero_crossing_rate, L.zero_crossing_rate, T);
+  cp(o->short_time_energy, L.short_time_energy, Te);
+  cp(o->energy_entropy, L.energy_entropy, Te);
+  cp(o->low_energy_ratio, L.low_energy_ratio, Te);
+  cp(o->high_energy_ratio, L.high_energy_ratio, Te);
+  cp(o->pitch_estimate, L.pitch_estimate, Tp);
+  cp(o->pitch_confidence, L.pitch_confidence, Tp);
+  cp(o->voicing_strength, L.voicing_strength, Tp);
+  cp(o->harmonic_ratio, L.harmonic_ratio, Tp);
+  cp(o->inharmonicity_ratio, L.inharmonicity_ratio, Tp);
+  cp(o->tonal_centroid, L.tonal_centroid, Tp);
+  o->energy_variance = f[L.scalars];
+  o->loudness_range = f[L.scalars + 1];
+  o->dynamic_range = 0;
+  o->silence_ratio = 0;
+  o->peak_amplitude = 0;
+  o->average_amplitude = 0;
+  o->onset_density = 0;
+  o->n_attack_time = 0;
+}
+
+struct Chunk {  // consecutive streams of one device with identical length
+  std::vector<int> ids;
+  int64_t n = 0;
+  FpShape sh;
+};
+
+struct DeviceJob {
+  int rc = SONAR_OK;
+  std::string err;
+};
+
+// One device's share of a host batch: chunks alternate between the two slots so that
+// the H2D of chunk k+1 overlaps the kernels and D2H of chunk k.
+void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, const std::vector<Chunk>* chunks,
+                      const sonar_fp_params* p, sonar_fp_out* outs, DeviceJob* job) {
+  set_current_ctx(ctx);
+  auto fail = [&](int rc) {
+    job->rc = rc;
+    job->err = sonar_last_error();
+  };
+  cudaError_t e = cudaSetDevice(dev->device);
+  if (e != cudaSuccess) return fail(cuda_error(e, "cudaSetDevice"));
+  const Chunk* pending[2] = {nullptr, nullptr};
+  auto finish = [&](int si) -> int {
+    const Chunk* c = pending[si];
+    if (!c) return SONAR_OK;
+    Slot& s = dev->slot[si];
+    SONAR_CUDA(cudaEventSynchronize(s.done));
+    const double* h = static_cast<const double*>(s.h_out.p);
+    for (size_t i = 0; i < c->ids.size(); i++) scatter_block(h + (int64_t)i * c->sh.L.total, c->sh, &outs[c->ids[i]]);
+    pending[si] = nullptr;
+    return SONAR_OK;
+  };
+  int k = 0;
+  for (const Chunk& c : *chunks) {
+    const int si = k++ & 1;
+    Slot& s = dev->slot[si];
+    int rc = finish(si);
+    if (rc) return fail(rc);
+    const int ns = (int)c.ids.size();
+    const int64_t stride = (c.n + 1) & ~(int64_t)1;
+    const size_t out_bytes = sizeof(double) * (size_t)c.sh.L.total * ns;
+    if ((rc = dev->ensure_dev(s.d_in, sizeof(double) * (size_t)stride * ns)) ||
+        (rc = dev->ensure_dev(s.d_out, out_bytes)) ||
+        (rc = dev->ensure_dev(s.d_tmp, sizeof(double) * c.sh.tmp_doubles_per_stream * ns)) ||
+        (rc = dev->ensure_host(s.h_out, out_bytes)))
+      return fail(rc);
+    double* d_in = static_cast<double*>(s.d_in.p);
+    for (int i = 0; i < ns; i++) {
+      e = cudaMemcpyAsync(d_in + (int64_t)i * stride, pcm[c.ids[i]], sizeof(double) * (size_t)c.n,
+                          cudaMemcpyHostToDevice, s.st);
+      if (e != cudaSuccess) return fail(cuda_error(e, "cudaMemcpyAsync(H2D pcm)"));
+    }
+    rc = enqueue_fingerprint(ctx, dev->device, p, c.sh, d_in, c.n, stride, ns, static_cast<double*>(s.d_out.p),
+                             static_cast<double*>(s.d_tmp.p), s.st);
+    if (rc) return fail(rc);
+    e = cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.st);
+    if (e != cudaSuccess) return fail(cuda_error(e, "cudaMemcpyAsync(D2H features)"));
+    e = cudaEventRecord(s.done, s.st);
+    if (e != cudaSuccess) return fail(cuda_error(e, "cudaEventRecord"));
+    pending[si] = &c;
+  }
+  for (int si = 0; si < 2; si++) {
+    int rc = finish((k + si) & 1);
+    if (rc) return fail(rc);
+  }
+}
+
+constexpr size_t kChunkBytes = (size_t)768 << 20;  // PCM bytes per in-flight chunk and slot
+
+}  // namespace
+}  // namespace sonar
+
+using namespace sonar;
+
+extern "C" {
+
+int sonar_fingerprint_batch_f64(sonar_ctx* ctx, const double* const* pcm, const int64_t* n, int n_streams,
+                                const sonar_fp_params* p, sonar_fp_out* outs) {
+  if (!ctx || !p || (n_streams > 0 && (!pcm || !n || !outs)))
+    return set_error(SONAR_ERR_INVALID, "audio data cannot be nil");  // fingerprint.go:139
+  if (n_streams <= 0) return SONAR_OK;
+  std::lock_guard<std::mutex> call_lock(ctx->call_mu);
+  set_current_ctx(ctx);
+  int rc = validate(p);
+  if (rc) return rc;
+  const int nd = (int)ctx->devs.size();
+  std::vector<std::vector<Chunk>> per_dev(nd);
+  for (int s = 0; s < n_streams; s++) {
+    if (!pcm[s]) return set_error(SONAR_ERR_INVALID, "audio data cannot be nil");
+    auto& chunks = per_dev[s % nd];
+    const bool extend = !chunks.empty() && chunks.back().n == n[s] &&
+                        (chunks.back().ids.size() + 1) * (size_t)n[s] * sizeof(double) <= kChunkBytes;
+    if (!extend) {
+      Chunk c;
+      c.n = n[s];
+      rc = fp_shape(p, n[s], &c.sh);
+      if (rc) return rc;
+      chunks.push_back(std::move(c));
+    }
+    chunks.back().ids.push_back(s);
+  }
+  std::vector<DeviceJob> jobs(nd);
+  if (nd == 1) {
+    run_device_batch(ctx, &ctx->devs[0], pcm, &per_dev[0], p, outs, &jobs[0]);
+  } else {
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++)
+      th.emplace_back(run_device_batch, ctx, &ctx->devs[d], pcm, &per_dev[d], p, outs, &jobs[d]);
+    for (auto& t : th) t.join();
+    cudaSetDevice(ctx->devs[0].device);
+  }
+  for (auto& j : jobs)
+    if (j.rc) return set_error(j.rc, j.err);
+  if (p->enable & SONAR_FP_ENABLE_TEMPORAL) {
+    rc = fingerprint_temporal_tail(ctx, pcm, n, n_streams, p, outs);
+    if (rc) return rc;
+  }
+  return SONAR_OK;
+}
+
+int sonar_fingerprint_f64(sonar_ctx* ctx, const double* pcm, int64_t n, const sonar_fp_params* p,
+                          sonar_fp_out* out) {
+  if (!ctx || !pcm || !p || !out) return set_error(SONAR_ERR_INVALID, "audio data cannot be nil");
+  const double* ptrs[1] = {pcm};
+  return sonar_fingerprint_batch_f64(ctx, ptrs, &n, 1, p, out);
+}
+
+int sonar_fingerprint_batch_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n, int64_t stride, int n_streams,
+                                const sonar_fp_params* p, double* feat_dev) {
+  if (!ctx || !pcm_dev || !p || !feat_dev) return set_error(SONAR_ERR_INVALID, "audio data cannot be nil");
+  if (n_streams <= 0) return SONAR_OK;
+  if (stride < n) return set_error(SONAR_ERR_INVALID, "stride must be >= n");
+  std::lock_guard<std::mutex> call_lock(ctx->call_mu);
+  set_current_ctx(ctx);
+  int rc = validate(p);
+  if (rc) return rc;
+  if (p->enable & SONAR_FP_ENABLE_TEMPORAL)
+    return set_error(SONAR_ERR_UNSUPPORTED, "temporal features are not part of the device layout");
+  FpShape sh;
+  rc = fp_shape(p, n, &sh);
+  if (rc) return rc;
+  DevCtx& dev = ctx->devs[0];
+  SONAR_CUDA(cudaSetDevice(dev.device));
+  Slot& s = dev.slot[0];
+  rc = dev.ensure_dev(s.d_tmp, sizeof(double) * sh.tmp_doubles_per_stream * (size_t)n_streams);
+  if (rc) return rc;
+  return enqueue_fingerprint(ctx, dev.device, p, sh, pcm_dev, n, stride, n_streams, feat_dev,
+                             static_cast<double*>(s.d_tmp.p), s.st);
+}
+
+int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int hop, int window_type, double* mag,
+                   double* phase, double* cplx) {
+  if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  if (!pcm || n <= 0) return set_error(SONAR_ERR_EMPTY, "empty signal");  // analyzers/spectral.go:387
+  if (win <= 0) return set_error(SONAR_ERR_INVALID, "window size must be positive");
+  if (hop <= 0) return set_error(SONAR_ERR_INVALID, "hop size must be positive");
+  const int64_t T = (n - win) / hop + 1;
+  if (T <= 0) return set_error(SONAR_ERR_TOO_SHORT, "signal too short for given window size and hop size");
+  if (!mag) return set_error(SONAR_ERR_INVALID, "nil argument");
+  if (!stft_supported(win))
+    return set_error(SONAR_ERR_UNSUPPORTED, "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
+  std::lock_guard<std::mutex> call_lock(ctx->call_mu);
+  set_current_ctx(ctx);
+  sonar_fp_params p;
+  sonar_fp_params_default(&p);
+  p.window_size = win;
+  p.hop_size = hop;
+  p.window_type = window_type;
+  DevCtx& dev = ctx->devs[0];
+  SONAR_CUDA(cudaSetDevice(dev.device));
+  std::shared_ptr<FpPlan> plan;
+  int rc = get_plan(ctx, dev.device, &p, &plan);
+  if (rc) return rc;
+  Slot& s = dev.slot[0];
+  const int B = win / 2 + 1;
+  const size_t per = sizeof(double) * (size_t)T * B;
+  const size_t out_bytes = per * (1 + (phase ? 1 : 0) + (cplx ? 2 : 0));
+  const int64_t stride = (n + 1) & ~(int64_t)1;
+  if ((rc = dev.ensure_dev(s.d_in, sizeof(double) * (size_t)stride)) || (rc = dev.ensure_dev(s.d_out, out_bytes)))
+    return rc;
+  SONAR_CUDA(cudaMemcpyAsync(s.d_in.p, pcm, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s.st));
+  const unsigned char* blob = static_cast<const unsigned char*>(plan->d_blob);
+  StftArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.pcm = static_cast<const double*>(s.d_in.p);
+  a.n = n;
+  a.stride = stride;
+  a.n_streams = 1;
+  a.T = T;
+  a.hop = hop;
+  a.win2 = reinterpret_cast<const float2*>(blob + plan->off_win2);
+  a.tw1 = reinterpret_cast<const float2*>(blob + plan->off_tw1);
+  a.wn = reinterpret_cast<const float2*>(blob + plan->off_wn);
+  double* d = static_cast<double*>(s.d_out.p);
+  a.mag = d;
+  d += (size_t)T * B;
+  if (phase) {
+    a.phase = d;
+    d += (size_t)T * B;
+  }
+  if (cplx) a.cplx = d;
+  rc = launch_stft_features(*plan, a, true, s.st);
+  if (rc) return rc;
+  SONAR_CUDA(cudaMemcpyAsync(mag, a.mag, per, cudaMemcpyDeviceToHost, s.st));
+  if (phase) SONAR_CUDA(cudaMemcpyAsync(phase, a.phase, per, cudaMemcpyDeviceToHost, s.st));
+  if (cplx) SONAR_CUDA(cudaMemcpyAsync(cplx, a.cplx, 2 * per, cudaMemcpyDeviceToHost, s.st));
+  SONAR_CUDA(cudaStreamSynchronize(s.st));
+  return SONAR_OK;
+}
+
+}  // extern "C"

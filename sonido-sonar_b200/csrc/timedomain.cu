@@ -1,0 +1,282 @@
+// Exact float64 time-domain kernels.  Compiled with -fmad=false: Go on amd64 never
+// contracts a*b+c, and the short-time energies computed here feed the
+// cross-correlation arg-max and the DTW path, which must be bit-identical to
+// the reference (SURVEY.md §7 "hard parts" #1).
+//
+//   pre-emphasis          algorithms/filters/pre_emphasis.go:135-155,184-190
+//   short-time RMS energy algorithms/temporal/energy.go:25-50   (sequential sum, ascending j)
+//   energy entropy        fingerprint/extractors/speech.go:429-434
+//   zero-crossing rate    algorithms/spectral/zero_crossing_rate.go:37-53 on pre[tH : tH+W]
+//   energy variance       algorithms/temporal/energy.go:97-118
+//   loudness range        algorithms/temporal/energy.go:157-225
+//   RMS envelope 512/256  fingerprint/extractors/speech.go:739-767
+//
+// Layout: a CTA stages the pre-emphasised samples of FPB consecutive frames of one
+// stream in shared memory once (coalesced f64 loads, one pad word per hop so that
+// the per-thread sequential walks are bank-conflict free) and then each thread
+// accumulates ONE frame in the reference's order.  The chain of dependent DADDs is
+// what bounds this kernel (shared-memory resident chains per SM), not HBM.
+#include <cmath>
+
+#include "common.h"
+
+namespace sonar {
+namespace {
+
+constexpr int kTdThreads = 128;
+constexpr int kTdMaxTile = 27000;  // doubles of shared memory for the sample tile
+
+__device__ __forceinline__ double preemph(const double* __restrict__ x, int64_t i, double alpha) {
+  const double prev = i > 0 ? x[i - 1] : 0.0;
+  return x[i] - alpha * prev;  // -fmad=false: separate multiply and subtract
+}
+
+template <bool ENERGY, bool ZCR>
+__global__ void __launch_bounds__(kTdThreads) frame_walk_kernel(
+    const double* __restrict__ pcm, int64_t n, int64_t stride, double alpha, int frame, int hop, int64_t Tn,
+    int fpb, int sr, double* __restrict__ out, int64_t out_stride, int64_t o_energy, int64_t o_entropy,
+    int64_t o_zcr) {
+  extern __shared__ double tile[];
+  const int s = blockIdx.y;
+  const int64_t f0 = (int64_t)blockIdx.x * fpb;
+  if (f0 >= Tn) return;
+  const int nf = (int)((Tn - f0 < fpb) ? (Tn - f0) : fpb);
+  const double* __restrict__ x = pcm + (int64_t)s * stride;
+  const int64_t s0 = f0 * hop;
+  const int count = (nf - 1) * hop + frame;  // samples staged
+  const int pad = (hop & 1) ? 0 : 1;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const int64_t gi = s0 + i;
+    tile[i + (i / hop) * pad] = preemph(x, gi, alpha);
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= nf) return;
+  const int rs = hop + pad;
+  int phys = t * rs, jj = 0;
+  double sum = 0.0;
+  int crossings = 0;
+  bool prev_neg = false;
+  for (int j = 0; j < frame; ++j) {
+    const double y = tile[phys];
+    if (ENERGY) sum += y * y;
+    if (ZCR) {
+      const bool neg = y < 0.0;
+      if (j > 0 && neg != prev_neg) crossings++;
+      prev_neg = neg;
+    }
+    ++phys;
+    if (++jj == hop) {
+      jj = 0;
+      phys += pad;
+    }
+  }
+  double* __restrict__ o = out + (int64_t)s * out_stride;
+  const int64_t f = f0 + t;
+  if (ENERGY) {
+    const double e = sqrt(sum / (double)frame);
+    o[o_energy + f] = e;
+    if (o_entropy >= 0) o[o_entropy + f] = e > 0.0 ? -e * log(e + 1e-10) : 0.0;
+  }
+  if (ZCR) {
+    const double dur = (double)frame / (double)sr;  // len(frame)/sampleRate; sr==0 -> +Inf -> zcr 0
+    o[o_zcr + f] = frame < 2 ? 0.0 : (double)crossings / dur;
+  }
+}
+
+// Unbiased variance (two passes, block tree reduction; tolerance 1e-4, not bit-exact).
+__global__ void __launch_bounds__(256) variance_kernel(const double* __restrict__ xs, int64_t n, int64_t stride,
+                                                       double* __restrict__ out, int64_t out_stride) {
+  __shared__ double red[256];
+  __shared__ double s_mean;
+  const double* x = xs + (int64_t)blockIdx.x * stride;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += x[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_mean = n > 0 ? red[0] / (double)n : 0.0;
+  __syncthreads();
+  const double mean = s_mean;
+  acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = x[i] - mean;
+    acc += d * d;
+  }
+  __syncthreads();
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[(int64_t)blockIdx.x * out_stride] = n < 2 ? 0.0 : red[0] / (double)(n - 1);
+}
+
+// RMS of pre-emphasised windows (one warp per window; tree reduction).
+__global__ void __launch_bounds__(256) rms_windows_kernel(const double* __restrict__ pcm, int64_t n,
+                                                          int64_t stride, double alpha, int win, int hop,
+                                                          int64_t nw, double* __restrict__ out,
+                                                          int64_t out_stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= nw) return;
+  const int s = blockIdx.y;
+  const double* x = pcm + (int64_t)s * stride;
+  const int64_t s0 = w * hop;
+  double acc = 0.0;
+  for (int j = lane; j < win; j += 32) {
+    const double y = preemph(x, s0 + j, alpha);
+    acc += y * y;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[(int64_t)s * out_stride + w] = sqrt(acc / (double)win);
+}
+
+// loudness units + 10th/95th percentile range on <= 4096 values per stream (bitonic sort in smem)
+__global__ void __launch_bounds__(256) loudness_range_kernel(const double* __restrict__ rms, int64_t nw,
+                                                             int64_t in_stride, double* __restrict__ out,
+                                                             int64_t out_stride) {
+  extern __shared__ double v[];
+  const int s = blockIdx.x;
+  int np2 = 1;
+  while (np2 < nw) np2 <<= 1;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    double lv = INFINITY;
+    if (i < nw) {
+      const double e = rms[(int64_t)s * in_stride + i];
+      lv = e > 0.0 ? -0.691 + 10.0 * log10(e * e) : -70.0;
+    }
+    v[i] = lv;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const double a = v[i], b = v[ixj];
+          if ((a > b) == up) {
+            v[i] = b;
+            v[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x == 0) {
+    double res = 0.0;
+    if (nw > 0) {
+      const int lo = (int)(0.10 * (double)(nw - 1)), hi = (int)(0.95 * (double)(nw - 1));
+      double lov = v[lo];
+      const double hiv = v[hi];
+      if (lov <= 0.0) lov = 1e-10;
+      res = hiv <= 0.0 ? 0.0 : 20.0 * log10(hiv / lov);
+    }
+    out[(int64_t)s * out_stride] = res;
+  }
+}
+
+__global__ void fill_kernel(double* p, int64_t n, double v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+__global__ void fill_strided_kernel(double* p, int64_t count, int64_t stride, double v) {
+  double* q = p + (int64_t)blockIdx.y * stride;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    q[i] = v;
+}
+
+}  // namespace
+
+int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int frame,
+                      int hop, int64_t Tn, int sr, double* out, int64_t out_stride, int64_t o_energy,
+                      int64_t o_entropy, int64_t o_zcr, cudaStream_t st) {
+  if (Tn <= 0 || n_streams <= 0) return SONAR_OK;
+  if (frame > kTdMaxTile - 2 * hop)
+    return set_error(SONAR_ERR_UNSUPPORTED, "energy frame too long for the shared-memory tile");
+  int fpb = (kTdMaxTile - frame) / (hop + 1) + 1;
+  if (fpb > kTdThreads) fpb = kTdThreads;
+  if (fpb >= 32) fpb &= ~31;
+  const int count = (fpb - 1) * hop + frame;
+  const size_t smem = sizeof(double) * (size_t)(count + count / hop + 2);
+  dim3 grid((unsigned)((Tn + fpb - 1) / fpb), (unsigned)n_streams);
+  const bool en = o_energy >= 0, zc = o_zcr >= 0;
+#define LAUNCH_FW(E, Z)                                                                                  \
+  do {                                                                                                   \
+    auto k = frame_walk_kernel<E, Z>;                                                                    \
+    SONAR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    k<<<grid, kTdThreads, smem, st>>>(pcm, n, stride, alpha, frame, hop, Tn, fpb, sr, out, out_stride,  \
+                                      o_energy, o_entropy, o_zcr);                                      \
+  } while (0)
+  if (en && zc)
+    LAUNCH_FW(true, true);
+  else if (en)
+    LAUNCH_FW(true, false);
+  else if (zc)
+    LAUNCH_FW(false, true);
+  else
+    return SONAR_OK;
+#undef LAUNCH_FW
+  count_launch();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
+int launch_variance(const double* x, int64_t n, int64_t stride, int n_streams, double* out, int64_t out_stride,
+                    cudaStream_t st) {
+  if (n_streams <= 0) return SONAR_OK;
+  variance_kernel<<<n_streams, 256, 0, st>>>(x, n, stride, out, out_stride);
+  count_launch();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
+int launch_rms_windows(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int win,
+                       int hop, int64_t nw, double* out, int64_t out_stride, cudaStream_t st) {
+  if (nw <= 0 || n_streams <= 0) return SONAR_OK;
+  dim3 grid((unsigned)((nw + 7) / 8), (unsigned)n_streams);
+  rms_windows_kernel<<<grid, 256, 0, st>>>(pcm, n, stride, alpha, win, hop, nw, out, out_stride);
+  count_launch();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
+int launch_loudness_range(const double* rms, int64_t nw, int64_t in_stride, int n_streams, double* out,
+                          int64_t out_stride, cudaStream_t st) {
+  if (n_streams <= 0) return SONAR_OK;
+  if (nw > 4096) return set_error(SONAR_ERR_UNSUPPORTED, "loudness range supports at most 4096 windows");
+  int np2 = 1;
+  while (np2 < nw) np2 <<= 1;
+  loudness_range_kernel<<<n_streams, 256, sizeof(double) * np2, st>>>(rms, nw, in_stride, out, out_stride);
+  count_launch();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
+int launch_fill(double* p, int64_t n, double v, cudaStream_t st) {
+  if (n <= 0) return SONAR_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n, v);
+  count_launch();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
+int launch_fill_strided(double* p, int64_t count, int64_t stride, int n_streams, double v, cudaStream_t st) {
+  if (count <= 0 || n_streams <= 0) return SONAR_OK;
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  fill_strided_kernel<<<dim3((unsigned)blocks, (unsigned)n_streams), 256, 0, st>>>(p, count, stride, v);
+  count_launch();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
+}  // namespace sonar
