@@ -7,3 +7,7 @@ of that ABI (capi.py), the host-side mirror of the reference's Go API
 (synth.py).  The directory name carries a hyphen (it is the reference's name);
 import it with importlib.import_module("sonido-sonar_b200").
 """
+
+from . import capi, synth  # noqa: E402,F401
+
+__all__ = ["capi", "synth"]
