@@ -121,42 +121,50 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
                int64_t scratch_stride, cudaStream_t st);
 
 // ---- cross-correlation (xcorr.cu) ------------------------------------------
-// z-score `count` sequences (population sigma, reference summation order): in[s*in_stride .. +n)
-int launch_znorm(const double* x, int64_t n, int64_t in_stride, int count, double* z, int64_t out_stride,
-                 cudaStream_t st);
+struct XcorrSeq {  // one sequence to z-score (population sigma, reference summation order)
+  const double* in;
+  double* out;
+  int64_t n;
+};
+struct XcorrPair {  // one pair, or one lag shard [idx_lo, idx_hi) of a pair
+  const double* za;
+  const double* zb;
+  double* corr;  // idx_hi - idx_lo values
+  int64_t na, nb, idx_lo, idx_hi;
+  int32_t aml, pad;
+};
 struct XcorrPairOut {  // device result of one pair (or one lag shard of a pair)
-  double peak;            // exact c[peak_index]
+  double peak;            // c[peak_index]
   double noise_sum, noise_cnt, max_sidelobe;
   double second_abs, second_val;
-  double c_prev, c_next;  // NaN when not inside [idx_lo, idx_hi)
-  int64_t peak_index;     // global lag index, -1 = empty shard
+  double c_peak, c_prev, c_next;  // around the (possibly overridden) peak; NaN when not inside [idx_lo, idx_hi)
+  int64_t peak_index;     // shard-local arg-max as a global lag index, -1 = empty shard
   int64_t second_index;   // -1 = none
   int32_t n_candidates, pad;
 };
-size_t xcorr_scratch_bytes(int64_t na, int64_t nb, int n_pairs, int64_t n_lags);
-// corr: n_pairs * corr_stride doubles (lag indices idx_lo..idx_hi-1 of each pair at corr + p*corr_stride)
-int launch_xcorr(const double* za, int64_t na, int64_t sa, const double* zb, int64_t nb, int64_t sb, int n_pairs,
-                 int aml, int64_t idx_lo, int64_t idx_hi, double* corr, int64_t corr_stride, void* scratch,
-                 XcorrPairOut* out, cudaStream_t st);
-int launch_xcorr_metrics(const double* corr, int64_t corr_stride, int n_pairs, int64_t idx_lo, int64_t idx_hi,
-                         const XcorrPairOut* peaks_dev, int64_t peak_override, XcorrPairOut* out,
-                         cudaStream_t st);
+int launch_znorm(const XcorrSeq* seqs_dev, int count, cudaStream_t st);
+int launch_xcorr(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags, cudaStream_t st);
+int launch_xcorr_finalize(const XcorrPair* pairs_dev, int n_pairs, int64_t peak_override, XcorrPairOut* outs_dev,
+                          cudaStream_t st);
 
 // ---- DTW (dtw.cu) -------------------------------------------------------------
 struct DtwGeom {
-  int n, m, band;   // band <= 0: unconstrained
-  int64_t W;        // cells per stored row
-  int64_t cells;    // cells per pair ((n+1) rows)
-  int max_diag;     // max cells on one anti-diagonal
+  int n, m, band;   // band == 0: unconstrained
+  int n_off;        // number of distinct offsets i - j the wavefront tracks
+  int64_t W;        // cells per stored row (2*band+1, or m)
+  int64_t cells;    // cells per pair (n rows)
 };
 int dtw_geometry(int n, int m, int band, DtwGeom* g);
 struct DtwPairOut {
   double total_cost;
   int64_t path_len;
 };
+// q: n_pairs*n*dim, r: n_pairs*m*dim (device); cells: n_pairs*g.cells; line_scratch: n_pairs*(g.n_off+2)
+// doubles, only needed when the offset line does not fit shared memory; paths are written back to front:
+// pair p's path occupies [p*path_cap + path_cap - len, p*path_cap + path_cap).
 int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, int dim, int step, double* cells,
-               int32_t* path_q, int32_t* path_r, double* path_c, int64_t path_cap, DtwPairOut* out,
-               cudaStream_t st);
+               double* line_scratch, int32_t* path_q, int32_t* path_r, double* path_c, int64_t path_cap,
+               DtwPairOut* out, cudaStream_t st);
 int launch_dtw_expand(const double* cells, const DtwGeom& g, double* full, cudaStream_t st);
 
 // ---- column statistics (colstats.cu) ----------------------------------------

@@ -1,0 +1,126 @@
+"""GPU parity: cross-correlation (bit-exact lag + correlations), lag sharding, alignment scalars."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SUMMARY_FLOAT = ("peak_correlation", "p_value", "snr", "sharpness", "second_peak", "peak_to_sidelobe")
+SUMMARY_INT = ("peak_lag", "peak_index", "actual_max_lag", "overlap_length", "is_significant")
+
+
+def same_float(a, b, rtol=1e-9):
+    if math.isinf(a) or math.isinf(b) or math.isnan(a) or math.isnan(b):
+        return (math.isnan(a) and math.isnan(b)) or a == b
+    return abs(a - b) <= rtol * max(1.0, abs(b))
+
+
+def check_summary(sa, sb):
+    for k in SUMMARY_INT:
+        assert getattr(sa, k) == getattr(sb, k), k
+    # the correlations are bit-exact, so the peak is too; the reductions use another order -> 1e-9
+    assert sa.peak_correlation == sb.peak_correlation
+    for k in SUMMARY_FLOAT:
+        assert same_float(getattr(sa, k), getattr(sb, k)), (k, getattr(sa, k), getattr(sb, k))
+
+
+def energies(gpu, synth, seconds, offset, seed=2):
+    q, r = synth.aligned_pair(seconds, offset_seconds=offset, seed=seed)
+    p = gpu.default_params(algo_sample_rate=44100)
+    return gpu.fingerprint(q, p).short_time_energy, gpu.fingerprint(r, p).short_time_energy
+
+
+@pytest.mark.parametrize("na,nb,max_lag", [(500, 500, 100), (777, 512, 300), (64, 300, 1000), (3, 3, 5),
+                                           (1, 9, 4), (2000, 2000, 0)])
+def test_xcorr_random_bit_exact(gpu, oracle, na, nb, max_lag):
+    rng = np.random.default_rng(na * 31 + nb)
+    a, b = rng.standard_normal(na), rng.standard_normal(nb)
+    ca, sa = gpu.xcorr(a, b, max_lag)
+    cb, sb = oracle.xcorr(a, b, max_lag)
+    assert ca.shape == cb.shape
+    assert np.array_equal(ca, cb)  # sequential f64 sums per lag: bit-exact
+    check_summary(sa, sb)
+
+
+def test_xcorr_degenerate_inputs(gpu, oracle):
+    # constant sequences: sigma < 1e-10 -> only de-meaned -> every correlation is 0 -> peak index 0
+    a, b = np.full(300, 0.25), np.full(280, -1.5)
+    ca, sa = gpu.xcorr(a, b, 50)
+    cb, sb = oracle.xcorr(a, b, 50)
+    assert np.array_equal(ca, cb)
+    check_summary(sa, sb)
+    assert sa.peak_index == 0
+    # exact ties: periodic signal, the first maximum must win (correlation.go:535-541)
+    t = np.arange(400)
+    a = np.sign(np.sin(2 * np.pi * t / 20.0) + 1e-9)
+    ca, sa = gpu.xcorr(a, a, 100)
+    cb, sb = oracle.xcorr(a, a, 100)
+    assert np.array_equal(ca, cb)
+    check_summary(sa, sb)
+
+
+def test_xcorr_errors(gpu, capi):
+    with pytest.raises(capi.SonarError) as e:
+        gpu.xcorr(np.zeros(0), np.zeros(5), 3)
+    assert e.value.code == capi.ERR_EMPTY and "empty signals provided" in e.value.msg
+
+
+def test_alignment_known_offset(gpu, oracle, synth):
+    ea, eb = energies(gpu, synth, 40.0, 3.7)
+    ca, xa, ra = gpu.align_xcorr(ea, eb, int(30 * 44100) // 256, 256, 44100, want_corr=True)
+    cb, xb, rb = oracle.align_xcorr(ea, eb, int(30 * 44100) // 256, 256, 44100, want_corr=True)
+    n = 2 * xa.actual_max_lag + 1
+    assert np.array_equal(ca[:n], cb[:n])
+    check_summary(xa, xb)
+    assert abs(xa.peak_lag - 3.7 * 44100 / 256) <= 1.0  # positive lag = CDN later
+    assert ra.offset == rb.offset == xa.peak_lag * 256
+    for k in ("offset_seconds", "confidence", "similarity", "alignment_quality", "noise_level"):
+        assert same_float(getattr(ra, k), getattr(rb, k)), k
+    assert ra.method == 1 and ra.query_length == ea.size and ra.reference_length == eb.size
+
+
+def test_alignment_negative_offset(gpu, oracle, synth):
+    ea, eb = energies(gpu, synth, 30.0, -2.1, seed=11)
+    _, xa, ra = gpu.align_xcorr(ea, eb, 2000, 256, 44100)
+    _, xb, rb = oracle.align_xcorr(ea, eb, 2000, 256, 44100)
+    check_summary(xa, xb)
+    assert xa.peak_lag < 0 and ra.offset == rb.offset
+
+
+def test_xcorr_batch_ragged(gpu, oracle):
+    rng = np.random.default_rng(5)
+    As = [rng.standard_normal(n) for n in (300, 1000, 17, 512, 999)]
+    Bs = [rng.standard_normal(n) for n in (280, 1000, 400, 100, 999)]
+    ca, sa = gpu.xcorr_batch(As, Bs, 128, want_corr=True)
+    cb, sb = oracle.xcorr_batch(As, Bs, 128, want_corr=True)
+    for i in range(len(As)):
+        n = 2 * sa[i].actual_max_lag + 1
+        assert np.array_equal(ca[i][:n], cb[i][:n])
+        check_summary(sa[i], sb[i])
+
+
+def test_xcorr_lag_sharding_matches_whole(gpu, oracle, capi, synth):
+    """one correlation split by lag range; merge of per-shard maxima == unsharded result."""
+    ea, eb = energies(gpu, synth, 30.0, 5.2, seed=21)
+    max_lag = 1500
+    _, whole = oracle.xcorr(ea, eb, max_lag)
+    nl = 2 * whole.actual_max_lag + 1
+    for n_shards in (1, 2, 3, 8):
+        step = -(-nl // n_shards)
+        shards, peaks = [], []
+        for g in range(n_shards):
+            sh, pk = gpu.xcorr_shard(ea, eb, max_lag, g * step, min(nl, (g + 1) * step))
+            shards.append(sh)
+            peaks.append(pk)
+        gidx = gpu.xcorr_merge_peaks(peaks)
+        assert gidx == whole.peak_index
+        parts = [gpu.xcorr_shard_metrics(sh, gidx) for sh in shards]
+        merged = gpu.xcorr_merge_metrics(parts, ea.size, eb.size, max_lag, gidx)
+        check_summary(merged, whole)
+        corr = np.concatenate([gpu.xcorr_shard_corr(sh, min(nl, (g + 1) * step) - g * step)
+                               for g, sh in enumerate(shards)])
+        cw, _ = oracle.xcorr(ea, eb, max_lag)
+        assert np.array_equal(corr, cw)
+        for sh in shards:
+            gpu.xcorr_shard_close(sh)

@@ -1,0 +1,169 @@
+"""GPU parity: GenerateFingerprint's compute (fused STFT + MFCC + spectral, FP64 energy/ZCR, YIN)
+against the CPU oracle through the C ABI.
+
+Tolerance (north star: "features within a stated relative tolerance, e.g. 1e-4"): the STFT/MFCC/
+spectral kernels compute in FP32, so for every feature array
+    |gpu - oracle| <= 1e-4 * max(|oracle|, max|oracle array|)
+i.e. 1e-4 relative, floored at 1e-4 of the array's own scale for near-zero entries.  Outputs computed
+in FP64 in the reference's summation order (short-time energy, ZCR, pitch track) must be bit-exact:
+they feed the cross-correlation arg-max and the DTW path.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FP32_FEATURES = ("mfcc", "spectral_centroid", "spectral_rolloff", "spectral_bandwidth", "spectral_flatness",
+                 "spectral_crest", "spectral_slope", "spectral_flux", "low_energy_ratio", "high_energy_ratio")
+EXACT = ("short_time_energy", "zero_crossing_rate")
+FP64_CLOSE = ("energy_entropy",)
+PITCH = ("pitch_estimate", "pitch_confidence", "voicing_strength", "harmonic_ratio", "inharmonicity_ratio",
+         "tonal_centroid")
+
+
+def feature_close(x, y, tol=1e-4):
+    assert x.shape == y.shape
+    if y.size == 0:
+        return
+    scale = np.max(np.abs(y))
+    bound = tol * np.maximum(np.abs(y), scale)
+    bad = np.abs(x - y) > bound
+    assert not bad.any(), f"{bad.sum()} of {y.size} outside tolerance; worst {np.max(np.abs(x - y) / np.maximum(bound, 1e-300)):.3g}x"
+
+
+def check_fp(a, b):
+    for k in FP32_FEATURES:
+        feature_close(a.arrays[k], b.arrays[k])
+    for k in EXACT:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k
+    for k in FP64_CLOSE:
+        np.testing.assert_allclose(a.arrays[k], b.arrays[k], rtol=1e-12, atol=1e-15)
+    for k in PITCH:
+        np.testing.assert_allclose(a.arrays[k], b.arrays[k], rtol=1e-9, atol=1e-12, err_msg=k)
+    assert a.energy_variance == pytest.approx(b.energy_variance, rel=1e-10)
+    assert a.loudness_range == pytest.approx(b.loudness_range, rel=1e-9, abs=1e-12)
+    assert a.sizes == b.sizes
+
+
+def voiced(seconds, sr, f0=440.0, seed=3):
+    """Gated tone with vibrato: the reference's windowed YIN (pitch_detection.go:349-420) only dips below
+    0.15 on nearly sinusoidal frames, so this is what exercises the pitch track (~60 % voiced frames)."""
+    n = int(seconds * sr)
+    t = np.arange(n) / sr
+    f = f0 * (1.0 + 0.2 * np.sin(2 * np.pi * 0.7 * t))
+    ph = 2 * np.pi * np.cumsum(f) / sr
+    x = np.sin(ph) + 0.05 * np.sin(2 * ph)
+    gate = (np.sin(2 * np.pi * 1.3 * t) > -0.3).astype(float)
+    rng = np.random.default_rng(seed)
+    return 0.4 * x * gate + 1e-4 * rng.standard_normal(n)
+
+
+CASES = {
+    "c1_music_fixed_sr": (lambda s: s.sweep_noise(4.0, seed=1), dict(algo_sample_rate=44100)),
+    "c1_music_parity_sr0": (lambda s: s.sweep_noise(4.0, seed=1), dict(algo_sample_rate=0)),
+    "c3_speech_512_160_40mel": (lambda s: s.speech_band_noise(6.0), dict(
+        window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=16000,
+        call_sample_rate=16000, n_mel=40)),
+    "c3_speech_stock_26mel_sr0": (lambda s: s.speech_band_noise(3.0), dict(
+        window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=0,
+        call_sample_rate=16000)),
+    "w2048_h512": (lambda s: s.sweep_noise(3.0, seed=3), dict(
+        window_size=2048, hop_size=512, energy_frame=2048, energy_hop=512, algo_sample_rate=44100)),
+    "w256_h64_odd_len": (lambda s: s.sweep_noise(1.0, seed=5)[:40001], dict(
+        window_size=256, hop_size=64, energy_frame=256, energy_hop=64, algo_sample_rate=44100)),
+    "odd_hop_441": (lambda s: s.sweep_noise(2.0, seed=6), dict(
+        window_size=1024, hop_size=441, energy_frame=1024, energy_hop=441, algo_sample_rate=44100)),
+    "energy_grid_differs_F4": (lambda s: s.sweep_noise(2.0, seed=7), dict(
+        algo_sample_rate=44100, energy_frame=2048, energy_hop=512)),
+    "energy_disabled_F4": (lambda s: s.sweep_noise(2.0, seed=7), dict(
+        algo_sample_rate=44100, energy_frame=0, energy_hop=0)),
+    "no_lifter_20mfcc": (lambda s: s.sweep_noise(2.0, seed=8), dict(
+        algo_sample_rate=44100, n_mfcc=20, n_mel=32, use_liftering=0, low_hz=100.0, high_hz=8000.0)),
+    "hamming": (lambda s: s.sweep_noise(2.0, seed=9), dict(algo_sample_rate=44100, window_type="hamming")),
+    "voiced_yin": (lambda s: voiced(4.0, 44100), dict(algo_sample_rate=44100)),
+    "voiced_yin_16k": (lambda s: voiced(4.0, 16000, f0=200.0), dict(
+        window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=16000,
+        call_sample_rate=16000)),
+    "single_frame": (lambda s: s.sweep_noise(1.0, seed=10)[:1024], dict(algo_sample_rate=44100)),
+    "silence": (lambda s: np.zeros(20000), dict(algo_sample_rate=44100)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fingerprint_matches_oracle(gpu, oracle, synth, name):
+    make, kw = CASES[name]
+    pcm = make(synth)
+    p = gpu.default_params(**kw)
+    check_fp(gpu.fingerprint(pcm, p), oracle.fingerprint(pcm, p))
+
+
+@pytest.mark.gpu
+def test_voiced_case_exercises_yin(oracle, synth):
+    p = oracle.default_params(algo_sample_rate=44100)
+    fp = oracle.fingerprint(voiced(4.0, 44100), p)
+    assert (fp.pitch_estimate > 0).mean() > 0.3  # otherwise the YIN parity case above proves nothing
+
+
+def test_parity_mode_degenerate_constants(gpu, synth):
+    """stock GenerateFingerprint builds every algorithm with sampleRate=0."""
+    fp = gpu.fingerprint(synth.sweep_noise(2.0, seed=1), gpu.default_params(algo_sample_rate=0))
+    assert np.allclose(fp.mfcc[:, 0], -117.40926320884498, rtol=1e-6)
+    assert np.all(np.abs(fp.mfcc[:, 1:]) < 1e-3)
+    for k in ("spectral_centroid", "spectral_rolloff", "spectral_bandwidth", "spectral_slope", "zero_crossing_rate",
+              "pitch_estimate", "harmonic_ratio"):
+        assert not fp.arrays[k].any(), k
+    assert np.all(fp.inharmonicity_ratio == 1.0)
+    assert fp.spectral_flatness.any() and fp.spectral_flux.any() and fp.short_time_energy.any()
+
+
+def test_batch_ragged_matches_single(gpu, synth):
+    p = gpu.default_params(algo_sample_rate=44100)
+    pcms = [synth.sweep_noise(s, seed=20 + i) for i, s in enumerate((1.0, 2.5, 1.0, 0.3, 2.5))]
+    batch = gpu.fingerprint_batch(pcms, p)
+    for x, fb in zip(pcms, batch):
+        fs = gpu.fingerprint(x, p)
+        for k in fs.arrays:
+            assert np.array_equal(fs.arrays[k], fb.arrays[k]), k  # same kernels, same order: identical
+
+
+def test_seams_between_runs_are_invisible(gpu, oracle, synth):
+    """A long stream is cut into per-warp runs of frames (flux needs frame t-1 across the seam)."""
+    pcm = synth.sweep_noise(20.0, seed=31)
+    p = gpu.default_params(algo_sample_rate=44100)
+    a, b = gpu.fingerprint(pcm, p), oracle.fingerprint(pcm, p)
+    feature_close(a.spectral_flux, b.spectral_flux)
+    feature_close(a.mfcc, b.mfcc)
+
+
+def test_stft_materialised(gpu, oracle, synth):
+    pcm = synth.sweep_noise(1.0, seed=7)
+    for win, hop in ((1024, 256), (512, 160), (256, 100), (2048, 512)):
+        mg, ph, cx = gpu.stft(pcm, win, hop, phase=True, cplx=True)
+        mr, pr, cr = oracle.stft(pcm, win, hop, phase=True, cplx=True)
+        scale = np.max(mr)
+        assert np.max(np.abs(mg - mr)) <= 2e-6 * scale
+        assert np.max(np.abs(cx - cr)) <= 2e-6 * scale
+        strong = mr > 1e-3 * scale  # phase is only meaningful where the bin is above the FP32 noise floor
+        d = np.angle(np.exp(1j * (ph - pr)))
+        assert np.max(np.abs(d[strong])) < 1e-3
+
+
+def test_fingerprint_errors(gpu, capi):
+    p = gpu.default_params()
+    for pcm, code, text in ((np.zeros(100), capi.ERR_TOO_SHORT, "signal too short for given window size and hop size"),
+                            (np.zeros(0), capi.ERR_EMPTY, "empty signal")):
+        with pytest.raises(capi.SonarError) as e:
+            gpu.fingerprint(pcm, p)
+        assert e.value.code == code and text in e.value.msg
+    with pytest.raises(capi.SonarError) as e:
+        gpu.fingerprint(np.zeros(5000), gpu.default_params(window_size=1000))
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    with pytest.raises(capi.SonarError) as e:
+        gpu.fingerprint(np.zeros(5000), gpu.default_params(call_sample_rate=0))
+    assert "sample rate must be positive" in e.value.msg
+
+
+def test_kernel_launch_counter(gpu, synth):
+    before = gpu.kernel_launches()
+    gpu.fingerprint(synth.sweep_noise(1.0, seed=1), gpu.default_params(algo_sample_rate=44100))
+    assert gpu.kernel_launches() > before
