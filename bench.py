@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the fingerprint + alignment hot path (BASELINE.json metric).
+
+One step = BASELINE config[1] ("C2") applied to P independent source/CDN pairs per GPU:
+  1. fingerprint both 5-min 44.1 kHz streams of every pair (1024/256 Hann STFT -> 26-mel/13-MFCC,
+     spectral descriptors, FP64 short-time energy / ZCR, YIN) with the algorithms built at the real
+     sample rate ("fixed-sr" mode, so the MFCC work is not degenerate);
+  2. normalised cross-correlation of the two short-time-energy series over +-60 s (20,671 lags);
+  3. banded DTW (r = 50) of the lag-trimmed energy series.
+`value` = audio-seconds fingerprinted per second of whole-step time with the PCM resident in HBM,
+`e2e`   = the same through the host-pointer C ABI (pinned host PCM, H2D + D2H inside the timing).
+`alignments_per_s` (extra key) = pairs per second of the same step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
+
+Under torchrun every rank runs its own P pairs on its own GPU (weak scaling, no data-path
+collective: SURVEY §8e); the timed region is bracketed by barrier + synchronize and the max over
+ranks is reported by rank 0 as ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR = 44100
+WIN, HOP = 1024, 256
+MAX_LAG_S = 60.0
+DTW_BAND = 50
+METRIC = "audio-sec/s fingerprinted (1024/256 MFCC); 5-min pair alignments/s @60s lag"
+UNIT = "audio-s/s"
+ALGO_BYTES_PER_FRAME = HOP * 8 + 13 * 8  # every input sample read once, 13 MFCC written
+
+
+def pkg():
+    return importlib.import_module("sonido-sonar_b200")
+
+
+def make_pair(synth, seconds, idx, seed0=200):
+    rng = np.random.default_rng(seed0 + idx)
+    off = float(rng.uniform(-0.9, 0.9)) * MAX_LAG_S * (seconds / 300.0) if idx else 7.3 * (seconds / 300.0)
+    return synth.aligned_pair(seconds, offset_seconds=off, sr=SR, seed=seed0 + 2 * idx)
+
+
+def trim_by_lag(ea, eb, lag, length):
+    """TruncateToAlignmentPCM's convention (extractors/alignment.go:239-243): lag > 0 skips the start of stream 2."""
+    if lag >= 0:
+        a, b = ea, eb[lag:]
+    else:
+        a, b = ea[-lag:], eb
+    return np.ascontiguousarray(a[:length]), np.ascontiguousarray(b[:length])
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the roofline kernel from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's Go path (no Go toolchain here: SURVEY §8c)
+# --------------------------------------------------------------------------------------
+
+def cpu_pipeline(ora, q, r, seconds):
+    """The same step on the CPU oracle for one pair; returns detected lag."""
+    p = ora.default_params(algo_sample_rate=SR)
+    ea = ora.fingerprint(q, p).short_time_energy
+    eb = ora.fingerprint(r, p).short_time_energy
+    max_lag = int(MAX_LAG_S * (seconds / 300.0) * SR) // HOP
+    _, xs, _ = ora.align_xcorr(ea, eb, max_lag, HOP, SR)
+    length = min(ea.size, eb.size) - max_lag
+    a, b = trim_by_lag(ea, eb, xs.peak_lag, length)
+    ora.dtw(a, b, band=DTW_BAND)
+    return xs.peak_lag
+
+
+def cpu_baseline_single(capi, synth):
+    ora = capi.SonarLib(os.path.join(ROOT, "oracle", "libsonar_oracle.so"))
+    seconds = 300.0
+    q, r = make_pair(synth, seconds, 0)
+    t0 = time.perf_counter()
+    cpu_pipeline(ora, q, r, seconds)
+    dt = time.perf_counter() - t0
+    return {"value": 2 * seconds / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"1 pair of 2x{int(seconds)} s streams (fingerprint both + NCC +-60 s + DTW r=50), "
+                      f"C++ -O2 oracle port of the Go path, 1 thread, {dt:.1f} s; the Go toolchain is absent so the "
+                      "reference itself cannot run here",
+            "alignments_per_s": 1.0 / dt}
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU path with every host thread, on a bounded sample per step."""
+    if rank != 0:
+        return
+    p = pkg()
+    capi, synth = p.capi, p.synth
+    cores = os.cpu_count() or 1
+    seconds = 60.0
+    from concurrent.futures import ThreadPoolExecutor
+    oras = [capi.SonarLib(os.path.join(ROOT, "oracle", "libsonar_oracle.so")) for _ in range(cores)]
+    pairs = [make_pair(synth, seconds, i % 4) for i in range(cores)]
+
+    def one(i):
+        return cpu_pipeline(oras[i], pairs[i][0], pairs[i][1], seconds)
+
+    times = []
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            list(ex.map(one, range(cores)))
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = cores * 2 * seconds / (ms / 1e3)
+    sample = (f"{cores} pairs of 2x{int(seconds)} s streams per step, one pair per host thread (ctypes releases the GIL), "
+              f"+-{MAX_LAG_S * seconds / 300:.0f} s lag, DTW r={DTW_BAND}; C++ -O2 oracle port (no Go toolchain on the box)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 pipeline: fingerprint both streams of each source/CDN pair (1024/256, 26-mel/13-MFCC, "
+                               "fixed-sr mode), NCC over +-60 s, banded DTW r=50", "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "alignments_per_s": cores / (ms / 1e3),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    p = pkg()
+    capi, synth = p.capi, p.synth
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = capi.SonarLib(init=False)
+    ids = (C.c_int * 1)(local_rank)
+    lib._chk(lib.lib.sonar_init(1, ids, C.byref(lib.ctx)))
+    assert lib.backend == "cuda-sm100a"
+    ext = torch.cuda.ExternalStream(lib.stream(), device=torch.device("cuda", local_rank))
+
+    P, seconds = args.pairs, float(args.seconds)
+    n = int(round(seconds * SR))
+    stride = (n + 1) & ~1
+    NS = 2 * P
+    prm = lib.default_params(algo_sample_rate=SR, call_sample_rate=SR)
+    sz = lib.fp_sizes(prm, n)
+    L = lib.fp_dev_layout(prm, n)
+    T, Te = sz.n_frames, sz.n_energy_frames
+    max_lag = int(MAX_LAG_S * SR) // HOP
+    dtw_len = Te - max_lag
+
+    # ---- synthetic inputs: pinned host PCM (e2e leg) and an HBM-resident copy (value leg) ----
+    host = torch.empty((NS, stride), dtype=torch.float64).pin_memory()
+    hv = host.numpy()
+    for i in range(P):
+        q, r = make_pair(synth, seconds, rank * P + i)
+        hv[2 * i, :n], hv[2 * i + 1, :n] = q, r
+    pcm_dev = host.to("cuda", non_blocking=False)
+    feat = torch.empty(NS * L.total, dtype=torch.float64, device="cuda")
+    summ = (capi.XcorrSummary * P)()
+    torch.cuda.synchronize()
+
+    def align_tail(ea_all, eb_all, lags):
+        qs, rs = [], []
+        for i in range(P):
+            a, b = trim_by_lag(ea_all[i], eb_all[i], lags[i], dtw_len)
+            qs.append(a)
+            rs.append(b)
+        return lib.dtw_batch(qs, rs, band=DTW_BAND)
+
+    def step_resident():
+        lib.fingerprint_batch_dev(pcm_dev.data_ptr(), n, stride, NS, prm, feat.data_ptr())
+        with torch.cuda.stream(ext):
+            e = feat.view(NS, L.total)[:, L.short_time_energy:L.short_time_energy + Te]
+            ea, eb = e[0::2].contiguous(), e[1::2].contiguous()
+        lib._chk(lib.lib.sonar_xcorr_batch_dev(lib.ctx, ea.data_ptr(), Te, eb.data_ptr(), Te, P, max_lag, None, summ))
+        with torch.cuda.stream(ext):
+            ea_h, eb_h = ea.cpu().numpy(), eb.cpu().numpy()
+        lags = [summ[i].peak_lag for i in range(P)]
+        paths = align_tail(ea_h, eb_h, lags)
+        return lags, paths
+
+    pcm_list = [hv[i, :n] for i in range(NS)]
+
+    def step_e2e():
+        fps = lib.fingerprint_batch(pcm_list, prm)  # H2D of the PCM + D2H of every feature array inside
+        eas = [fps[2 * i].short_time_energy for i in range(P)]
+        ebs = [fps[2 * i + 1].short_time_energy for i in range(P)]
+        _, xs = lib.xcorr_batch(eas, ebs, max_lag)
+        lags = [s.peak_lag for s in xs]
+        paths = align_tail(eas, ebs, lags)
+        return lags, paths, fps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lib.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value leg: device-resident, CUDA events on the library's stream ----
+    for _ in range(args.warmup):
+        lags, paths = step_resident()
+    lib.profile_read()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = lib.kernel_launches()
+    lib.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lags, paths = step_resident()
+    ev1.record(ext)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms = ev0.elapsed_time(ev1)
+    lib.profile_enable(False)
+    launches = lib.kernel_launches() - l0
+    kern = lib.profile_read()
+    clocks = sampler.stop() if sampler else None
+    step_ms = reduce_max(dev_ms / args.steps)
+    audio_s = world * NS * seconds
+    value = audio_s / (step_ms / 1e3)
+
+    # ---- e2e leg: host buffers through the public C ABI (wall clock: the calls block the host) ----
+    n_e2e = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        lags_e, paths_e, fps = step_e2e()
+    barrier()
+    e2e_ms = reduce_max(1e3 * (time.perf_counter() - t0) / n_e2e)
+    assert lags_e == lags, "host-pointer and device-resident legs disagree on the detected lags"
+    h2d = NS * n * 8 + 2 * P * Te * 8 + 2 * P * dtw_len * 8
+    d2h = sum(a.nbytes for a in fps[0].arrays.values()) * NS + P * (2 * max_lag + 1) * 0 + \
+        sum(len(pp["path_query"]) * 16 for pp in paths_e)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        k_ms, k_n = kern.get("stft_features_kernel", (0.0, 0))
+        frames_per_launch = NS * T
+        roof = None
+        if k_n:
+            avg_ms = k_ms / k_n
+            achieved = frames_per_launch * ALGO_BYTES_PER_FRAME / (avg_ms / 1e3) / 1e9
+            tr = ncu_traffic()
+            roof = {"kernel": "stft_features_kernel (fused framed STFT + MFCC + spectral descriptors)", "bound": "hbm",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": tr.get("dram_bytes_per_launch") if tr else None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": frames_per_launch * ALGO_BYTES_PER_FRAME,
+                    "avg_launch_ms": avg_ms, "launches_timed": k_n}
+        total_k = sum(v[0] for v in kern.values()) or 1.0
+        shares = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                      "share": v[0] / total_k} for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+        cpu = cpu_baseline_single(capi, synth) if (world == 1 and not args.no_cpu) else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"C2 pipeline x {P} pairs/GPU: fingerprint both {int(seconds)} s 44.1 kHz streams of each "
+                            "source/CDN pair (1024/256 Hann, 26-mel/13-MFCC, fixed-sr mode; STFT/MFCC FP32, "
+                            f"energy/ZCR/YIN FP64), NCC over +-{int(MAX_LAG_S)} s ({2 * max_lag + 1} lags), banded DTW r={DTW_BAND}",
+                "pairs_per_gpu": P, "streams_per_gpu": NS, "frames_per_stream": int(T), "parallelism": f"pair-sharded x{world}",
+                "l2": f"inputs {NS * n * 8 / 1e9:.2f} GB per step exceed the 126 MB L2; no flush needed",
+                "timing": "CUDA events on the library stream, max over ranks",
+            },
+            "alignments_per_s": world * P / (step_ms / 1e3),
+            "wall_ms_per_step": wall_ms / args.steps,
+            "e2e": {"value": audio_s / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "timing": "wall clock around blocking C-ABI calls",
+                    "alignments_per_s": world * P / (e2e_ms / 1e3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernels": shares,
+            "cpu_baseline": cpu,
+            "detected_lags_frames": lags,
+        }
+        print(json.dumps(line), flush=True)
+    lib.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=8, help="source/CDN pairs per GPU per step")
+    ap.add_argument("--seconds", type=float, default=300.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -99,6 +99,22 @@ int sonar_synchronize(sonar_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench claim). */
 uint64_t sonar_kernel_launches(sonar_ctx* ctx);
 
+/* The CUDA stream (a cudaStream_t) the `_dev` entry points enqueue on, for callers that chain
+ * their own device work behind them or time them with CUDA events. NULL for the oracle. */
+void* sonar_stream(sonar_ctx* ctx);
+
+/* Per-kernel device timing (replaces the reference's stubbed getTimeMs()/ProcessingTime fields,
+ * algorithms/stats/correlation.go:777-780). While enabled every kernel launch is bracketed by
+ * two CUDA events on its stream; sonar_profile_read synchronises, sums them per kernel name
+ * into out[0..*n_out) (at most cap entries) and clears the log. */
+typedef struct sonar_kernel_time {
+  char kernel[48];
+  double total_ms;
+  int64_t launches;
+} sonar_kernel_time;
+int sonar_profile_enable(sonar_ctx* ctx, int on);
+int sonar_profile_read(sonar_ctx* ctx, sonar_kernel_time* out, int cap, int* n_out);
+
 /* ------------------------------------------------------------------------- */
 /* windows                                                                    */
 /* ------------------------------------------------------------------------- */

@@ -125,6 +125,10 @@ class DtwOut(C.Structure):
     ]
 
 
+class KernelTime(C.Structure):
+    _fields_ = [("kernel", C.c_char * 48), ("total_ms", C.c_double), ("launches", C.c_int64)]
+
+
 class CmpFeatures(C.Structure):
     _fields_ = [
         ("mfcc", c_double_p), ("mfcc_frames", C.c_int64), ("mfcc_dim", C.c_int32),
@@ -161,7 +165,8 @@ class CmpResult(C.Structure):
 EXPORTS = (
     "sonar_init", "sonar_destroy", "sonar_last_error", "sonar_abi_version", "sonar_backend",
     "sonar_host_alloc", "sonar_host_free", "sonar_dev_alloc", "sonar_dev_free", "sonar_memcpy_h2d",
-    "sonar_memcpy_d2h", "sonar_synchronize", "sonar_kernel_launches", "sonar_window_f64",
+    "sonar_memcpy_d2h", "sonar_synchronize", "sonar_kernel_launches", "sonar_stream",
+    "sonar_profile_enable", "sonar_profile_read", "sonar_window_f64",
     "sonar_fp_params_default", "sonar_fp_sizes", "sonar_fingerprint_f64",
     "sonar_fingerprint_batch_f64", "sonar_fingerprint_batch_dev", "sonar_fp_dev_layout",
     "sonar_stft_f64", "sonar_xcorr_ncc_f64", "sonar_xcorr_batch_f64", "sonar_xcorr_batch_dev",
@@ -211,6 +216,10 @@ class SonarLib:
         L.sonar_backend.restype = C.c_char_p
         L.sonar_kernel_launches.restype = C.c_uint64
         L.sonar_kernel_launches.argtypes = [C.c_void_p]
+        L.sonar_stream.restype = C.c_void_p
+        L.sonar_stream.argtypes = [C.c_void_p]
+        L.sonar_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.sonar_profile_read.argtypes = [C.c_void_p, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]
         L.sonar_destroy.restype = None
         L.sonar_destroy.argtypes = [C.c_void_p]
         L.sonar_xcorr_shard_close.restype = None
@@ -283,6 +292,19 @@ class SonarLib:
 
     def kernel_launches(self) -> int:
         return int(self.lib.sonar_kernel_launches(self.ctx))
+
+    def stream(self) -> int:
+        return int(self.lib.sonar_stream(self.ctx) or 0)
+
+    def profile_enable(self, on: bool = True):
+        self._chk(self.lib.sonar_profile_enable(self.ctx, int(on)))
+
+    def profile_read(self) -> dict:
+        """{kernel name: (total ms, launches)} since the last read; synchronises."""
+        buf = (KernelTime * 64)()
+        n = C.c_int()
+        self._chk(self.lib.sonar_profile_read(self.ctx, buf, 64, C.byref(n)))
+        return {buf[i].kernel.decode(): (buf[i].total_ms, int(buf[i].launches)) for i in range(n.value)}
 
     def synchronize(self):
         self._chk(self.lib.sonar_synchronize(self.ctx))

@@ -54,8 +54,9 @@ __global__ void __launch_bounds__(kCsThreads) colstats_kernel(const double* __re
 
 int launch_colstats(const double* x, int64_t t, int dim, double* stats, cudaStream_t st) {
   if (t <= 0 || dim <= 0) return SONAR_OK;
+  prof_begin("colstats_kernel", st);
   colstats_kernel<<<dim, kCsThreads, 0, st>>>(x, t, dim, stats);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }

@@ -195,10 +195,22 @@ struct sonar_ctx {
   std::mutex call_mu;  // one in-flight call per context (slots and their buffers are per context)
   std::map<std::string, std::shared_ptr<sonar::FpPlan>> plans;
   std::atomic<uint64_t> launches{0};
+  // per-kernel CUDA-event timing (off by default)
+  struct ProfRec {
+    const char* name;
+    cudaEvent_t a, b;
+  };
+  std::atomic<bool> profiling{false};
+  std::mutex prof_mu;
+  std::vector<ProfRec> prof;
 };
 
 namespace sonar {
-void count_launch(int n = 1);  // adds to the calling thread's current context counter
+// Every kernel launch is bracketed by prof_begin(name, stream) / prof_end(): the pair counts the
+// launch on the calling thread's current context and, when profiling is enabled on it
+// (sonar_profile_enable), records a CUDA event before and after the kernel on its own stream.
+void prof_begin(const char* kernel, cudaStream_t st);
+void prof_end();
 void set_current_ctx(sonar_ctx* c);
 // speech.go:370-408 temporal block (temporal.cu)
 int fingerprint_temporal_tail(sonar_ctx* ctx, const double* const* pcm, const int64_t* n, int n_streams,

@@ -25,8 +25,30 @@ int cuda_error(cudaError_t e, const char* what) {
   return e == cudaErrorMemoryAllocation ? SONAR_ERR_NOMEM : SONAR_ERR_CUDA;
 }
 const std::string& last_error_string() { return g_err; }
-void count_launch(int n) {
-  if (g_cur) g_cur->launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+namespace {
+thread_local sonar_ctx::ProfRec g_open{nullptr, nullptr, nullptr};
+thread_local cudaStream_t g_open_st = nullptr;
+}  // namespace
+void prof_begin(const char* kernel, cudaStream_t st) {
+  g_open = sonar_ctx::ProfRec{nullptr, nullptr, nullptr};
+  if (!g_cur) return;
+  g_cur->launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_cur->profiling.load(std::memory_order_relaxed)) return;
+  sonar_ctx::ProfRec r{kernel, nullptr, nullptr};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  cudaEventRecord(r.a, st);
+  g_open = r;
+  g_open_st = st;
+}
+void prof_end() {
+  if (!g_open.name || !g_cur) return;
+  cudaEventRecord(g_open.b, g_open_st);
+  std::lock_guard<std::mutex> lk(g_cur->prof_mu);
+  g_cur->prof.push_back(g_open);
+  g_open = sonar_ctx::ProfRec{nullptr, nullptr, nullptr};
 }
 void set_current_ctx(sonar_ctx* c) { g_cur = c; }
 
@@ -200,6 +222,45 @@ int sonar_synchronize(sonar_ctx* ctx) {
   return SONAR_OK;
 }
 uint64_t sonar_kernel_launches(sonar_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+void* sonar_stream(sonar_ctx* ctx) { return ctx ? (void*)ctx->devs[0].slot[0].st : nullptr; }
+
+int sonar_profile_enable(sonar_ctx* ctx, int on) {
+  if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  ctx->profiling.store(on != 0);
+  return SONAR_OK;
+}
+
+int sonar_profile_read(sonar_ctx* ctx, sonar_kernel_time* out, int cap, int* n_out) {
+  if (!ctx || !n_out) return set_error(SONAR_ERR_INVALID, "nil argument");
+  int rc = sonar_synchronize(ctx);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->prof_mu);
+  int n = 0;
+  for (auto& r : ctx->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) {
+      cudaGetLastError();
+      ms = 0.f;
+    }
+    int k = 0;
+    for (; k < n; k++)
+      if (std::strcmp(out[k].kernel, r.name) == 0) break;
+    if (k == n) {
+      if (n >= cap) continue;
+      std::memset(&out[n], 0, sizeof(out[n]));
+      std::strncpy(out[n].kernel, r.name, sizeof(out[n].kernel) - 1);
+      n++;
+    }
+    out[k].total_ms += (double)ms;
+    out[k].launches += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->prof.clear();
+  *n_out = n;
+  return SONAR_OK;
+}
 
 int sonar_window_f64(int type, int size, int symmetric, int normalize, double beta, double alpha, double* out) {
   if (!out) return set_error(SONAR_ERR_INVALID, "nil argument");

@@ -217,11 +217,13 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
   threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
   const size_t smem = in_smem ? line_bytes : 0;
   SONAR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+  prof_begin("dtw_fill_kernel", st);
   dtw_fill_kernel<<<n_pairs, threads, smem, st>>>(q, r, g, dim, step, cells, line_scratch, in_smem);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
+  prof_begin("dtw_backtrack_kernel", st);
   dtw_backtrack_kernel<<<n_pairs, kBtThreads, 0, st>>>(cells, g, path_q, path_r, path_c, path_cap, out);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }
@@ -230,8 +232,9 @@ int launch_dtw_expand(const double* cells, const DtwGeom& g, double* full, cudaS
   const int64_t total = (int64_t)g.n * (g.m + 1);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  prof_begin("dtw_expand_kernel", st);
   dtw_expand_kernel<<<(unsigned)blocks, 256, 0, st>>>(cells, g, full);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }

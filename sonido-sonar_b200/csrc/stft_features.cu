@@ -480,6 +480,7 @@ int launch_geom(const FpPlan& plan, StftArgs& a, bool spectrum, cudaStream_t st)
   int64_t ctas = (a.total_runs + kWarps - 1) / kWarps;
   if (ctas > sms) ctas = sms;  // persistent: one CTA per SM, warps stride over the runs
   if (ctas < 1) ctas = 1;
+  prof_begin(spectrum ? "stft_spectrum_kernel" : "stft_features_kernel", st);
   if (spectrum) {
     auto k = stft_kernel<R1, R2, MODE_SPECTRUM>;
     SONAR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -489,7 +490,7 @@ int launch_geom(const FpPlan& plan, StftArgs& a, bool spectrum, cudaStream_t st)
     SONAR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     k<<<(unsigned)ctas, kWarps * 32, L.total, st>>>(a);
   }
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }

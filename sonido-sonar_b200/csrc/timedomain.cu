@@ -214,6 +214,7 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
     k<<<grid, kTdThreads, smem, st>>>(pcm, n, stride, alpha, frame, hop, Tn, fpb, sr, out, out_stride,  \
                                       o_energy, o_entropy, o_zcr);                                      \
   } while (0)
+  prof_begin("frame_walk_kernel", st);
   if (en && zc)
     LAUNCH_FW(true, true);
   else if (en)
@@ -223,7 +224,7 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
   else
     return SONAR_OK;
 #undef LAUNCH_FW
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }
@@ -231,8 +232,9 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
 int launch_variance(const double* x, int64_t n, int64_t stride, int n_streams, double* out, int64_t out_stride,
                     cudaStream_t st) {
   if (n_streams <= 0) return SONAR_OK;
+  prof_begin("variance_kernel", st);
   variance_kernel<<<n_streams, 256, 0, st>>>(x, n, stride, out, out_stride);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }
@@ -241,8 +243,9 @@ int launch_rms_windows(const double* pcm, int64_t n, int64_t stride, int n_strea
                        int hop, int64_t nw, double* out, int64_t out_stride, cudaStream_t st) {
   if (nw <= 0 || n_streams <= 0) return SONAR_OK;
   dim3 grid((unsigned)((nw + 7) / 8), (unsigned)n_streams);
+  prof_begin("rms_windows_kernel", st);
   rms_windows_kernel<<<grid, 256, 0, st>>>(pcm, n, stride, alpha, win, hop, nw, out, out_stride);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }
@@ -253,8 +256,9 @@ int launch_loudness_range(const double* rms, int64_t nw, int64_t in_stride, int 
   if (nw > 4096) return set_error(SONAR_ERR_UNSUPPORTED, "loudness range supports at most 4096 windows");
   int np2 = 1;
   while (np2 < nw) np2 <<= 1;
+  prof_begin("loudness_range_kernel", st);
   loudness_range_kernel<<<n_streams, 256, sizeof(double) * np2, st>>>(rms, nw, in_stride, out, out_stride);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }
@@ -263,8 +267,9 @@ int launch_fill(double* p, int64_t n, double v, cudaStream_t st) {
   if (n <= 0) return SONAR_OK;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  prof_begin("fill_kernel", st);
   fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n, v);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }
@@ -273,8 +278,9 @@ int launch_fill_strided(double* p, int64_t count, int64_t stride, int n_streams,
   if (count <= 0 || n_streams <= 0) return SONAR_OK;
   int64_t blocks = (count + 255) / 256;
   if (blocks > 64) blocks = 64;
+  prof_begin("fill_strided_kernel", st);
   fill_strided_kernel<<<dim3((unsigned)blocks, (unsigned)n_streams), 256, 0, st>>>(p, count, stride, v);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }

@@ -232,8 +232,9 @@ __global__ void __launch_bounds__(kFinThreads) xcorr_finalize_kernel(const Xcorr
 
 int launch_znorm(const XcorrSeq* seqs_dev, int count, cudaStream_t st) {
   if (count <= 0) return SONAR_OK;
+  prof_begin("znorm_kernel", st);
   znorm_kernel<<<count, 32, 0, st>>>(seqs_dev);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }
@@ -241,8 +242,9 @@ int launch_znorm(const XcorrSeq* seqs_dev, int count, cudaStream_t st) {
 int launch_xcorr(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags, cudaStream_t st) {
   if (n_pairs <= 0 || max_shard_lags <= 0) return SONAR_OK;
   dim3 grid((unsigned)((max_shard_lags + kNccThreads - 1) / kNccThreads), (unsigned)n_pairs);
+  prof_begin("ncc_exact_kernel", st);
   ncc_exact_kernel<<<grid, kNccThreads, 0, st>>>(pairs_dev);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }
@@ -250,8 +252,9 @@ int launch_xcorr(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags
 int launch_xcorr_finalize(const XcorrPair* pairs_dev, int n_pairs, int64_t peak_override, XcorrPairOut* outs_dev,
                           cudaStream_t st) {
   if (n_pairs <= 0) return SONAR_OK;
+  prof_begin("xcorr_finalize_kernel", st);
   xcorr_finalize_kernel<<<n_pairs, kFinThreads, 0, st>>>(pairs_dev, peak_override, outs_dev);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }

@@ -206,21 +206,24 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
     // frequency = sampleRate/period = 0 fails the [80,1000] Hz gate for every frame
     // (pitch_detection.go:394-400): the outputs are constants, no kernel work needed.
     dim3 grid((unsigned)std::min<int64_t>((Tp + 255) / 256, 64), (unsigned)n_streams);
+    prof_begin("yin_zero_kernel", st);
     yin_zero_kernel<<<grid, 256, 0, st>>>(n_streams, Tp, feat, feat_stride, o_pitch, o_conf, o_voicing,
                                           o_hratio, o_inharm, o_tonal);
-    count_launch();
+    prof_end();
     SONAR_CUDA(cudaGetLastError());
     return SONAR_OK;
   }
   if (Tp > 0x7fffffffLL) return set_error(SONAR_ERR_UNSUPPORTED, "too many pitch frames");
   dim3 grid((unsigned)Tp, (unsigned)n_streams);
+  prof_begin("yin_frame_kernel", st);
   yin_frame_kernel<<<grid, kYinThreads, 0, st>>>(pcm, stride, alpha, sr, Tp, hann_dev, scratch, scratch_stride);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
+  prof_begin("yin_track_kernel", st);
   yin_track_kernel<<<(n_streams + 63) / 64, 64, 0, st>>>(scratch, scratch_stride, n_streams, Tp, feat, feat_stride,
                                                          o_pitch, o_conf, o_voicing, o_hratio, o_inharm,
                                                          o_tonal);
-  count_launch();
+  prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
 }
