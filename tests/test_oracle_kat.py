@@ -1,0 +1,378 @@
+"""Pins for the CPU oracle (oracle/sonar_oracle.cpp).
+
+The reference ships no tests, no golden vectors and cannot be compiled here (no Go toolchain;
+SURVEY.md §4, §8c), so parity is *unpinned by the reference itself*.  What pins the oracle instead:
+  * known answers derived from the reference's formulas (window end points / power normalisation,
+    DCT row 0, the sampleRate=0 degenerate constants of SURVEY F3, pure-tone centroid, shifted-copy lag);
+  * independent numpy restatements of the same Go code written from the reference source
+    (file:line cited at each), compared with the C++ oracle;
+  * the committed fixtures under tests/golden/ (regression pins, see tests/golden/make_golden.py).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---------------------------------------------------------------- windows / STFT
+
+def test_hann_known_answers(oracle):
+    # analyzers/windowing.go:246-256 (symmetric: divide by N-1), :427-437 (power normalisation)
+    w = oracle.window("hann", 1024, symmetric=True, normalize=False)
+    assert w[0] == 0.0 and abs(w[-1]) < 1e-30 and np.allclose(w, w[::-1], atol=1e-15)
+    i = np.arange(1024)
+    assert np.allclose(w, 0.5 * (1 - np.cos(2 * np.pi * i / 1023)), rtol=0, atol=1e-16)
+    wn = oracle.window("hann", 1024)
+    assert abs((wn ** 2).sum() / 1024 - 1.0) < 1e-13
+    assert wn[512] / w[512] == pytest.approx(1.63379, rel=1e-5)
+    wp = oracle.window("hann", 1024, symmetric=False, normalize=False)
+    assert np.allclose(wp, 0.5 * (1 - np.cos(2 * np.pi * i / 1024)), atol=1e-16)
+
+
+@pytest.mark.parametrize("name,formula", [
+    ("hamming", lambda a, i, n: 0.54 - 0.46 * np.cos(a)),
+    ("blackman", lambda a, i, n: 0.42 - 0.5 * np.cos(a) + 0.08 * np.cos(2 * a)),
+    ("blackman_harris", lambda a, i, n: 0.35875 - 0.48829 * np.cos(a) + 0.14128 * np.cos(2 * a) - 0.01168 * np.cos(3 * a)),
+    ("rectangular", lambda a, i, n: np.ones_like(a)),
+    ("welch", lambda a, i, n: 1 - ((i - (n - 1) / 2) / ((n - 1) / 2)) ** 2),
+    ("bartlett", lambda a, i, n: np.where(i <= n // 2, 2 * i / (n - 1), 2 - 2 * i / (n - 1))),
+])
+def test_other_windows(oracle, name, formula):
+    n = 257
+    i = np.arange(n, dtype=np.float64)
+    a = 2 * np.pi * i / (n - 1)
+    w = oracle.window(name, n, symmetric=True, normalize=False)
+    assert np.allclose(w, formula(a, i, n), atol=1e-14)
+
+
+def np_stft(pcm, win, hop, w):
+    T = (pcm.size - win) // hop + 1  # analyzers/spectral.go:409
+    idx = np.arange(win)[None, :] + hop * np.arange(T)[:, None]
+    return np.fft.rfft(pcm[idx] * w[None, :], axis=1)
+
+
+def test_stft_against_numpy_rfft(oracle, synth):
+    pcm = synth.sweep_noise(0.5, seed=1)
+    for win, hop in ((1024, 256), (512, 160)):
+        mag, ph, cx = oracle.stft(pcm, win, hop, phase=True, cplx=True)
+        X = np_stft(pcm, win, hop, oracle.window("hann", win))
+        assert mag.shape == X.shape
+        scale = np.abs(X).max()
+        assert np.max(np.abs(mag - np.abs(X))) < 1e-11 * scale
+        assert np.max(np.abs(cx[..., 0] - X.real)) < 1e-11 * scale and np.max(np.abs(cx[..., 1] - X.imag)) < 1e-11 * scale
+        strong = np.abs(X) > 1e-6 * scale
+        assert np.max(np.abs(np.angle(np.exp(1j * (ph - np.angle(X))))[strong])) < 1e-8
+
+
+# ---------------------------------------------------------------- MFCC + spectral descriptors
+
+def np_mel_bank(n_mel, fft_size, sr, lo, hi):
+    # algorithms/spectral/mel_scale.go:29-86
+    hz2mel = lambda f: 2595.0 * np.log10(1.0 + f / 700.0)
+    mel2hz = lambda m: 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    mels = hz2mel(lo) + np.arange(n_mel + 2) * (hz2mel(hi) - hz2mel(lo)) / (n_mel + 1)
+    bins = np.minimum(np.floor((fft_size + 1.0) * mel2hz(mels) / sr + 0.5).astype(int), fft_size // 2)
+    fb = np.zeros((n_mel, fft_size // 2 + 1))
+    for m in range(1, n_mel + 1):
+        l, c, r = bins[m - 1], bins[m], bins[m + 1]
+        for k in range(l, c):
+            fb[m - 1, k] = (k - l) / (c - l)
+        for k in range(c, r):
+            fb[m - 1, k] = (r - k) / (r - c)
+    return fb
+
+
+def np_mfcc(mag, sr, n_mfcc=13, n_mel=26, lifter=22.0):
+    # algorithms/spectral/mfcc.go:113-164 (power, filter bank, ln with 1e-10 floor, DCT-II, lifter)
+    B = mag.shape[1]
+    fb = np_mel_bank(n_mel, (B - 1) * 2, sr, 0.0, sr / 2.0)
+    mel = (mag ** 2) @ fb.T
+    lg = np.where(mel > 0, np.log(np.where(mel > 0, mel, 1.0)), math.log(1e-10))
+    k = np.arange(n_mfcc)[:, None]
+    n = np.arange(n_mel)[None, :]
+    D = np.cos(np.pi * k * (n + 0.5) / n_mel) * np.where(k == 0, math.sqrt(1.0 / n_mel), math.sqrt(2.0 / n_mel))
+    c = lg @ D.T
+    c[:, 1:] *= 1.0 + (lifter / 2.0) * np.sin(np.pi * np.arange(1, n_mfcc) / lifter)
+    return c
+
+
+def test_dct_row0_known_answer():
+    # mfcc.go:205-209: D[0][n] = sqrt(1/M)
+    assert math.sqrt(1.0 / 26) == pytest.approx(0.19611613513818404)
+
+
+def test_mfcc_against_numpy_restatement(oracle, synth):
+    pcm = synth.sweep_noise(1.0, seed=2)
+    p = oracle.default_params(algo_sample_rate=44100)
+    fp = oracle.fingerprint(pcm, p)
+    mag, _, _ = oracle.stft(pcm, 1024, 256)
+    ref = np_mfcc(mag, 44100)
+    assert np.allclose(fp.mfcc, ref, rtol=1e-9, atol=1e-9)
+    p40 = oracle.default_params(algo_sample_rate=16000, call_sample_rate=16000, window_size=512, hop_size=160,
+                                energy_frame=512, energy_hop=160, n_mel=40)
+    x = synth.speech_band_noise(1.0)
+    mag, _, _ = oracle.stft(x, 512, 160)
+    assert np.allclose(oracle.fingerprint(x, p40).mfcc, np_mfcc(mag, 16000, n_mel=40), rtol=1e-9, atol=1e-9)
+
+
+def test_parity_mode_constants_F3(oracle, synth):
+    """sampleRate = 0 -> empty mel bank -> C0 = 26*ln(1e-10)*sqrt(1/26)."""
+    fp = oracle.fingerprint(synth.sweep_noise(1.0, seed=1), oracle.default_params(algo_sample_rate=0))
+    assert np.allclose(fp.mfcc[:, 0], -117.40926320884498, rtol=1e-14)
+    assert np.max(np.abs(fp.mfcc[:, 1:])) < 1e-10
+    for k in ("spectral_centroid", "spectral_rolloff", "spectral_bandwidth", "spectral_slope", "zero_crossing_rate",
+              "pitch_estimate", "pitch_confidence", "harmonic_ratio"):
+        assert not fp.arrays[k].any(), k
+    assert np.all(fp.inharmonicity_ratio == 1.0) and fp.loudness_range == 0.0
+    assert fp.spectral_flatness.any() and fp.spectral_crest.any() and fp.spectral_flux.any()
+
+
+def test_spectral_descriptors_against_numpy(oracle, synth):
+    sr = 44100
+    pcm = synth.sweep_noise(1.0, seed=3)
+    fp = oracle.fingerprint(pcm, oracle.default_params(algo_sample_rate=sr))
+    mag, _, _ = oracle.stft(pcm, 1024, 256)
+    B = mag.shape[1]
+    f = np.arange(B) * sr / (2.0 * (B - 1))  # spectral_centroid.go:59-65
+    sm = mag.sum(1)
+    cen = (mag * f).sum(1) / sm
+    assert np.allclose(fp.spectral_centroid, cen, rtol=1e-11)
+    bw = np.sqrt((((f[None, :] - cen[:, None]) ** 2) * mag).sum(1) / sm)  # spectral_bandwidth.go:22
+    assert np.allclose(fp.spectral_bandwidth, bw, rtol=1e-10)
+    p2 = mag ** 2
+    cum = np.cumsum(p2, axis=1)
+    ro = f[(cum >= 0.85 * cum[:, -1:]).argmax(1)]  # spectral_rolloff.go:19-55
+    assert np.array_equal(fp.spectral_rolloff, ro)
+    crest = mag.max(1) / np.sqrt(p2.sum(1) / B)  # spectral_crest.go:18
+    assert np.allclose(fp.spectral_crest, crest, rtol=1e-11)
+    flat = np.exp(np.log(mag).mean(1)) / mag.mean(1)  # spectral_flatness.go:31 (all bins > 1e-10 here)
+    assert (mag > 1e-10).all() and np.allclose(fp.spectral_flatness, np.minimum(flat, 1.0), rtol=1e-10)
+    x, y = np.log10(f[1:]), np.log10(mag[:, 1:])  # spectral_slope.go:24-67
+    n = B - 1
+    slope = (n * (x * y).sum(1) - x.sum() * y.sum(1)) / (n * (x * x).sum() - x.sum() ** 2)
+    assert np.allclose(fp.spectral_slope, slope, rtol=1e-8)
+    d = np.maximum(mag[1:] - mag[:-1], 0.0)  # spectral_flux.go:17-36
+    assert np.allclose(fp.spectral_flux, np.sqrt((d * d).sum(1)), rtol=1e-11)
+    split = B // 4  # extractors/speech.go:436-456
+    low = p2[:, :split].sum(1) / p2.sum(1)
+    assert np.allclose(fp.low_energy_ratio, low, rtol=1e-10) and np.allclose(fp.high_energy_ratio, 1 - low, rtol=1e-9)
+
+
+def test_pure_tone_centroid_and_pitch(oracle):
+    sr, f0 = 44100, 3000.0
+    t = np.arange(sr) / sr
+    fp = oracle.fingerprint(0.5 * np.sin(2 * np.pi * f0 * t), oracle.default_params(algo_sample_rate=sr))
+    assert abs(np.median(fp.spectral_centroid) - f0) < 40.0  # leakage of the Hann main lobe only
+    fp = oracle.fingerprint(0.5 * np.sin(2 * np.pi * 440.0 * t), oracle.default_params(algo_sample_rate=sr))
+    voiced = fp.pitch_estimate[fp.pitch_estimate > 0]
+    assert voiced.size > 0.9 * fp.pitch_estimate.size and abs(np.median(voiced) - 440.0) < 3.0
+
+
+# ---------------------------------------------------------------- time domain (bit-exact restatements)
+
+def seq_sum(x):
+    """Left-to-right float64 sum (np.add.accumulate is sequential; np.sum is pairwise)."""
+    return np.add.accumulate(x)[-1] if x.size else 0.0
+
+
+def test_pre_emphasis_energy_zcr_bit_exact(oracle, synth):
+    sr = 44100
+    pcm = synth.sweep_noise(0.5, seed=4)
+    fp = oracle.fingerprint(pcm, oracle.default_params(algo_sample_rate=sr))
+    y = pcm.copy()
+    y[1:] = pcm[1:] - 0.97 * pcm[:-1]  # filters/pre_emphasis.go:135-155
+    T = (pcm.size - 1024) // 256 + 1
+    ste = np.array([math.sqrt(seq_sum(y[t * 256:t * 256 + 1024] ** 2) / 1024) for t in range(T)])  # temporal/energy.go:25-50
+    assert np.array_equal(fp.short_time_energy, ste)
+    neg = y < 0
+    zc = np.array([(neg[t * 256 + 1:t * 256 + 1024] != neg[t * 256:t * 256 + 1023]).sum() / (1024 / sr) for t in range(T)])
+    assert np.array_equal(fp.zero_crossing_rate, zc)  # spectral/zero_crossing_rate.go:37-53
+    ent = np.where(ste > 0, -ste * np.log(ste + 1e-10), 0.0)  # extractors/speech.go:429-434
+    assert np.allclose(fp.energy_entropy, ent, rtol=1e-14)
+    var = ((ste - ste.mean()) ** 2).sum() / (T - 1)  # temporal/energy.go:97-118
+    assert fp.energy_variance == pytest.approx(var, rel=1e-10)
+
+
+# ---------------------------------------------------------------- cross-correlation
+
+def np_ncc(a, b, max_lag):
+    # algorithms/stats/correlation.go:203-228,373-409,421-501 (sequential sums)
+    def z(s):
+        mean = seq_sum(s) / s.size
+        sd = math.sqrt(seq_sum((s - mean) ** 2) / s.size)
+        return s - mean if sd < 1e-10 else (s - mean) / sd
+    za, zb = z(a), z(b)
+    L = max(0, min(max_lag, a.size - 1, b.size - 1))
+    out = []
+    for lag in range(-L, L + 1):
+        if lag >= 0:
+            n = min(a.size, b.size - lag)
+            x, y = za[:n], zb[lag:lag + n]
+        else:
+            n = min(a.size + lag, b.size)
+            x, y = za[-lag:-lag + n], zb[:n]
+        den = math.sqrt(seq_sum(x * x) * seq_sum(y * y))
+        out.append(0.0 if den < 1e-10 else seq_sum(x * y) / den)
+    return np.array(out), L
+
+
+def test_xcorr_against_numpy_bit_exact(oracle):
+    rng = np.random.default_rng(0)
+    for na, nb, ml in ((200, 200, 50), (150, 230, 400), (90, 40, 10)):
+        a, b = rng.standard_normal(na), rng.standard_normal(nb)
+        c, s = oracle.xcorr(a, b, ml)
+        ref, L = np_ncc(a, b, ml)
+        assert s.actual_max_lag == L and np.array_equal(c, ref)
+        best = int(np.argmax(np.abs(ref)))  # first maximum, strict '>' (correlation.go:535-541)
+        assert (s.peak_index, s.peak_lag, s.peak_correlation) == (best, best - L, ref[best])
+
+
+def test_shifted_copy_returns_the_exact_lag_and_sign(oracle):
+    """c(lag) = sum q[i] * r[i + lag]: reference delayed by d  ->  peak at +d."""
+    rng = np.random.default_rng(1)
+    base = np.convolve(rng.standard_normal(3000), np.ones(20) / 20, mode="same")
+    for d in (37, -112, 0):
+        q = base[200:2200]
+        r = base[200 - d:2200 - d]
+        _, s = oracle.xcorr(q, r, 300)
+        assert s.peak_lag == d and s.peak_correlation > 0.99
+
+
+def test_peak_metrics_formulas(oracle):
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal(400)
+    b = np.roll(a, 9) + 0.3 * rng.standard_normal(400)
+    c, s = oracle.xcorr(a, b, 60)
+    pk = s.peak_index
+    idx = np.arange(c.size)
+    noise = c[np.abs(idx - pk) > 5]
+    assert s.snr == pytest.approx(20 * math.log10(abs(c[pk]) / math.sqrt((noise ** 2).mean())), rel=1e-12)
+    assert s.sharpness == pytest.approx(-(c[pk + 1] - 2 * c[pk] + c[pk - 1]), rel=1e-12)
+    side = np.abs(c[np.abs(idx - pk) > 10]).max()
+    assert s.peak_to_sidelobe == pytest.approx(20 * math.log10(abs(c[pk]) / side), rel=1e-12)
+    others = np.where(idx != pk, np.abs(c), -1)
+    assert s.second_peak == c[int(np.argmax(others))]
+    assert s.overlap_length == min(400, 400 - s.peak_lag) and s.p_value == 0.01 and s.is_significant == 1
+
+
+def test_confidence_quality_spot_values(oracle, synth):
+    """stats/alignment.go:183-305 re-derived by hand for one case."""
+    q, r = synth.aligned_pair(20.0, offset_seconds=1.0, seed=5)
+    p = oracle.default_params(algo_sample_rate=44100)
+    ea, eb = oracle.fingerprint(q, p).short_time_energy, oracle.fingerprint(r, p).short_time_energy
+    _, xs, ar = oracle.align_xcorr(ea, eb, 1000, 256, 44100)
+    P = abs(xs.peak_correlation)
+    peak_score = P + (P - 0.6) * 0.5 if P >= 0.6 else P
+    sharp = min(0.9, xs.sharpness * 8)
+    side = min(0.8, xs.peak_to_sidelobe / 15) if 0 < xs.peak_to_sidelobe < math.inf else 0.0
+    snr = min(0.7, xs.snr / 25) if xs.snr > 0 else 0.0
+    ratio = abs(xs.second_peak) / P
+    pen = (ratio - 0.7) * 0.25 if (xs.second_peak != 0 and ratio > 0.7) else 0.0
+    bonus = 0.12 if P >= 0.75 else (0.08 if P >= 0.6 else 0.0)
+    conf = min(0.95, max(0.0, 0.55 * peak_score + 0.22 * sharp + 0.12 * side + 0.06 * snr + 0.05 * 0.15 + bonus - pen))
+    assert ar.confidence == pytest.approx(conf, rel=1e-12)
+    assert ar.offset == xs.peak_lag * 256 and ar.offset_seconds == ar.offset / 44100
+    assert ar.similarity == min(1.0, P) and ar.noise_level == pytest.approx(1 - xs.snr / 20)
+    assert abs(xs.peak_lag - 44100 / 256) <= 1
+
+
+# ---------------------------------------------------------------- DTW
+
+def py_dtw(q, r, band, step=0):
+    n, m = len(q), len(r)
+    C = np.full((n + 1, m + 1), np.inf)
+    C[0, 0] = 0
+    for i in range(1, n + 1):
+        for j in range(1, m + 1):
+            if band > 0 and abs(i - j) > band:
+                continue
+            ld = math.sqrt(sum((x - y) * (x - y) for x, y in zip(q[i - 1], r[j - 1])))
+            v, h, d = C[i - 1, j], C[i, j - 1], C[i - 1, j - 1]
+            C[i, j] = ld + (min(min(v, h), d) if step == 0 else min(v, h) if step == 1 else min(v + 1, min(h + 1, d)))
+    i, j, path = n, m, []
+    while i > 0 or j > 0:
+        cost = C[i, j] - C[i - 1, j - 1] if (i > 0 and j > 0) else 0.0
+        path.append((i - 1, j - 1, cost))
+        if i == 0:
+            j -= 1
+        elif j == 0:
+            i -= 1
+        else:
+            cs = (C[i - 1, j], C[i, j - 1], C[i - 1, j - 1])
+            mi = 0
+            for k in range(3):
+                if cs[k] < cs[mi]:
+                    mi = k
+            i, j = (i - 1, j) if mi == 0 else (i, j - 1) if mi == 1 else (i - 1, j - 1)
+    return path[::-1], C
+
+
+@pytest.mark.parametrize("n,m,dim,band,step", [(30, 30, 1, -1, 0), (25, 40, 3, -1, 1), (40, 35, 2, 6, 2),
+                                               (30, 50, 1, 5, 0), (1, 7, 1, -1, 0)])
+def test_dtw_against_pure_python(oracle, n, m, dim, band, step):
+    rng = np.random.default_rng(n + m)
+    q = np.cumsum(rng.standard_normal((n, dim)), 0)
+    r = np.cumsum(rng.standard_normal((m, dim)), 0)
+    with np.errstate(invalid="ignore"):
+        path, Cm = py_dtw(q.tolist(), r.tolist(), band, step)
+    d = oracle.dtw(q, r, band=band, step=step, want_matrix=True)
+    assert [p[0] for p in path] == d["path_query"].tolist() and [p[1] for p in path] == d["path_ref"].tolist()
+    assert np.array_equal(np.array([p[2] for p in path]), d["path_cost"], equal_nan=True)
+    assert np.array_equal(Cm[1:], d["cost_matrix"])
+    tc = Cm[n, m]
+    assert d["total_cost"] == tc and (d["distance"] == tc / len(path) or math.isnan(d["distance"]))
+
+
+def test_dtw_identical_sequences_quirks(oracle):
+    """Identical inputs: pure diagonal; the first path point's Cost is C[1][1]-C[0][0] = 0 (dtw.go:171-174)."""
+    x = np.sin(np.arange(64) * 0.2)
+    d = oracle.dtw(x, x)
+    assert d["path_query"].tolist() == list(range(64)) == d["path_ref"].tolist()
+    assert d["total_cost"] == 0.0 and not d["path_cost"].any()
+
+
+# ---------------------------------------------------------------- compare
+
+def test_colstats_and_cosine_against_numpy(oracle):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((500, 13)) + np.arange(13)
+    y = rng.standard_normal((400, 13)) * 2
+    st = oracle.colstats(x)
+    assert np.allclose(st[:13], x.mean(0), rtol=1e-13) and np.allclose(st[13:], x.std(0, ddof=1), rtol=1e-12)
+    v1 = np.concatenate([x.mean(0), x.std(0, ddof=1)])
+    v2 = np.concatenate([y.mean(0), y.std(0, ddof=1)])
+    cos = v1 @ v2 / (np.linalg.norm(v1) * np.linalg.norm(v2))
+    assert oracle.colstats_cosine(x, y) == pytest.approx(cos, rel=1e-12)
+
+
+def test_compare_confidence_steps(oracle, synth):
+    p = oracle.default_params(algo_sample_rate=44100)
+    fp = oracle.fingerprint(synth.sweep_noise(1.0, seed=6), p)
+    f1, _k1 = oracle.cmp_features(fp, harmonic=False)
+    r = oracle.compare(f1, f1, [0.35, 0.15, 0.3, 0.0, 0.0, 0.2, 0.0])
+    # identical fingerprints: mfcc and spectral both 1 -> similarity 1 -> 0.5 + 0.3 + 0.1 + 2*0.05 (comparison.go:1011-1037)
+    assert r.overall_similarity == pytest.approx(1.0, abs=1e-12) and r.n_features == 2
+    assert r.confidence == pytest.approx(1.0)
+
+
+# ---------------------------------------------------------------- committed fixtures
+
+@pytest.mark.parametrize("name", ["c1_fixed_sr", "c1_parity", "c3_speech_40mel"])
+def test_golden_fingerprint_fixtures(oracle, name):
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    kw = {k[3:]: int(g[k]) for k in g.files if k.startswith("kw_")}
+    fp = oracle.fingerprint(g["pcm"], oracle.default_params(**kw))
+    for k in g.files:
+        if k.startswith("out_"):
+            assert np.array_equal(fp.arrays[k[4:]], g[k]), k
+
+
+def test_golden_alignment_fixture(oracle):
+    g = np.load(os.path.join(GOLDEN, "c2_alignment.npz"))
+    c, s = oracle.xcorr(g["ea"], g["eb"], int(g["max_lag"]))
+    assert np.array_equal(c, g["corr"]) and s.peak_lag == int(g["peak_lag"])
+    d = oracle.dtw(g["dq"], g["dr"], band=int(g["band"]))
+    assert np.array_equal(d["path_query"], g["path_query"]) and np.array_equal(d["path_ref"], g["path_ref"])
