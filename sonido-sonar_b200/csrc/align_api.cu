@@ -207,7 +207,7 @@ int run_dtw_chunk(DevCtx& dev, Slot& s, const double* const* q, const double* co
   const int n = g.n, m = g.m;
   const int64_t cap = (int64_t)n + m;
   const size_t q_d = (size_t)np * n * dim, r_d = (size_t)np * m * dim;
-  const bool need_line = sizeof(double) * (size_t)(g.n_off + 2) > 200 * 1024;
+  const bool need_line = sizeof(double) * (size_t)(g.n_off + 2) > 140 * 1024;
   const size_t line_d = need_line ? (size_t)np * (g.n_off + 2) : 0;
   const size_t cells_d = (size_t)np * (size_t)g.cells;
   const size_t path_bytes = (size_t)np * cap * (sizeof(int32_t) * 2 + sizeof(double)) + sizeof(DtwPairOut) * np;

@@ -7,7 +7,7 @@
 //   parabolicInterpolation       :743-764
 //   postProcessResult / updateTemporalTracking   :767-921,978-1007 (sequential over frames)
 //
-// Kernel 1 (one CTA per 1024/512 frame) produces the raw (frequency, confidence)
+// Kernel 1 (four 1024/512 frames per CTA, 64 threads each) produces the raw (frequency, confidence)
 // of every frame; kernel 2 (one thread per stream) replays the reference's
 // sequential 20-deep history logic (octave correction vs the median of the last
 // five, confidence gate, median-of-three smoothing) and writes the six
@@ -19,85 +19,171 @@
 namespace sonar {
 namespace {
 
-constexpr int kYinFrame = 1024, kYinHop = 512, kYinHalf = 512, kYinThreads = 256;
+constexpr int kYinFrame = 1024, kYinHop = 512, kYinHalf = 512;
+constexpr int kYinFpb = 4;                     // frames per CTA
+constexpr int kYinTpf = 64;                    // threads per frame: 8 lags each
+constexpr int kYinThreads = kYinFpb * kYinTpf;
+constexpr int kYinPad = kYinFrame + kYinFrame / 8 + 8;  // p[e] stored at e + (e >> 3): stride-8 reads hit distinct banks
 
+__device__ __forceinline__ int pidx(int e) { return e + (e >> 3); }
+
+// Difference function through the autocorrelation identity
+//   d[tau] = sum_j (p[j] - p[j+tau])^2 = E(0) + E(tau) - 2 r[tau],
+//   r[tau] = sum_{j<512} p[j] p[j+tau],  E(tau) = sum_{j<512} p[j+tau]^2 = S[tau+512] - S[tau]
+// (one DFMA per (j, tau) instead of subtract/multiply/add; values agree with the reference's direct
+// form to ~1e-13 relative, far inside the feature tolerance).  Each thread owns 8 consecutive lags
+// and slides an 8-value register window over p, so the inner loop is 2 shared loads per 8 DFMAs.
 __global__ void __launch_bounds__(kYinThreads) yin_frame_kernel(const double* __restrict__ pcm, int64_t stride,
                                                                 double alpha, int sr, int64_t Tp,
                                                                 const double* __restrict__ hann,
                                                                 double* __restrict__ raw, int64_t raw_stride) {
-  __shared__ double p[kYinFrame];
-  __shared__ double d[kYinHalf];
-  __shared__ double cm[kYinHalf];
-  __shared__ double wsum[kYinThreads / 32];
-  __shared__ int s_min;
-  const int64_t f = blockIdx.x;
+  extern __shared__ double yin_smem[];
+  double (*sp)[kYinPad] = reinterpret_cast<double (*)[kYinPad]>(yin_smem);
+  double (*sS)[kYinFrame + 2] = reinterpret_cast<double (*)[kYinFrame + 2]>(yin_smem + kYinFpb * kYinPad);  // prefix sums of p^2
+  double (*sd)[kYinHalf] = reinterpret_cast<double (*)[kYinHalf]>(yin_smem + kYinFpb * (kYinPad + kYinFrame + 2));
   const int s = blockIdx.y;
+  const int fl = threadIdx.x / kYinTpf, tf = threadIdx.x % kYinTpf;
+  const int64_t f0 = (int64_t)blockIdx.x * kYinFpb;
   const double* __restrict__ x = pcm + (int64_t)s * stride;
-  const int64_t s0 = f * kYinHop;
-  const int tid = threadIdx.x;
-  // stream-level pre-emphasis (speech.go:161) then the detector's own (pitch_detection.go:299-314)
-  for (int i = tid; i < kYinFrame; i += kYinThreads) {
-    const int64_t g = s0 + i;
-    const double xm1 = g > 0 ? x[g - 1] : 0.0, xm2 = g > 1 ? x[g - 2] : 0.0;
-    const double y = x[g] - alpha * xm1;
-    double v = y;
-    if (i > 0) {
-      const double ym1 = xm1 - alpha * xm2;
-      v = y - 0.97 * ym1;
+  // ---- stage: stream-level pre-emphasis (speech.go:161), the detector's own (pitch_detection.go:299-314), Hann
+  for (int e = threadIdx.x; e < kYinFpb * kYinFrame; e += kYinThreads) {
+    const int ff = e / kYinFrame, i = e % kYinFrame;
+    const int64_t f = f0 + ff;
+    double v = 0.0;
+    if (f < Tp) {
+      const int64_t g = f * kYinHop + i;
+      const double xm1 = g > 0 ? x[g - 1] : 0.0, xm2 = g > 1 ? x[g - 2] : 0.0;
+      const double y = x[g] - alpha * xm1;
+      v = y;
+      if (i > 0) {
+        const double ym1 = xm1 - alpha * xm2;
+        v = y - 0.97 * ym1;
+      }
+      v *= hann[i];
     }
-    p[i] = v * hann[i];
-  }
-  if (tid == 0) s_min = kYinHalf;
-  __syncthreads();
-  // difference function d[tau] = sum_j (p[j] - p[j+tau])^2
-  for (int tau = tid; tau < kYinHalf; tau += kYinThreads) {
-    double acc = 0.0;
-#pragma unroll 8
-    for (int j = 0; j < kYinHalf; ++j) {
-      const double dl = p[j] - p[j + tau];
-      acc += dl * dl;
-    }
-    d[tau] = acc;
+    sp[ff][pidx(i)] = v;
   }
   __syncthreads();
-  // inclusive prefix sum of d[1..] (two values per thread, block scan)
+  // ---- prefix sums of squares: warp w of the CTA scans frame w (8 warps: two passes of 4 frames x ... )
   {
-    const int i0 = 2 * tid, i1 = 2 * tid + 1;
-    const double a = i0 >= 1 ? d[i0] : 0.0, b = d[i1];
-    double v = a + b;
-    const int lane = tid & 31, w = tid >> 5;
-    double incl = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const double up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w < kYinFpb) {
+      double* S = sS[w];
+      const double* P = sp[w];
+      double run = 0.0;  // lane handles 32 consecutive samples
+      double loc[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const double v = P[pidx(lane * 32 + k)];
+        run = fma(v, v, run);
+        loc[k] = run;
+      }
+      double incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const double base = incl - run;
+      if (lane == 0) S[0] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) S[lane * 32 + k + 1] = base + loc[k];
     }
-    if (lane == 31) wsum[w] = incl;
-    __syncthreads();
-    double base = 0.0;
-    for (int k = 0; k < w; ++k) base += wsum[k];
-    const double run1 = base + incl;      // running sum through i1
-    const double run0 = run1 - b;          // running sum through i0
-    cm[i0] = i0 == 0 ? 1.0 : d[i0] / (run0 / (double)i0);
-    cm[i1] = d[i1] / (run1 / (double)i1);
+  }
+  // ---- autocorrelation r[tau0 .. tau0+8) with a sliding register window
+  const double* __restrict__ P = sp[fl];
+  const int tau0 = tf * 8;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = P[pidx(tau0 + k)];
+  for (int j = 0; j < kYinHalf; j += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const double a = P[pidx(j + u)];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fma(a, w[(u + k) & 7], acc[k]);
+      w[u & 7] = P[pidx(j + u + tau0 + 8)];  // j+u+tau0+8 <= 511+504+8 = 1023
+    }
+  }
+  __syncthreads();  // sS complete
+  {
+    const double* S = sS[fl];
+    const double e0 = S[kYinHalf];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int tau = tau0 + k;
+      const double et = S[tau + kYinHalf] - S[tau];
+      double dv = (e0 + et) - 2.0 * acc[k];
+      sd[fl][tau] = dv > 0.0 ? dv : 0.0;
+    }
   }
   __syncthreads();
-  for (int tau = tid; tau < kYinHalf; tau += kYinThreads)
-    if (tau >= 1 && tau + 1 < kYinHalf && cm[tau] < 0.15 && cm[tau] < cm[tau + 1]) atomicMin(&s_min, tau);
-  __syncthreads();
-  if (tid == 0) {
+  // ---- CMNDF + first dip below 0.15 (pitch_detection.go:363-383): one warp per frame, 16 lags per lane
+  const int wv = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (wv >= kYinFpb) return;
+  const int64_t f = f0 + wv;
+  const double* d = sd[wv];
+  double loc[16], run = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int tau = lane * 16 + k;
+    run += tau >= 1 ? d[tau] : 0.0;
+    loc[k] = run;
+  }
+  double incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  const double base = incl - run;
+  double cm[17];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int tau = lane * 16 + k;
+    cm[k] = tau == 0 ? 1.0 : d[tau] / ((base + loc[k]) / (double)tau);
+  }
+  cm[16] = __shfl_down_sync(0xffffffffu, cm[0], 1);
+  int first = kYinHalf;
+#pragma unroll
+  for (int k = 15; k >= 0; --k) {
+    const int tau = lane * 16 + k;
+    if (tau >= 1 && tau + 1 < kYinHalf && cm[k] < 0.15 && cm[k] < cm[k + 1]) first = tau;
+  }
+  const int mt = __reduce_min_sync(0xffffffffu, first);
+  if (f >= Tp) return;
+  // the owner lane of mt has cm[mt-1..mt+1] at hand except across lane borders: fetch from shared d-derived values
+  const int owner = mt < kYinHalf ? mt / 16 : 0;
+  double y1 = 0.0, y2 = 0.0, y3 = 0.0;
+  if (mt < kYinHalf) {
+    const int k = mt % 16;
+    // cm[k-1] may live in the previous lane
+    double prev_last = __shfl_up_sync(0xffffffffu, cm[15], 1);
+    double c_m1 = 0.0, c_0 = 0.0, c_p1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (q == k) {
+        c_0 = cm[q];
+        c_p1 = cm[q + 1];
+        c_m1 = q > 0 ? cm[q - 1] : prev_last;
+      }
+    y1 = __shfl_sync(0xffffffffu, c_m1, owner);
+    y2 = __shfl_sync(0xffffffffu, c_0, owner);
+    y3 = __shfl_sync(0xffffffffu, c_p1, owner);
+  }
+  if (lane == 0) {
     double pitch = 0.0, conf = 0.0;
-    const int mt = s_min;
     if (mt < kYinHalf && mt > 0) {
       double period = (double)mt;
-      if (!(mt <= 0 || mt >= kYinHalf - 1)) {
-        const double y1 = cm[mt - 1], y2 = cm[mt], y3 = cm[mt + 1];
+      if (!(mt <= 0 || mt >= kYinHalf - 1)) {  // parabolicInterpolation :743-764
         const double a = (y1 - 2 * y2 + y3) / 2, b = (y3 - y1) / 2;
         if (a != 0) period = (double)mt + (-b / (2 * a));
       }
       const double freq = (double)sr / period;
       if (freq >= 80.0 && freq <= 1000.0) {
         pitch = freq;
-        conf = 1.0 - cm[mt];
+        conf = 1.0 - y2;
       }
     }
     double* r = raw + (int64_t)s * raw_stride;
@@ -124,58 +210,83 @@ __device__ double median_nonzero(const double* v, int n) {  // pitch_detection.g
   return (m % 2 == 0) ? (f[m / 2 - 1] + f[m / 2]) / 2.0 : f[m / 2];
 }
 
-__global__ void yin_track_kernel(const double* __restrict__ raw, int64_t raw_stride, int n_streams, int64_t Tp,
-                                 double* __restrict__ feat, int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
-                                 int64_t o_voicing, int64_t o_hratio, int64_t o_inharm, int64_t o_tonal) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_streams) return;
+// One warp per stream: lanes stage 32 frames of raw (pitch, confidence) in shared memory with coalesced
+// loads, lane 0 replays the reference's sequential history logic on them, all lanes write the six output
+// arrays coalesced.
+__global__ void __launch_bounds__(32) yin_track_kernel(const double* __restrict__ raw, int64_t raw_stride,
+                                                       int n_streams, int64_t Tp, double* __restrict__ feat,
+                                                       int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
+                                                       int64_t o_voicing, int64_t o_hratio, int64_t o_inharm,
+                                                       int64_t o_tonal) {
+  __shared__ double in_p[32], in_c[32], out_p[32], out_c[32], out_v[32];
+  const int s = blockIdx.x;
+  const int lane = threadIdx.x;
   const double* r = raw + (int64_t)s * raw_stride;
   double* fo = feat + (int64_t)s * feat_stride;
   double hist[5] = {0, 0, 0, 0, 0};  // last five history entries, hist[4] newest
   int64_t hlen = 0;
   double previous = 0.0;
-  for (int64_t i = 0; i < Tp; i++) {
-    double pitch = r[i], conf = r[Tp + i], voicing = conf;
-    // applyOctaveCorrection :792-829
-    if (!(pitch == 0.0 || hlen == 0)) {
-      const int cnt = hlen < 5 ? (int)hlen : 5;
-      if (cnt >= 3) {
-        const double med = median_nonzero(hist + 5 - cnt, cnt);
-        const double ratios[4] = {0.5, 2.0, 1.0 / 3.0, 3.0};
-        for (int k = 0; k < 4; k++) {
-          const double expect = med * ratios[k];
-          if (fabs(pitch - expect) / expect < 0.1) {
-            if (fabs(pitch - med) > fabs(expect - med)) pitch = expect;
-            break;
+  for (int64_t base = 0; base < Tp; base += 32) {
+    const int cnt = (int)((Tp - base < 32) ? (Tp - base) : 32);
+    if (lane < cnt) {
+      in_p[lane] = r[base + lane];
+      in_c[lane] = r[Tp + base + lane];
+    }
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = 0; i < cnt; i++) {
+        double pitch = in_p[i], conf = in_c[i], voicing = conf;
+        // applyOctaveCorrection :792-829
+        if (!(pitch == 0.0 || hlen == 0)) {
+          const int c5 = hlen < 5 ? (int)hlen : 5;
+          if (c5 >= 3) {
+            const double med = median_nonzero(hist + 5 - c5, c5);
+            const double ratios[4] = {0.5, 2.0, 1.0 / 3.0, 3.0};
+            for (int k = 0; k < 4; k++) {
+              const double expect = med * ratios[k];
+              if (fabs(pitch - expect) / expect < 0.1) {
+                if (fabs(pitch - med) > fabs(expect - med)) pitch = expect;
+                break;
+              }
+            }
           }
         }
+        if (conf < 0.5) {  // :782-786
+          pitch = 0.0;
+          conf = 0.0;
+          voicing = 0.0;
+        }
+        // updateTemporalTracking :876-902 (only the last five entries are ever read)
+        hist[0] = hist[1];
+        hist[1] = hist[2];
+        hist[2] = hist[3];
+        hist[3] = hist[4];
+        hist[4] = pitch;
+        hlen++;
+        if (hlen > 1) {  // applyTemporalSmoothing :905-921
+          if (hlen >= 3)
+            pitch = median_nonzero(hist + 2, 3);
+          else
+            pitch = 0.3 * pitch + (1 - 0.3) * previous;
+        }
+        previous = pitch;
+        out_p[i] = pitch;
+        out_c[i] = conf;
+        out_v[i] = voicing;
       }
     }
-    if (conf < 0.5) {  // :782-786
-      pitch = 0.0;
-      conf = 0.0;
-      voicing = 0.0;
+    __syncwarp();
+    if (lane < cnt) {
+      const int64_t i = base + lane;
+      const double pitch = out_p[lane], voicing = out_v[lane];
+      fo[o_pitch + i] = pitch;
+      fo[o_conf + i] = out_c[lane];
+      fo[o_voicing + i] = voicing;
+      fo[o_hratio + i] = voicing * 10.0;          // speech.go:499
+      fo[o_inharm + i] = 1.0 - voicing;           // speech.go:500
+      fo[o_tonal + i] = pitch > 0 ? pitch : 0.0;  // speech.go:503-505
     }
-    // updateTemporalTracking :876-902 (only the last five entries are ever read)
-    hist[0] = hist[1];
-    hist[1] = hist[2];
-    hist[2] = hist[3];
-    hist[3] = hist[4];
-    hist[4] = pitch;
-    hlen++;
-    if (hlen > 1) {  // applyTemporalSmoothing :905-921
-      if (hlen >= 3)
-        pitch = median_nonzero(hist + 2, 3);
-      else
-        pitch = 0.3 * pitch + (1 - 0.3) * previous;
-    }
-    previous = pitch;
-    fo[o_pitch + i] = pitch;
-    fo[o_conf + i] = conf;
-    fo[o_voicing + i] = voicing;
-    fo[o_hratio + i] = voicing * 10.0;          // speech.go:499
-    fo[o_inharm + i] = 1.0 - voicing;           // speech.go:500
-    fo[o_tonal + i] = pitch > 0 ? pitch : 0.0;  // speech.go:503-505
+    __syncwarp();
   }
 }
 
@@ -214,13 +325,15 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
     return SONAR_OK;
   }
   if (Tp > 0x7fffffffLL) return set_error(SONAR_ERR_UNSUPPORTED, "too many pitch frames");
-  dim3 grid((unsigned)Tp, (unsigned)n_streams);
+  dim3 grid((unsigned)((Tp + kYinFpb - 1) / kYinFpb), (unsigned)n_streams);
+  const size_t smem = sizeof(double) * kYinFpb * (kYinPad + kYinFrame + 2 + kYinHalf);
+  SONAR_CUDA(cudaFuncSetAttribute(yin_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin("yin_frame_kernel", st);
-  yin_frame_kernel<<<grid, kYinThreads, 0, st>>>(pcm, stride, alpha, sr, Tp, hann_dev, scratch, scratch_stride);
+  yin_frame_kernel<<<grid, kYinThreads, smem, st>>>(pcm, stride, alpha, sr, Tp, hann_dev, scratch, scratch_stride);
   prof_end();
   SONAR_CUDA(cudaGetLastError());
   prof_begin("yin_track_kernel", st);
-  yin_track_kernel<<<(n_streams + 63) / 64, 64, 0, st>>>(scratch, scratch_stride, n_streams, Tp, feat, feat_stride,
+  yin_track_kernel<<<n_streams, 32, 0, st>>>(scratch, scratch_stride, n_streams, Tp, feat, feat_stride,
                                                          o_pitch, o_conf, o_voicing, o_hratio, o_inharm,
                                                          o_tonal);
   prof_end();
