@@ -1,0 +1,221 @@
+// Package sonargpu is the thin cgo layer over libsonar.so (include/sonar.h).
+//
+// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Go toolchain (SURVEY.md §8c).  It is the
+// binding a maintainer of RyanBlaney/sonido-sonar adds to switch the hot path to the B200 library; the
+// same entry points are exercised from C++ (sonido-sonar_b200/host/sonar_host.hpp) and Python
+// (sonido-sonar_b200/capi.py) in this repo's tests.
+//
+// cgo rules honoured here: Go owns every input and output buffer, C never retains a Go pointer after the
+// call returns, and no Go pointer to a Go pointer crosses the boundary — every [][]float64 is flattened
+// into one backing array first.
+package sonargpu
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../sonido-sonar_b200 -lsonar -Wl,-rpath,${SRCDIR}/../../sonido-sonar_b200
+#include <stdlib.h>
+#include "sonar.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"runtime"
+	"sync"
+	"unsafe"
+)
+
+var (
+	once   sync.Once
+	ctx    *C.sonar_ctx
+	ctxErr error
+)
+
+// Ctx returns the process-wide context (one per process; the C layer is re-entrant).
+func Ctx() (*C.sonar_ctx, error) {
+	once.Do(func() {
+		if rc := C.sonar_init(0, nil, &ctx); rc != C.SONAR_OK {
+			ctxErr = errors.New(C.GoString(C.sonar_last_error())) // no CPU fallback: surfaces "no usable CUDA device"
+		}
+	})
+	return ctx, ctxErr
+}
+
+func lastError() error {
+	return errors.New(C.GoString(C.sonar_last_error()))
+}
+
+func ptr(s []float64) *C.double {
+	if len(s) == 0 {
+		return nil
+	}
+	return (*C.double)(unsafe.Pointer(&s[0]))
+}
+
+// FpParams mirrors sonar_fp_params: exactly what the reference's algorithm objects are constructed with.
+type FpParams struct {
+	WindowSize, HopSize, WindowType  int
+	AlgoSampleRate, CallSampleRate   int // AlgoSampleRate is 0 through stock GenerateFingerprint (F2/F3)
+	EnergyFrame, EnergyHop           int // FeatureConfig.WindowSize/HopSize as temporal.NewEnergy sees them (F4)
+	MFCCCoefficients                 int
+	EnableMFCC                       bool
+}
+
+// Fingerprint holds the flat outputs of sonar_fingerprint_f64 (row-major MFCC).
+type Fingerprint struct {
+	Frames, EnergyFrames, PitchFrames, NMFCC int
+	MFCC                                      []float64
+	Centroid, Rolloff, Bandwidth, Flatness    []float64
+	Crest, Slope, Flux, ZCR                   []float64
+	ShortTimeEnergy, EnergyEntropy            []float64
+	LowEnergyRatio, HighEnergyRatio           []float64
+	Pitch, PitchConfidence, Voicing           []float64
+	HarmonicRatio, Inharmonicity, TonalCentroid []float64
+	EnergyVariance, LoudnessRange             float64
+}
+
+// GenerateFingerprint replaces ComputeSTFTWithWindow + SpeechFeatureExtractor.ExtractFeatures
+// (fingerprint/fingerprint.go:190-207).
+func GenerateFingerprint(pcm []float64, p FpParams) (*Fingerprint, error) {
+	c, err := Ctx()
+	if err != nil {
+		return nil, err
+	}
+	var cp C.sonar_fp_params
+	C.sonar_fp_params_default(&cp)
+	cp.window_size, cp.hop_size, cp.window_type = C.int32_t(p.WindowSize), C.int32_t(p.HopSize), C.int32_t(p.WindowType)
+	cp.algo_sample_rate, cp.call_sample_rate = C.int32_t(p.AlgoSampleRate), C.int32_t(p.CallSampleRate)
+	cp.energy_frame, cp.energy_hop = C.int32_t(p.EnergyFrame), C.int32_t(p.EnergyHop)
+	cp.n_mfcc = C.int32_t(p.MFCCCoefficients)
+	cp.enable = 0
+	if p.EnableMFCC {
+		cp.enable |= C.SONAR_FP_ENABLE_MFCC
+	}
+	var sz C.sonar_fp_sizes_t
+	if rc := C.sonar_fp_sizes(&cp, C.int64_t(len(pcm)), &sz); rc != C.SONAR_OK {
+		return nil, lastError() // "empty signal", "signal too short for given window size and hop size", ...
+	}
+	T, Te, Tp, K := int(sz.n_frames), int(sz.n_energy_frames), int(sz.n_pitch_frames), int(sz.n_mfcc)
+	f := &Fingerprint{Frames: T, EnergyFrames: Te, PitchFrames: Tp, NMFCC: K}
+	mk := func(n int) []float64 { return make([]float64, n) }
+	f.MFCC = mk(T * K)
+	f.Centroid, f.Rolloff, f.Bandwidth, f.Flatness = mk(T), mk(T), mk(T), mk(T)
+	f.Crest, f.Slope, f.Flux, f.ZCR = mk(T), mk(T), mk(int(sz.n_flux)), mk(T)
+	f.ShortTimeEnergy, f.EnergyEntropy, f.LowEnergyRatio, f.HighEnergyRatio = mk(Te), mk(Te), mk(Te), mk(Te)
+	f.Pitch, f.PitchConfidence, f.Voicing = mk(Tp), mk(Tp), mk(Tp)
+	f.HarmonicRatio, f.Inharmonicity, f.TonalCentroid = mk(Tp), mk(Tp), mk(Tp)
+	// sonar_fp_out holds Go pointers, so it must live in C memory for the duration of the call (cgo rule:
+	// a Go struct containing Go pointers may not be passed); the pinner keeps the slices in place.
+	out := (*C.sonar_fp_out)(C.calloc(1, C.size_t(unsafe.Sizeof(C.sonar_fp_out{}))))
+	defer C.free(unsafe.Pointer(out))
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	set := func(dst **C.double, s []float64) {
+		if len(s) > 0 {
+			pin.Pin(&s[0])
+			*dst = ptr(s)
+		}
+	}
+	set(&out.mfcc, f.MFCC)
+	set(&out.spectral_centroid, f.Centroid)
+	set(&out.spectral_rolloff, f.Rolloff)
+	set(&out.spectral_bandwidth, f.Bandwidth)
+	set(&out.spectral_flatness, f.Flatness)
+	set(&out.spectral_crest, f.Crest)
+	set(&out.spectral_slope, f.Slope)
+	set(&out.spectral_flux, f.Flux)
+	set(&out.zero_crossing_rate, f.ZCR)
+	set(&out.short_time_energy, f.ShortTimeEnergy)
+	set(&out.energy_entropy, f.EnergyEntropy)
+	set(&out.low_energy_ratio, f.LowEnergyRatio)
+	set(&out.high_energy_ratio, f.HighEnergyRatio)
+	set(&out.pitch_estimate, f.Pitch)
+	set(&out.pitch_confidence, f.PitchConfidence)
+	set(&out.voicing_strength, f.Voicing)
+	set(&out.harmonic_ratio, f.HarmonicRatio)
+	set(&out.inharmonicity_ratio, f.Inharmonicity)
+	set(&out.tonal_centroid, f.TonalCentroid)
+	if rc := C.sonar_fingerprint_f64(c, ptr(pcm), C.int64_t(len(pcm)), &cp, out); rc != C.SONAR_OK {
+		return nil, lastError()
+	}
+	f.EnergyVariance, f.LoudnessRange = float64(out.energy_variance), float64(out.loudness_range)
+	return f, nil
+}
+
+// XcorrSummary mirrors stats.CorrelationResult without the arrays (algorithms/stats/correlation.go:44-71).
+type XcorrSummary struct {
+	PeakCorrelation, PValue, SNR, Sharpness, SecondPeak, PeakToSidelobe float64
+	PeakLag, PeakIndex, MaxLag, OverlapLength                           int
+	IsSignificant                                                       bool
+}
+
+// AlignResult mirrors the scalar fields of stats.AlignmentResult (algorithms/stats/alignment.go:34-58).
+type AlignResult struct {
+	Offset                                                              int
+	OffsetSeconds, Confidence, Similarity, AlignmentQuality, NoiseLevel float64
+}
+
+// AlignCrossCorrelation replaces AlignmentAnalyzer.AlignFeatures(method = AlignmentCrossCorrelation) as
+// extractors.alignWithFeatures calls it for "corr_energy" (fingerprint/extractors/alignment.go:357-409).
+func AlignCrossCorrelation(query, reference []float64, maxLagFrames, hopSize, sampleRate int) ([]float64, *XcorrSummary, *AlignResult, error) {
+	c, err := Ctx()
+	if err != nil {
+		return nil, nil, nil, err
+	}
+	if maxLagFrames < 0 {
+		maxLagFrames = 0
+	}
+	corr := make([]float64, 2*maxLagFrames+1)
+	var xs C.sonar_xcorr_summary
+	var ar C.sonar_align_result
+	rc := C.sonar_align_xcorr_f64(c, ptr(query), C.int64_t(len(query)), ptr(reference), C.int64_t(len(reference)),
+		C.int(maxLagFrames), C.int(hopSize), C.int(sampleRate), ptr(corr), &xs, &ar)
+	if rc != C.SONAR_OK {
+		return nil, nil, nil, lastError() // "empty feature sequences provided"
+	}
+	s := &XcorrSummary{float64(xs.peak_correlation), float64(xs.p_value), float64(xs.snr), float64(xs.sharpness),
+		float64(xs.second_peak), float64(xs.peak_to_sidelobe), int(xs.peak_lag), int(xs.peak_index),
+		int(xs.actual_max_lag), int(xs.overlap_length), xs.is_significant != 0}
+	a := &AlignResult{int(ar.offset), float64(ar.offset_seconds), float64(ar.confidence), float64(ar.similarity),
+		float64(ar.alignment_quality), float64(ar.noise_level)}
+	return corr[:2*s.MaxLag+1], s, a, nil
+}
+
+// DTW replaces DTWAlignment.Align (algorithms/stats/dtw.go:55-217).  q and r are row-major [n][dim].
+func DTW(q []float64, n int, r []float64, m, dim, band int) (pathQ, pathR []int32, pathCost []float64, distance float64, err error) {
+	c, err := Ctx()
+	if err != nil {
+		return nil, nil, nil, 0, err
+	}
+	pathQ, pathR, pathCost = make([]int32, n+m), make([]int32, n+m), make([]float64, n+m)
+	out := (*C.sonar_dtw_out)(C.calloc(1, C.size_t(unsafe.Sizeof(C.sonar_dtw_out{}))))
+	defer C.free(unsafe.Pointer(out))
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	pin.Pin(&pathQ[0])
+	pin.Pin(&pathR[0])
+	pin.Pin(&pathCost[0])
+	out.path_query = (*C.int32_t)(unsafe.Pointer(&pathQ[0]))
+	out.path_ref = (*C.int32_t)(unsafe.Pointer(&pathR[0]))
+	out.path_cost = ptr(pathCost)
+	out.path_cap = C.int64_t(n + m)
+	if rc := C.sonar_dtw_f64(c, ptr(q), C.int(n), ptr(r), C.int(m), C.int(dim), C.int(band),
+		C.SONAR_STEP_SYMMETRIC2, C.SONAR_METRIC_EUCLIDEAN, out); rc != C.SONAR_OK {
+		return nil, nil, nil, 0, lastError() // "empty sequences provided"
+	}
+	l := int(out.path_len)
+	return pathQ[:l], pathR[:l], pathCost[:l], float64(out.distance), nil
+}
+
+// ColStatsCosine replaces extractMFCCStatistics x2 + cosineSimilarity (fingerprint/comparison.go:774-873).
+func ColStatsCosine(x []float64, tx int, y []float64, ty, dim int) (float64, error) {
+	c, err := Ctx()
+	if err != nil {
+		return 0, err
+	}
+	var sim C.double
+	if rc := C.sonar_colstats_cosine_f64(c, ptr(x), C.int64_t(tx), ptr(y), C.int64_t(ty), C.int(dim), &sim); rc != C.SONAR_OK {
+		return 0, lastError()
+	}
+	return float64(sim), nil
+}
