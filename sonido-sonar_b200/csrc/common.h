@@ -151,8 +151,8 @@ int launch_xcorr_finalize(const XcorrPair* pairs_dev, int n_pairs, int64_t peak_
 struct DtwGeom {
   int n, m, band;   // band == 0: unconstrained
   int n_off;        // number of distinct offsets i - j the wavefront tracks
-  int64_t W;        // cells per stored row (2*band+1, or m)
-  int64_t cells;    // cells per pair (n rows)
+  int64_t W;        // banded: cells per stored anti-diagonal (band+1); unconstrained: cells per stored row (m)
+  int64_t cells;    // cells per pair
 };
 int dtw_geometry(int n, int m, int band, DtwGeom* g);
 struct DtwPairOut {

@@ -38,6 +38,15 @@ __device__ __forceinline__ double local_dist(const double* __restrict__ q, const
   return sqrt(s);
 }
 
+// Banded cost store, DIAGONAL-major: cell (i, j) lives at (i + j) * Wd + ((i - j + band) >> 1), Wd = band + 1.
+// The cells of one anti-diagonal are produced together, so this makes every store of the fill kernels a
+// contiguous, fully covered run of sectors.  (A row-major band store turns each cell into an isolated
+// 8-byte write: the L2 has to fetch the rest of the sector first, and with ~600 cycles per such write and a
+// bounded number of writes in flight per SM the fill ran at one store per ~10 cycles.)
+__device__ __forceinline__ int64_t band_index(const DtwGeom& g, int i, int j) {
+  return (int64_t)(i + j) * g.W + ((i - j + g.band) >> 1);
+}
+
 // implicit borders: C[0][0] = 0, first row/column +Inf, out-of-band +Inf
 __device__ __forceinline__ double cell_get(const double* __restrict__ cells, const DtwGeom& g, int i, int j) {
   if (i == 0 && j == 0) return 0.0;
@@ -45,7 +54,7 @@ __device__ __forceinline__ double cell_get(const double* __restrict__ cells, con
   if (g.band > 0) {
     const int df = i - j;
     if (df > g.band || df < -g.band) return d_inf();
-    return cells[(int64_t)(i - 1) * g.W + (j - i + g.band)];
+    return cells[band_index(g, i, j)];
   }
   return cells[(int64_t)(i - 1) * g.W + (j - 1)];
 }
@@ -110,8 +119,7 @@ __global__ void __launch_bounds__(1024) dtw_fill_kernel(const double* __restrict
       const int i = ilo + t;
       if (i <= ihi) {
         const int j = d - i;
-        const int64_t col = band > 0 ? (j - i + band) : (j - 1);
-        cells[(int64_t)(i - 1) * g.W + col] = s_stage[e];
+        cells[band > 0 ? band_index(g, i, j) : (int64_t)(i - 1) * g.W + (j - 1)] = s_stage[e];
       }
     }
   };
@@ -152,8 +160,7 @@ __global__ void __launch_bounds__(1024) dtw_fill_kernel(const double* __restrict
       if constexpr (ONECELL) {
         s_stage[staged * blockDim.x + threadIdx.x] = c;
       } else {
-        const int64_t col = band > 0 ? (j - i + band) : (j - 1);
-        cells[(int64_t)(i - 1) * g.W + col] = c;
+        cells[band > 0 ? band_index(g, i, j) : (int64_t)(i - 1) * g.W + (j - 1)] = c;
       }
     }
     if constexpr (STAGED) {  // one cell per thread (blockDim >= band + 1): prefetch its distance for d + 1
@@ -174,96 +181,86 @@ __global__ void __launch_bounds__(1024) dtw_fill_kernel(const double* __restrict
   }
 }
 
-// Fast path for the configuration the alignment pipeline uses (dim == 1, 0 < band <= 511): thread t owns
-// one fixed offset i - j per diagonal parity, so row/column indices, the band-store address and the
-// three shared-memory line slots only ever advance by constants; the per-diagonal work is ~25
-// instructions and the dependent chain is LDS -> min -> min -> add -> STS -> barrier.
-template <int STEP>
-__global__ void __launch_bounds__(512) dtw_fill_band1_kernel(const double* __restrict__ qs,
-                                                             const double* __restrict__ rs, DtwGeom g,
-                                                             double* __restrict__ cells_all) {
-  extern __shared__ double s_mem[];
-  double* ring_q = s_mem;
-  double* ring_r = s_mem + kRing;
-  double* line = s_mem + 2 * kRing;  // line[delta + band + 1], +Inf sentinels at both ends
-  const int pair = blockIdx.x, t = threadIdx.x;
+// Register-resident wavefront for narrow bands (dim == 1, 2*band+1 <= 32*NPL): ONE warp per pair, lane l
+// keeps the latest cost of the NPL offsets k = NPL*l .. NPL*l+NPL-1 (k = i - j + band) in registers.  A
+// diagonal only touches offsets of one parity and reads the two neighbouring offsets of the other parity,
+// so a step is NPL/2 independent relaxations per lane plus ONE warp shuffle for the value that lives in the
+// neighbouring lane — no shared-memory line, no block barrier, and the dependent chain per diagonal is
+// shuffle -> min -> min -> add.
+template <int NPL, int STEP>
+__global__ void __launch_bounds__(32) dtw_fill_warp_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
+                                                           DtwGeom g, double* __restrict__ cells_all) {
+  __shared__ double ring_q[kRing], ring_r[kRing];
+  const int pair = blockIdx.x, lane = threadIdx.x;
   const int n = g.n, m = g.m, band = g.band, W = (int)g.W;
   const double* __restrict__ q = qs + (int64_t)pair * n;
   const double* __restrict__ r = rs + (int64_t)pair * m;
   double* __restrict__ cells = cells_all + (int64_t)pair * g.cells;
-  for (int k = t; k < 2 * band + 3; k += blockDim.x) line[k] = d_inf();
-  __syncthreads();
-  if (t == 0) line[band + 1] = 0.0;  // C[0][0]
-  // even diagonals carry offsets of even parity, odd diagonals of odd parity
-  const int de = -band + (band & 1) + 2 * t, dod = -band + ((band + 1) & 1) + 2 * t;
-  const bool act_e = de <= band, act_o = dod <= band;
-  int ie = (2 + de) >> 1, je = 2 - ie;  // cell of this thread on d = 2
-  int io = (3 + dod) >> 1, jo = 3 - io;  // ... and on d = 3
-  int64_t offe = (int64_t)(ie - 1) * W + (band - de), offo = (int64_t)(io - 1) * W + (band - dod);
-  const int oe = de + band + 1, oo = dod + band + 1;
-  auto dist = [&](int i, int j) -> double {
-    const double df = ring_q[(i - 1) & (kRing - 1)] - ring_r[(j - 1) & (kRing - 1)];
-    const double ad = fabs(df);
-    // sqrt(x*x) == |x| in binary floating point whenever x*x neither underflows nor overflows
-    return (ad > 1e-150 && ad < 1e150) ? ad : sqrt(df * df);
-  };
-  auto relax = [&](int o, double ld) -> double {
-    const double v = line[o - 1], h = line[o + 1], dg = line[o];
-    double mc;
-    if (STEP == SONAR_STEP_SYMMETRIC2)
-      mc = fmin(fmin(v, h), dg);
-    else if (STEP == SONAR_STEP_ASYMMETRIC)
-      mc = fmin(v, h);
-    else
-      mc = fmin(v + 1.0, fmin(h + 1.0, dg));
-    const double c = ld + mc;
-    line[o] = c;
-    return c;
-  };
+  const double inf = d_inf();
+  double L[NPL];
+#pragma unroll
+  for (int x = 0; x < NPL; ++x) L[x] = (NPL * lane + x == band) ? 0.0 : inf;  // C[0][0] sits at offset 0
+  const int kbase = NPL * lane;
   int loaded = 0;
-  double lde = 0.0, ldo = 0.0;
   const int last = n + m;
-  // A barrier that follows a global store waits for the store's L2 round trip, so the cells of 16
-  // diagonals (8 per parity and thread) are kept in registers and written out together.
-  for (int d = 2; d <= last; d += 16) {
+  for (int d = 2; d <= last; ++d) {
     if (((d - 2) & 255) == 0) {
       const int target = ((d + 258 + band) >> 1) + 2;
-      for (int e = loaded + t; e < target; e += blockDim.x) {
+      __syncwarp();
+      for (int e = loaded + lane; e < target; e += 32) {
         if (e < n) ring_q[e & (kRing - 1)] = q[e];
         if (e < m) ring_r[e & (kRing - 1)] = r[e];
       }
       loaded = target;
-      __syncthreads();
-      // distances of the two diagonals this refill makes reachable first
-      if (act_e && (unsigned)(ie - 1) < (unsigned)n && (unsigned)(je - 1) < (unsigned)m) lde = dist(ie, je);
-      if (act_o && (unsigned)(io - 1) < (unsigned)n && (unsigned)(jo - 1) < (unsigned)m) ldo = dist(io, jo);
+      __syncwarp();
     }
-    double ce[8], co[8];
-    unsigned me = 0, mo = 0;
-    const int64_t be = offe, bo = offo;
+    const int par = (d + band) & 1;  // parity of the offsets k active on this diagonal
+    const int dbase = d - band + kbase;
+    // local distances first: independent of the recurrence, overlaps the shuffle
+    double ld[NPL / 2];
+    bool ok[NPL / 2];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      // ---- even diagonal d + 2u
-      if (d + 2 * u <= last && act_e && (unsigned)(ie - 1) < (unsigned)n && (unsigned)(je - 1) < (unsigned)m) {
-        ce[u] = relax(oe, lde);
-        me |= 1u << u;
+    for (int h = 0; h < NPL / 2; ++h) {
+      const int x = 2 * h + par;
+      const int i = (dbase + x) >> 1, j = d - i;
+      ok[h] = (kbase + x <= 2 * band) && (unsigned)(i - 1) < (unsigned)n && (unsigned)(j - 1) < (unsigned)m;
+      const double df = ring_q[(i - 1) & (kRing - 1)] - ring_r[(j - 1) & (kRing - 1)];
+      const double ad = fabs(df);
+      // sqrt(x*x) == |x| in binary floating point whenever x*x neither underflows nor overflows
+      ld[h] = (ad > 1e-150 && ad < 1e150) ? ad : sqrt(df * df);
+    }
+    double up = __shfl_up_sync(0xffffffffu, L[NPL - 1], 1);
+    double down = __shfl_down_sync(0xffffffffu, L[0], 1);
+    if (lane == 0) up = inf;
+    if (lane == 31) down = inf;
+    double c[NPL / 2];
+#pragma unroll
+    for (int h = 0; h < NPL / 2; ++h) {
+      // par is warp-uniform; both variants are straight-line selects
+      const double v0 = (h == 0) ? up : L[(2 * h - 1 + NPL) % NPL], h0 = L[2 * h + 1], g0 = L[2 * h];     // x = 2h
+      const double v1 = L[2 * h], h1 = (h == NPL / 2 - 1) ? down : L[(2 * h + 2) % NPL], g1 = L[2 * h + 1];  // x = 2h+1
+      const double v = par ? v1 : v0, hh = par ? h1 : h0, dg = par ? g1 : g0;
+      double mc;
+      if (STEP == SONAR_STEP_SYMMETRIC2) {
+        const double t = v < hh ? v : hh;
+        mc = t < dg ? t : dg;
+      } else if (STEP == SONAR_STEP_ASYMMETRIC) {
+        mc = v < hh ? v : hh;
+      } else {
+        const double a = v + 1.0, b = hh + 1.0;
+        const double t = b < dg ? b : dg;
+        mc = a < t ? a : t;
       }
-      ++ie, ++je, offe += W;
-      if (act_e && (unsigned)(ie - 1) < (unsigned)n && (unsigned)(je - 1) < (unsigned)m) lde = dist(ie, je);
-      __syncthreads();
-      // ---- odd diagonal d + 2u + 1
-      if (d + 2 * u + 1 <= last && act_o && (unsigned)(io - 1) < (unsigned)n && (unsigned)(jo - 1) < (unsigned)m) {
-        co[u] = relax(oo, ldo);
-        mo |= 1u << u;
-      }
-      ++io, ++jo, offo += W;
-      if (act_o && (unsigned)(io - 1) < (unsigned)n && (unsigned)(jo - 1) < (unsigned)m) ldo = dist(io, jo);
-      __syncthreads();
+      c[h] = ld[h] + mc;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (me & (1u << u)) cells[be + (int64_t)u * W] = ce[u];
-      if (mo & (1u << u)) cells[bo + (int64_t)u * W] = co[u];
+    for (int h = 0; h < NPL / 2; ++h) {
+      if (par) {
+        if (ok[h]) L[2 * h + 1] = c[h];
+      } else {
+        if (ok[h]) L[2 * h] = c[h];
+      }
+      if (ok[h]) cells[(int64_t)d * W + (kbase >> 1) + h] = c[h];  // ((i - j + band) >> 1) == (kbase + x) >> 1
     }
   }
 }
@@ -350,54 +347,42 @@ __global__ void __launch_bounds__(kBtThreads) dtw_backtrack_kernel(const double*
   }
 }
 
-// Banded store: the band is narrow enough to hold whole rows, so the walk proceeds through blocks of
-// kBbRows consecutive rows (all 2*band+1 columns, borders normalised while loading).  Which block
-// comes next does not depend on the path, so warps 1..7 prefetch block k+1 into the other buffer
-// while lane 0 of warp 0 walks block k out of shared memory.
+// Banded backtrack.  The store is diagonal-major, a step moves to diagonal d-1 (vertical / horizontal) or
+// d-2 (diagonal), and which diagonals come next does not depend on the path: the walk proceeds through
+// blocks of `nd` consecutive diagonals held in shared memory (borders normalised to +Inf / C[0][0] = 0
+// while loading, one +Inf sentinel slot on each side of every diagonal so the walker needs no bounds
+// checks), and warps 1..7 prefetch block k+1 — one contiguous, coalesced region of HBM — into the other
+// buffer while lane 0 of warp 0 walks block k.
 constexpr int kBbThreads = 256;
 
-// Rows are dealt to warps two at a time; a lane loads up to 4 columns of each row with loads that do not
-// depend on one another (address clamped to a valid location, value selected afterwards), so a warp has
-// 8 DRAM requests in flight per lane.
-__device__ __forceinline__ void bb_load_block(const double* __restrict__ cells, const DtwGeom& g, int ibase, int rows,
+__device__ __forceinline__ void bb_load_block(const double* __restrict__ cells, const DtwGeom& g, int dbase, int nd,
                                               double* __restrict__ buf, int t0, int nt) {
-  const int W = (int)g.W, band = g.band, m = g.m;
-  const int warp = t0 >> 5, lane = t0 & 31, nwarps = nt >> 5;
-  for (int li0 = 2 * warp; li0 <= rows; li0 += 2 * nwarps) {
-    for (int cb = 0; cb < W; cb += 128) {
-      double v[2][4];
-      bool ok[2][4];
+  const int Wd = (int)g.W, Wp = Wd + 2, band = g.band;
+  const int total = (nd + 1) * Wp;
+  for (int e0 = t0; e0 < total; e0 += 4 * nt) {
+    double v[4];
+    bool ok[4], zero[4];
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int i = ibase - (li0 + rr);
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * nt;
+      const int dl = e / Wp, kk = e - dl * Wp - 1;  // kk == -1 / Wd are the sentinel slots
+      const int d = dbase - dl;
+      const int s2 = 2 * kk + ((d + band) & 1);     // i - j + band
+      const int i = (d + s2 - band) >> 1, j = d - i;
+      ok[u] = e < total && kk >= 0 && kk < Wd && s2 <= 2 * band && d >= 2 && i >= 1 && i <= g.n && j >= 1 && j <= g.m;
+      zero[u] = e < total && d == 0 && s2 == band;  // C[0][0]
+      v[u] = __ldg(cells + (ok[u] ? (int64_t)d * Wd + kk : 0));
+    }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = cb + lane + 32 * k;
-          const int j = c + i - band;
-          ok[rr][k] = (li0 + rr <= rows) && c < W && i > 0 && j >= 1 && j <= m;
-          const int64_t off = ok[rr][k] ? (int64_t)(i - 1) * W + c : 0;
-          v[rr][k] = __ldg(cells + off);
-        }
-      }
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int li = li0 + rr, i = ibase - li;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = cb + lane + 32 * k;
-          if (li <= rows && c < W) {
-            double x = ok[rr][k] ? v[rr][k] : d_inf();
-            if (i == 0 && c == band) x = 0.0;  // C[0][0]
-            buf[li * W + c] = x;
-          }
-        }
-      }
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * nt;
+      if (e < total) buf[e] = zero[u] ? 0.0 : (ok[u] ? v[u] : d_inf());
     }
   }
 }
 
 __global__ void __launch_bounds__(kBbThreads) dtw_backtrack_banded_kernel(const double* __restrict__ cells_all,
-                                                                          DtwGeom g, int rows,
+                                                                          DtwGeom g, int nd,
                                                                           int32_t* __restrict__ path_q,
                                                                           int32_t* __restrict__ path_r,
                                                                           double* __restrict__ path_c,
@@ -406,8 +391,8 @@ __global__ void __launch_bounds__(kBbThreads) dtw_backtrack_banded_kernel(const 
   extern __shared__ double bb_smem[];
   __shared__ int s_i, s_j, s_done;
   __shared__ int64_t s_len;
-  const int W = (int)g.W;
-  const int blk = (rows + 1) * W;
+  const int Wd = (int)g.W, Wp = Wd + 2;
+  const int blk = (nd + 1) * Wp;
   double* bufs[2] = {bb_smem, bb_smem + blk};
   const int pair = blockIdx.x;
   const double* __restrict__ cells = cells_all + (int64_t)pair * g.cells;
@@ -420,62 +405,64 @@ __global__ void __launch_bounds__(kBbThreads) dtw_backtrack_banded_kernel(const 
     s_len = 0;
     s_done = 0;
   }
-  int ibase = g.n;
-  bb_load_block(cells, g, ibase, rows, bufs[0], threadIdx.x, kBbThreads);
+  int dbase = g.n + g.m;
+  bb_load_block(cells, g, dbase, nd, bufs[0], threadIdx.x, kBbThreads);
   __syncthreads();
   for (int k = 0;; ++k) {
     const double* cur = bufs[k & 1];
     if (threadIdx.x >= 32) {
-      if (ibase - rows > 0 || (ibase - rows == 0))  // a further block exists (it may only contain row 0)
-        bb_load_block(cells, g, ibase - rows, rows, bufs[(k + 1) & 1], threadIdx.x - 32, kBbThreads - 32);
+      if (dbase - nd + 1 >= 0)  // the next block starts one diagonal above this block's floor
+        bb_load_block(cells, g, dbase - nd + 1, nd, bufs[(k + 1) & 1], threadIdx.x - 32, kBbThreads - 32);
     } else if (threadIdx.x == 0) {
       int i = s_i, j = s_j;
-      int64_t len = s_len;
-      const int band = g.band, floor_i = ibase - rows;
-      auto get = [&](int ii, int jj) -> double {
-        const int c = jj - ii + band;
-        if (c < 0 || c >= W) return d_inf();
-        return cur[(ibase - ii) * W + c];
-      };
-      while ((i > 0 || j > 0) && (i == 0 || i - 1 >= floor_i)) {
-        double cost = 0.0, cv = 0.0, ch = 0.0, cd = 0.0;
+      int64_t pos = path_cap - 1 - s_len;
+      const int band = g.band;
+      const int floor_d = dbase - nd;  // lowest diagonal held by this block
+      // a cell reads diagonals d-1 and d-2: stay while d - 2 >= floor_d (or no cell value is needed: i == 0 / j == 0)
+      while ((i > 0 || j > 0) && (i == 0 || j == 0 || i + j - 2 >= floor_d)) {
+        double cost = 0.0;
+        int mi;
         if (i > 0 && j > 0) {
-          cv = get(i - 1, j);
-          ch = get(i, j - 1);
-          cd = get(i - 1, j - 1);
-          cost = get(i, j) - cd;
-        }
-        const int64_t pos = path_cap - 1 - len;
-        if (pos >= 0) {
-          pq[pos] = i - 1;
-          pr[pos] = j - 1;
-          pc[pos] = cost;
-        }
-        ++len;
-        if (i == 0) {
-          j = j - 1;
-        } else if (j == 0) {
-          i = i - 1;
-        } else {
-          int mi = 0;
+          const int s2 = i - j + band;
+          double cij = d_inf(), cv = d_inf(), ch = d_inf(), cd = d_inf();
+          if (s2 >= -1 && s2 <= 2 * band + 1) {  // within one step of the band: slots (incl. sentinels) exist
+            const int b0 = s2 & 1, kk = s2 >> 1;  // arithmetic shift: s2 == -1 -> kk == -1 (sentinel)
+            const int idx = (dbase - (i + j)) * Wp + kk + 1;
+            if (s2 >= 0 && s2 <= 2 * band) {
+              cij = cur[idx];
+              cd = cur[idx + 2 * Wp];
+            }
+            cv = cur[idx + Wp - 1 + b0];  // (i-1, j): offset s2 - 1 on diagonal d - 1
+            ch = cur[idx + Wp + b0];      // (i, j-1): offset s2 + 1 on diagonal d - 1
+          }
+          cost = cij - cd;
+          mi = 0;
           double best = cv;
           if (ch < best) {
             mi = 1;
             best = ch;
           }
           if (cd < best) mi = 2;
-          if (mi != 1) i = i - 1;
-          if (mi != 0) j = j - 1;
+        } else {
+          mi = (i == 0) ? 1 : 0;
         }
+        if (pos >= 0) {
+          pq[pos] = i - 1;
+          pr[pos] = j - 1;
+          pc[pos] = cost;
+        }
+        --pos;
+        if (mi != 1) --i;
+        if (mi != 0) --j;
       }
       s_i = i;
       s_j = j;
-      s_len = len;
+      s_len = path_cap - 1 - pos;
       if (i <= 0 && j <= 0) s_done = 1;
     }
     __syncthreads();
     if (s_done) break;
-    ibase -= rows;
+    dbase -= nd - 1;
   }
   if (threadIdx.x == 0) {
     outs[pair].total_cost = cell_get(cells, g, g.n, g.m);
@@ -499,13 +486,14 @@ int dtw_geometry(int n, int m, int band, DtwGeom* g) {
   g->m = m;
   g->band = band > 0 ? band : 0;
   if (g->band > 0) {
-    g->W = 2 * (int64_t)g->band + 1;
-    g->n_off = (int)g->W;
+    g->W = (int64_t)g->band + 1;  // cells per stored anti-diagonal
+    g->n_off = 2 * g->band + 1;
+    g->cells = ((int64_t)n + m + 1) * g->W;
   } else {
-    g->W = m;
+    g->W = m;  // cells per stored row
     g->n_off = n + m + 1;
+    g->cells = (int64_t)n * g->W;
   }
-  g->cells = (int64_t)n * g->W;
   return SONAR_OK;
 }
 
@@ -520,16 +508,26 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
   if (g.band > 0 && diag > g.band + 1) diag = g.band + 1;
   int threads = (diag + 31) & ~31;
   threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
-  if (dim == 1 && g.band > 0 && g.band <= 511) {
-    const int thr = ((g.band + 1) + 31) & ~31;
-    const size_t sm = sizeof(double) * (2 * kRing + 2 * (size_t)g.band + 3);
-    prof_begin("dtw_fill_band1_kernel", st);
-    if (step == SONAR_STEP_SYMMETRIC2)
-      dtw_fill_band1_kernel<SONAR_STEP_SYMMETRIC2><<<n_pairs, thr, sm, st>>>(q, r, g, cells);
-    else if (step == SONAR_STEP_ASYMMETRIC)
-      dtw_fill_band1_kernel<SONAR_STEP_ASYMMETRIC><<<n_pairs, thr, sm, st>>>(q, r, g, cells);
+  if (dim == 1 && g.band > 0 && 2 * g.band + 1 <= 32 * 8) {
+    // min(a, b) as (a < b ? a : b) equals fmin for the non-NaN values this recurrence produces
+#define SONAR_DTW_WARP(NPL)                                                                       \
+  do {                                                                                            \
+    if (step == SONAR_STEP_SYMMETRIC2)                                                            \
+      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC2><<<n_pairs, 32, 0, st>>>(q, r, g, cells);   \
+    else if (step == SONAR_STEP_ASYMMETRIC)                                                       \
+      dtw_fill_warp_kernel<NPL, SONAR_STEP_ASYMMETRIC><<<n_pairs, 32, 0, st>>>(q, r, g, cells);   \
+    else                                                                                          \
+      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC1><<<n_pairs, 32, 0, st>>>(q, r, g, cells);   \
+  } while (0)
+    const int offs = 2 * g.band + 1;
+    prof_begin("dtw_fill_warp_kernel", st);
+    if (offs <= 64)
+      SONAR_DTW_WARP(2);
+    else if (offs <= 128)
+      SONAR_DTW_WARP(4);
     else
-      dtw_fill_band1_kernel<SONAR_STEP_SYMMETRIC1><<<n_pairs, thr, sm, st>>>(q, r, g, cells);
+      SONAR_DTW_WARP(8);
+#undef SONAR_DTW_WARP
     prof_end();
     SONAR_CUDA(cudaGetLastError());
   } else {
@@ -561,14 +559,15 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
   prof_end();
   SONAR_CUDA(cudaGetLastError());
   }
-  const int bb_rows = g.band > 0 ? (int)((100 * 1024 / sizeof(double)) / (size_t)g.W) - 1 : 0;
-  if (bb_rows >= 16) {
-    const int rows = bb_rows > 64 ? 64 : bb_rows;
-    const size_t bsm = sizeof(double) * 2 * (size_t)(rows + 1) * (size_t)g.W;
+  // diagonals per shared-memory block of the banded backtrack (two buffers of (nd + 1) * (band + 3) doubles)
+  const int bb_nd = g.band > 0 ? (int)((100 * 1024 / sizeof(double)) / (size_t)(g.W + 2)) - 1 : 0;
+  if (bb_nd >= 16) {
+    const int nd = bb_nd > 192 ? 192 : bb_nd;
+    const size_t bsm = sizeof(double) * 2 * (size_t)(nd + 1) * (size_t)(g.W + 2);
     SONAR_CUDA(cudaFuncSetAttribute(dtw_backtrack_banded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(216 * 1024)));
     prof_begin("dtw_backtrack_banded_kernel", st);
-    dtw_backtrack_banded_kernel<<<n_pairs, kBbThreads, bsm, st>>>(cells, g, rows, path_q, path_r, path_c, path_cap,
+    dtw_backtrack_banded_kernel<<<n_pairs, kBbThreads, bsm, st>>>(cells, g, nd, path_q, path_r, path_c, path_cap,
                                                                   out);
     prof_end();
     SONAR_CUDA(cudaGetLastError());
