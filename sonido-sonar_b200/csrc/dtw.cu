@@ -181,87 +181,145 @@ __global__ void __launch_bounds__(1024) dtw_fill_kernel(const double* __restrict
   }
 }
 
+// |q - r| for dim == 1.  sqrt(x*x) == |x| in binary floating point whenever x*x neither underflows nor
+// overflows; the rare remainder takes the out-of-line exact path (kept out of line so that the compiler
+// cannot if-convert an FP64 square-root sequence into the wavefront's dependent chain).
+__device__ __noinline__ double dist1_slow(double df) { return sqrt(df * df); }
+__device__ __forceinline__ double dist1(double a, double b) {
+  const double df = a - b;
+  // biased exponent in [400, 1640]  <=>  2^-623 <= |df| < 2^618: df*df is a normal number
+  const unsigned e = ((unsigned)__double2hiint(df) >> 20) & 0x7ffu;
+  if (e - 400u > 1240u) return dist1_slow(df);
+  return fabs(df);
+}
+
 // Register-resident wavefront for narrow bands (dim == 1, 2*band+1 <= 32*NPL): ONE warp per pair, lane l
 // keeps the latest cost of the NPL offsets k = NPL*l .. NPL*l+NPL-1 (k = i - j + band) in registers.  A
 // diagonal only touches offsets of one parity and reads the two neighbouring offsets of the other parity,
 // so a step is NPL/2 independent relaxations per lane plus ONE warp shuffle for the value that lives in the
-// neighbouring lane — no shared-memory line, no block barrier, and the dependent chain per diagonal is
-// shuffle -> min -> min -> add.
+// neighbouring lane — no shared-memory line, no block barrier; the dependent chain per diagonal is
+// shuffle -> min -> min -> add.  Two diagonals (one of each parity) form one loop iteration: the q / r
+// values a lane needs slide by one element per iteration, so they live in a small register window fed by
+// two shared-memory loads per iteration (prefetched one iteration ahead), and a cell's validity is one
+// unsigned compare against its offset's precomputed diagonal range.
+template <int NPL, int STEP>
+__device__ __forceinline__ double dtw_relax(double v, double hh, double dg, double ld) {
+  double mc;
+  if (STEP == SONAR_STEP_SYMMETRIC2) {  // min(a, b) as (a < b ? a : b) equals math.Min for non-NaN values
+    const double t = v < hh ? v : hh;
+    mc = t < dg ? t : dg;
+  } else if (STEP == SONAR_STEP_ASYMMETRIC) {
+    mc = v < hh ? v : hh;
+  } else {
+    const double a = v + 1.0, b = hh + 1.0;
+    const double t = b < dg ? b : dg;
+    mc = a < t ? a : t;
+  }
+  return ld + mc;
+}
+
 template <int NPL, int STEP>
 __global__ void __launch_bounds__(32) dtw_fill_warp_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
                                                            DtwGeom g, double* __restrict__ cells_all) {
+  constexpr int H = NPL / 2;
   __shared__ double ring_q[kRing], ring_r[kRing];
   const int pair = blockIdx.x, lane = threadIdx.x;
   const int n = g.n, m = g.m, band = g.band, W = (int)g.W;
   const double* __restrict__ q = qs + (int64_t)pair * n;
   const double* __restrict__ r = rs + (int64_t)pair * m;
-  double* __restrict__ cells = cells_all + (int64_t)pair * g.cells;
   const double inf = d_inf();
-  double L[NPL];
-#pragma unroll
-  for (int x = 0; x < NPL; ++x) L[x] = (NPL * lane + x == band) ? 0.0 : inf;  // C[0][0] sits at offset 0
   const int kbase = NPL * lane;
-  int loaded = 0;
+  double L[NPL];
+  int dlo[NPL];
+  unsigned span[NPL];
+#pragma unroll
+  for (int x = 0; x < NPL; ++x) {
+    const int k = kbase + x, delta = k - band;
+    L[x] = (k == band) ? 0.0 : inf;  // C[0][0] sits at offset i - j = 0
+    const int lo = 2 + (delta < 0 ? -delta : delta);
+    const int hi = (2 * n - delta) < (2 * m + delta) ? (2 * n - delta) : (2 * m + delta);
+    const bool any = k <= 2 * band && hi >= lo;
+    dlo[x] = any ? lo : 0x3fffffff;  // cell of offset k on diagonal d is inside the matrix iff lo <= d <= hi
+    span[x] = any ? (unsigned)(hi - lo) : 0u;
+  }
+  double* __restrict__ row = cells_all + (int64_t)pair * g.cells + (int64_t)2 * W + (kbase >> 1);  // diagonal d = 2
   const int last = n + m;
-  for (int d = 2; d <= last; ++d) {
-    if (((d - 2) & 255) == 0) {
-      const int target = ((d + 258 + band) >> 1) + 2;
-      __syncwarp();
-      for (int e = loaded + lane; e < target; e += 32) {
-        if (e < n) ring_q[e & (kRing - 1)] = q[e];
-        if (e < m) ring_r[e & (kRing - 1)] = r[e];
-      }
-      loaded = target;
-      __syncwarp();
+  int loaded = 0;
+  auto refill = [&](int d) {
+    const int target = ((d + 262 + band) >> 1) + 4;
+    __syncwarp();
+    for (int e = loaded + lane; e < target; e += 32) {
+      if (e < n) ring_q[e & (kRing - 1)] = q[e];
+      if (e < m) ring_r[e & (kRing - 1)] = r[e];
     }
-    const int par = (d + band) & 1;  // parity of the offsets k active on this diagonal
-    const int dbase = d - band + kbase;
-    // local distances first: independent of the recurrence, overlaps the shuffle
-    double ld[NPL / 2];
-    bool ok[NPL / 2];
+    loaded = target;
+    __syncwarp();
+  };
+  auto half = [&](int d, int par, const double (&ld)[H]) {  // par is a compile-time constant at both call sites
+    double edge;
+    if (par == 0) {
+      edge = __shfl_up_sync(0xffffffffu, L[NPL - 1], 1);
+      if (lane == 0) edge = inf;
+    } else {
+      edge = __shfl_down_sync(0xffffffffu, L[0], 1);
+      if (lane == 31) edge = inf;
+    }
 #pragma unroll
-    for (int h = 0; h < NPL / 2; ++h) {
+    for (int h = 0; h < H; ++h) {
       const int x = 2 * h + par;
-      const int i = (dbase + x) >> 1, j = d - i;
-      ok[h] = (kbase + x <= 2 * band) && (unsigned)(i - 1) < (unsigned)n && (unsigned)(j - 1) < (unsigned)m;
-      const double df = ring_q[(i - 1) & (kRing - 1)] - ring_r[(j - 1) & (kRing - 1)];
-      const double ad = fabs(df);
-      // sqrt(x*x) == |x| in binary floating point whenever x*x neither underflows nor overflows
-      ld[h] = (ad > 1e-150 && ad < 1e150) ? ad : sqrt(df * df);
-    }
-    double up = __shfl_up_sync(0xffffffffu, L[NPL - 1], 1);
-    double down = __shfl_down_sync(0xffffffffu, L[0], 1);
-    if (lane == 0) up = inf;
-    if (lane == 31) down = inf;
-    double c[NPL / 2];
-#pragma unroll
-    for (int h = 0; h < NPL / 2; ++h) {
-      // par is warp-uniform; both variants are straight-line selects
-      const double v0 = (h == 0) ? up : L[(2 * h - 1 + NPL) % NPL], h0 = L[2 * h + 1], g0 = L[2 * h];     // x = 2h
-      const double v1 = L[2 * h], h1 = (h == NPL / 2 - 1) ? down : L[(2 * h + 2) % NPL], g1 = L[2 * h + 1];  // x = 2h+1
-      const double v = par ? v1 : v0, hh = par ? h1 : h0, dg = par ? g1 : g0;
-      double mc;
-      if (STEP == SONAR_STEP_SYMMETRIC2) {
-        const double t = v < hh ? v : hh;
-        mc = t < dg ? t : dg;
-      } else if (STEP == SONAR_STEP_ASYMMETRIC) {
-        mc = v < hh ? v : hh;
-      } else {
-        const double a = v + 1.0, b = hh + 1.0;
-        const double t = b < dg ? b : dg;
-        mc = a < t ? a : t;
+      const double v = (x == 0) ? edge : L[x == 0 ? 0 : x - 1];               // (i-1, j): offset k-1
+      const double hh = (x == NPL - 1) ? edge : L[x == NPL - 1 ? x : x + 1];  // (i, j-1): offset k+1
+      const double c = dtw_relax<NPL, STEP>(v, hh, L[x], ld[h]);
+      if ((unsigned)(d - dlo[x]) <= span[x]) {
+        L[x] = c;
+        row[h] = c;  // diagonal-major store: ((i - j + band) >> 1) == (kbase >> 1) + h
       }
-      c[h] = ld[h] + mc;
+    }
+  };
+  int d = 2;
+  refill(d);
+  int next_refill = d + 256;
+  if ((d - band) & 1) {  // odd band: diagonal 2 carries the odd offsets; do it alone so that pairs start aligned
+    const int ib = (d - band + kbase + 1) >> 1;
+    double ld[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+      ld[h] = dist1(ring_q[(ib + h - 1) & (kRing - 1)], ring_r[(d - ib - h - 1) & (kRing - 1)]);
+    half(d, 1, ld);
+    ++d;
+    row += W;
+  }
+  // from here d - band is even: this iteration does diagonal d (even offsets) and d + 1 (odd offsets)
+  int ib = (d - band + kbase) >> 1, j = d - ib;
+  double Q[H + 1], R[H];
+#pragma unroll
+  for (int h = 0; h <= H; ++h) Q[h] = ring_q[(ib + h - 1) & (kRing - 1)];
+#pragma unroll
+  for (int h = 0; h < H; ++h) R[h] = ring_r[(j - h - 1) & (kRing - 1)];
+  for (; d <= last; d += 2, row += 2 * W, ++ib, ++j) {
+    if (d >= next_refill) {
+      refill(d);
+      next_refill += 256;
+    }
+    const double qn = ring_q[(ib + H) & (kRing - 1)], rn = ring_r[j & (kRing - 1)];  // next iteration's new elements
+    double lda[H], ldb[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      lda[h] = dist1(Q[h], R[h]);      // cell (ib + h,     j - h) on diagonal d
+      ldb[h] = dist1(Q[h + 1], R[h]);  // cell (ib + h + 1, j - h) on diagonal d + 1
+    }
+    half(d, 0, lda);
+    if (d + 1 <= last) {
+      row += W;
+      half(d + 1, 1, ldb);
+      row -= W;
     }
 #pragma unroll
-    for (int h = 0; h < NPL / 2; ++h) {
-      if (par) {
-        if (ok[h]) L[2 * h + 1] = c[h];
-      } else {
-        if (ok[h]) L[2 * h] = c[h];
-      }
-      if (ok[h]) cells[(int64_t)d * W + (kbase >> 1) + h] = c[h];  // ((i - j + band) >> 1) == (kbase + x) >> 1
-    }
+    for (int h = 0; h < H; ++h) Q[h] = Q[h + 1];
+    Q[H] = qn;
+#pragma unroll
+    for (int h = H - 1; h > 0; --h) R[h] = R[h - 1];
+    R[0] = rn;
   }
 }
 
