@@ -478,6 +478,36 @@ __global__ void __launch_bounds__(kBbThreads) dtw_backtrack_banded_kernel(const 
       const int floor_d = dbase - nd;  // lowest diagonal held by this block
       // a cell reads diagonals d-1 and d-2: stay while d - 2 >= floor_d (or no cell value is needed: i == 0 / j == 0)
       while ((i > 0 || j > 0) && (i == 0 || j == 0 || i + j - 2 >= floor_d)) {
+        {  // fast path: interior cell inside the band, indices maintained incrementally
+          int s2 = i - j + band;
+          if (i > 1 && j > 1 && s2 >= 0 && s2 <= 2 * band) {
+            int idx = (dbase - (i + j)) * Wp + (s2 >> 1) + 1;
+            int dd = i + j;
+            do {
+              const int b0 = s2 & 1;
+              const double cij = cur[idx], cv = cur[idx + Wp - 1 + b0], ch = cur[idx + Wp + b0], cd = cur[idx + 2 * Wp];
+              if (pos >= 0) {
+                pq[pos] = i - 1;
+                pr[pos] = j - 1;
+                pc[pos] = cij - cd;
+              }
+              --pos;
+              double best = cv;
+              int step_idx = Wp - 1 + b0, di = 1, dj = 0, ds = -1;
+              if (ch < best) {
+                best = ch;
+                step_idx = Wp + b0, di = 0, dj = 1, ds = 1;
+              }
+              if (cd < best) step_idx = 2 * Wp, di = 1, dj = 1, ds = 0;
+              idx += step_idx;
+              i -= di;
+              j -= dj;
+              s2 += ds;
+              dd -= di + dj;
+            } while (i > 1 && j > 1 && (unsigned)s2 <= (unsigned)(2 * band) && dd - 2 >= floor_d);
+            continue;
+          }
+        }
         double cost = 0.0;
         int mi;
         if (i > 0 && j > 0) {
