@@ -34,9 +34,19 @@ namespace sonar {
 
 namespace {
 
-constexpr int kWarps = 8;         // warps per CTA
+#ifndef SONAR_STFT_WARPS
+#define SONAR_STFT_WARPS 8
+#endif
+#ifndef SONAR_STFT_MINBLOCKS
+#define SONAR_STFT_MINBLOCKS 1
+#endif
+constexpr int kWarps = SONAR_STFT_WARPS;  // warps per CTA
 constexpr int kRunIters = 16;     // warp iterations per run (first frame of a run is flux warm-up)
 constexpr unsigned kFull = 0xffffffffu;
+// Per-lane row of mel partial sums (slot r = falling part of filter r-1 + rising part of filter r).  68 floats,
+// 16-byte aligned; the row stride of 68 words puts lane j's column c in bank (4j + c) mod 32, so the strided
+// column reads of the final reduction are at worst 2-way conflicted.
+constexpr int kMelRow = kMaxMel + 4;
 
 enum { MODE_FEATURES = 0, MODE_SPECTRUM = 1 };
 
@@ -148,7 +158,7 @@ __device__ __forceinline__ float slot_max(float v) {
 
 struct SmemLayout {
   size_t off_tw1, off_xtab, off_dct, off_lift, off_regions, off_chunk, off_warp, per_warp, total;
-  size_t w_xbuf, w_carry, w_mel;
+  size_t w_xbuf, w_carry, w_mel, w_melpriv;
 };
 
 template <int R1, int R2>
@@ -177,13 +187,14 @@ __host__ __device__ inline SmemLayout smem_layout(int n_mel, int n_mfcc, int n_r
   L.w_xbuf = wtake(sizeof(float2) * G::F * G::XSLOT);
   L.w_carry = wtake(sizeof(float) * 2 * G::MAGROW);
   L.w_mel = wtake(sizeof(float) * G::F * (kMaxMel + 4));
+  L.w_melpriv = wtake(sizeof(float) * 32 * kMelRow);  // one private row of mel partials per lane
   L.per_warp = w;
   L.total = o + w * kWarps;
   return L;
 }
 
 template <int R1, int R2, int MODE>
-__global__ void __launch_bounds__(kWarps * 32, 1) stft_kernel(const StftArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, SONAR_STFT_MINBLOCKS) stft_kernel(const StftArgs a) {
   using G = FftGeom<R1, R2>;
   constexpr int F = G::F;
   constexpr int WARM = (MODE == MODE_FEATURES) ? 1 : 0;
@@ -206,6 +217,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft_kernel(const StftArgs a) 
   float2* xbuf = reinterpret_cast<float2*>(wbase + L.w_xbuf);
   float* carry = reinterpret_cast<float*>(wbase + L.w_carry);
   float* melacc = reinterpret_cast<float*>(wbase + L.w_mel);
+  float* melpriv = reinterpret_cast<float*>(wbase + L.w_melpriv) + lane * kMelRow;
 
   // ---- stage the tables -------------------------------------------------------
   for (int i = threadIdx.x; i < G::M; i += blockDim.x) s_tw1[i] = a.tw1[i];
@@ -300,7 +312,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft_kernel(const StftArgs a) 
         const float skm = slot_sum<R1>(ps.skm);
         const float kc = sm > 0.f ? skm / sm : 0.f;  // centroid in bin units
         float* macc = melacc + slot * (kMaxMel + 4);
-        for (int i = k1; i < a.n_mel + 3; i += R1) macc[i] = 0.f;
+        // Mel partials: every lane scans a contiguous run of bins, i.e. a contiguous run of filter regions.
+        // It writes its partial sums to a PRIVATE row with plain stores (each slot once: the falling part of
+        // the region being left is merged with the pending rising part of the previous one), and the rows
+        // of the slot's R1 lanes are summed afterwards — no shared-memory atomics (float atomicAdd on
+        // shared memory is a compare-and-swap loop).
+        {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4* zr = reinterpret_cast<float4*>(melpriv);
+          for (int i = 0; i < (a.n_mel + 3 + 3) / 4; ++i) zr[i] = z;
+        }
+        float pend = 0.f;
         __syncwarp();
 
         // ================= phase B: contiguous scan =================
@@ -321,8 +343,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft_kernel(const StftArgs a) 
           const float p = m * m;
           const float kf = (float)k;
           while (k >= reg.next_b) {
-            atomicAdd(&macc[r > 0 ? r - 1 : 0], mlo);
-            atomicAdd(&macc[r], mhi);
+            melpriv[r > 0 ? r - 1 : 0] = pend + mlo;
+            pend = mhi;
             mlo = 0.f;
             mhi = 0.f;
             ++r;
@@ -355,8 +377,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft_kernel(const StftArgs a) 
           const float d = m - mp;
           if (d > 0.f) fl = fmaf(d, d, fl);
         }
-        atomicAdd(&macc[r > 0 ? r - 1 : 0], mlo);
-        atomicAdd(&macc[r], mhi);
+        melpriv[r > 0 ? r - 1 : 0] = pend + mlo;
+        melpriv[r] = mhi;
 
         // ---- reductions over the R1 lanes of this slot ----
         float pre = seg;  // inclusive prefix of segment energies (bins ascending with k1)
@@ -403,12 +425,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft_kernel(const StftArgs a) 
         const unsigned cb = __ballot_sync(kFull, crossing) & slot_mask;
         if (cb) rk = __shfl_sync(kFull, rk, __ffs(cb) - 1);
 
-        __syncwarp();  // mel atomics visible
+        __syncwarp();  // private mel rows visible
 
         // ---- ln + DCT-II + lifter (mfcc.go:136-157) ----
         if (a.mfcc_on) {
+          const float* rows = melpriv - lane * kMelRow + (slot * R1) * kMelRow;  // the R1 rows of this slot
           for (int f = k1; f < a.n_mel; f += R1) {
-            const float v = macc[f + 1];
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < R1; ++j) v += rows[j * kMelRow + f + 1];
             macc[f + 1] = v > 0.f ? __logf(v) : -23.025850929940457f;  // ln(1e-10)
           }
           __syncwarp();
@@ -478,7 +503,7 @@ int launch_geom(const FpPlan& plan, StftArgs& a, bool spectrum, cudaStream_t st)
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t ctas = (a.total_runs + kWarps - 1) / kWarps;
-  if (ctas > sms) ctas = sms;  // persistent: one CTA per SM, warps stride over the runs
+  if (ctas > (int64_t)sms * SONAR_STFT_MINBLOCKS) ctas = (int64_t)sms * SONAR_STFT_MINBLOCKS;  // persistent: resident CTAs only, warps stride over the runs
   if (ctas < 1) ctas = 1;
   prof_begin(spectrum ? "stft_spectrum_kernel" : "stft_features_kernel", st);
   if (spectrum) {
