@@ -11,11 +11,10 @@
 //   loudness range        algorithms/temporal/energy.go:157-225
 //   RMS envelope 512/256  fingerprint/extractors/speech.go:739-767
 //
-// Layout: a CTA stages the pre-emphasised samples of FPB consecutive frames of one
-// stream in shared memory once (coalesced f64 loads, one pad word per hop so that
-// the per-thread sequential walks are bank-conflict free) and then each thread
-// accumulates ONE frame in the reference's order.  The chain of dependent DADDs is
-// what bounds this kernel (shared-memory resident chains per SM), not HBM.
+// Layout: a CTA stages the raw samples of 32 consecutive frames of one stream in shared
+// memory (cp.async, one pad word per hop so that the per-lane sequential walks are
+// bank-conflict free) and one warp accumulates ONE frame per lane in the reference's
+// order.  The chain of dependent DADDs is what bounds this kernel, not HBM.
 #include <cmath>
 
 #include "common.h"
@@ -23,53 +22,82 @@
 namespace sonar {
 namespace {
 
-constexpr int kTdThreads = 128;
-constexpr int kTdMaxTile = 27000;  // doubles of shared memory for the sample tile
+constexpr int kTdThreads = 64;     // two warps stage a tile, warp 0 walks it
+constexpr int kTdFrames = 32;      // frames (sequential float64 chains) per CTA: one per lane of warp 0
 
 __device__ __forceinline__ double preemph(const double* __restrict__ x, int64_t i, double alpha) {
   const double prev = i > 0 ? x[i - 1] : 0.0;
   return x[i] - alpha * prev;  // -fmad=false: separate multiply and subtract
 }
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
+}
+
+// One CTA = 32 consecutive frames of one stream.  The RAW samples they cover (plus the one sample before
+// the first frame, needed by the pre-emphasis) are copied to shared memory with cp.async — no registers,
+// every request in flight at once — one pad word per hop so that the 32 sequential walks are bank-conflict
+// free.  Lane t of warp 0 then walks frame t in the reference's order: y = x[i] - alpha*x[i-1] (x[-1] = 0),
+// sum += y*y, sign changes of y counted on the way.  The dependent DADD chain of each frame is the only
+// serial part; loads, the pre-emphasis and the squares of later samples are independent of it.  Tiles are
+// ~70 KB so three CTAs share an SM and one CTA's staging overlaps the others' walks.
 template <bool ENERGY, bool ZCR>
 __global__ void __launch_bounds__(kTdThreads) frame_walk_kernel(
     const double* __restrict__ pcm, int64_t n, int64_t stride, double alpha, int frame, int hop, int64_t Tn,
-    int fpb, int sr, double* __restrict__ out, int64_t out_stride, int64_t o_energy, int64_t o_entropy,
+    int sr, double* __restrict__ out, int64_t out_stride, int64_t o_energy, int64_t o_entropy,
     int64_t o_zcr) {
   extern __shared__ double tile[];
   const int s = blockIdx.y;
-  const int64_t f0 = (int64_t)blockIdx.x * fpb;
+  const int64_t f0 = (int64_t)blockIdx.x * kTdFrames;
   if (f0 >= Tn) return;
-  const int nf = (int)((Tn - f0 < fpb) ? (Tn - f0) : fpb);
+  const int nf = (int)((Tn - f0 < kTdFrames) ? (Tn - f0) : kTdFrames);
   const double* __restrict__ x = pcm + (int64_t)s * stride;
-  const int64_t s0 = f0 * hop;
-  const int count = (nf - 1) * hop + frame;  // samples staged
-  const int pad = (hop & 1) ? 0 : 1;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) {
-    const int64_t gi = s0 + i;
-    tile[i + (i / hop) * pad] = preemph(x, gi, alpha);
+  const int64_t g0 = f0 * hop - 1;                // global index of staged element 0
+  const int count = (nf - 1) * hop + frame + 1;  // staged elements
+  // element e lives at e + e / hop
+  for (int e = threadIdx.x; e < count; e += kTdThreads) {
+    const int64_t gi = g0 + e;
+    double* dst = tile + e + e / hop;
+    if (gi >= 0)
+      cp_async8(dst, x + gi);
+    else
+      *dst = 0.0;  // x[-1] = 0 (pre_emphasis.go:135-155, lastSample starts at 0)
   }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const int t = threadIdx.x;
   if (t >= nf) return;
-  const int rs = hop + pad;
-  int phys = t * rs, jj = 0;
+  // thread t: elements t*hop + u, u = 0 (previous sample), 1 .. frame; physical = t*(hop+1) + u + u/hop
+  const double* __restrict__ base = tile + t * (hop + 1);
+  double xprev = base[0];
   double sum = 0.0;
   int crossings = 0;
   bool prev_neg = false;
-  for (int j = 0; j < frame; ++j) {
-    const double y = tile[phys];
-    if (ENERGY) sum += y * y;
-    if (ZCR) {
-      const bool neg = y < 0.0;
-      if (j > 0 && neg != prev_neg) crossings++;
-      prev_neg = neg;
+  int u = 1, j = 0, b = 0;  // b = u / hop
+  while (j < frame) {
+    int cnt = (b + 1) * hop - u;
+    if (cnt > frame - j) cnt = frame - j;
+    const double* __restrict__ p = base + u + b;
+#pragma unroll 8
+    for (int c = 0; c < cnt; ++c) {
+      const double xv = p[c];
+      const double y = xv - alpha * xprev;
+      xprev = xv;
+      if (ENERGY) sum += y * y;
+      if (ZCR) {
+        const bool neg = y < 0.0;
+        crossings += (neg != prev_neg) ? 1 : 0;
+        prev_neg = neg;
+      }
     }
-    ++phys;
-    if (++jj == hop) {
-      jj = 0;
-      phys += pad;
-    }
+    u += cnt;
+    j += cnt;
+    if (u == (b + 1) * hop) ++b;
+  }
+  if (ZCR) {  // the first sample has no predecessor inside the frame (zero_crossing_rate.go:43: i from 1)
+    const double y0 = base[1] - alpha * base[0];
+    if (y0 < 0.0) crossings -= 1;  // undo the spurious change against the initial prev_neg = false
   }
   double* __restrict__ o = out + (int64_t)s * out_stride;
   const int64_t f = f0 + t;
@@ -198,20 +226,18 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
                       int hop, int64_t Tn, int sr, double* out, int64_t out_stride, int64_t o_energy,
                       int64_t o_entropy, int64_t o_zcr, cudaStream_t st) {
   if (Tn <= 0 || n_streams <= 0) return SONAR_OK;
-  if (frame > kTdMaxTile - 2 * hop)
-    return set_error(SONAR_ERR_UNSUPPORTED, "energy frame too long for the shared-memory tile");
-  int fpb = (kTdMaxTile - frame) / (hop + 1) + 1;
-  if (fpb > kTdThreads) fpb = kTdThreads;
-  if (fpb >= 32) fpb &= ~31;
-  const int count = (fpb - 1) * hop + frame;
+  const int64_t count = (int64_t)(kTdFrames - 1) * hop + frame + 1;
   const size_t smem = sizeof(double) * (size_t)(count + count / hop + 2);
-  dim3 grid((unsigned)((Tn + fpb - 1) / fpb), (unsigned)n_streams);
+  if (smem > 200 * 1024)
+    return set_error(SONAR_ERR_UNSUPPORTED, "energy frame / hop too long for the shared-memory tile");
+  dim3 grid((unsigned)((Tn + kTdFrames - 1) / kTdFrames), (unsigned)n_streams);
   const bool en = o_energy >= 0, zc = o_zcr >= 0;
+  if (!en && !zc) return SONAR_OK;
 #define LAUNCH_FW(E, Z)                                                                                  \
   do {                                                                                                   \
     auto k = frame_walk_kernel<E, Z>;                                                                    \
     SONAR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    k<<<grid, kTdThreads, smem, st>>>(pcm, n, stride, alpha, frame, hop, Tn, fpb, sr, out, out_stride,  \
+    k<<<grid, kTdThreads, smem, st>>>(pcm, n, stride, alpha, frame, hop, Tn, sr, out, out_stride,       \
                                       o_energy, o_entropy, o_zcr);                                      \
   } while (0)
   prof_begin("frame_walk_kernel", st);
@@ -219,10 +245,8 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
     LAUNCH_FW(true, true);
   else if (en)
     LAUNCH_FW(true, false);
-  else if (zc)
-    LAUNCH_FW(false, true);
   else
-    return SONAR_OK;
+    LAUNCH_FW(false, true);
 #undef LAUNCH_FW
   prof_end();
   SONAR_CUDA(cudaGetLastError());
