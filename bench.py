@@ -65,49 +65,74 @@ def trim_by_lag(ea, eb, lag, length):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md), sampled through NVML in a
+    thread (spawning `nvidia-smi -lms` next to the timed loop measurably slows the launches it is meant to
+    observe); falls back to a low-rate nvidia-smi loop when pynvml is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period=0.05):
+        self.sm, self.bits, self.max_mhz, self.how = [], 0, None, "nvml"
+        self._stop = threading.Event()
+        self.proc = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._loop_nvml, args=(period,), daemon=True)
             self.th.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.nv, self.how = None, "nvidia-smi"
+            try:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                              str(index), "-lms", "500"], stdout=subprocess.PIPE,
+                                             stderr=subprocess.DEVNULL, text=True)
+                self.th = threading.Thread(target=self._loop_smi, daemon=True)
+                self.th.start()
+            except OSError:
+                self.proc = None
 
-    def _read(self):
+    def _loop_nvml(self, period):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            self._stop.wait(period)
+
+    def _loop_smi(self):
+        names = (0x8, 0x40, 0x20, 0x4)
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+            r = [x.strip() for x in line.split(",")]
             if len(r) < 6:
                 continue
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                self.sm.append(float(r[0]))
+                self.max_mhz = float(r[1])
             except ValueError:
                 continue
-            for nm, v in zip(names, r[2:6]):
+            for bit, v in zip(names, r[2:6]):
                 if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.bits |= bit
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            time.sleep(0.1)
+            self.proc.terminate()
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "how": self.how}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b), "samples": len(self.sm),
+                "how": self.how}
 
 
 def measured_peak():
@@ -287,9 +312,9 @@ def run_ours(args, rank, world, local_rank):
         lags, paths = step_resident()
     lib.profile_read()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
     l0 = lib.kernel_launches()
-    lib.profile_enable(True)
+    lib.profile_enable(not args.no_profile)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(ext)
     t0 = time.perf_counter()
@@ -321,6 +346,30 @@ def run_ours(args, rank, world, local_rank):
     d2h = sum(a.nbytes for a in fps[0].arrays.values()) * NS + P * (2 * max_lag + 1) * 0 + \
         sum(len(pp["path_query"]) * 16 for pp in paths_e)
 
+    # ---- N > 1 only: ONE long correlation (10-min pair, +-60 s) split by lag range over the ranks, NCCL
+    #      all-gather of the per-shard maxima.  Reported beside the main metric, not inside it.
+    lag_sharded = None
+    if world > 1:
+        rng = np.random.default_rng(7)  # identical on every rank: both sequences are replicated
+        t10 = (int(600 * SR) - WIN) // HOP + 1
+        base = np.convolve(rng.standard_normal(t10 + 6000), np.ones(32) / 32, mode="same") + 1.0
+        qa, rb = base[3000:3000 + t10].copy(), base[3000 - 2345:3000 - 2345 + t10] + 0.01 * rng.standard_normal(t10)
+        dev = torch.device("cuda", local_rank)
+        p.sharding.xcorr_lag_sharded(lib, qa, rb, max_lag, device=dev)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        sh_summ, (lo, hi), _ = p.sharding.xcorr_lag_sharded(lib, qa, rb, max_lag, device=dev)
+        barrier()
+        sh_ms = reduce_max(1e3 * (time.perf_counter() - t0))
+        if rank == 0:
+            t0 = time.perf_counter()
+            _, whole = lib.xcorr(qa, rb, max_lag, want_corr=False)
+            one_ms = 1e3 * (time.perf_counter() - t0)
+            lag_sharded = {"frames": int(t10), "lags": 2 * max_lag + 1, "ranks": world, "ms": sh_ms,
+                           "single_gpu_ms": one_ms, "peak_lag": sh_summ.peak_lag,
+                           "matches_unsharded": bool(sh_summ.peak_lag == whole.peak_lag and
+                                                     sh_summ.peak_correlation == whole.peak_correlation),
+                           "collectives": "all_gather(16 B/rank) + all_gather(72 B/rank) over NCCL"}
     if rank == 0:
         peak, peak_src = measured_peak()
         k_ms, k_n = kern.get("stft_features_kernel", (0.0, 0))
@@ -362,6 +411,7 @@ def run_ours(args, rank, world, local_rank):
             "kernels": shares,
             "cpu_baseline": cpu,
             "detected_lags_frames": lags,
+            "lag_sharded": lag_sharded,
         }
         print(json.dumps(line), flush=True)
     lib.close()
@@ -372,12 +422,14 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=8, help="source/CDN pairs per GPU per step")
     ap.add_argument("--seconds", type=float, default=300.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks (diagnostic)")
+    ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

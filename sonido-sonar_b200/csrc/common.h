@@ -203,6 +203,7 @@ struct sonar_ctx {
   std::atomic<bool> profiling{false};
   std::mutex prof_mu;
   std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_pool;
 };
 
 namespace sonar {

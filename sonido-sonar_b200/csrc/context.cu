@@ -35,7 +35,16 @@ void prof_begin(const char* kernel, cudaStream_t st) {
   g_cur->launches.fetch_add(1, std::memory_order_relaxed);
   if (!g_cur->profiling.load(std::memory_order_relaxed)) return;
   sonar_ctx::ProfRec r{kernel, nullptr, nullptr};
-  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+  {
+    std::lock_guard<std::mutex> lk(g_cur->prof_mu);  // events come from a pool: creating them per launch costs host time
+    if (g_cur->prof_pool.size() >= 2) {
+      r.a = g_cur->prof_pool.back();
+      g_cur->prof_pool.pop_back();
+      r.b = g_cur->prof_pool.back();
+      g_cur->prof_pool.pop_back();
+    }
+  }
+  if (!r.a && (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess)) {
     cudaGetLastError();
     return;
   }
@@ -227,6 +236,14 @@ void* sonar_stream(sonar_ctx* ctx) { return ctx ? (void*)ctx->devs[0].slot[0].st
 
 int sonar_profile_enable(sonar_ctx* ctx, int on) {
   if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  if (on) {
+    std::lock_guard<std::mutex> lk(ctx->prof_mu);
+    while (ctx->prof_pool.size() < 512) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return cuda_error(cudaGetLastError(), "cudaEventCreate");
+      ctx->prof_pool.push_back(e);
+    }
+  }
   ctx->profiling.store(on != 0);
   return SONAR_OK;
 }
@@ -254,8 +271,8 @@ int sonar_profile_read(sonar_ctx* ctx, sonar_kernel_time* out, int cap, int* n_o
     }
     out[k].total_ms += (double)ms;
     out[k].launches += 1;
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
+    ctx->prof_pool.push_back(r.a);
+    ctx->prof_pool.push_back(r.b);
   }
   ctx->prof.clear();
   *n_out = n;
