@@ -233,6 +233,7 @@ def run_ours(args, rank, world, local_rank):
     p = pkg()
     capi, synth = p.capi, p.synth
     torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.SonarLib(init=False)

@@ -192,100 +192,118 @@ __global__ void __launch_bounds__(kYinThreads) yin_frame_kernel(const double* __
   }
 }
 
-__device__ double median_nonzero(const double* v, int n) {  // pitch_detection.go:978-1007
-  double f[5];
-  int m = 0;
-  for (int i = 0; i < n; i++)
-    if (v[i] > 0) f[m++] = v[i];
+// medianFilter over the non-zero entries (pitch_detection.go:978-1007), register-only.
+// Zero entries are "absent"; every value is >= 0.
+__device__ __forceinline__ double median_nonzero3(double a, double b, double c) {
+  const int m = (a > 0) + (b > 0) + (c > 0);
   if (m == 0) return 0.0;
-  for (int i = 1; i < m; i++) {  // insertion sort, m <= 5
-    const double key = f[i];
-    int j = i - 1;
-    while (j >= 0 && f[j] > key) {
-      f[j + 1] = f[j];
-      j--;
-    }
-    f[j + 1] = key;
-  }
-  return (m % 2 == 0) ? (f[m / 2 - 1] + f[m / 2]) / 2.0 : f[m / 2];
+  const double lo = fmin(a, b), hi = fmax(a, b);
+  if (m == 3) return fmax(lo, fmin(hi, c));  // middle of three
+  const double mx = fmax(hi, c);
+  if (m == 1) return mx;
+  // two present: (smaller + larger) / 2; the absent one is 0 and adding it is exact
+  const double mid = fmax(lo, fmin(hi, c));  // with one zero, the middle of {0, x, y} is min(x, y)
+  return (mid + mx) / 2.0;
 }
 
-// One warp per stream: lanes stage 32 frames of raw (pitch, confidence) in shared memory with coalesced
-// loads, lane 0 replays the reference's sequential history logic on them, all lanes write the six output
-// arrays coalesced.
+__device__ __forceinline__ void cswap(double& x, double& y) {
+  const double lo = fmin(x, y), hi = fmax(x, y);
+  x = lo;
+  y = hi;
+}
+
+// last `n` (3..5) history entries h[5-n..4]; zeros are absent
+__device__ __forceinline__ double median_nonzero5(const double (&h)[5], int n) {
+  double v0 = n >= 5 ? h[0] : 0.0, v1 = n >= 4 ? h[1] : 0.0, v2 = h[2], v3 = h[3], v4 = h[4];
+  const int m = (v0 > 0) + (v1 > 0) + (v2 > 0) + (v3 > 0) + (v4 > 0);
+  if (m == 0) return 0.0;
+  // 9-comparator sorting network, ascending: the m present values end up in the top m slots
+  cswap(v0, v1); cswap(v3, v4); cswap(v2, v4); cswap(v2, v3); cswap(v0, v3);
+  cswap(v0, v2); cswap(v1, v4); cswap(v1, v3); cswap(v1, v2);
+  const double s[5] = {v0, v1, v2, v3, v4};
+  const int first = 5 - m;
+  double lo = 0.0, hi = 0.0;  // sorted[m/2 - 1] and sorted[m/2] of the present values
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k == first + m / 2) hi = s[k];
+    if (k == first + m / 2 - 1) lo = s[k];
+  }
+  return (m & 1) ? hi : (lo + hi) / 2.0;
+}
+
+// One warp per stream, 32 frames per round.  Only the octave correction is a recurrence (it looks at the
+// last five corrected pitches), and it only fires for frames that carry a pitch with confidence >= 0.5;
+// everything else — the confidence gate, the median-of-three smoothing, the derived arrays — is a pure
+// function of a three-frame window and runs one frame per lane.  Lane 0 therefore walks just the gated
+// frames of a round (ballot + find-first-set), in order, with the reference's arithmetic.
 __global__ void __launch_bounds__(32) yin_track_kernel(const double* __restrict__ raw, int64_t raw_stride,
                                                        int n_streams, int64_t Tp, double* __restrict__ feat,
                                                        int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
                                                        int64_t o_voicing, int64_t o_hratio, int64_t o_inharm,
                                                        int64_t o_tonal) {
-  __shared__ double in_p[32], in_c[32], out_p[32], out_c[32], out_v[32];
+  __shared__ double c_sm[5 + 32];  // corrected pitches: [0..4] = the five frames before this round
+  __shared__ double raw_sm[32];
   const int s = blockIdx.x;
   const int lane = threadIdx.x;
   const double* r = raw + (int64_t)s * raw_stride;
   double* fo = feat + (int64_t)s * feat_stride;
-  double hist[5] = {0, 0, 0, 0, 0};  // last five history entries, hist[4] newest
-  int64_t hlen = 0;
-  double previous = 0.0;
+  if (lane < 5) c_sm[lane] = 0.0;
+  __syncwarp();
   for (int64_t base = 0; base < Tp; base += 32) {
     const int cnt = (int)((Tp - base < 32) ? (Tp - base) : 32);
+    const int64_t i = base + lane;
+    double rawp = 0.0, conf = 0.0;
     if (lane < cnt) {
-      in_p[lane] = r[base + lane];
-      in_c[lane] = r[Tp + base + lane];
+      rawp = r[i];
+      conf = r[Tp + i];
     }
+    const bool gate = lane < cnt && rawp != 0.0 && conf >= 0.5;  // :782-786: below 0.5 everything is zeroed
+    raw_sm[lane] = rawp;
+    c_sm[5 + lane] = gate ? rawp : 0.0;
+    unsigned todo = __ballot_sync(0xffffffffu, gate);
     __syncwarp();
     if (lane == 0) {
-      for (int i = 0; i < cnt; i++) {
-        double pitch = in_p[i], conf = in_c[i], voicing = conf;
-        // applyOctaveCorrection :792-829
-        if (!(pitch == 0.0 || hlen == 0)) {
-          const int c5 = hlen < 5 ? (int)hlen : 5;
-          if (c5 >= 3) {
-            const double med = median_nonzero(hist + 5 - c5, c5);
-            const double ratios[4] = {0.5, 2.0, 1.0 / 3.0, 3.0};
-            for (int k = 0; k < 4; k++) {
-              const double expect = med * ratios[k];
-              if (fabs(pitch - expect) / expect < 0.1) {
-                if (fabs(pitch - med) > fabs(expect - med)) pitch = expect;
-                break;
-              }
+      while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t hlen = base + k;  // history entries before this frame
+        double pitch = raw_sm[k];
+        if (hlen >= 3) {  // applyOctaveCorrection :792-829 (needs >= 3 of the last five)
+          const double h[5] = {c_sm[k], c_sm[k + 1], c_sm[k + 2], c_sm[k + 3], c_sm[k + 4]};
+          const double med = median_nonzero5(h, hlen < 5 ? (int)hlen : 5);
+          const double ratios[4] = {0.5, 2.0, 1.0 / 3.0, 3.0};
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const double expect = med * ratios[q];
+            if (fabs(pitch - expect) / expect < 0.1) {
+              if (fabs(pitch - med) > fabs(expect - med)) pitch = expect;
+              break;
             }
           }
         }
-        if (conf < 0.5) {  // :782-786
-          pitch = 0.0;
-          conf = 0.0;
-          voicing = 0.0;
-        }
-        // updateTemporalTracking :876-902 (only the last five entries are ever read)
-        hist[0] = hist[1];
-        hist[1] = hist[2];
-        hist[2] = hist[3];
-        hist[3] = hist[4];
-        hist[4] = pitch;
-        hlen++;
-        if (hlen > 1) {  // applyTemporalSmoothing :905-921
-          if (hlen >= 3)
-            pitch = median_nonzero(hist + 2, 3);
-          else
-            pitch = 0.3 * pitch + (1 - 0.3) * previous;
-        }
-        previous = pitch;
-        out_p[i] = pitch;
-        out_c[i] = conf;
-        out_v[i] = voicing;
+        c_sm[5 + k] = pitch;
       }
     }
     __syncwarp();
     if (lane < cnt) {
-      const int64_t i = base + lane;
-      const double pitch = out_p[lane], voicing = out_v[lane];
+      const double c0 = c_sm[5 + lane], c1 = c_sm[4 + lane], c2 = c_sm[3 + lane];
+      double pitch = c0;  // applyTemporalSmoothing :905-921 on the history that already includes this frame
+      if (i >= 2)
+        pitch = median_nonzero3(c2, c1, c0);
+      else if (i == 1)
+        pitch = 0.3 * c0 + (1 - 0.3) * c1;  // history of two: blend with the previous (unsmoothed) output
+      const double cf = conf < 0.5 ? 0.0 : conf;
       fo[o_pitch + i] = pitch;
-      fo[o_conf + i] = out_c[lane];
-      fo[o_voicing + i] = voicing;
-      fo[o_hratio + i] = voicing * 10.0;          // speech.go:499
-      fo[o_inharm + i] = 1.0 - voicing;           // speech.go:500
+      fo[o_conf + i] = cf;
+      fo[o_voicing + i] = cf;
+      fo[o_hratio + i] = cf * 10.0;               // speech.go:499
+      fo[o_inharm + i] = 1.0 - cf;                // speech.go:500
       fo[o_tonal + i] = pitch > 0 ? pitch : 0.0;  // speech.go:503-505
     }
+    __syncwarp();
+    const double carry = (lane < 5) ? c_sm[32 + lane] : 0.0;
+    __syncwarp();
+    if (lane < 5) c_sm[lane] = carry;
     __syncwarp();
   }
 }
