@@ -285,9 +285,10 @@ def run_ours(args, rank, world, local_rank):
         return lags, paths
 
     pcm_list = [hv[i, :n] for i in range(NS)]
+    out_bufs = lib.alloc_batch_outputs([n] * NS, prm)  # caller-owned result arrays, reused every step (as a Go caller would)
 
     def step_e2e():
-        fps = lib.fingerprint_batch(pcm_list, prm)  # H2D of the PCM + D2H of every feature array inside
+        fps = lib.fingerprint_batch(pcm_list, prm, buffers=out_bufs)  # H2D of the PCM + D2H of every feature array inside
         eas = [fps[2 * i].short_time_energy for i in range(P)]
         ebs = [fps[2 * i + 1].short_time_energy for i in range(P)]
         _, xs = lib.xcorr_batch(eas, ebs, max_lag)

@@ -368,19 +368,25 @@ class SonarLib:
         self._chk(self.lib.sonar_fingerprint_f64(self.ctx, _dp(pcm), pcm.size, C.byref(p), C.byref(out)))
         return self._finish_fp(sizes, arrays, out)
 
-    def fingerprint_batch(self, pcms, p: FpParams) -> list[Fingerprint]:
+    def alloc_batch_outputs(self, lengths, p: FpParams):
+        """Caller-owned output buffers for fingerprint_batch (reusable across calls, like the Go shim's slices)."""
+        ns = len(lengths)
+        outs = (FpOut * ns)()
+        keep = []
+        for i, n in enumerate(lengths):
+            sizes, arrays, o = self._alloc_fp(p, n)
+            outs[i] = o
+            keep.append((sizes, arrays))
+        return outs, keep
+
+    def fingerprint_batch(self, pcms, p: FpParams, buffers=None) -> list[Fingerprint]:
         pcms = [_f64(x) for x in pcms]
         ns = len(pcms)
         ptrs = (c_double_p * ns)(*[_dp(x) for x in pcms])
         lens = (C.c_int64 * ns)(*[x.size for x in pcms])
-        outs = (FpOut * ns)()
-        keep = []
-        for i, x in enumerate(pcms):
-            sizes, arrays, o = self._alloc_fp(p, x.size)
-            outs[i] = o
-            keep.append((sizes, arrays))
+        outs, keep = buffers if buffers is not None else self.alloc_batch_outputs([x.size for x in pcms], p)
         self._chk(self.lib.sonar_fingerprint_batch_f64(self.ctx, ptrs, lens, ns, C.byref(p), outs))
-        return [self._finish_fp(k[0], k[1], outs[i]) for i, k in enumerate(keep)]
+        return [self._finish_fp(k[0], dict(k[1]), outs[i]) for i, k in enumerate(keep)]
 
     def fp_dev_layout(self, p: FpParams, n: int) -> FpDevLayout:
         L = FpDevLayout()

@@ -182,7 +182,8 @@ struct Slot {  // one in-flight unit of work on a device: its stream and buffers
 };
 struct DevCtx {
   int device = 0;
-  Slot slot[2];
+  static constexpr int kSlots = 3;
+  Slot slot[kSlots];
   int ensure_dev(Buf& b, size_t bytes);
   int ensure_host(Buf& b, size_t bytes);
 };

@@ -234,8 +234,9 @@ struct DeviceJob {
   std::string err;
 };
 
-// One device's share of a host batch: chunks alternate between the two slots so that
-// the H2D of chunk k+1 overlaps the kernels and D2H of chunk k.
+// One device's share of a host batch: chunks rotate through the device's slots (stream + buffers each), so
+// the H2D copy of chunk k+1 and k+2 overlaps the kernels and the D2H of chunk k, and the host-side scatter of
+// a finished chunk into the caller's arrays overlaps the GPU work queued on the other slots.
 void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, const std::vector<Chunk>* chunks,
                       const sonar_fp_params* p, sonar_fp_out* outs, DeviceJob* job) {
   set_current_ctx(ctx);
@@ -245,7 +246,8 @@ void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, con
   };
   cudaError_t e = cudaSetDevice(dev->device);
   if (e != cudaSuccess) return fail(cuda_error(e, "cudaSetDevice"));
-  const Chunk* pending[2] = {nullptr, nullptr};
+  constexpr int NS = DevCtx::kSlots;
+  const Chunk* pending[NS] = {};
   auto finish = [&](int si) -> int {
     const Chunk* c = pending[si];
     if (!c) return SONAR_OK;
@@ -258,7 +260,7 @@ void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, con
   };
   int k = 0;
   for (const Chunk& c : *chunks) {
-    const int si = k++ & 1;
+    const int si = k++ % NS;
     Slot& s = dev->slot[si];
     int rc = finish(si);
     if (rc) return fail(rc);
@@ -285,13 +287,13 @@ void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, con
     if (e != cudaSuccess) return fail(cuda_error(e, "cudaEventRecord"));
     pending[si] = &c;
   }
-  for (int si = 0; si < 2; si++) {
-    int rc = finish((k + si) & 1);
+  for (int j = 0; j < NS; j++) {
+    int rc = finish((k + j) % NS);  // oldest first
     if (rc) return fail(rc);
   }
 }
 
-constexpr size_t kChunkBytes = (size_t)768 << 20;  // PCM bytes per in-flight chunk and slot
+constexpr size_t kChunkBytes = (size_t)256 << 20;  // PCM bytes per in-flight chunk and slot
 
 }  // namespace
 }  // namespace sonar
