@@ -260,41 +260,23 @@ def run_ours(args, rank, world, local_rank):
         q, r = make_pair(synth, seconds, rank * P + i)
         hv[2 * i, :n], hv[2 * i + 1, :n] = q, r
     pcm_dev = host.to("cuda", non_blocking=False)
-    feat = torch.empty(NS * L.total, dtype=torch.float64, device="cuda")
-    summ = (capi.XcorrSummary * P)()
     torch.cuda.synchronize()
 
-    def align_tail(ea_all, eb_all, lags):
-        qs, rs = [], []
-        for i in range(P):
-            a, b = trim_by_lag(ea_all[i], eb_all[i], lags[i], dtw_len)
-            qs.append(a)
-            rs.append(b)
-        return lib.dtw_batch(qs, rs, band=DTW_BAND)
+    # The public call for this workload is the chained pair pipeline (include/sonar.h: sonar_align_pairs_*):
+    # fingerprint both streams -> "corr_energy" NCC -> trim by the detected lag -> banded DTW, per pair, with
+    # nothing returning to the host in between.  Result buffers are caller-owned and reused every step.
+    bufs_dev = lib.alloc_pair_outputs(P, n, prm, MAX_LAG_S, features=False, corr=False)
+    bufs_e2e = lib.alloc_pair_outputs(P, n, prm, MAX_LAG_S, features=True, corr=True)
+    q_list = [hv[2 * i, :n] for i in range(P)]
+    r_list = [hv[2 * i + 1, :n] for i in range(P)]
 
-    def step_resident():
-        lib.fingerprint_batch_dev(pcm_dev.data_ptr(), n, stride, NS, prm, feat.data_ptr())
-        with torch.cuda.stream(ext):
-            e = feat.view(NS, L.total)[:, L.short_time_energy:L.short_time_energy + Te]
-            ea, eb = e[0::2].contiguous(), e[1::2].contiguous()
-        lib._chk(lib.lib.sonar_xcorr_batch_dev(lib.ctx, ea.data_ptr(), Te, eb.data_ptr(), Te, P, max_lag, None, summ))
-        with torch.cuda.stream(ext):
-            ea_h, eb_h = ea.cpu().numpy(), eb.cpu().numpy()
-        lags = [summ[i].peak_lag for i in range(P)]
-        paths = align_tail(ea_h, eb_h, lags)
-        return lags, paths
+    def step_resident():  # PCM already in HBM; per-pair results (lag summary + DTW path) return to the host
+        res = lib.align_pairs_dev(pcm_dev.data_ptr(), n, stride, P, prm, MAX_LAG_S, DTW_BAND, buffers=bufs_dev)
+        return [x["xcorr"].peak_lag for x in res], res
 
-    pcm_list = [hv[i, :n] for i in range(NS)]
-    out_bufs = lib.alloc_batch_outputs([n] * NS, prm)  # caller-owned result arrays, reused every step (as a Go caller would)
-
-    def step_e2e():
-        fps = lib.fingerprint_batch(pcm_list, prm, buffers=out_bufs)  # H2D of the PCM + D2H of every feature array inside
-        eas = [fps[2 * i].short_time_energy for i in range(P)]
-        ebs = [fps[2 * i + 1].short_time_energy for i in range(P)]
-        _, xs = lib.xcorr_batch(eas, ebs, max_lag)
-        lags = [s.peak_lag for s in xs]
-        paths = align_tail(eas, ebs, lags)
-        return lags, paths, fps
+    def step_e2e():  # host PCM in, every feature array + correlation curve + DTW path out
+        res = lib.align_pairs(q_list, r_list, prm, MAX_LAG_S, DTW_BAND, buffers=bufs_e2e)
+        return [x["xcorr"].peak_lag for x in res], res, res
 
     def barrier():
         if world > 1:
@@ -344,8 +326,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_ms = reduce_max(1e3 * (time.perf_counter() - t0) / n_e2e)
     assert lags_e == lags, "host-pointer and device-resident legs disagree on the detected lags"
-    h2d = NS * n * 8 + 2 * P * Te * 8 + 2 * P * dtw_len * 8
-    d2h = sum(a.nbytes for a in fps[0].arrays.values()) * NS + P * (2 * max_lag + 1) * 0 + \
+    h2d = NS * n * 8
+    d2h = sum(a.nbytes for a in fps[0]["query"].arrays.values()) * NS + P * (2 * max_lag + 1) * 8 + \
         sum(len(pp["path_query"]) * 16 for pp in paths_e)
 
     # ---- N > 1 only: ONE long correlation (10-min pair, +-60 s) split by lag range over the ranks, NCCL

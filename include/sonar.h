@@ -397,6 +397,44 @@ int sonar_align_dtw_scalars(const sonar_dtw_out* dtw, int n, int m, int sample_r
                             sonar_align_result* out);
 
 /* ------------------------------------------------------------------------- */
+/* the chained pair pipeline                                                  */
+/* ------------------------------------------------------------------------- */
+
+/* Result of one source/CDN pair.  Feature pointers inside `query` / `reference`, `corr` and the path arrays of
+ * `dtw` are caller-allocated (NULL = not wanted); everything else is written by the call. */
+typedef struct sonar_pair_out {
+  sonar_fp_out query, reference;      /* GenerateFingerprint's features of the two streams            */
+  sonar_xcorr_summary xcorr;          /* "corr_energy" cross-correlation (extractors/alignment.go:323-332) */
+  sonar_align_result corr_alignment;  /* stats.AlignmentResult scalars of it (stats/alignment.go:151-181) */
+  double* corr;                       /* optional [n_lags] correlation curve                            */
+  sonar_dtw_out dtw;                  /* banded DTW of the lag-trimmed energy series (dtw_length frames each) */
+  int32_t dtw_length, reserved0;
+} sonar_pair_out;
+
+/* n_lags = 2*clamped_max_lag_frames+1 and dtw_length = energy_frames - clamped_max_lag_frames for streams of n
+ * samples (so the caller can size `corr` and the path arrays: path_cap = 2*dtw_length). */
+int sonar_align_pairs_sizes(const sonar_fp_params* p, int64_t n, double max_lag_seconds, int32_t* n_lags,
+                            int32_t* dtw_length);
+
+/* The whole CDN-latency loop for n_pairs pairs of equally long streams, chained on the device
+ * (SURVEY §8 f3): GenerateFingerprint of both streams (fingerprint/fingerprint.go:137-236), the "corr_energy"
+ * alignment of ExtractAlignmentFeatures (fingerprint/extractors/alignment.go:139-219,357-409) with the lag clamp
+ * of NewAlignmentExtractorWithMaxLag (:99-136), and DTWAlignment.Align (algorithms/stats/dtw.go:55-217,
+ * band = dtw_band > 0, "symmetric2", Euclidean) of the two short-time-energy series after trimming by the
+ * detected lag as TruncateToAlignmentPCM does (alignment.go:239-243) and truncating both to dtw_length.  This is
+ * also the shape of AlignmentExtractor.AlignAudioFiles (alignment.go:489-560).  Results are identical to calling
+ * sonar_fingerprint_f64 x2, sonar_align_xcorr_f64 and sonar_dtw_f64 one after the other; the point of the call
+ * is that nothing returns to the host in between and the PCIe copy of the next pairs overlaps the kernels. */
+int sonar_align_pairs_f64(sonar_ctx* ctx, const double* const* query_pcm, const double* const* reference_pcm,
+                          int64_t n, int n_pairs, const sonar_fp_params* p, double max_lag_seconds, int dtw_band,
+                          sonar_pair_out* outs);
+
+/* Device-resident form: pair i = streams 2i (query) and 2i+1 (reference) of pcm_dev, `stride` (= n rounded up to
+ * even) samples apart. */
+int sonar_align_pairs_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n, int64_t stride, int n_pairs,
+                          const sonar_fp_params* p, double max_lag_seconds, int dtw_band, sonar_pair_out* outs);
+
+/* ------------------------------------------------------------------------- */
 /* comparison                                                                 */
 /* ------------------------------------------------------------------------- */
 

@@ -125,6 +125,11 @@ class DtwOut(C.Structure):
     ]
 
 
+class PairOut(C.Structure):
+    _fields_ = [("query", FpOut), ("reference", FpOut), ("xcorr", XcorrSummary), ("corr_alignment", AlignResult),
+                ("corr", c_double_p), ("dtw", DtwOut), ("dtw_length", C.c_int32), ("reserved0", C.c_int32)]
+
+
 class KernelTime(C.Structure):
     _fields_ = [("kernel", C.c_char * 48), ("total_ms", C.c_double), ("launches", C.c_int64)]
 
@@ -174,6 +179,7 @@ EXPORTS = (
     "sonar_xcorr_shard_close", "sonar_xcorr_merge_peaks", "sonar_xcorr_merge_metrics",
     "sonar_align_xcorr_f64", "sonar_dtw_f64", "sonar_dtw_batch_f64", "sonar_align_dtw_scalars",
     "sonar_colstats_cosine_f64", "sonar_colstats_f64", "sonar_compare_f64",
+    "sonar_align_pairs_sizes", "sonar_align_pairs_f64", "sonar_align_pairs_dev",
 )
 
 
@@ -272,6 +278,11 @@ class SonarLib:
                                                 C.c_int, c_double_p]
         L.sonar_compare_f64.argtypes = [C.c_void_p, C.POINTER(CmpFeatures), C.POINTER(CmpFeatures),
                                         C.POINTER(CmpWeights), C.c_int, C.POINTER(CmpResult)]
+        L.sonar_align_pairs_sizes.argtypes = [C.POINTER(FpParams), C.c_int64, C.c_double, c_int32_p, c_int32_p]
+        L.sonar_align_pairs_f64.argtypes = [C.c_void_p, C.POINTER(c_double_p), C.POINTER(c_double_p), C.c_int64, C.c_int,
+                                            C.POINTER(FpParams), C.c_double, C.c_int, C.POINTER(PairOut)]
+        L.sonar_align_pairs_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.POINTER(FpParams),
+                                            C.c_double, C.c_int, C.POINTER(PairOut)]
         self.ctx = C.c_void_p()
         if init:
             self._chk(L.sonar_init(n_devices, None, C.byref(self.ctx)))
@@ -529,6 +540,67 @@ class SonarLib:
         ar = AlignResult()
         self._chk(self.lib.sonar_align_dtw_scalars(C.byref(dtw_res["_out"]), n, m, sr, C.byref(ar)))
         return ar
+
+    # -- chained pair pipeline ---------------------------------------------------
+    def align_pairs_sizes(self, p: FpParams, n: int, max_lag_seconds: float):
+        nl, dl = C.c_int32(), C.c_int32()
+        self._chk(self.lib.sonar_align_pairs_sizes(C.byref(p), n, max_lag_seconds, C.byref(nl), C.byref(dl)))
+        return nl.value, dl.value
+
+    def alloc_pair_outputs(self, n_pairs: int, n: int, p: FpParams, max_lag_seconds: float, features=True, corr=True):
+        """Caller-owned result buffers for align_pairs / align_pairs_dev (reusable across calls)."""
+        nl, dl = self.align_pairs_sizes(p, n, max_lag_seconds)
+        outs = (PairOut * n_pairs)()
+        keep = []
+        for i in range(n_pairs):
+            k = {}
+            if features:
+                sq, aq, oq = self._alloc_fp(p, n)
+                sr, ar, orr = self._alloc_fp(p, n)
+                outs[i].query, outs[i].reference = oq, orr
+                k["query"], k["reference"] = (sq, aq), (sr, ar)
+            if corr:
+                k["corr"] = np.zeros(nl)
+                outs[i].corr = _dp(k["corr"])
+            cap = 2 * dl
+            k["pq"], k["pr"], k["pc"] = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+            outs[i].dtw.path_query = k["pq"].ctypes.data_as(c_int32_p)
+            outs[i].dtw.path_ref = k["pr"].ctypes.data_as(c_int32_p)
+            outs[i].dtw.path_cost = _dp(k["pc"])
+            outs[i].dtw.path_cap = cap
+            keep.append(k)
+        return outs, keep
+
+    def _pair_results(self, outs, keep):
+        res = []
+        for i, k in enumerate(keep):
+            o = outs[i]
+            L = o.dtw.path_len
+            d = {"xcorr": o.xcorr, "corr_alignment": o.corr_alignment, "corr": k.get("corr"),
+                 "dtw_length": o.dtw_length, "path_query": k["pq"][:L], "path_ref": k["pr"][:L],
+                 "path_cost": k["pc"][:L], "distance": o.dtw.distance, "total_cost": o.dtw.total_cost}
+            if "query" in k:
+                d["query"] = self._finish_fp(k["query"][0], dict(k["query"][1]), o.query)
+                d["reference"] = self._finish_fp(k["reference"][0], dict(k["reference"][1]), o.reference)
+            res.append(d)
+        return res
+
+    def align_pairs(self, queries, references, p: FpParams, max_lag_seconds: float, dtw_band: int, buffers=None):
+        qs, rs = [_f64(x) for x in queries], [_f64(x) for x in references]
+        npairs, n = len(qs), qs[0].size
+        outs, keep = buffers if buffers is not None else self.alloc_pair_outputs(npairs, n, p, max_lag_seconds)
+        pq = (c_double_p * npairs)(*[_dp(x) for x in qs])
+        pr = (c_double_p * npairs)(*[_dp(x) for x in rs])
+        self._chk(self.lib.sonar_align_pairs_f64(self.ctx, pq, pr, n, npairs, C.byref(p), max_lag_seconds, dtw_band, outs))
+        return self._pair_results(outs, keep)
+
+    def align_pairs_dev(self, pcm_dev: int, n: int, stride: int, n_pairs: int, p: FpParams, max_lag_seconds: float,
+                        dtw_band: int, buffers=None):
+        outs, keep = buffers if buffers is not None else self.alloc_pair_outputs(n_pairs, n, p, max_lag_seconds,
+                                                                                 features=False)
+        self._chk(self.lib.sonar_align_pairs_dev(self.ctx, pcm_dev, n, stride, n_pairs, C.byref(p), max_lag_seconds,
+                                                 dtw_band, outs))
+        return self._pair_results(outs, keep)
 
     # -- comparison ------------------------------------------------------------
     def colstats(self, x, dim=None) -> np.ndarray:

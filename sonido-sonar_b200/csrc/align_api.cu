@@ -45,6 +45,31 @@ void summarize(double c0, double cm, double cp, double ns, double nc, double ms,
   o->n_candidates = (int32_t)std::min<int64_t>(n_eval, 0x7fffffff);
 }
 
+}  // namespace
+
+void summarize_xcorr(const XcorrPairOut& o, int aml, int64_t na, int64_t nb, int64_t n_eval, sonar_xcorr_summary* s) {
+  summarize(o.c_peak, o.c_prev, o.c_next, o.noise_sum, o.noise_cnt, o.max_sidelobe, o.second_val, o.peak_index, aml, na,
+            nb, n_eval, s);
+}
+
+// AlignmentAnalyzer.alignWithCrossCorrelation's scalars (algorithms/stats/alignment.go:151-181)
+void fill_align_from_xcorr(const sonar_xcorr_summary* xc, int64_t nq, int64_t nr, int max_lag, int hop, int sr,
+                           sonar_align_result* out) {
+  std::memset(out, 0, sizeof(*out));
+  out->method = 1;
+  out->query_length = (int32_t)nq;
+  out->reference_length = (int32_t)nr;
+  out->sample_rate = sr;
+  out->offset = xc->peak_lag * hop;                                                    // :164
+  out->offset_seconds = (double)out->offset / (double)sr;                              // :165
+  out->similarity = std::fmin(1.0, std::fmax(0.0, std::fabs(xc->peak_correlation)));  // :171-174
+  out->confidence = corr_confidence(xc);
+  out->alignment_quality = corr_quality(xc, max_lag);
+  out->noise_level = 1.0 - xc->snr / 20.0;  // :178
+}
+
+namespace {
+
 struct PairJob {
   const double* a;
   int64_t na;
@@ -576,17 +601,7 @@ int sonar_align_xcorr_f64(sonar_ctx* ctx, const double* q, int64_t nq, const dou
   if (!xc) xc = &local;
   int rc = sonar_xcorr_ncc_f64(ctx, q, nq, r, nr, ml, corr, xc);
   if (rc) return rc;
-  std::memset(out, 0, sizeof(*out));
-  out->method = 1;
-  out->query_length = (int32_t)nq;
-  out->reference_length = (int32_t)nr;
-  out->sample_rate = sr;
-  out->offset = xc->peak_lag * hop;                                                    // stats/alignment.go:164
-  out->offset_seconds = (double)out->offset / (double)sr;                              // :165
-  out->similarity = std::fmin(1.0, std::fmax(0.0, std::fabs(xc->peak_correlation)));  // :171-174
-  out->confidence = corr_confidence(xc);
-  out->alignment_quality = corr_quality(xc, ml);
-  out->noise_level = 1.0 - xc->snr / 20.0;  // :178
+  fill_align_from_xcorr(xc, nq, nr, ml, hop, sr, out);
   return SONAR_OK;
 }
 

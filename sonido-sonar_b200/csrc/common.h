@@ -99,6 +99,14 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out);
 int launch_stft_features(const FpPlan& plan, StftArgs& a, bool spectrum_mode, cudaStream_t st);
 bool stft_supported(int window_size);
 
+// ---- fingerprint sequencing shared by the host-pointer, device-resident and pipeline entry points ----------
+struct FpShape {
+  sonar_fp_sizes_t sz;
+  sonar_fp_dev_layout_t L;
+  int64_t lr_win = 0, lr_hop = 0, lr_nw = 0;  // loudness-range windows (energy.go:157-179)
+  size_t tmp_doubles_per_stream = 0;
+};
+
 // ---- exact FP64 time-domain kernels (timedomain.cu) -------------------------
 // o_* are offsets (doubles) into each stream's output block; < 0 = not wanted.
 int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int frame,
@@ -108,7 +116,7 @@ int launch_variance(const double* x, int64_t n, int64_t stride, int n_streams, d
                     cudaStream_t st);
 int launch_rms_windows(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int win,
                        int hop, int64_t nw, double* out, int64_t out_stride, cudaStream_t st);
-int launch_loudness_range(const double* rms, int64_t nw, int64_t in_stride, int n_streams, double* out,
+int launch_loudness_range(double* rms, int64_t nw, int64_t in_stride, int n_streams, double* out,
                           int64_t out_stride, cudaStream_t st);
 int launch_fill(double* p, int64_t n, double v, cudaStream_t st);
 int launch_fill_strided(double* p, int64_t count, int64_t stride, int n_streams, double v, cudaStream_t st);
@@ -146,6 +154,10 @@ int launch_znorm(const XcorrSeq* seqs_dev, int count, cudaStream_t st);
 int launch_xcorr(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags, cudaStream_t st);
 int launch_xcorr_finalize(const XcorrPair* pairs_dev, int n_pairs, int64_t peak_override, XcorrPairOut* outs_dev,
                           cudaStream_t st);
+// TruncateToAlignmentPCM's convention on the feature series (extractors/alignment.go:239-243): a positive lag skips
+// the start of the second sequence, a negative one the start of the first.  Writes the trimmed start pointers.
+int launch_xcorr_trim(const XcorrSeq* seqs_dev, const XcorrPair* pairs_dev, const XcorrPairOut* outs_dev, int n_pairs,
+                      const double** qptr_dev, const double** rptr_dev, cudaStream_t st);
 
 // ---- DTW (dtw.cu) -------------------------------------------------------------
 struct DtwGeom {
@@ -162,9 +174,11 @@ struct DtwPairOut {
 // q: n_pairs*n*dim, r: n_pairs*m*dim (device); cells: n_pairs*g.cells; line_scratch: n_pairs*(g.n_off+2)
 // doubles, only needed when the offset line does not fit shared memory; paths are written back to front:
 // pair p's path occupies [p*path_cap + path_cap - len, p*path_cap + path_cap).
+// qptr / rptr (nullable, device arrays of n_pairs device pointers) override the packed q / r layout.
 int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, int dim, int step, double* cells,
                double* line_scratch, int32_t* path_q, int32_t* path_r, double* path_c, int64_t path_cap,
-               DtwPairOut* out, cudaStream_t st);
+               DtwPairOut* out, cudaStream_t st, const double* const* qptr = nullptr,
+               const double* const* rptr = nullptr);
 int launch_dtw_expand(const double* cells, const DtwGeom& g, double* full, cudaStream_t st);
 
 // ---- column statistics (colstats.cu) ----------------------------------------
@@ -175,14 +189,17 @@ struct Buf {  // growable allocation (device or pinned host)
   void* p = nullptr;
   size_t bytes = 0;
 };
-struct Slot {  // one in-flight unit of work on a device: its stream and buffers
-  cudaStream_t st = nullptr;
+struct Slot {  // one in-flight unit of work on a device: its streams and buffers
+  cudaStream_t st = nullptr;   // H2D + the kernels that saturate the GPU
+  cudaStream_t st2 = nullptr;  // latency-bound tails (DTW) + D2H of the pair pipeline, so they overlap other slots
   cudaEvent_t done = nullptr;
+  cudaEvent_t mid = nullptr;   // hand-off st -> st2
   Buf d_in, d_out, d_tmp, h_in, h_out;
 };
 struct DevCtx {
   int device = 0;
-  static constexpr int kSlots = 3;
+  static constexpr int kSlots = 8;
+  static constexpr int kStageSlots = 3;  // slots whose d_in stages host PCM
   Slot slot[kSlots];
   int ensure_dev(Buf& b, size_t bytes);
   int ensure_host(Buf& b, size_t bytes);
@@ -215,6 +232,15 @@ void prof_begin(const char* kernel, cudaStream_t st);
 void prof_end();
 void set_current_ctx(sonar_ctx* c);
 // speech.go:370-408 temporal block (temporal.cu)
+int fp_validate(const sonar_fp_params* p);
+int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s);
+// enqueues every kernel of one uniform batch of streams on `st` (fingerprint_api.cu)
+int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, const FpShape& sh, const double* pcm_dev,
+                        int64_t n, int64_t stride, int ns, double* feat_dev, double* tmp_dev, cudaStream_t st);
+void scatter_block(const double* f, const FpShape& sh, sonar_fp_out* o);
+void summarize_xcorr(const XcorrPairOut& o, int aml, int64_t na, int64_t nb, int64_t n_eval, sonar_xcorr_summary* s);
+void fill_align_from_xcorr(const sonar_xcorr_summary* xc, int64_t nq, int64_t nr, int max_lag, int hop, int sr,
+                           sonar_align_result* out);
 int fingerprint_temporal_tail(sonar_ctx* ctx, const double* const* pcm, const int64_t* n, int n_streams,
                               const sonar_fp_params* p, sonar_fp_out* outs);
 }  // namespace sonar

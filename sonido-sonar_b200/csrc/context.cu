@@ -148,7 +148,9 @@ int sonar_init(int n_devices, const int* device_ids, sonar_ctx** out) {
     }
     for (auto& s : d.slot) {
       if ((e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)) != cudaSuccess ||
-          (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) {
+          (e = cudaStreamCreateWithFlags(&s.st2, cudaStreamNonBlocking)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s.mid, cudaEventDisableTiming)) != cudaSuccess) {
         delete ctx;
         return cuda_error(e, "cudaStreamCreate");
       }
@@ -173,7 +175,9 @@ void sonar_destroy(sonar_ctx* ctx) {
       if (s.h_in.p) cudaFreeHost(s.h_in.p);
       if (s.h_out.p) cudaFreeHost(s.h_out.p);
       if (s.done) cudaEventDestroy(s.done);
+      if (s.mid) cudaEventDestroy(s.mid);
       if (s.st) cudaStreamDestroy(s.st);
+      if (s.st2) cudaStreamDestroy(s.st2);
     }
   }
   if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].device);
@@ -225,7 +229,10 @@ int sonar_synchronize(sonar_ctx* ctx) {
   if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
   for (auto& d : ctx->devs) {
     SONAR_CUDA(cudaSetDevice(d.device));
-    for (auto& s : d.slot) SONAR_CUDA(cudaStreamSynchronize(s.st));
+    for (auto& s : d.slot) {
+      SONAR_CUDA(cudaStreamSynchronize(s.st));
+      SONAR_CUDA(cudaStreamSynchronize(s.st2));
+    }
   }
   SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
   return SONAR_OK;

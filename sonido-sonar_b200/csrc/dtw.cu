@@ -75,15 +75,16 @@ template <bool STAGED, bool ONECELL>
 __global__ void __launch_bounds__(1024) dtw_fill_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
                                                         DtwGeom g, int dim, int step, double* __restrict__ cells_all,
                                                         double* __restrict__ line_global, int line_in_smem,
-                                                        int stage_diags) {
+                                                        int stage_diags, const double* const* __restrict__ qptr,
+                                                        const double* const* __restrict__ rptr) {
   extern __shared__ double s_mem[];
   double* ring_q = s_mem;
   double* ring_r = s_mem + kRing;
   double* s_stage = s_mem + (STAGED ? 2 * kRing : 0);
   double* s_line = s_stage + (ONECELL ? (size_t)stage_diags * blockDim.x : 0);
   const int pair = blockIdx.x;
-  const double* __restrict__ q = qs + (int64_t)pair * g.n * dim;
-  const double* __restrict__ r = rs + (int64_t)pair * g.m * dim;
+  const double* __restrict__ q = qptr ? qptr[pair] : qs + (int64_t)pair * g.n * dim;
+  const double* __restrict__ r = rptr ? rptr[pair] : rs + (int64_t)pair * g.m * dim;
   double* __restrict__ cells = cells_all + (int64_t)pair * g.cells;
   const int shift = g.band > 0 ? g.band : g.m;  // o = i - j + shift in [0, n_off)
   const int n_off = g.n_off;
@@ -220,13 +221,15 @@ __device__ __forceinline__ double dtw_relax(double v, double hh, double dg, doub
 
 template <int NPL, int STEP>
 __global__ void __launch_bounds__(32) dtw_fill_warp_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
-                                                           DtwGeom g, double* __restrict__ cells_all) {
+                                                           DtwGeom g, double* __restrict__ cells_all,
+                                                           const double* const* __restrict__ qptr,
+                                                           const double* const* __restrict__ rptr) {
   constexpr int H = NPL / 2;
   __shared__ double ring_q[kRing], ring_r[kRing];
   const int pair = blockIdx.x, lane = threadIdx.x;
   const int n = g.n, m = g.m, band = g.band, W = (int)g.W;
-  const double* __restrict__ q = qs + (int64_t)pair * n;
-  const double* __restrict__ r = rs + (int64_t)pair * m;
+  const double* __restrict__ q = qptr ? qptr[pair] : qs + (int64_t)pair * n;
+  const double* __restrict__ r = rptr ? rptr[pair] : rs + (int64_t)pair * m;
   const double inf = d_inf();
   const int kbase = NPL * lane;
   double L[NPL];
@@ -587,7 +590,7 @@ int dtw_geometry(int n, int m, int band, DtwGeom* g) {
 
 int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, int dim, int step, double* cells,
                double* line_scratch, int32_t* path_q, int32_t* path_r, double* path_c, int64_t path_cap,
-               DtwPairOut* out, cudaStream_t st) {
+               DtwPairOut* out, cudaStream_t st, const double* const* qptr, const double* const* rptr) {
   if (n_pairs <= 0) return SONAR_OK;
   const size_t line_bytes = sizeof(double) * (size_t)(g.n_off + 2);
   const int in_smem = line_bytes <= 140 * 1024;
@@ -601,11 +604,11 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
 #define SONAR_DTW_WARP(NPL)                                                                       \
   do {                                                                                            \
     if (step == SONAR_STEP_SYMMETRIC2)                                                            \
-      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC2><<<n_pairs, 32, 0, st>>>(q, r, g, cells);   \
+      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC2><<<n_pairs, 32, 0, st>>>(q, r, g, cells, qptr, rptr);   \
     else if (step == SONAR_STEP_ASYMMETRIC)                                                       \
-      dtw_fill_warp_kernel<NPL, SONAR_STEP_ASYMMETRIC><<<n_pairs, 32, 0, st>>>(q, r, g, cells);   \
+      dtw_fill_warp_kernel<NPL, SONAR_STEP_ASYMMETRIC><<<n_pairs, 32, 0, st>>>(q, r, g, cells, qptr, rptr);   \
     else                                                                                          \
-      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC1><<<n_pairs, 32, 0, st>>>(q, r, g, cells);   \
+      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC1><<<n_pairs, 32, 0, st>>>(q, r, g, cells, qptr, rptr);   \
   } while (0)
     const int offs = 2 * g.band + 1;
     prof_begin("dtw_fill_warp_kernel", st);
@@ -635,7 +638,7 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
                                     (int)(224 * 1024)));                                                        \
     prof_begin("dtw_fill_kernel", st);                                                                          \
     dtw_fill_kernel<S, O><<<n_pairs, threads, smem, st>>>(q, r, g, dim, step, cells, line_scratch, in_smem,    \
-                                                          stage_diags);                                         \
+                                                          stage_diags, qptr, rptr);                             \
   } while (0)
   if (staged && onecell)
     SONAR_DTW_FILL(true, true);

@@ -48,7 +48,9 @@ int get_plan(sonar_ctx* ctx, int device, const sonar_fp_params* p, std::shared_p
   return SONAR_OK;
 }
 
-int validate(const sonar_fp_params* p) {
+}  // namespace
+
+int fp_validate(const sonar_fp_params* p) {
   if (p->call_sample_rate <= 0) return set_error(SONAR_ERR_INVALID, "sample rate must be positive");  // speech.go:143
   if (p->enable & SONAR_FP_ENABLE_SPEECH)
     return set_error(SONAR_ERR_UNSUPPORTED, "speech feature group is outside this path's scope");
@@ -56,13 +58,6 @@ int validate(const sonar_fp_params* p) {
     return set_error(SONAR_ERR_UNSUPPORTED, "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
   return SONAR_OK;
 }
-
-struct FpShape {
-  sonar_fp_sizes_t sz;
-  sonar_fp_dev_layout_t L;
-  int64_t lr_win = 0, lr_hop = 0, lr_nw = 0;  // loudness-range windows (energy.go:157-179)
-  size_t tmp_doubles_per_stream = 0;
-};
 
 int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s) {
   int rc = host_fp_sizes(p, n, &s->sz);
@@ -223,6 +218,8 @@ void scatter_block(const double* f, const FpShape& sh, sonar_fp_out* o) {
   o->n_attack_time = 0;
 }
 
+namespace {
+
 struct Chunk {  // consecutive streams of one device with identical length
   std::vector<int> ids;
   int64_t n = 0;
@@ -246,7 +243,7 @@ void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, con
   };
   cudaError_t e = cudaSetDevice(dev->device);
   if (e != cudaSuccess) return fail(cuda_error(e, "cudaSetDevice"));
-  constexpr int NS = DevCtx::kSlots;
+  constexpr int NS = DevCtx::kStageSlots;
   const Chunk* pending[NS] = {};
   auto finish = [&](int si) -> int {
     const Chunk* c = pending[si];
@@ -309,7 +306,7 @@ int sonar_fingerprint_batch_f64(sonar_ctx* ctx, const double* const* pcm, const 
   if (n_streams <= 0) return SONAR_OK;
   std::lock_guard<std::mutex> call_lock(ctx->call_mu);
   set_current_ctx(ctx);
-  int rc = validate(p);
+  int rc = fp_validate(p);
   if (rc) return rc;
   const int nd = (int)ctx->devs.size();
   std::vector<std::vector<Chunk>> per_dev(nd);
@@ -360,7 +357,7 @@ int sonar_fingerprint_batch_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n
   if (stride < n) return set_error(SONAR_ERR_INVALID, "stride must be >= n");
   std::lock_guard<std::mutex> call_lock(ctx->call_mu);
   set_current_ctx(ctx);
-  int rc = validate(p);
+  int rc = fp_validate(p);
   if (rc) return rc;
   if (p->enable & SONAR_FP_ENABLE_TEMPORAL)
     return set_error(SONAR_ERR_UNSUPPORTED, "temporal features are not part of the device layout");

@@ -209,6 +209,74 @@ __global__ void __launch_bounds__(256) loudness_range_kernel(const double* __res
   }
 }
 
+// Same result for any number of windows (1 h at 16 kHz has 36,000): the two order statistics are found
+// exactly with an 8-pass byte-wise radix select over the order-preserving 64-bit keys of the loudness
+// values (converted in place in the scratch array), one CTA per stream.
+__device__ __forceinline__ unsigned long long f64_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(256) loudness_select_kernel(double* __restrict__ rms, int64_t nw, int64_t in_stride,
+                                                              double* __restrict__ out, int64_t out_stride) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ long long s_k;
+  double* v = rms + (int64_t)blockIdx.x * in_stride;
+  for (int64_t i = threadIdx.x; i < nw; i += blockDim.x) {
+    const double e = v[i];
+    v[i] = e > 0.0 ? -0.691 + 10.0 * log10(e * e) : -70.0;
+  }
+  __syncthreads();
+  double picked[2] = {0.0, 0.0};
+  for (int which = 0; which < 2; ++which) {
+    if (threadIdx.x == 0) {
+      s_prefix = 0ull;
+      s_k = (long long)((which == 0 ? 0.10 : 0.95) * (double)(nw - 1));  // int() truncation as in energy.go:203-213
+    }
+    __syncthreads();
+    unsigned long long mask = 0ull;
+    for (int pass = 7; pass >= 0; --pass) {
+      hist[threadIdx.x] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int64_t i = threadIdx.x; i < nw; i += blockDim.x) {
+        const unsigned long long k = f64_key(v[i]);
+        if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> (8 * pass)) & 0xffu], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        long long k = s_k;
+        int b = 0;
+        for (; b < 256; ++b) {
+          if (k < (long long)hist[b]) break;
+          k -= hist[b];
+        }
+        s_k = k;
+        s_prefix = prefix | ((unsigned long long)b << (8 * pass));
+      }
+      mask |= 0xffull << (8 * pass);
+      __syncthreads();
+    }
+    picked[which] = key_f64(s_prefix);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double res = 0.0;
+    if (nw > 0) {
+      double lov = picked[0];
+      const double hiv = picked[1];
+      if (lov <= 0.0) lov = 1e-10;
+      res = hiv <= 0.0 ? 0.0 : 20.0 * log10(hiv / lov);
+    }
+    out[(int64_t)blockIdx.x * out_stride] = res;
+  }
+}
+
 __global__ void fill_kernel(double* p, int64_t n, double v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = v;
@@ -274,10 +342,16 @@ int launch_rms_windows(const double* pcm, int64_t n, int64_t stride, int n_strea
   return SONAR_OK;
 }
 
-int launch_loudness_range(const double* rms, int64_t nw, int64_t in_stride, int n_streams, double* out,
+int launch_loudness_range(double* rms, int64_t nw, int64_t in_stride, int n_streams, double* out,
                           int64_t out_stride, cudaStream_t st) {
   if (n_streams <= 0) return SONAR_OK;
-  if (nw > 4096) return set_error(SONAR_ERR_UNSUPPORTED, "loudness range supports at most 4096 windows");
+  if (nw > 4096) {
+    prof_begin("loudness_select_kernel", st);
+    loudness_select_kernel<<<n_streams, 256, 0, st>>>(rms, nw, in_stride, out, out_stride);
+    prof_end();
+    SONAR_CUDA(cudaGetLastError());
+    return SONAR_OK;
+  }
   int np2 = 1;
   while (np2 < nw) np2 <<= 1;
   prof_begin("loudness_range_kernel", st);

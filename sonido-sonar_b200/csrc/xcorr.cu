@@ -228,7 +228,27 @@ __global__ void __launch_bounds__(kFinThreads) xcorr_finalize_kernel(const Xcorr
   }
 }
 
+__global__ void xcorr_trim_kernel(const XcorrSeq* __restrict__ seqs, const XcorrPair* __restrict__ pairs,
+                                  const XcorrPairOut* __restrict__ outs, int n_pairs, const double** __restrict__ qptr,
+                                  const double** __restrict__ rptr) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const int64_t lag = outs[p].peak_index - pairs[p].aml;
+  qptr[p] = seqs[2 * p].in + (lag < 0 ? -lag : 0);
+  rptr[p] = seqs[2 * p + 1].in + (lag >= 0 ? lag : 0);
+}
+
 }  // namespace
+
+int launch_xcorr_trim(const XcorrSeq* seqs_dev, const XcorrPair* pairs_dev, const XcorrPairOut* outs_dev, int n_pairs,
+                      const double** qptr_dev, const double** rptr_dev, cudaStream_t st) {
+  if (n_pairs <= 0) return SONAR_OK;
+  prof_begin("xcorr_trim_kernel", st);
+  xcorr_trim_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(seqs_dev, pairs_dev, outs_dev, n_pairs, qptr_dev, rptr_dev);
+  prof_end();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
 
 int launch_znorm(const XcorrSeq* seqs_dev, int count, cudaStream_t st) {
   if (count <= 0) return SONAR_OK;

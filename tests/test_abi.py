@@ -45,7 +45,7 @@ def test_struct_layouts_match_the_c_compiler(capi, tmp_path):
         "sonar_xcorr_shard_peak": capi.XcorrShardPeak, "sonar_xcorr_shard_metrics": capi.XcorrShardMetrics,
         "sonar_align_result": capi.AlignResult, "sonar_dtw_out": capi.DtwOut, "sonar_cmp_features": capi.CmpFeatures,
         "sonar_cmp_weights": capi.CmpWeights, "sonar_cmp_result": capi.CmpResult,
-        "sonar_kernel_time": capi.KernelTime,
+        "sonar_kernel_time": capi.KernelTime, "sonar_pair_out": capi.PairOut,
     }
     body = "\n".join(f'  printf("{n} %zu\\n", sizeof({n}));' for n in structs)
     src = tmp_path / "sz.c"

@@ -124,3 +124,41 @@ def test_xcorr_lag_sharding_matches_whole(gpu, oracle, capi, synth):
         assert np.array_equal(corr, cw)
         for sh in shards:
             gpu.xcorr_shard_close(sh)
+
+
+def test_chained_pair_pipeline_equals_the_separate_calls(gpu, oracle, synth):
+    """sonar_align_pairs_f64 / _dev (fingerprint x2 -> NCC -> trim -> banded DTW, chained on the device) must
+    return exactly what the individual entry points return, and match the oracle's composition."""
+    import torch
+    p = gpu.default_params(algo_sample_rate=44100)
+    secs, max_lag_s, band = 12.0, 3.0, 50
+    pairs = [synth.aligned_pair(secs, offset_seconds=o, seed=40 + i) for i, o in enumerate((1.1, -0.7, 0.0, 2.4))]
+    qs, rs = [a for a, _ in pairs], [b for _, b in pairs]
+    got = gpu.align_pairs(qs, rs, p, max_lag_s, band)
+    ref = oracle.align_pairs(qs, rs, p, max_lag_s, band)
+    n = qs[0].size
+    nl, dl = gpu.align_pairs_sizes(p, n, max_lag_s)
+    assert (nl, dl) == oracle.align_pairs_sizes(p, n, max_lag_s)
+    for g, o, q, r in zip(got, ref, qs, rs):
+        fq, fr = gpu.fingerprint(q, p), gpu.fingerprint(r, p)
+        for k in fq.arrays:  # the chained call runs the same kernels: identical bits
+            assert np.array_equal(g["query"].arrays[k], fq.arrays[k]), k
+            assert np.array_equal(g["reference"].arrays[k], fr.arrays[k]), k
+        assert np.array_equal(g["corr"], o["corr"])  # bit-exact energies -> bit-exact correlations
+        check_summary(g["xcorr"], o["xcorr"])
+        assert g["corr_alignment"].offset == o["corr_alignment"].offset
+        assert g["dtw_length"] == o["dtw_length"] == dl
+        assert np.array_equal(g["path_query"], o["path_query"]) and np.array_equal(g["path_ref"], o["path_ref"])
+        assert np.array_equal(g["path_cost"], o["path_cost"], equal_nan=True)
+        assert g["total_cost"] == o["total_cost"]
+    # device-resident form
+    stride = (n + 1) & ~1
+    dev = torch.zeros((2 * len(qs), stride), dtype=torch.float64, device="cuda")
+    for i, (q, r) in enumerate(zip(qs, rs)):
+        dev[2 * i, :n] = torch.from_numpy(q).cuda()
+        dev[2 * i + 1, :n] = torch.from_numpy(r).cuda()
+    torch.cuda.synchronize()
+    got_dev = gpu.align_pairs_dev(dev.data_ptr(), n, stride, len(qs), p, max_lag_s, band)
+    for g, d in zip(got, got_dev):
+        assert g["xcorr"].peak_lag == d["xcorr"].peak_lag and np.array_equal(g["corr"], d["corr"])
+        assert np.array_equal(g["path_query"], d["path_query"]) and np.array_equal(g["path_ref"], d["path_ref"])

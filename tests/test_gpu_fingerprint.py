@@ -173,3 +173,16 @@ def test_kernel_launch_counter(gpu, synth):
     before = gpu.kernel_launches()
     gpu.fingerprint(synth.sweep_noise(1.0, seed=1), gpu.default_params(algo_sample_rate=44100))
     assert gpu.kernel_launches() > before
+
+
+def test_loudness_range_many_windows(gpu, oracle, synth):
+    """> 4096 loudness windows (long 16 kHz streams) take the radix-select path; same value as the oracle's sort."""
+    sr = 16000
+    # (11.2e6 - 6400) / 1600 + 1 = 6997 windows; loud enough for positive loudness units (-0.691 + 10 log10 e^2)
+    pcm = 20.0 * synth.speech_band_noise(700.0, sr=sr, seed=12)
+    p = gpu.default_params(window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=sr,
+                           call_sample_rate=sr)
+    a, b = gpu.fingerprint(pcm, p), oracle.fingerprint(pcm, p)
+    assert b.loudness_range > 0
+    assert a.loudness_range == pytest.approx(b.loudness_range, rel=1e-10)
+    assert np.array_equal(a.short_time_energy, b.short_time_energy)
