@@ -8,10 +8,11 @@
 // Everything between the H2D copy of a pair's PCM and the D2H copy of its results is enqueued on ONE stream
 // without a host round trip: the z-score kernels read the short-time energies straight out of the feature
 // blocks, a tiny kernel turns the detected lag into the trimmed start pointers the DTW kernels consume
-// (TruncateToAlignmentPCM's sign convention, alignment.go:239-243).  Eight pairs are in flight per device: three
-// PCM staging buffers feed the GPU-filling front half (fingerprint, NCC) on their own streams, and each pair's
-// latency-bound tail (one DTW warp, then the D2H copy) runs on a second stream, so the PCIe copy and the
-// kernels of the following pairs overlap it and the host-side scatter of finished pairs.
+// (TruncateToAlignmentPCM's sign convention, alignment.go:239-243).  Pairs travel in chunks (as many as fit a
+// 512 MB PCM staging buffer; all of them when the PCM is already resident), up to eight chunks in flight per
+// device: three staging buffers feed the GPU-filling front half (fingerprint, NCC) on their own streams, and each
+// chunk's latency-bound tail (one DTW warp per pair, then the D2H copy) runs on a second stream, so the PCIe copy
+// and the kernels of the following chunks overlap it and the host-side scatter of finished chunks.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -32,19 +33,7 @@ struct PairGeom {
   int band = 0;
   DtwGeom g{};
   int64_t path_cap = 0;
-  // per-pair scratch layout in d_tmp (doubles unless noted)
-  size_t fp_tmp = 0, z = 0, corr = 0, cells = 0, desc_bytes = 0, total_bytes = 0;
-  // per-pair result layout in d_out / h_out (bytes)
-  size_t feat_bytes = 0, res_off = 0, res_bytes = 0;
-};
-
-struct PairDesc {  // device-side descriptors of one pair, packed behind its scratch
-  XcorrSeq seqs[2];
-  XcorrPair pair;
-  XcorrPairOut xo;
-  DtwPairOut dout;
-  const double* qptr;
-  const double* rptr;
+  size_t z_pair = 0, corr_pair = 0;  // doubles per pair (even)
 };
 
 inline size_t up(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -69,106 +58,124 @@ int pair_geometry(const sonar_fp_params* p, int64_t n, double max_lag_seconds, i
   G->path_cap = 2 * (int64_t)G->dtw_len;
   if (sizeof(double) * (size_t)(G->g.n_off + 2) > 140 * 1024)
     return set_error(SONAR_ERR_UNSUPPORTED, "sonar_align_pairs needs a Sakoe-Chiba band (dtw_band > 0) for long streams");
-  G->fp_tmp = 2 * G->sh.tmp_doubles_per_stream;
-  G->z = 2 * (size_t)((G->Te + 1) & ~(int64_t)1);
-  G->corr = (size_t)((G->nl + 1) & ~(int64_t)1);
-  G->cells = (size_t)G->g.cells;
-  G->desc_bytes = up(sizeof(PairDesc));
-  G->total_bytes = up(sizeof(double) * (G->fp_tmp + G->z + G->corr + G->cells)) + G->desc_bytes;
-  G->feat_bytes = up(sizeof(double) * 2 * (size_t)G->sh.L.total);
-  // results: corr | path_c (double) | path_q, path_r (int32) | PairDesc copy (xo + dout)
-  G->res_off = G->feat_bytes;
-  G->res_bytes = up(sizeof(double) * G->corr) + up(sizeof(double) * (size_t)G->path_cap) +
-                 up(sizeof(int32_t) * 2 * (size_t)G->path_cap) + up(sizeof(PairDesc));
+  G->z_pair = 2 * (size_t)((G->Te + 1) & ~(int64_t)1);
+  G->corr_pair = (size_t)((G->nl + 1) & ~(int64_t)1);
   return SONAR_OK;
 }
 
-struct PairDevPtrs {
-  double* feat;     // 2 feature blocks
-  double* fp_tmp;
-  double* z;
-  double* corr;
-  double* cells;
-  PairDesc* desc;
-  double* path_c;
-  int32_t* path_q;
-  int32_t* path_r;
+// Byte layout of one chunk of C pairs: scratch (d_tmp) and results (d_out, mirrored in pinned h_out).
+struct ChunkLayout {
+  int C = 0;
+  // d_tmp
+  size_t t_fp = 0, t_z = 0, t_cells = 0, tmp_bytes = 0;
+  // d_out / h_out
+  size_t o_feat = 0, o_corr = 0, o_pc = 0, o_pq = 0, o_pr = 0, o_seqs = 0, o_pairs = 0, o_xo = 0, o_dout = 0, o_qptr = 0,
+         o_rptr = 0, out_bytes = 0;
 };
 
-// Front half of ONE pair on `st`: fingerprint -> NCC -> trim (these kernels fill the GPU).  The PCM (query at
-// pcm_dev, reference at pcm_dev + stride) is already on the device or queued on the same stream.
-int enqueue_pair_front(sonar_ctx* ctx, int device, const sonar_fp_params* p, const PairGeom& G, const double* pcm_dev,
-                       const PairDevPtrs& d, cudaStream_t st) {
-  int rc = enqueue_fingerprint(ctx, device, p, G.sh, pcm_dev, G.n, G.stride, 2, d.feat, d.fp_tmp, st);
+ChunkLayout chunk_layout(const PairGeom& G, int C) {
+  ChunkLayout L;
+  L.C = C;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t r = o;
+    o += up(bytes);
+    return r;
+  };
+  L.t_fp = take(sizeof(double) * 2 * (size_t)C * G.sh.tmp_doubles_per_stream);
+  L.t_z = take(sizeof(double) * (size_t)C * G.z_pair);
+  L.t_cells = take(sizeof(double) * (size_t)C * (size_t)G.g.cells);
+  L.tmp_bytes = o;
+  o = 0;
+  L.o_feat = take(sizeof(double) * 2 * (size_t)C * (size_t)G.sh.L.total);
+  L.o_corr = take(sizeof(double) * (size_t)C * G.corr_pair);
+  L.o_pc = take(sizeof(double) * (size_t)C * (size_t)G.path_cap);
+  L.o_pq = take(sizeof(int32_t) * (size_t)C * (size_t)G.path_cap);
+  L.o_pr = take(sizeof(int32_t) * (size_t)C * (size_t)G.path_cap);
+  L.o_seqs = take(sizeof(XcorrSeq) * 2 * (size_t)C);
+  L.o_pairs = take(sizeof(XcorrPair) * (size_t)C);
+  L.o_xo = take(sizeof(XcorrPairOut) * (size_t)C);
+  L.o_dout = take(sizeof(DtwPairOut) * (size_t)C);
+  L.o_qptr = take(sizeof(double*) * (size_t)C);
+  L.o_rptr = take(sizeof(double*) * (size_t)C);
+  L.out_bytes = o;
+  return L;
+}
+
+template <class T>
+T* at(void* base, size_t off) {
+  return reinterpret_cast<T*>(static_cast<unsigned char*>(base) + off);
+}
+template <class T>
+const T* at(const void* base, size_t off) {
+  return reinterpret_cast<const T*>(static_cast<const unsigned char*>(base) + off);
+}
+
+// Front half of a chunk of c pairs on `st`: fingerprint of the 2c streams -> NCC -> trim (these kernels fill the
+// GPU).  Stream 2i is pair i's query, 2i+1 its reference, `stride` apart starting at pcm_dev.
+int enqueue_front(sonar_ctx* ctx, int device, const sonar_fp_params* p, const PairGeom& G, const ChunkLayout& L, int c,
+                  const double* pcm_dev, void* d_tmp, void* d_out, cudaStream_t st) {
+  double* feat = at<double>(d_out, L.o_feat);
+  int rc = enqueue_fingerprint(ctx, device, p, G.sh, pcm_dev, G.n, G.stride, 2 * c, feat, at<double>(d_tmp, L.t_fp), st);
   if (rc) return rc;
-  PairDesc h;
-  std::memset(&h, 0, sizeof(h));
-  const double* ea = d.feat + G.sh.L.short_time_energy;
-  const double* eb = d.feat + G.sh.L.total + G.sh.L.short_time_energy;
-  double* za = d.z;
-  double* zb = d.z + G.z / 2;
-  h.seqs[0] = XcorrSeq{ea, za, G.Te};
-  h.seqs[1] = XcorrSeq{eb, zb, G.Te};
-  h.pair = XcorrPair{za, zb, d.corr, G.Te, G.Te, 0, G.nl, G.aml, 0};
-  SONAR_CUDA(cudaMemcpyAsync(d.desc, &h, sizeof(h), cudaMemcpyHostToDevice, st));  // pageable source: staged before return
-  if ((rc = launch_znorm(d.desc->seqs, 2, st))) return rc;
-  if ((rc = launch_xcorr(&d.desc->pair, 1, G.nl, st))) return rc;
-  if ((rc = launch_xcorr_finalize(&d.desc->pair, 1, -1, &d.desc->xo, st))) return rc;
-  return launch_xcorr_trim(d.desc->seqs, &d.desc->pair, &d.desc->xo, 1, &d.desc->qptr, &d.desc->rptr, st);
+  std::vector<XcorrSeq> seqs(2 * (size_t)c);
+  std::vector<XcorrPair> pairs(c);
+  double* z = at<double>(d_tmp, L.t_z);
+  double* corr = at<double>(d_out, L.o_corr);
+  for (int i = 0; i < c; i++) {
+    const double* ea = feat + (size_t)(2 * i) * G.sh.L.total + G.sh.L.short_time_energy;
+    const double* eb = feat + (size_t)(2 * i + 1) * G.sh.L.total + G.sh.L.short_time_energy;
+    double* za = z + (size_t)i * G.z_pair;
+    double* zb = za + G.z_pair / 2;
+    seqs[2 * i] = XcorrSeq{ea, za, G.Te};
+    seqs[2 * i + 1] = XcorrSeq{eb, zb, G.Te};
+    pairs[i] = XcorrPair{za, zb, corr + (size_t)i * G.corr_pair, G.Te, G.Te, 0, G.nl, G.aml, 0};
+  }
+  XcorrSeq* d_seqs = at<XcorrSeq>(d_out, L.o_seqs);
+  XcorrPair* d_pairs = at<XcorrPair>(d_out, L.o_pairs);
+  XcorrPairOut* d_xo = at<XcorrPairOut>(d_out, L.o_xo);
+  // pageable sources: staged by the runtime before these calls return
+  SONAR_CUDA(cudaMemcpyAsync(d_seqs, seqs.data(), sizeof(XcorrSeq) * seqs.size(), cudaMemcpyHostToDevice, st));
+  SONAR_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(XcorrPair) * pairs.size(), cudaMemcpyHostToDevice, st));
+  if ((rc = launch_znorm(d_seqs, 2 * c, st))) return rc;
+  if ((rc = launch_xcorr(d_pairs, c, G.nl, st))) return rc;
+  if ((rc = launch_xcorr_finalize(d_pairs, c, -1, d_xo, st))) return rc;
+  return launch_xcorr_trim(d_seqs, d_pairs, d_xo, c, at<const double*>(d_out, L.o_qptr), at<const double*>(d_out, L.o_rptr),
+                           st);
 }
 
-// Tail of the pair on `st`: the banded DTW is a single latency-bound warp, so it runs on the lane's second
-// stream where it overlaps the front halves of the following pairs.
-int enqueue_pair_tail(const PairGeom& G, const PairDevPtrs& d, cudaStream_t st) {
-  return launch_dtw(nullptr, nullptr, 1, G.g, 1, SONAR_STEP_SYMMETRIC2, d.cells, nullptr, d.path_q, d.path_r, d.path_c,
-                    G.path_cap, &d.desc->dout, st, &d.desc->qptr, &d.desc->rptr);
+// Tail of the chunk on `st`: the banded DTWs are single latency-bound warps, so they run on the lane's second
+// stream where they overlap the front halves of the following chunks.
+int enqueue_tail(const PairGeom& G, const ChunkLayout& L, int c, void* d_tmp, void* d_out, cudaStream_t st) {
+  return launch_dtw(nullptr, nullptr, c, G.g, 1, SONAR_STEP_SYMMETRIC2, at<double>(d_tmp, L.t_cells), nullptr,
+                    at<int32_t>(d_out, L.o_pq), at<int32_t>(d_out, L.o_pr), at<double>(d_out, L.o_pc), G.path_cap,
+                    at<DtwPairOut>(d_out, L.o_dout), st, at<const double*>(d_out, L.o_qptr),
+                    at<const double*>(d_out, L.o_rptr));
 }
 
-PairDevPtrs carve(const PairGeom& G, unsigned char* tmp, unsigned char* out) {
-  PairDevPtrs d;
-  double* t = reinterpret_cast<double*>(tmp);
-  d.fp_tmp = t;
-  d.z = t + G.fp_tmp;
-  d.corr = nullptr;  // lives in the result block
-  d.cells = t + G.fp_tmp + G.z;
-  d.desc = reinterpret_cast<PairDesc*>(tmp + up(sizeof(double) * (G.fp_tmp + G.z + G.corr + G.cells)));
-  d.feat = reinterpret_cast<double*>(out);
-  unsigned char* r = out + G.res_off;
-  d.corr = reinterpret_cast<double*>(r);
-  r += up(sizeof(double) * G.corr);
-  d.path_c = reinterpret_cast<double*>(r);
-  r += up(sizeof(double) * (size_t)G.path_cap);
-  d.path_q = reinterpret_cast<int32_t*>(r);
-  d.path_r = d.path_q + G.path_cap;
-  return d;
-}
-
-// host side of one finished pair: h = pinned copy of the pair's result block (features | results | descriptor)
-int finish_pair(const sonar_fp_params* p, const PairGeom& G, const unsigned char* h, bool have_features,
+// host side of pair i of a finished chunk: h = pinned copy of the chunk's result block
+int finish_pair(const sonar_fp_params* p, const PairGeom& G, const ChunkLayout& L, const void* h, int i, bool feat,
                 sonar_pair_out* o) {
-  if (have_features) {
-    const double* f = reinterpret_cast<const double*>(h);
+  if (feat) {
+    const double* f = at<double>(h, L.o_feat) + (size_t)(2 * i) * G.sh.L.total;
     scatter_block(f, G.sh, &o->query);
     scatter_block(f + G.sh.L.total, G.sh, &o->reference);
   }
-  const unsigned char* r = h + G.res_off;
-  const double* corr = reinterpret_cast<const double*>(r);
-  r += up(sizeof(double) * G.corr);
-  const double* pc = reinterpret_cast<const double*>(r);
-  r += up(sizeof(double) * (size_t)G.path_cap);
-  const int32_t* pq = reinterpret_cast<const int32_t*>(r);
-  const int32_t* pr = pq + G.path_cap;
-  r += up(sizeof(int32_t) * 2 * (size_t)G.path_cap);
-  const PairDesc* d = reinterpret_cast<const PairDesc*>(r);
-  summarize_xcorr(d->xo, G.aml, G.Te, G.Te, G.nl, &o->xcorr);
+  const double* corr = at<double>(h, L.o_corr) + (size_t)i * G.corr_pair;
+  const double* pc = at<double>(h, L.o_pc) + (size_t)i * G.path_cap;
+  const int32_t* pq = at<int32_t>(h, L.o_pq) + (size_t)i * G.path_cap;
+  const int32_t* pr = at<int32_t>(h, L.o_pr) + (size_t)i * G.path_cap;
+  const XcorrPairOut& xo = at<XcorrPairOut>(h, L.o_xo)[i];
+  const DtwPairOut& dout = at<DtwPairOut>(h, L.o_dout)[i];
+  summarize_xcorr(xo, G.aml, G.Te, G.Te, G.nl, &o->xcorr);
   fill_align_from_xcorr(&o->xcorr, G.Te, G.Te, G.aml, p->energy_hop, p->call_sample_rate, &o->corr_alignment);
   if (o->corr) std::memcpy(o->corr, corr, sizeof(double) * (size_t)G.nl);
   o->dtw_length = G.dtw_len;
   sonar_dtw_out& w = o->dtw;
-  const int64_t len = d->dout.path_len;
+  const int64_t len = dout.path_len;
   w.path_len = len;
-  w.total_cost = d->dout.total_cost;
-  w.distance = d->dout.total_cost / (double)len;
+  w.total_cost = dout.total_cost;
+  w.distance = dout.total_cost / (double)len;
   const int64_t take = std::min<int64_t>(len, w.path_cap);
   const int64_t off = G.path_cap - len;
   if (take > 0) {
@@ -186,7 +193,21 @@ struct DevJob {
   std::string err;
 };
 
-// pcm_q / pcm_r: host pointers (host_pcm) or device pointers on this device
+bool wants_features(const sonar_fp_out& o) {
+  const double* const ptrs[] = {o.mfcc, o.spectral_centroid, o.spectral_rolloff, o.spectral_bandwidth,
+                                o.spectral_flatness, o.spectral_crest, o.spectral_slope, o.spectral_flux,
+                                o.zero_crossing_rate, o.short_time_energy, o.energy_entropy, o.low_energy_ratio,
+                                o.high_energy_ratio, o.pitch_estimate, o.pitch_confidence, o.voicing_strength,
+                                o.harmonic_ratio, o.inharmonicity_ratio, o.tonal_centroid};
+  for (const double* q : ptrs)
+    if (q) return true;
+  return false;
+}
+
+constexpr size_t kPairChunkBytes = (size_t)512 << 20;  // host PCM bytes staged per chunk
+
+// pcm_q / pcm_r: host pointers (host_pcm) or, device-resident, pcm_q[i] = device pointer of pair i's query with the
+// reference `stride` behind it and consecutive pairs 2*stride apart.
 void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, const double* const* pcm_r,
                       const std::vector<int>* ids, const sonar_fp_params* p, const PairGeom* Gp, bool host_pcm,
                       sonar_pair_out* outs, DevJob* job) {
@@ -198,63 +219,89 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
   };
   cudaError_t e = cudaSetDevice(dev->device);
   if (e != cudaSuccess) return fail(cuda_error(e, "cudaSetDevice"));
-  constexpr int NL = DevCtx::kSlots;       // lanes: result + scratch buffers, second stream, one pair in flight each
+  constexpr int NL = DevCtx::kSlots;       // lanes: result + scratch buffers, second stream, one chunk in flight each
   constexpr int NP = DevCtx::kStageSlots;  // PCM staging buffers + front-half streams
-  int pending[NL];
-  for (int& x : pending) x = -1;
-  const size_t out_bytes = G.feat_bytes + G.res_bytes;
+  const int total = (int)ids->size();
+  // pairs per chunk: host path = what fits the staging budget (the PCIe copy of the next chunk overlaps this one);
+  // device-resident = contiguous runs as large as possible (batched launches hide the latency-bound kernels)
+  int C = host_pcm ? (int)std::max<size_t>(1, kPairChunkBytes / (sizeof(double) * 2 * (size_t)G.stride)) : 32;
+  C = std::min(C, total);
+  const ChunkLayout L = chunk_layout(G, C);
+  struct Pending {
+    int first = -1, count = 0;
+    bool feat = false;
+  } pending[NL];
   auto finish = [&](int li) -> int {
-    if (pending[li] < 0) return SONAR_OK;
+    if (pending[li].first < 0) return SONAR_OK;
     Slot& s = dev->slot[li];
     SONAR_CUDA(cudaEventSynchronize(s.done));
-    const int id = pending[li];
-    pending[li] = -1;
-    return finish_pair(p, G, static_cast<const unsigned char*>(s.h_out.p), true, &outs[id]);
+    const Pending pd = pending[li];
+    pending[li].first = -1;
+    for (int i = 0; i < pd.count; i++) {
+      int rc = finish_pair(p, G, L, s.h_out.p, i, pd.feat, &outs[(*ids)[pd.first + i]]);
+      if (rc) return rc;
+    }
+    return SONAR_OK;
   };
   int k = 0;
-  for (int id : *ids) {
+  for (int first = 0; first < total; ++k) {
+    int c = std::min(C, total - first);
+    if (!host_pcm)  // a device-resident chunk must be contiguous in the caller's layout
+      for (int i = 1; i < c; i++)
+        if (pcm_q[(*ids)[first + i]] != pcm_q[(*ids)[first]] + (int64_t)2 * i * G.stride) {
+          c = i;
+          break;
+        }
     const int li = k % NL, pi = k % NP;
-    ++k;
     Slot& lane = dev->slot[li];
     Slot& stage = dev->slot[pi];
     int rc = finish(li);
     if (rc) return fail(rc);
-    if ((host_pcm && (rc = dev->ensure_dev(stage.d_in, sizeof(double) * 2 * (size_t)G.stride))) ||
-        (rc = dev->ensure_dev(lane.d_tmp, G.total_bytes)) || (rc = dev->ensure_dev(lane.d_out, out_bytes)) ||
-        (rc = dev->ensure_host(lane.h_out, out_bytes)))
+    if ((host_pcm && (rc = dev->ensure_dev(stage.d_in, sizeof(double) * 2 * (size_t)C * (size_t)G.stride))) ||
+        (rc = dev->ensure_dev(lane.d_tmp, L.tmp_bytes)) || (rc = dev->ensure_dev(lane.d_out, L.out_bytes)) ||
+        (rc = dev->ensure_host(lane.h_out, L.out_bytes)))
       return fail(rc);
     const double* pcm_dev;
     if (host_pcm) {
-      // the staging buffer's previous user (pair k - NP) ran its fingerprint kernels on this same stream: ordered
+      // the staging buffer's previous user (chunk k - NP) ran its fingerprint kernels on this same stream: ordered
       double* d_in = static_cast<double*>(stage.d_in.p);
-      if ((e = cudaMemcpyAsync(d_in, pcm_q[id], sizeof(double) * (size_t)G.n, cudaMemcpyHostToDevice, stage.st)) !=
-              cudaSuccess ||
-          (e = cudaMemcpyAsync(d_in + G.stride, pcm_r[id], sizeof(double) * (size_t)G.n, cudaMemcpyHostToDevice,
-                               stage.st)) != cudaSuccess)
-        return fail(cuda_error(e, "cudaMemcpyAsync(H2D pcm)"));
+      for (int i = 0; i < c; i++) {
+        const int id = (*ids)[first + i];
+        if ((e = cudaMemcpyAsync(d_in + (int64_t)(2 * i) * G.stride, pcm_q[id], sizeof(double) * (size_t)G.n,
+                                 cudaMemcpyHostToDevice, stage.st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(d_in + (int64_t)(2 * i + 1) * G.stride, pcm_r[id], sizeof(double) * (size_t)G.n,
+                                 cudaMemcpyHostToDevice, stage.st)) != cudaSuccess)
+          return fail(cuda_error(e, "cudaMemcpyAsync(H2D pcm)"));
+      }
       pcm_dev = d_in;
     } else {
-      pcm_dev = pcm_q[id];  // device-resident: query and reference adjacent, `stride` apart
+      pcm_dev = pcm_q[(*ids)[first]];
     }
-    const PairDevPtrs d = carve(G, static_cast<unsigned char*>(lane.d_tmp.p), static_cast<unsigned char*>(lane.d_out.p));
-    rc = enqueue_pair_front(ctx, dev->device, p, G, pcm_dev, d, stage.st);
+    rc = enqueue_front(ctx, dev->device, p, G, L, c, pcm_dev, lane.d_tmp.p, lane.d_out.p, stage.st);
     if (rc) return fail(rc);
     if ((e = cudaEventRecord(lane.mid, stage.st)) != cudaSuccess ||
         (e = cudaStreamWaitEvent(lane.st2, lane.mid, 0)) != cudaSuccess)
       return fail(cuda_error(e, "cudaEventRecord/cudaStreamWaitEvent"));
-    rc = enqueue_pair_tail(G, d, lane.st2);
+    rc = enqueue_tail(G, L, c, lane.d_tmp.p, lane.d_out.p, lane.st2);
     if (rc) return fail(rc);
-    // results: features + corr + paths in one copy, then the descriptor block (xcorr partials, DTW totals)
-    unsigned char* h = static_cast<unsigned char*>(lane.h_out.p);
-    const size_t body = G.feat_bytes + G.res_bytes - up(sizeof(PairDesc));
-    if ((e = cudaMemcpyAsync(h, lane.d_out.p, body, cudaMemcpyDeviceToHost, lane.st2)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(h + body, d.desc, sizeof(PairDesc), cudaMemcpyDeviceToHost, lane.st2)) != cudaSuccess)
+    bool feat = false;  // the feature blocks only travel when somebody asked for a feature array
+    for (int i = 0; i < c && !feat; i++) {
+      const sonar_pair_out& o = outs[(*ids)[first + i]];
+      feat = wants_features(o.query) || wants_features(o.reference);
+    }
+    const size_t from = feat ? 0 : L.o_corr;
+    if ((e = cudaMemcpyAsync(static_cast<unsigned char*>(lane.h_out.p) + from,
+                             static_cast<unsigned char*>(lane.d_out.p) + from, L.out_bytes - from,
+                             cudaMemcpyDeviceToHost, lane.st2)) != cudaSuccess)
       return fail(cuda_error(e, "cudaMemcpyAsync(D2H results)"));
     if ((e = cudaEventRecord(lane.done, lane.st2)) != cudaSuccess) return fail(cuda_error(e, "cudaEventRecord"));
-    pending[li] = id;
+    pending[li].first = first;
+    pending[li].count = c;
+    pending[li].feat = feat;
+    first += c;
   }
   for (int j = 0; j < NL; j++) {
-    int rc = finish((k + j) % NL);
+    int rc = finish((k + j) % NL);  // oldest first: their host-side scatter overlaps the GPU work still queued
     if (rc) return fail(rc);
   }
 }
