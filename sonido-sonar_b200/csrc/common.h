@@ -105,6 +105,10 @@ struct FpShape {
   sonar_fp_dev_layout_t L;
   int64_t lr_win = 0, lr_hop = 0, lr_nw = 0;  // loudness-range windows (energy.go:157-179)
   size_t tmp_doubles_per_stream = 0;
+  // temporal group (only with SONAR_FP_ENABLE_TEMPORAL): two more arrays behind the public layout (L.total is
+  // bumped accordingly) and a partial-sum area in the scratch
+  bool temporal = false;
+  int64_t o_env = 0, o_att = 0, o_part = 0;
 };
 
 // ---- exact FP64 time-domain kernels (timedomain.cu) -------------------------
@@ -241,6 +245,10 @@ void scatter_block(const double* f, const FpShape& sh, sonar_fp_out* o);
 void summarize_xcorr(const XcorrPairOut& o, int aml, int64_t na, int64_t nb, int64_t n_eval, sonar_xcorr_summary* s);
 void fill_align_from_xcorr(const sonar_xcorr_summary* xc, int64_t nq, int64_t nr, int max_lag, int hop, int sr,
                            sonar_align_result* out);
-int fingerprint_temporal_tail(sonar_ctx* ctx, const double* const* pcm, const int64_t* n, int n_streams,
-                              const sonar_fp_params* p, sonar_fp_out* outs);
+// speech.go:370-408 temporal block (temporal.cu): scalars [2..6] of the stream's scalar area receive silence ratio,
+// peak / average amplitude, onset density and the onset count; attack times go to feat + o_att
+int launch_temporal(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, double* feat,
+                    int64_t feat_stride, int64_t o_energy, int64_t o_scalars, int64_t o_att, int64_t Te, double* tmp,
+                    int64_t tmp_stride, int64_t o_part, int call_sr, int algo_sr, int energy_hop, cudaStream_t st);
+int temporal_partials_doubles();
 }  // namespace sonar

@@ -72,6 +72,14 @@ int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s) {
     s->lr_nw = (n < s->lr_win || s->lr_win <= 0) ? 0 : (n - s->lr_win) / s->lr_hop + 1;
   }
   s->tmp_doubles_per_stream = (size_t)(2 * s->sz.n_pitch_frames + s->lr_nw + 2);
+  s->temporal = (p->enable & SONAR_FP_ENABLE_TEMPORAL) != 0;
+  if (s->temporal) {
+    s->o_env = s->L.total;
+    s->o_att = s->o_env + s->sz.n_envelope;
+    s->L.total = (s->o_att + s->sz.n_energy_frames + 1) & ~(int64_t)1;
+    s->o_part = (int64_t)s->tmp_doubles_per_stream;
+    s->tmp_doubles_per_stream += (size_t)temporal_partials_doubles();
+  }
   return SONAR_OK;
 }
 
@@ -175,6 +183,19 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
     if (rc) return rc;
   }
 
+  // temporal block (speech.go:370-408): envelope = 512/256 RMS of the pre-emphasised PCM, the rest in temporal.cu
+  if (sh.temporal) {
+    if (sh.sz.n_envelope > 0) {
+      rc = launch_rms_windows(pcm_dev, n, stride, ns, p->pre_emph_alpha, 512, 256, sh.sz.n_envelope, feat_dev + sh.o_env,
+                              L.total, st);
+      if (rc) return rc;
+    }
+    rc = launch_temporal(pcm_dev, n, stride, ns, p->pre_emph_alpha, feat_dev, L.total, L.short_time_energy, L.scalars,
+                         sh.o_att, Te, tmp_dev, tstride, sh.o_part, p->call_sample_rate, p->algo_sample_rate,
+                         p->energy_hop, st);
+    if (rc) return rc;
+  }
+
   // harmonic block (speech.go:464-509)
   const double* hann = reinterpret_cast<const double*>(blob + plan->off_hann);
   rc = launch_yin(pcm_dev, stride, ns, p->pre_emph_alpha, p->algo_sample_rate, Tp, hann, feat_dev, L.total,
@@ -216,6 +237,17 @@ void scatter_block(const double* f, const FpShape& sh, sonar_fp_out* o) {
   o->average_amplitude = 0;
   o->onset_density = 0;
   o->n_attack_time = 0;
+  if (sh.temporal) {  // extractTemporalFeatures (speech.go:370-408)
+    cp(o->rms_energy, L.short_time_energy, Te);  // RMSEnergy is the same ComputeShortTimeEnergy call
+    cp(o->envelope_shape, sh.o_env, sh.sz.n_envelope);
+    o->dynamic_range = o->loudness_range;  // ComputeLoudnessRange again
+    o->silence_ratio = f[L.scalars + 2];
+    o->peak_amplitude = f[L.scalars + 3];
+    o->average_amplitude = f[L.scalars + 4];
+    o->onset_density = f[L.scalars + 5];
+    o->n_attack_time = (int64_t)f[L.scalars + 6];
+    cp(o->attack_time, sh.o_att, std::min<int64_t>(o->n_attack_time, o->attack_time_cap));
+  }
 }
 
 namespace {
@@ -336,10 +368,6 @@ int sonar_fingerprint_batch_f64(sonar_ctx* ctx, const double* const* pcm, const 
   }
   for (auto& j : jobs)
     if (j.rc) return set_error(j.rc, j.err);
-  if (p->enable & SONAR_FP_ENABLE_TEMPORAL) {
-    rc = fingerprint_temporal_tail(ctx, pcm, n, n_streams, p, outs);
-    if (rc) return rc;
-  }
   return SONAR_OK;
 }
 

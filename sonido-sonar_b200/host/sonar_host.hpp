@@ -187,11 +187,16 @@ struct EnergyFeatures {  // features.go:97-110
 struct HarmonicFeatures {  // features.go:115-124
   std::vector<double> PitchEstimate, PitchConfidence, VoicingStrength, HarmonicRatio, InharmonicityRatio, TonalCentroid;
 };
+struct TemporalFeatures {  // features.go:70-92
+  std::vector<double> RMSEnergy, AttackTime, EnvelopeShape;
+  double DynamicRange = 0, SilenceRatio = 0, PeakAmplitude = 0, AverageAmplitude = 0, OnsetDensity = 0;
+};
 struct ExtractedFeatures {  // features.go:5-27
   std::vector<std::vector<double>> MFCC, ChromaFeatures;
   std::shared_ptr<extractors::SpectralFeatures> SpectralFeatures;
   std::shared_ptr<extractors::EnergyFeatures> EnergyFeatures;
   std::shared_ptr<extractors::HarmonicFeatures> HarmonicFeatures;
+  std::shared_ptr<extractors::TemporalFeatures> TemporalFeatures;
   std::map<std::string, std::string> ExtractionMetadata;
 };
 
@@ -231,9 +236,10 @@ class SpeechFeatureExtractor : public FeatureExtractor {
     p.n_mfcc = config_.MFCCCoefficients;  // spectral.NewMFCC(sr, n): n <= 0 -> 13
     p.enable = 0;
     if (config_.EnableMFCC) p.enable |= SONAR_FP_ENABLE_MFCC;
-    // EnableTemporalFeatures / EnableSpeechFeatures (news, talk): both groups are non-fatal in the reference
-    // ("Continuing without ...", speech.go:181-211).  They are SURVEY §8 f1 / out-of-scope rows and not built
-    // on the GPU path yet, so the fingerprint is produced without them and the metadata says so.
+    if (config_.EnableTemporalFeatures) p.enable |= SONAR_FP_ENABLE_TEMPORAL;  // speech.go:201-211
+    // EnableSpeechFeatures (news, talk): LPC / formant / voice-quality analysis is host-side Go outside this
+    // path's scope; the group is non-fatal in the reference ("Continuing without speech features",
+    // speech.go:181-188), so the fingerprint is produced without it and the metadata says so.
     return p;
   }
   Result<ExtractedFeatures> ExtractFeatures(const analyzers::SpectrogramResult* spectrogram,
@@ -261,8 +267,18 @@ class SpeechFeatureExtractor : public FeatureExtractor {
     for (auto* v : {&hf->PitchEstimate, &hf->PitchConfidence, &hf->VoicingStrength, &hf->HarmonicRatio,
                     &hf->InharmonicityRatio, &hf->TonalCentroid})
       v->assign(Tp, 0.0);
+    auto tf = std::make_shared<extractors::TemporalFeatures>();
     sonar_fp_out o;
     std::memset(&o, 0, sizeof(o));
+    if (config_.EnableTemporalFeatures) {
+      tf->RMSEnergy.assign(Te, 0.0);
+      tf->EnvelopeShape.assign((size_t)sz.n_envelope, 0.0);
+      tf->AttackTime.assign(Te > 0 ? Te : 1, 0.0);
+      o.rms_energy = tf->RMSEnergy.data();
+      o.envelope_shape = tf->EnvelopeShape.data();
+      o.attack_time = tf->AttackTime.data();
+      o.attack_time_cap = (int64_t)tf->AttackTime.size();
+    }
     o.mfcc = mfcc.data();
     o.spectral_centroid = sf->SpectralCentroid.data();
     o.spectral_rolloff = sf->SpectralRolloff.data();
@@ -294,6 +310,12 @@ class SpeechFeatureExtractor : public FeatureExtractor {
     f->SpectralFeatures = sf;  // unconditional in the reference (speech.go:193,215,224)
     f->EnergyFeatures = ef;
     f->HarmonicFeatures = hf;
+    if (config_.EnableTemporalFeatures) {
+      tf->AttackTime.resize((size_t)o.n_attack_time);
+      tf->DynamicRange = o.dynamic_range, tf->SilenceRatio = o.silence_ratio, tf->PeakAmplitude = o.peak_amplitude;
+      tf->AverageAmplitude = o.average_amplitude, tf->OnsetDensity = o.onset_density;
+      f->TemporalFeatures = tf;
+    }
     f->ExtractionMetadata = {{"extractor_type", "speech"},  // speech.go:233-239
                              {"content_subtype", isNews_ ? "news" : "talk"},
                              {"algorithms_used", "speech,spectral,temporal,filters,tonal"},
@@ -302,7 +324,6 @@ class SpeechFeatureExtractor : public FeatureExtractor {
                              {"spectrogram_frames", std::to_string(spectrogram->TimeFrames)},
                              {"optimization", "speech_optimized"},
                              {"backend", sonar_backend()}};
-    if (config_.EnableTemporalFeatures) f->ExtractionMetadata["temporal_features"] = "skipped: not built on the GPU path yet";
     if (config_.EnableSpeechFeatures) f->ExtractionMetadata["speech_features"] = "skipped: outside the GPU path's scope";
     return Result<ExtractedFeatures>{f, ""};
   }
@@ -675,6 +696,12 @@ class FingerprintComparator {
       f.spectral_centroid = x.SpectralFeatures->SpectralCentroid.data(), f.n_centroid = (int64_t)x.SpectralFeatures->SpectralCentroid.size();
       f.spectral_rolloff = x.SpectralFeatures->SpectralRolloff.data(), f.n_rolloff = (int64_t)x.SpectralFeatures->SpectralRolloff.size();
       f.spectral_flux = x.SpectralFeatures->SpectralFlux.data(), f.n_flux = (int64_t)x.SpectralFeatures->SpectralFlux.size();
+    }
+    if (x.TemporalFeatures) {  // comparison.go:688-718
+      f.has_temporal = 1;
+      f.rms_energy = x.TemporalFeatures->RMSEnergy.data(), f.n_rms = (int64_t)x.TemporalFeatures->RMSEnergy.size();
+      f.dynamic_range = x.TemporalFeatures->DynamicRange, f.silence_ratio = x.TemporalFeatures->SilenceRatio;
+      f.onset_density = x.TemporalFeatures->OnsetDensity;
     }
     if (x.HarmonicFeatures) {
       f.has_harmonic = 1;

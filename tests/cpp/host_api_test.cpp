@@ -114,6 +114,24 @@ int main() {
     CHECK(al4.ok() && !al4->BestAlignment && al4->Method.empty());
   }
 
+  // ---- news content: temporal group on, speech group skipped, extractor reports "news"
+  {
+    transcode::AudioData nw = q;
+    nw.Metadata = std::make_shared<transcode::StreamMetadata>();
+    nw.Metadata->ContentType = "news";
+    auto fn = gen->GenerateFingerprint(&nw);
+    CHECK(fn.ok() && fn->ContentType == "news" && fn->Features->TemporalFeatures);
+    if (fn.ok() && fn->Features->TemporalFeatures) {
+      const auto& tfe = *fn->Features->TemporalFeatures;
+      CHECK(tfe.RMSEnergy == fn->Features->EnergyFeatures->ShortTimeEnergy);
+      CHECK(tfe.SilenceRatio > 0.09 && tfe.SilenceRatio < 0.12);  // sorted[T/10] threshold -> ~10 % + ties
+      CHECK(tfe.PeakAmplitude > tfe.AverageAmplitude && tfe.AverageAmplitude > 0);
+      CHECK(tfe.EnvelopeShape.size() == (size_t)((n - 512) / 256 + 1));
+      CHECK(fn->Features->ExtractionMetadata["content_subtype"] == "news");
+      CHECK(fn->Features->ExtractionMetadata.count("speech_features") == 1);
+    }
+  }
+
   // ---- compare (comparison.go:133-194)
   config::ComparisonConfig cc = config::DefaultComparisonConfig();
   auto cmp = fingerprint::NewFingerprintComparator(&cc);

@@ -186,3 +186,32 @@ def test_loudness_range_many_windows(gpu, oracle, synth):
     assert b.loudness_range > 0
     assert a.loudness_range == pytest.approx(b.loudness_range, rel=1e-10)
     assert np.array_equal(a.short_time_energy, b.short_time_energy)
+
+
+@pytest.mark.parametrize("algo_sr", [16000, 0])
+def test_temporal_feature_group(gpu, oracle, synth, capi, algo_sr):
+    """speech.go:370-408 (news / talk): silence ratio through an exact order statistic instead of the O(T^2)
+    bubble sort, onset peak-pick, attack times (NaN / 0.1 artefacts of sampleRate = 0 included), 512/256 envelope."""
+    sr = 16000
+    rng = np.random.default_rng(5)  # noise bursts with abrupt onsets over a quiet floor
+    n = 20 * sr
+    pcm = 0.02 * rng.standard_normal(n)
+    t = 0
+    while t < n:
+        on, off = int(rng.uniform(0.05, 0.2) * sr), int(rng.uniform(0.2, 0.6) * sr)
+        if t + on <= n:
+            pcm[t:t + on] += rng.uniform(0.2, 0.8) * rng.standard_normal(on)
+        t += on + off
+    kw = dict(window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=algo_sr,
+              call_sample_rate=sr, enable=capi.FP_ENABLE_MFCC | capi.FP_ENABLE_TEMPORAL)
+    a, b = gpu.fingerprint(pcm, gpu.default_params(**kw)), oracle.fingerprint(pcm, oracle.default_params(**kw))
+    check_fp(a, b)
+    assert b.n_attack_time > 5, "the case must contain onsets"
+    assert a.n_attack_time == b.n_attack_time
+    assert np.array_equal(a.rms_energy, b.rms_energy) and np.array_equal(a.rms_energy, a.short_time_energy)
+    np.testing.assert_allclose(a.envelope_shape, b.envelope_shape, rtol=1e-12)
+    assert np.array_equal(a.attack_time, b.attack_time, equal_nan=True)
+    for k in ("silence_ratio", "peak_amplitude", "dynamic_range"):
+        assert a.scalars[k] == b.scalars[k], k
+    for k in ("average_amplitude", "onset_density"):
+        assert a.scalars[k] == pytest.approx(b.scalars[k], rel=1e-12), k
