@@ -151,7 +151,7 @@ struct FftGeom {
   static constexpr int P1_ROUNDS = F / P1_FPR;
   static constexpr int XROW = R2 + 1;               // exchange row stride, float2 units
   static constexpr int XSLOT = R1 * XROW;
-  static constexpr int MAGROW = B + (B >> 5) + 2;   // padded magnitude row, floats
+  static constexpr int MAGROW = (B + (B >> 5) + 2 + 31) & ~31;  // padded magnitude row, floats (multiple of 32 banks)
   static_assert(R1 <= 32 && R2 <= 32 && F >= 1 && P1_ROUNDS >= 1, "unsupported geometry");
   SONAR_HD static int mag_index(int k) { return k + (k >> 5); }
 };

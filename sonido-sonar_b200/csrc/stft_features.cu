@@ -172,11 +172,12 @@ __host__ __device__ inline SmemLayout smem_layout(int n_mel, int n_mfcc, int n_r
     return r;
   };
   L.off_tw1 = take(sizeof(float2) * G::M);
-  L.off_xtab = take(sizeof(float) * (G::B + 1));
+  L.off_xtab = take(sizeof(float) * (G::B + (G::B >> 5) + 2));  // padded like a magnitude row (index k + (k >> 5))
   L.off_dct = take(sizeof(float) * (size_t)n_mfcc * (n_mel | 1));
   L.off_lift = take(sizeof(float) * n_mfcc);
   L.off_regions = take(sizeof(MelRegion) * n_regions);
   L.off_chunk = take(sizeof(int) * R1);
+  o = (o + 127) & ~(size_t)127;  // per-warp regions start on a bank-0 boundary
   L.off_warp = o;
   size_t w = 0;
   auto wtake = [&](size_t bytes) {
@@ -184,12 +185,18 @@ __host__ __device__ inline SmemLayout smem_layout(int n_mel, int n_mfcc, int n_r
     w += (bytes + 15) & ~(size_t)15;
     return r;
   };
+  // Phase B reads one magnitude row per slot with the same instruction; with two slots per warp (F == 2) slot 0
+  // reads a row of the exchange tile and slot 1 a carry row (or vice versa for the previous-frame rows).  The
+  // exchange tile starts on bank 0, every row is a multiple of 32 words long and the carry rows start on bank
+  // 16, so the two half-warps always hit disjoint halves of the banks.
   L.w_xbuf = wtake(sizeof(float2) * G::F * G::XSLOT);
+  w = ((w + 127) & ~(size_t)127) + 64;
   L.w_carry = wtake(sizeof(float) * 2 * G::MAGROW);
+  w = (w + 127) & ~(size_t)127;
   L.w_mel = wtake(sizeof(float) * G::F * (kMaxMel + 4));
   L.w_melpriv = wtake(sizeof(float) * 32 * kMelRow);  // one private row of mel partials per lane
-  L.per_warp = w;
-  L.total = o + w * kWarps;
+  L.per_warp = (w + 127) & ~(size_t)127;
+  L.total = o + L.per_warp * kWarps;
   return L;
 }
 
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(kWarps * 32, SONAR_STFT_MINBLOCKS) stft_kernel
   // ---- stage the tables -------------------------------------------------------
   for (int i = threadIdx.x; i < G::M; i += blockDim.x) s_tw1[i] = a.tw1[i];
   if (MODE == MODE_FEATURES) {
-    for (int i = threadIdx.x; i < G::B; i += blockDim.x) s_xtab[i] = a.xtab[i];
+    for (int i = threadIdx.x; i < G::B; i += blockDim.x) s_xtab[G::mag_index(i)] = a.xtab[i];
     const int nmp = a.n_mel | 1;
     for (int i = threadIdx.x; i < a.n_mfcc * a.n_mel; i += blockDim.x)
       s_dct[(i / a.n_mel) * nmp + (i % a.n_mel)] = a.dct[i];
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(kWarps * 32, SONAR_STFT_MINBLOCKS) stft_kernel
           const int idx = G::mag_index(k);
           const float m = mrow[idx];
           const float mp = prow[idx];
-          const float xv = s_xtab[k];
+          const float xv = s_xtab[idx];  // padded like the magnitude rows: the 16 lanes of a slot hit 16 banks
           const float p = m * m;
           const float kf = (float)k;
           while (k >= reg.next_b) {
