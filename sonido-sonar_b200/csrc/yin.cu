@@ -14,7 +14,10 @@
 // HarmonicFeatures arrays.
 #include <cmath>
 
+#include <cstdlib>
+
 #include "common.h"
+#include "fft_regs_f64.cuh"
 
 namespace sonar {
 namespace {
@@ -26,6 +29,79 @@ constexpr int kYinThreads = kYinFpb * kYinTpf;
 constexpr int kYinPad = kYinFrame + kYinFrame / 8 + 8;  // p[e] stored at e + (e >> 3): stride-8 reads hit distinct banks
 
 __device__ __forceinline__ int pidx(int e) { return e + (e >> 3); }
+
+// CMNDF + first dip below 0.15 + parabolic refinement (pitch_detection.go:363-420,743-764) of one frame by one
+// warp: d = the 512 difference-function values in shared memory, 16 lags per lane.
+template <int LS>  // LS = distance between the 16-lag runs of consecutive lanes (16, or 17 for padded rows)
+__device__ __forceinline__ void yin_pick(const double* __restrict__ d, int64_t f, int64_t Tp, int sr, int lane,
+                                         double* __restrict__ r) {
+  double dv[16], loc[16], run = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int tau = lane * 16 + k;
+    dv[k] = d[lane * LS + k];
+    run += tau >= 1 ? dv[k] : 0.0;
+    loc[k] = run;
+  }
+  double incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  const double base = incl - run;
+  double cm[17];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int tau = lane * 16 + k;
+    cm[k] = tau == 0 ? 1.0 : dv[k] / ((base + loc[k]) / (double)tau);
+  }
+  cm[16] = __shfl_down_sync(0xffffffffu, cm[0], 1);
+  int first = kYinHalf;
+#pragma unroll
+  for (int k = 15; k >= 0; --k) {
+    const int tau = lane * 16 + k;
+    if (tau >= 1 && tau + 1 < kYinHalf && cm[k] < 0.15 && cm[k] < cm[k + 1]) first = tau;
+  }
+  const int mt = __reduce_min_sync(0xffffffffu, first);
+  if (f >= Tp) return;
+  // the owner lane of mt has cm[mt-1..mt+1] at hand except across lane borders: fetch from shared d-derived values
+  const int owner = mt < kYinHalf ? mt / 16 : 0;
+  double y1 = 0.0, y2 = 0.0, y3 = 0.0;
+  if (mt < kYinHalf) {
+    const int k = mt % 16;
+    // cm[k-1] may live in the previous lane
+    double prev_last = __shfl_up_sync(0xffffffffu, cm[15], 1);
+    double c_m1 = 0.0, c_0 = 0.0, c_p1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (q == k) {
+        c_0 = cm[q];
+        c_p1 = cm[q + 1];
+        c_m1 = q > 0 ? cm[q - 1] : prev_last;
+      }
+    y1 = __shfl_sync(0xffffffffu, c_m1, owner);
+    y2 = __shfl_sync(0xffffffffu, c_0, owner);
+    y3 = __shfl_sync(0xffffffffu, c_p1, owner);
+  }
+  if (lane == 0) {
+    double pitch = 0.0, conf = 0.0;
+    if (mt < kYinHalf && mt > 0) {
+      double period = (double)mt;
+      if (!(mt <= 0 || mt >= kYinHalf - 1)) {  // parabolicInterpolation :743-764
+        const double a = (y1 - 2 * y2 + y3) / 2, b = (y3 - y1) / 2;
+        if (a != 0) period = (double)mt + (-b / (2 * a));
+      }
+      const double freq = (double)sr / period;
+      if (freq >= 80.0 && freq <= 1000.0) {
+        pitch = freq;
+        conf = 1.0 - y2;
+      }
+    }
+    r[f] = pitch;
+    r[Tp + f] = conf;
+  }
+}
 
 // Difference function through the autocorrelation identity
 //   d[tau] = sum_j (p[j] - p[j+tau])^2 = E(0) + E(tau) - 2 r[tau],
@@ -119,76 +195,324 @@ __global__ void __launch_bounds__(kYinThreads) yin_frame_kernel(const double* __
     }
   }
   __syncthreads();
-  // ---- CMNDF + first dip below 0.15 (pitch_detection.go:363-383): one warp per frame, 16 lags per lane
+  // ---- CMNDF + first dip below 0.15: one warp per frame
   const int wv = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (wv >= kYinFpb) return;
-  const int64_t f = f0 + wv;
-  const double* d = sd[wv];
-  double loc[16], run = 0.0;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int tau = lane * 16 + k;
-    run += tau >= 1 ? d[tau] : 0.0;
-    loc[k] = run;
+  yin_pick<16>(sd[wv], f0 + wv, Tp, sr, lane, raw + (int64_t)s * raw_stride);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FFT form of the same difference function (default path).
+//
+// r[tau] = sum_{j<512} p[j] p[j+tau] is the linear cross-correlation of a = p[0..512) (zero padded) with
+// b = p[0..1024), so r = IFFT(conj(A) B) with 1024-point transforms and no wrap-around (j + tau <= 1022).
+// Per frame: ONE complex forward FFT of z = a + i b (A and B fall out of the Hermitian split), and HALF an
+// inverse FFT — the spectra conj(A)B of two frames are packed as Q = P0 + i P1, whose inverse carries r of
+// frame 0 in its real part and r of frame 1 in its imaginary part.  ~66 k FP64 operations per frame
+// instead of 262 k DFMA.
+//
+// 1024 = 16 x 4 x 16, 64 threads per transform, data in shared memory as a 16 x 64 tile of double2
+// (row stride 68, one pad every 16 columns: every pass below is bank-conflict free):
+//   pass 1  column n2 (stride-64 elements): 16-point DFT over n1, twiddle W_1024^(n2 k1)
+//   pass 2a row k1, n2 = 16 m1 + m2:        4-point DFT over m1, twiddle W_64^(m2 j1)
+//   pass 2b row k1, fixed j1:               16-point DFT over m2
+// which leaves X[k1 + 16 j1 + 64 j2] at (row k1, column 16 j1 + j2).  The spectra are only multiplied
+// point-wise, so they stay in that digit-reversed order and the inverse runs the three passes backwards
+// (conjugate twiddle first, then the inverse butterflies), ending in natural order in registers.
+constexpr int kFRow = 68;
+constexpr int kFBuf = 16 * kFRow;  // double2 per transform
+constexpr int kFftFpb = 4;         // frames per CTA iteration (two packed pairs)
+constexpr int kFftThreads = 64 * kFftFpb;
+
+__device__ __forceinline__ int fpos(int row, int c) { return row * kFRow + c + (c >> 4); }
+__device__ __forceinline__ int kpos(int k) { return (k & 15) * kFRow + 17 * ((k >> 4) & 3) + (k >> 6); }
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int K>
+__device__ __forceinline__ void ld16(double2 (&v)[16], const double2* __restrict__ p, int stride) {
+  if constexpr (K < 16) {
+    v[K] = p[K * stride];
+    ld16<K + 1>(v, p, stride);
   }
-  double incl = run;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double up = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += up;
+}
+template <int K>
+__device__ __forceinline__ void st16(const double2 (&v)[16], double2* __restrict__ p, int stride) {
+  if constexpr (K < 16) {
+    p[K * stride] = v[K];
+    st16<K + 1>(v, p, stride);
   }
-  const double base = incl - run;
-  double cm[17];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int tau = lane * 16 + k;
-    cm[k] = tau == 0 ? 1.0 : d[tau] / ((base + loc[k]) / (double)tau);
+}
+template <int K>
+__device__ __forceinline__ void swap16(double2 (&v)[16]) {
+  if constexpr (K < 16) {
+    v[K] = dswap(v[K]);
+    swap16<K + 1>(v);
   }
-  cm[16] = __shfl_down_sync(0xffffffffu, cm[0], 1);
-  int first = kYinHalf;
-#pragma unroll
-  for (int k = 15; k >= 0; --k) {
-    const int tau = lane * 16 + k;
-    if (tau >= 1 && tau + 1 < kYinHalf && cm[k] < 0.15 && cm[k] < cm[k + 1]) first = tau;
+}
+
+// v[k] *= W_1024^(n2 k) (CONJ: the conjugate), k = 1..15.  Odd powers come from the table (conflict-free:
+// odd strides), even powers by squaring.
+template <bool CONJ>
+__device__ __forceinline__ void twiddle16(double2 (&v)[16], const double2* __restrict__ W, int n2) {
+  const double2 w1 = W[n2], w3 = W[3 * n2], w5 = W[5 * n2], w7 = W[7 * n2];
+  const double2 w2 = dsqr(w1), w6 = dsqr(w3), w10 = dsqr(w5), w14 = dsqr(w7);
+  const double2 w4 = dsqr(w2), w12 = dsqr(w6);
+  const double2 w8 = dsqr(w4);
+  const double2 w9 = W[9 * n2], w11 = W[11 * n2], w13 = W[13 * n2], w15 = W[15 * n2];
+#define SONAR_TW(K, WK) v[K] = CONJ ? dmul_conj(v[K], WK) : dmul(v[K], WK)
+  SONAR_TW(1, w1); SONAR_TW(2, w2); SONAR_TW(3, w3); SONAR_TW(4, w4); SONAR_TW(5, w5);
+  SONAR_TW(6, w6); SONAR_TW(7, w7); SONAR_TW(8, w8); SONAR_TW(9, w9); SONAR_TW(10, w10);
+  SONAR_TW(11, w11); SONAR_TW(12, w12); SONAR_TW(13, w13); SONAR_TW(14, w14); SONAR_TW(15, w15);
+#undef SONAR_TW
+}
+
+// forward transform of the tile Z by the 64 threads tf of barrier `bar`; result in digit-reversed order
+__device__ __forceinline__ void fft1024_fwd(double2* __restrict__ Z, const double2* __restrict__ W,
+                                            const double2* __restrict__ W64, int tf, int bar) {
+  {
+    double2 v[16];
+    ld16<0>(v, Z + tf + (tf >> 4), kFRow);
+    FftReg64<16>::run(v);
+    twiddle16<false>(v, W, tf);
+    st16<0>(v, Z + tf + (tf >> 4), kFRow);
   }
-  const int mt = __reduce_min_sync(0xffffffffu, first);
-  if (f >= Tp) return;
-  // the owner lane of mt has cm[mt-1..mt+1] at hand except across lane borders: fetch from shared d-derived values
-  const int owner = mt < kYinHalf ? mt / 16 : 0;
-  double y1 = 0.0, y2 = 0.0, y3 = 0.0;
-  if (mt < kYinHalf) {
-    const int k = mt % 16;
-    // cm[k-1] may live in the previous lane
-    double prev_last = __shfl_up_sync(0xffffffffu, cm[15], 1);
-    double c_m1 = 0.0, c_0 = 0.0, c_p1 = 0.0;
+  bar_sync(bar, 64);
+  {
+    const int m2 = tf & 15;
+    const double2 w1 = W64[m2], w3 = W64[3 * m2];
+    const double2 w2 = dsqr(w1);
 #pragma unroll
-    for (int q = 0; q < 16; ++q)
-      if (q == k) {
-        c_0 = cm[q];
-        c_p1 = cm[q + 1];
-        c_m1 = q > 0 ? cm[q - 1] : prev_last;
+    for (int q = 0; q < 4; ++q) {
+      double2* p = Z + ((tf >> 4) + 4 * q) * kFRow + m2;
+      double2 u[4] = {p[0], p[17], p[34], p[51]};
+      FftReg64<4>::run(u);
+      p[0] = u[0];
+      p[17] = dmul(u[1], w1);
+      p[34] = dmul(u[2], w2);
+      p[51] = dmul(u[3], w3);
+    }
+  }
+  bar_sync(bar, 64);
+  {
+    double2 v[16];
+    double2* p = Z + (tf >> 2) * kFRow + 17 * (tf & 3);
+    ld16<0>(v, p, 1);
+    FftReg64<16>::run(v);
+    st16<0>(v, p, 1);
+  }
+}
+
+// unscaled inverse of fft1024_fwd: digit-reversed spectrum in Q -> x[64 n1 + tf] in v[n1] (natural order)
+__device__ __forceinline__ void fft1024_inv(double2* __restrict__ Q, const double2* __restrict__ W,
+                                            const double2* __restrict__ W64, int tf, int bar, double2 (&v)[16]) {
+  {
+    double2* p = Q + (tf >> 2) * kFRow + 17 * (tf & 3);
+    ld16<0>(v, p, 1);
+    swap16<0>(v);  // IDFT(x) = swap(DFT(swap(x)))
+    FftReg64<16>::run(v);
+    swap16<0>(v);
+    st16<0>(v, p, 1);
+  }
+  bar_sync(bar, 64);
+  {
+    const int m2 = tf & 15;
+    const double2 w1 = W64[m2], w3 = W64[3 * m2];
+    const double2 w2 = dsqr(w1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double2* p = Q + ((tf >> 4) + 4 * q) * kFRow + m2;
+      double2 u[4] = {dswap(p[0]), dswap(dmul_conj(p[17], w1)), dswap(dmul_conj(p[34], w2)),
+                      dswap(dmul_conj(p[51], w3))};
+      FftReg64<4>::run(u);
+      p[0] = dswap(u[0]);
+      p[17] = dswap(u[1]);
+      p[34] = dswap(u[2]);
+      p[51] = dswap(u[3]);
+    }
+  }
+  bar_sync(bar, 64);
+  ld16<0>(v, Q + tf + (tf >> 4), kFRow);
+  twiddle16<true>(v, W, tf);
+  swap16<0>(v);
+  FftReg64<16>::run(v);
+  swap16<0>(v);
+}
+
+constexpr int kERow = kYinHalf + kYinHalf / 16;  // E / d rows: one pad double per 16 (16-lag runs per lane, no conflicts)
+__device__ __forceinline__ int epos(int tau) { return tau + (tau >> 4); }
+constexpr int kRawPair = 2 * kYinHop + kYinHop + 2;  // raw samples a pair of frames needs: 2 history + 1536
+
+__device__ __forceinline__ void cp_async8_zfill(double* smem_dst, const double* gmem_src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(n));
+}
+
+// Raw PCM of the pair of frames starting at frame fp of stream x -> `dst` (the pair's idle second tile), padded
+// by two doubles per 16 so that the 18-sample windows of the staging threads are conflict-free LDS.128 runs.
+// Issued by the 64 threads of the pair's second frame while the first frame's threads run the inverse FFT.
+__device__ __forceinline__ void prefetch_pair(double* __restrict__ dst, const double* __restrict__ x, int64_t fp,
+                                              int64_t limit, int tf) {
+  const int64_t g0 = fp * kYinHop - 2;
+  for (int j = tf; j < kRawPair; j += 64) {
+    const int64_t gi = g0 + j;
+    const bool ok = gi >= 0 && gi < limit;
+    cp_async8_zfill(dst + j + 2 * (j >> 4), x + (ok ? gi : 0), ok);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kFftThreads, 2)
+    yin_frame_fft_kernel(const double* __restrict__ pcm, int64_t stride, double alpha, int sr, int64_t Tp,
+                         int groups_per_stream, int64_t total_groups, const double* __restrict__ hann,
+                         double* __restrict__ raw, int64_t raw_stride) {
+  extern __shared__ __align__(16) double yin_smem[];
+  double2* sW = reinterpret_cast<double2*>(yin_smem);                         // W_1024^k
+  double2* sW64 = sW + 1024;                                                  // W_64^k
+  double2* sZ = sW64 + 64;                                                    // kFftFpb tiles
+  double (*sE)[kERow] = reinterpret_cast<double (*)[kERow]>(sZ + kFftFpb * kFBuf);  // E(tau), then d[tau]
+  const int tid = threadIdx.x;
+  const int fl = tid >> 6, tf = tid & 63;
+  const int pr = fl >> 1, hf = fl & 1, tp = tid & 127;
+  const int64_t limit = (Tp + 1) * kYinHop;  // samples [0, limit) belong to the Tp frames
+  for (int k = tid; k < 1024; k += kFftThreads) {
+    double sn, cs;
+    sincospi(-(double)k / 512.0, &sn, &cs);
+    sW[k] = make_double2(cs, sn);
+    if (k < 64) {
+      sincospi(-(double)k / 32.0, &sn, &cs);
+      sW64[k] = make_double2(cs, sn);
+    }
+  }
+  double2* Z = sZ + fl * kFBuf;
+  double* rawbuf = reinterpret_cast<double*>(sZ + (2 * pr + 1) * kFBuf);  // the pair's second tile
+  if (hf && blockIdx.x < total_groups) {
+    const int64_t grp = blockIdx.x;
+    prefetch_pair(rawbuf, pcm + (grp / groups_per_stream) * stride, (grp % groups_per_stream) * kFftFpb + 2 * pr, limit, tf);
+  }
+
+  for (int64_t grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+    const int s = (int)(grp / groups_per_stream);
+    const int64_t f0 = (grp % groups_per_stream) * kFftFpb;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // raw samples landed; previous iteration's CMNDF is done with sE
+    // ---- stage: thread tf of frame fl owns samples [16 tf, 16 tf + 16): stream-level pre-emphasis (speech.go:161),
+    //      the detector's own (pitch_detection.go:299-314), un-normalised Hann; exclusive prefix sums of p^2
+    double v[16], ex[16], run = 0.0;
+    {
+      double w[18];
+      const double2* rp = reinterpret_cast<const double2*>(rawbuf + 18 * (hf * 32 + tf));
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 t = rp[k < 8 ? k : 9];  // samples 16, 17 of the window sit behind the pad pair
+        w[2 * k] = t.x;
+        w[2 * k + 1] = t.y;
       }
-    y1 = __shfl_sync(0xffffffffu, c_m1, owner);
-    y2 = __shfl_sync(0xffffffffu, c_0, owner);
-    y3 = __shfl_sync(0xffffffffu, c_p1, owner);
-  }
-  if (lane == 0) {
-    double pitch = 0.0, conf = 0.0;
-    if (mt < kYinHalf && mt > 0) {
-      double period = (double)mt;
-      if (!(mt <= 0 || mt >= kYinHalf - 1)) {  // parabolicInterpolation :743-764
-        const double a = (y1 - 2 * y2 + y3) / 2, b = (y3 - y1) / 2;
-        if (a != 0) period = (double)mt + (-b / (2 * a));
-      }
-      const double freq = (double)sr / period;
-      if (freq >= 80.0 && freq <= 1000.0) {
-        pitch = freq;
-        conf = 1.0 - y2;
+      const bool live = f0 + fl < Tp;
+      const double2* hp = reinterpret_cast<const double2*>(hann + 16 * tf);
+#pragma unroll
+      for (int k = 0; k < 16; k += 2) {
+        const double2 h2 = __ldg(hp + (k >> 1));
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const double y = w[k + u + 2] - alpha * w[k + u + 1];
+          double t = y;
+          if (tf > 0 || k + u > 0) t = y - 0.97 * (w[k + u + 1] - alpha * w[k + u]);
+          t *= u ? h2.y : h2.x;
+          t = live ? t : 0.0;
+          v[k + u] = t;
+          ex[k + u] = run;
+          run = fma(t, t, run);
+        }
       }
     }
-    double* r = raw + (int64_t)s * raw_stride;
-    r[f] = pitch;
-    r[Tp + f] = conf;
+    __syncthreads();  // every window is in registers before the tiles are overwritten
+    {
+      double2* zp = Z + (tf >> 2) * kFRow + 17 * (tf & 3);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) zp[k] = make_double2(tf < 32 ? v[k] : 0.0, v[k]);  // z = a + i b
+    }
+    // ---- E(tau) = S[tau + 512] - S[tau]
+    {
+      double incl = run;
+      const int lane = tid & 31;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      double base = incl - run;  // sum over the lower lanes of this warp
+      double* E = sE[fl];
+      if (tf == 31) E[0] = incl;  // total of the lower warp (samples 0..511)
+      bar_sync(1 + fl, 64);
+      if (tf >= 32) base += E[0];
+      bar_sync(1 + fl, 64);
+      if (tf >= 32) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) E[17 * (tf - 32) + k] = base + ex[k];  // S[tau + 512]
+      }
+      bar_sync(1 + fl, 64);  // also orders the z stores before pass 1
+      if (tf < 32) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) E[17 * tf + k] -= base + ex[k];  // - S[tau]
+      }
+    }
+    fft1024_fwd(Z, sW, sW64, tf, 1 + fl);
+    // ---- P = conj(A) B per frame, Q = P0 + i P1 per pair, written over the pair's first tile
+    bar_sync(5 + pr, 128);
+    {
+      double2* Z0 = sZ + (2 * pr) * kFBuf;
+      double2* Z1 = Z0 + kFBuf;
+      for (int it = 0; it < 5; ++it) {
+        int k;
+        if (it < 4) {
+          k = 64 * (tp & 7) + (tp >> 3) + 16 * it;
+        } else {
+          if (tp != 0) break;
+          k = 512;
+        }
+        const int pk = kpos(k), pn = kpos((1024 - k) & 1023);
+        double2 P[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double2* Zh = h ? Z1 : Z0;
+          const double2 zk = Zh[pk], zn = Zh[pn];
+          // A = (zk + conj(zn))/2, B = -i (zk - conj(zn))/2, P = conj(A) B (the 1/4 is folded into the final scale)
+          const double sr_ = zk.x + zn.x, si = zk.y - zn.y, dr = zk.x - zn.x, di = zk.y + zn.y;
+          P[h] = make_double2(fma(sr_, di, -(si * dr)), -fma(sr_, dr, si * di));
+        }
+        Z0[pk] = make_double2(P[0].x - P[1].y, P[0].y + P[1].x);
+        if (pn != pk) Z0[pn] = make_double2(P[0].x + P[1].y, P[1].x - P[0].y);
+      }
+    }
+    bar_sync(5 + pr, 128);
+    if (hf) {
+      // the second tile is idle from here on: fetch the next group's samples into it
+      const int64_t nxt = grp + gridDim.x;
+      if (nxt < total_groups)
+        prefetch_pair(rawbuf, pcm + (nxt / groups_per_stream) * stride, (nxt % groups_per_stream) * kFftFpb + 2 * pr, limit,
+                      tf);
+    } else {
+      double2 q[16];
+      fft1024_inv(Z, sW, sW64, tf, 1 + fl, q);
+      const double scale = 1.0 / 4096.0;  // 1/4 (split) * 1/1024 (inverse)
+      double* E0 = sE[fl];
+      double* E1 = sE[fl + 1];
+      const double e00 = E0[0], e10 = E1[0];
+      bar_sync(1 + fl, 64);  // everyone has read E[0] before tau = 0 is overwritten
+#pragma unroll
+      for (int n1 = 0; n1 < 8; ++n1) {
+        const int ep = epos(64 * n1 + tf);
+        const double d0 = (e00 + E0[ep]) - 2.0 * (q[n1].x * scale);
+        const double d1 = (e10 + E1[ep]) - 2.0 * (q[n1].y * scale);
+        E0[ep] = d0 > 0.0 ? d0 : 0.0;
+        E1[ep] = d1 > 0.0 ? d1 : 0.0;
+      }
+    }
+    __syncthreads();
+    // ---- CMNDF + first dip below 0.15 (pitch_detection.go:363-383): one warp per frame, 16 lags per lane
+    const int wv = tid >> 5, lane = tid & 31;
+    if (wv < kFftFpb) yin_pick<17>(sE[wv], f0 + wv, Tp, sr, lane, raw + (int64_t)s * raw_stride);
   }
 }
 
@@ -343,12 +667,28 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
     return SONAR_OK;
   }
   if (Tp > 0x7fffffffLL) return set_error(SONAR_ERR_UNSUPPORTED, "too many pitch frames");
-  dim3 grid((unsigned)((Tp + kYinFpb - 1) / kYinFpb), (unsigned)n_streams);
-  const size_t smem = sizeof(double) * kYinFpb * (kYinPad + kYinFrame + 2 + kYinHalf);
-  SONAR_CUDA(cudaFuncSetAttribute(yin_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  prof_begin("yin_frame_kernel", st);
-  yin_frame_kernel<<<grid, kYinThreads, smem, st>>>(pcm, stride, alpha, sr, Tp, hann_dev, scratch, scratch_stride);
-  prof_end();
+  static const bool direct = std::getenv("SONAR_YIN_DIRECT") != nullptr;  // diagnostic: the O(W^2) form
+  if (direct) {
+    dim3 grid((unsigned)((Tp + kYinFpb - 1) / kYinFpb), (unsigned)n_streams);
+    const size_t smem = sizeof(double) * kYinFpb * (kYinPad + kYinFrame + 2 + kYinHalf);
+    SONAR_CUDA(cudaFuncSetAttribute(yin_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin("yin_frame_kernel", st);
+    yin_frame_kernel<<<grid, kYinThreads, smem, st>>>(pcm, stride, alpha, sr, Tp, hann_dev, scratch, scratch_stride);
+    prof_end();
+  } else {
+    const int gps = (int)((Tp + kFftFpb - 1) / kFftFpb);
+    const int64_t total = (int64_t)gps * n_streams;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = sizeof(double2) * (1024 + 64 + kFftFpb * kFBuf) + sizeof(double) * kFftFpb * kERow;
+    SONAR_CUDA(cudaFuncSetAttribute(yin_frame_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned ctas = (unsigned)std::min<int64_t>(total, (int64_t)2 * sms);  // persistent: 2 CTAs per SM
+    prof_begin("yin_frame_kernel", st);
+    yin_frame_fft_kernel<<<ctas, kFftThreads, smem, st>>>(pcm, stride, alpha, sr, Tp, gps, total, hann_dev, scratch,
+                                                         scratch_stride);
+    prof_end();
+  }
   SONAR_CUDA(cudaGetLastError());
   prof_begin("yin_track_kernel", st);
   yin_track_kernel<<<n_streams, 32, 0, st>>>(scratch, scratch_stride, n_streams, Tp, feat, feat_stride,
