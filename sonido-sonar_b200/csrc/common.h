@@ -168,8 +168,13 @@ struct DtwGeom {
   int n, m, band;   // band == 0: unconstrained
   int n_off;        // number of distinct offsets i - j the wavefront tracks
   int64_t W;        // banded: cells per stored anti-diagonal (band+1); unconstrained: cells per stored row (m)
-  int64_t cells;    // cells per pair
+  int64_t cells;    // doubles per pair: the cost store plus, for narrow bands, the backtrack side arrays below
+  // narrow bands only (dirs_off > 0): one direction byte per cost cell (same diagonal-major indexing) and the
+  // block tables of the parallel backtrack, as offsets in doubles from the start of the pair's region
+  int64_t dirs_off, tbl_off, chain_off;
+  int bt_nb;        // number of kDtwBtDiags-diagonal blocks covering diagonals n+m .. 0
 };
+constexpr int kDtwBtDiags = 256;
 int dtw_geometry(int n, int m, int band, DtwGeom* g);
 struct DtwPairOut {
   double total_cost;

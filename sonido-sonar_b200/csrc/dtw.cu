@@ -22,6 +22,9 @@
 // shared-memory access instead of a DRAM round trip, and writes the path back to front.
 #include <cmath>
 
+#include <algorithm>
+#include <type_traits>
+
 #include "common.h"
 
 namespace sonar {
@@ -194,16 +197,20 @@ __device__ __forceinline__ double dist1(double a, double b) {
   return fabs(df);
 }
 
-// Register-resident wavefront for narrow bands (dim == 1, 2*band+1 <= 32*NPL): ONE warp per pair, lane l
-// keeps the latest cost of the NPL offsets k = NPL*l .. NPL*l+NPL-1 (k = i - j + band) in registers.  A
-// diagonal only touches offsets of one parity and reads the two neighbouring offsets of the other parity,
-// so a step is NPL/2 independent relaxations per lane plus ONE warp shuffle for the value that lives in the
-// neighbouring lane — no shared-memory line, no block barrier; the dependent chain per diagonal is
-// shuffle -> min -> min -> add.  Two diagonals (one of each parity) form one loop iteration: the q / r
-// values a lane needs slide by one element per iteration, so they live in a small register window fed by
-// two shared-memory loads per iteration (prefetched one iteration ahead), and a cell's validity is one
-// unsigned compare against its offset's precomputed diagonal range.
-template <int NPL, int STEP>
+// Register-resident wavefront for narrow bands (dim == 1, 2*band+3 <= 32*NPL): ONE warp per pair, lane l
+// keeps the latest cost of the NPL offsets k = NPL*l - 1 .. NPL*l + NPL - 2 (k = i - j + band) in registers
+// (slot x <-> k = NPL*l + x - 1, so slot 0 of lane 0 and the last slot of lane 31 are never inside the band
+// and the values shuffled into them need no masking).  A diagonal only touches offsets of one parity and
+// reads the two neighbouring offsets of the other parity, so a step is NPL/2 independent relaxations per
+// lane plus ONE warp shuffle for the value that lives in the neighbouring lane — no shared-memory line, no
+// block barrier.  The single warp issues in order, so everything that does not depend on the previous
+// diagonal is kept off the dependent chain shuffle -> min -> add:
+//   * the local distances of both diagonals of an iteration (and their validity, folded in as +Inf) are
+//     computed from a register window of q / r that slides by one element per iteration;
+//   * |q - r| needs no per-cell range test when the sequences were pre-screened (FAST, see dtw_safe_range);
+// The backtrack's choice at every cell (findPreviousStep's strict-'<' scan: vertical, horizontal, diagonal)
+// is a function of the finished cost store; dtw_dirs_kernel derives it for all cells in parallel afterwards.
+template <int STEP>
 __device__ __forceinline__ double dtw_relax(double v, double hh, double dg, double ld) {
   double mc;
   if (STEP == SONAR_STEP_SYMMETRIC2) {  // min(a, b) as (a < b ? a : b) equals math.Min for non-NaN values
@@ -218,34 +225,60 @@ __device__ __forceinline__ double dtw_relax(double v, double hh, double dg, doub
   }
   return ld + mc;
 }
+// findPreviousStep (dtw.go:191-217): 0 = vertical (i-1, j), 1 = horizontal (i, j-1), 2 = diagonal
+__device__ __forceinline__ unsigned dtw_dir(double cv, double ch, double cd) {
+  const bool p1 = ch < cv;
+  const double best = p1 ? ch : cv;
+  return cd < best ? 2u : (p1 ? 1u : 0u);
+}
 
-template <int NPL, int STEP>
-__global__ void __launch_bounds__(32) dtw_fill_warp_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
-                                                           DtwGeom g, double* __restrict__ cells_all,
-                                                           const double* const* __restrict__ qptr,
-                                                           const double* const* __restrict__ rptr) {
+// |x| of every non-zero element in [2^-458, 2^500] (and finite): then every difference a - b is either 0 or
+// has a square that is a normal number, so sqrt((a-b)^2) == |a - b| exactly and dist1's range test can go.
+__device__ __forceinline__ bool dtw_safe_range(const double* __restrict__ q, int n, const double* __restrict__ r, int m,
+                                               int lane) {
+  bool ok = true;
+  auto scan = [&](const double* __restrict__ x, int len) {
+    for (int e0 = lane; e0 < len; e0 += 128) {
+      unsigned ex[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + 32 * u;
+        const double v = e < len ? x[e] : 1.0;
+        ex[u] = (v == 0.0) ? 1023u : (((unsigned)__double2hiint(v) >> 20) & 0x7ffu);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ok = ok && (ex[u] - 565u <= 958u);  // biased exponent in [1023-458, 1023+500]
+    }
+  };
+  scan(q, n);
+  scan(r, m);
+  return __all_sync(0xffffffffu, ok);
+}
+
+template <int NPL, int STEP, bool FAST>
+__device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q, const double* __restrict__ r,
+                                                   const DtwGeom& g, double* __restrict__ cells, double* ring_q,
+                                                   double* ring_r) {
   constexpr int H = NPL / 2;
-  __shared__ double ring_q[kRing], ring_r[kRing];
-  const int pair = blockIdx.x, lane = threadIdx.x;
+  const int lane = threadIdx.x;
   const int n = g.n, m = g.m, band = g.band, W = (int)g.W;
-  const double* __restrict__ q = qptr ? qptr[pair] : qs + (int64_t)pair * n;
-  const double* __restrict__ r = rptr ? rptr[pair] : rs + (int64_t)pair * m;
   const double inf = d_inf();
-  const int kbase = NPL * lane;
+  const int kbase = NPL * lane - 1;  // offset of slot 0
   double L[NPL];
   int dlo[NPL];
   unsigned span[NPL];
+  bool inband[NPL];
 #pragma unroll
   for (int x = 0; x < NPL; ++x) {
     const int k = kbase + x, delta = k - band;
     L[x] = (k == band) ? 0.0 : inf;  // C[0][0] sits at offset i - j = 0
     const int lo = 2 + (delta < 0 ? -delta : delta);
     const int hi = (2 * n - delta) < (2 * m + delta) ? (2 * n - delta) : (2 * m + delta);
-    const bool any = k <= 2 * band && hi >= lo;
+    inband[x] = k >= 0 && k <= 2 * band;
+    const bool any = inband[x] && hi >= lo;
     dlo[x] = any ? lo : 0x3fffffff;  // cell of offset k on diagonal d is inside the matrix iff lo <= d <= hi
     span[x] = any ? (unsigned)(hi - lo) : 0u;
   }
-  double* __restrict__ row = cells_all + (int64_t)pair * g.cells + (int64_t)2 * W + (kbase >> 1);  // diagonal d = 2
   const int last = n + m;
   int loaded = 0;
   auto refill = [&](int d) {
@@ -258,72 +291,125 @@ __global__ void __launch_bounds__(32) dtw_fill_warp_kernel(const double* __restr
     loaded = target;
     __syncwarp();
   };
-  auto half = [&](int d, int par, const double (&ld)[H]) {  // par is a compile-time constant at both call sites
-    double edge;
-    if (par == 0) {
-      edge = __shfl_up_sync(0xffffffffu, L[NPL - 1], 1);
-      if (lane == 0) edge = inf;
-    } else {
-      edge = __shfl_down_sync(0xffffffffu, L[0], 1);
-      if (lane == 31) edge = inf;
+  // The single warp is issue-bound (one instruction every ~2 cycles), so the loop body is kept minimal: the
+  // invalid slots get their +Inf through the local distance, stores are predicated (no branches), the store
+  // pointers advance incrementally, and the steady-state loop below takes the validity flags as invariants.
+  auto local = [&](double a, double b, bool ok) -> double {
+    double df;
+    if (FAST) {
+      df = a - b;
+      df = ok ? df : inf;
+      return fabs(df);
+    }
+    df = dist1(a, b);
+    return ok ? df : inf;
+  };
+  // odd slots (even offsets k = NPL*l + 2h) of a diagonal whose row starts at `row`; store slot (k >> 1) = half_l + h
+  auto half_b = [&](double* __restrict__ row, const double (&Q)[H], const double (&R)[H + 1], const bool (&ok)[H]) {
+    const double edge = __shfl_down_sync(0xffffffffu, L[0], 1);  // offset k+1 of the last odd slot: lane+1, slot 0
+    double c[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const int x = 2 * h + 1;
+      const double hh = (h == H - 1) ? edge : L[x + 1 < NPL ? x + 1 : x];
+      c[h] = dtw_relax<STEP>(L[x - 1], hh, L[x], local(Q[h], R[h + 1], ok[h]));  // cell (ib+h, jb-h): q[ib+h-1], r[jb-h-1]
     }
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      const int x = 2 * h + par;
-      const double v = (x == 0) ? edge : L[x == 0 ? 0 : x - 1];               // (i-1, j): offset k-1
-      const double hh = (x == NPL - 1) ? edge : L[x == NPL - 1 ? x : x + 1];  // (i, j-1): offset k+1
-      const double c = dtw_relax<NPL, STEP>(v, hh, L[x], ld[h]);
-      if ((unsigned)(d - dlo[x]) <= span[x]) {
-        L[x] = c;
-        row[h] = c;  // diagonal-major store: ((i - j + band) >> 1) == (kbase >> 1) + h
-      }
+      L[2 * h + 1] = c[h];  // invalid cells carry +Inf, which is what the offset line must hold there
+      if (ok[h]) row[h] = c[h];
     }
   };
+  // even slots (odd offsets k = NPL*l + 2h - 1); store slot half_l + h - 1 (row is passed already shifted by -1)
+  auto half_a = [&](double* __restrict__ row, const double (&Q)[H], const double (&R)[H + 1], const bool (&ok)[H]) {
+    const double edge = __shfl_up_sync(0xffffffffu, L[NPL - 1], 1);  // offset k-1 of slot 0: lane-1, last slot
+    double c[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const int x = 2 * h;
+      const double v = (h == 0) ? edge : L[x > 0 ? x - 1 : 0];
+      c[h] = dtw_relax<STEP>(v, L[x + 1], L[x], local(Q[h], R[h], ok[h]));  // cell (ib+h, jb-h+1): q[ib+h-1], r[jb-h]
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      L[2 * h] = c[h];
+      if (ok[h]) row[h] = c[h];
+    }
+  };
+  const int half_l = (NPL / 2) * lane;  // (NPL*lane) >> 1
   int d = 2;
   refill(d);
   int next_refill = d + 256;
-  if ((d - band) & 1) {  // odd band: diagonal 2 carries the odd offsets; do it alone so that pairs start aligned
-    const int ib = (d - band + kbase + 1) >> 1;
-    double ld[H];
+  // Cells of an aligned iteration (d - band even): odd slots on d are (ib + h, jb - h), even slots on d + 1 are
+  // (ib + h, jb - h + 1), with ib = (d - band + NPL*lane) / 2, jb = d - ib; Q[h] = q[ib + h - 1], R[u] = r[jb - u].
+  double Q[H], R[H + 1];
+  if ((d - band) & 1) {  // odd band: diagonal 2 carries the odd offsets (even slots); do it alone
+    const int ib = (d - 1 - band + NPL * lane) >> 1, jb = d - 1 - ib;
+    bool ok[H];
 #pragma unroll
-    for (int h = 0; h < H; ++h)
-      ld[h] = dist1(ring_q[(ib + h - 1) & (kRing - 1)], ring_r[(d - ib - h - 1) & (kRing - 1)]);
-    half(d, 1, ld);
+    for (int h = 0; h < H; ++h) {
+      ok[h] = (unsigned)(d - dlo[2 * h]) <= span[2 * h];
+      Q[h] = ring_q[(ib + h - 1) & (kRing - 1)];
+    }
+#pragma unroll
+    for (int u = 0; u <= H; ++u) R[u] = ring_r[(jb - u) & (kRing - 1)];
+    half_a(cells + (int64_t)d * W + half_l - 1, Q, R, ok);
     ++d;
-    row += W;
   }
-  // from here d - band is even: this iteration does diagonal d (even offsets) and d + 1 (odd offsets)
-  int ib = (d - band + kbase) >> 1, j = d - ib;
-  double Q[H + 1], R[H];
+  int ib = (d - band + NPL * lane) >> 1, jb = d - ib;
 #pragma unroll
-  for (int h = 0; h <= H; ++h) Q[h] = ring_q[(ib + h - 1) & (kRing - 1)];
+  for (int h = 0; h < H; ++h) Q[h] = ring_q[(ib + h - 1) & (kRing - 1)];
 #pragma unroll
-  for (int h = 0; h < H; ++h) R[h] = ring_r[(j - h - 1) & (kRing - 1)];
-  for (; d <= last; d += 2, row += 2 * W, ++ib, ++j) {
+  for (int u = 0; u <= H; ++u) R[u] = ring_r[(jb - u) & (kRing - 1)];
+  double* __restrict__ rowb = cells + (int64_t)d * W + half_l;  // diagonal d, odd slots; diagonal d + 1's even slots: + W - 1
+  // steady state: every in-band offset has a cell on the diagonal; [sd0, sd1) in steps of two from d
+  const int mn = n < m ? n : m;
+  const int sd0 = band + 4 + ((band + 4 - d) & 1), sd1 = 2 * mn - band - 2;
+  auto iterate = [&](auto steady_tag) {
+    constexpr bool STEADY = decltype(steady_tag)::value;
     if (d >= next_refill) {
       refill(d);
       next_refill += 256;
     }
-    const double qn = ring_q[(ib + H) & (kRing - 1)], rn = ring_r[j & (kRing - 1)];  // next iteration's new elements
-    double lda[H], ldb[H];
+    const double qn = ring_q[(ib + H - 1) & (kRing - 1)], rn = ring_r[(jb + 1) & (kRing - 1)];  // next iteration's
+    bool okb[H], oka[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      lda[h] = dist1(Q[h], R[h]);      // cell (ib + h,     j - h) on diagonal d
-      ldb[h] = dist1(Q[h + 1], R[h]);  // cell (ib + h + 1, j - h) on diagonal d + 1
+      okb[h] = STEADY ? inband[2 * h + 1] : ((unsigned)(d - dlo[2 * h + 1]) <= span[2 * h + 1]);
+      oka[h] = STEADY ? inband[2 * h] : ((unsigned)(d + 1 - dlo[2 * h]) <= span[2 * h]);
     }
-    half(d, 0, lda);
-    if (d + 1 <= last) {
-      row += W;
-      half(d + 1, 1, ldb);
-      row -= W;
-    }
+    half_b(rowb, Q, R, okb);
+    half_a(rowb + W - 1, Q, R, oka);  // beyond the last diagonal every cell is invalid: nothing is stored
 #pragma unroll
-    for (int h = 0; h < H; ++h) Q[h] = Q[h + 1];
-    Q[H] = qn;
+    for (int h = 0; h + 1 < H; ++h) Q[h] = Q[h + 1];
+    Q[H - 1] = qn;
 #pragma unroll
-    for (int h = H - 1; h > 0; --h) R[h] = R[h - 1];
+    for (int u = H; u > 0; --u) R[u] = R[u - 1];
     R[0] = rn;
-  }
+    d += 2;
+    ++ib;
+    ++jb;
+    rowb += 2 * W;
+  };
+  while (d <= last && d < sd0) iterate(std::false_type{});
+  while (d + 1 < sd1) iterate(std::true_type{});
+  while (d <= last) iterate(std::false_type{});
+}
+
+template <int NPL, int STEP>
+__global__ void __launch_bounds__(32) dtw_fill_warp_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
+                                                           DtwGeom g, double* __restrict__ cells_all,
+                                                           const double* const* __restrict__ qptr,
+                                                           const double* const* __restrict__ rptr) {
+  __shared__ double ring_q[kRing], ring_r[kRing];
+  const int pair = blockIdx.x;
+  const double* __restrict__ q = qptr ? qptr[pair] : qs + (int64_t)pair * g.n;
+  const double* __restrict__ r = rptr ? rptr[pair] : rs + (int64_t)pair * g.m;
+  double* cells = cells_all + (int64_t)pair * g.cells;
+  if (dtw_safe_range(q, g.n, r, g.m, threadIdx.x))
+    dtw_fill_warp_body<NPL, STEP, true>(q, r, g, cells, ring_q, ring_r);
+  else
+    dtw_fill_warp_body<NPL, STEP, false>(q, r, g, cells, ring_q, ring_r);
 }
 
 constexpr int kBtTile = 64;
@@ -448,8 +534,10 @@ __global__ void __launch_bounds__(kBbThreads) dtw_backtrack_banded_kernel(const 
                                                                           int32_t* __restrict__ path_r,
                                                                           double* __restrict__ path_c,
                                                                           int64_t path_cap,
-                                                                          DtwPairOut* __restrict__ outs) {
+                                                                          DtwPairOut* __restrict__ outs,
+                                                                          int only_flagged) {
   extern __shared__ double bb_smem[];
+  if (only_flagged && outs[blockIdx.x].path_len >= 0) return;  // the parallel backtrack already produced this path
   __shared__ int s_i, s_j, s_done;
   __shared__ int64_t s_len;
   const int Wd = (int)g.W, Wp = Wd + 2;
@@ -561,6 +649,200 @@ __global__ void __launch_bounds__(kBbThreads) dtw_backtrack_banded_kernel(const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Parallel backtrack over the direction bytes the register wavefront recorded.
+//
+// The predecessor of a cell is a function of the cell alone, so the walk from (n, m) is a pointer chase
+// through a forest whose edges are already known.  The diagonals n+m .. 0 are cut into blocks of
+// kDtwBtDiags; a step moves down one or two diagonals, so a walk enters a block on its top diagonal or the
+// one below it, in one of W slots: 2W possible entry states per block.
+//   1. dtw_bt_exits_kernel  — one CTA per (block, pair): the block's bytes are staged in shared memory and
+//      one thread per entry state walks to the block's floor, recording the state in which it enters the
+//      next block and the number of steps taken (all blocks and states in parallel).
+//   2. dtw_bt_chain_kernel  — one thread per pair hops from block to block through those tables starting at
+//      (n, m): entry state and path position of every block, total path length.
+//   3. dtw_bt_emit_kernel   — one CTA per (block, pair) re-walks its block from the now known entry state
+//      and writes the path indices at their final positions.
+//   4. dtw_bt_cost_kernel   — point.Cost = C[i][j] - C[i-1][j-1] for every path point, fully parallel.
+// A walk that leaves the band or the matrix (only possible when |n - m| > band or the costs are not
+// finite: the reference then follows +Inf/NaN comparisons) flags the pair (path_len = -1) and the
+// cell-comparing walker below handles it.
+// One direction byte per stored cell (same diagonal-major index as the cost store).
+__global__ void __launch_bounds__(256) dtw_dirs_kernel(double* __restrict__ cells_all, DtwGeom g) {
+  const int pair = blockIdx.y, W = (int)g.W, band = g.band;
+  double* cells = cells_all + (int64_t)pair * g.cells;
+  unsigned char* dirs = reinterpret_cast<unsigned char*>(cells + g.dirs_off);
+  const int last = g.n + g.m;
+  for (int d = 2 + blockIdx.x * 4 + (threadIdx.x >> 6); d <= last; d += gridDim.x * 4) {
+    const int par = (d + band) & 1;
+    for (int kk = threadIdx.x & 63; kk < W; kk += 64) {
+      const int s2 = 2 * kk + par;
+      const int i = (d + s2 - band) >> 1, j = d - i;
+      if (s2 > 2 * band || i < 1 || i > g.n || j < 1 || j > g.m) continue;
+      dirs[(int64_t)d * W + kk] =
+          (unsigned char)dtw_dir(cell_get(cells, g, i - 1, j), cell_get(cells, g, i, j - 1), cell_get(cells, g, i - 1, j - 1));
+    }
+  }
+}
+
+constexpr int kBtDone = 0xfffe, kBtBail = 0xffff;
+
+struct BtState {
+  int i, j;
+};
+// entry state c of the block whose top diagonal is dtop: c < W -> (dtop, slot c), else (dtop - 1, slot c - W)
+__device__ __forceinline__ bool bt_state_cell(const DtwGeom& g, int dtop, int c, BtState* st) {
+  const int W = (int)g.W;
+  const int d = c < W ? dtop : dtop - 1, slot = c < W ? c : c - W;
+  const int s2 = 2 * slot + ((d + g.band) & 1);
+  st->i = (d + s2 - g.band) >> 1;
+  st->j = d - st->i;
+  if (d == 0 && s2 == g.band) return true;  // (0, 0)
+  return d >= 2 && s2 <= 2 * g.band && st->i >= 1 && st->i <= g.n && st->j >= 1 && st->j <= g.m;
+}
+
+// Walks from (i, j) down to below diagonal dbot.  sm holds the bytes of diagonals dbot .. (row (d - dbot) * W).
+// Returns the exit code; EMIT writes the path points at pos, pos-1, ...
+template <bool EMIT>
+__device__ __forceinline__ int bt_walk(const DtwGeom& g, const unsigned char* __restrict__ sm, int dbot, int i, int j,
+                                       int* steps_out, int32_t* __restrict__ pq, int32_t* __restrict__ pr,
+                                       int64_t pos) {
+  const int W = (int)g.W, band = g.band;
+  int steps = 0, code;
+  for (;;) {
+    const int d = i + j, s2 = i - j + band;
+    if (i == 0 && j == 0) {
+      code = kBtDone;
+      break;
+    }
+    if (i < 1 || j < 1 || (unsigned)s2 > (unsigned)(2 * band)) {
+      code = kBtBail;
+      break;
+    }
+    if (d < dbot) {
+      code = (d == dbot - 1) ? (s2 >> 1) : W + (s2 >> 1);
+      break;
+    }
+    const unsigned dir = sm[(d - dbot) * W + (s2 >> 1)];
+    if (EMIT) {
+      if (pos >= 0) {
+        pq[pos] = i - 1;
+        pr[pos] = j - 1;
+      }
+      --pos;
+    }
+    ++steps;
+    i -= (dir != 1u);
+    j -= (dir != 0u);
+  }
+  *steps_out = steps;
+  return code;
+}
+
+__device__ __forceinline__ void bt_stage_block(const unsigned char* __restrict__ dirs, const DtwGeom& g, int dbot,
+                                               int dtop, unsigned char* __restrict__ sm) {
+  // bytes of diagonals dbot .. dtop are contiguous in the store; copy as 4-byte words from an aligned base
+  const int64_t b0 = (int64_t)dbot * g.W, b1 = (int64_t)(dtop + 1) * g.W;
+  const int64_t a0 = b0 & ~(int64_t)3;
+  const int nw = (int)((b1 - a0 + 3) >> 2);
+  const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(dirs + a0);
+  unsigned* dst = reinterpret_cast<unsigned*>(sm);
+  for (int e = threadIdx.x; e < nw; e += blockDim.x) dst[e] = src[e];
+}
+
+constexpr int kBtxThreads = 256;
+
+__global__ void __launch_bounds__(kBtxThreads) dtw_bt_exits_kernel(double* __restrict__ cells_all, DtwGeom g) {
+  extern __shared__ __align__(16) unsigned char bt_sm[];
+  const int blk = blockIdx.x, pair = blockIdx.y, W = (int)g.W;
+  double* cells = cells_all + (int64_t)pair * g.cells;
+  const unsigned char* dirs = reinterpret_cast<const unsigned char*>(cells + g.dirs_off);
+  int* tbl = reinterpret_cast<int*>(cells + g.tbl_off) + (int64_t)blk * 2 * W;
+  const int dtop = g.n + g.m - blk * kDtwBtDiags;
+  const int dbot = dtop - kDtwBtDiags + 1 > 0 ? dtop - kDtwBtDiags + 1 : 0;
+  bt_stage_block(dirs, g, dbot, dtop, bt_sm);
+  __syncthreads();
+  const unsigned char* sm = bt_sm + (((int64_t)dbot * W) & 3);
+  for (int c = threadIdx.x; c < 2 * W; c += blockDim.x) {
+    BtState st;
+    int steps = 0, code = kBtBail;
+    if (bt_state_cell(g, dtop, c, &st)) code = bt_walk<false>(g, sm, dbot, st.i, st.j, &steps, nullptr, nullptr, 0);
+    tbl[c] = (steps << 16) | code;
+  }
+}
+
+__global__ void dtw_bt_chain_kernel(double* __restrict__ cells_all, DtwGeom g, int n_pairs, DtwPairOut* __restrict__ outs) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_pairs) return;
+  double* cells = cells_all + (int64_t)pair * g.cells;
+  const int* tbl = reinterpret_cast<const int*>(cells + g.tbl_off);
+  int* chain = reinterpret_cast<int*>(cells + g.chain_off);
+  const int W = (int)g.W;
+  int64_t len = -1;
+  const int s2 = g.n - g.m + g.band;
+  if (s2 >= 0 && s2 <= 2 * g.band) {
+    int c = s2 >> 1;
+    int64_t total = 0;
+    for (int b = 0; b < g.bt_nb; ++b) {
+      chain[2 * b] = c;
+      chain[2 * b + 1] = (int)total;
+      const int e = tbl[(int64_t)b * 2 * W + c];
+      total += e >> 16;
+      const int code = e & 0xffff;
+      if (code == kBtDone) {
+        len = total;
+        for (int bb = b + 1; bb < g.bt_nb; ++bb) chain[2 * bb] = -1;
+        break;
+      }
+      if (code == kBtBail) break;
+      c = code;
+    }
+  }
+  outs[pair].path_len = len;
+  outs[pair].total_cost = cell_get(cells, g, g.n, g.m);
+}
+
+__global__ void __launch_bounds__(kBtxThreads) dtw_bt_emit_kernel(const double* __restrict__ cells_all, DtwGeom g,
+                                                                  int32_t* __restrict__ path_q,
+                                                                  int32_t* __restrict__ path_r, int64_t path_cap,
+                                                                  const DtwPairOut* __restrict__ outs) {
+  extern __shared__ __align__(16) unsigned char bt_sm[];
+  const int blk = blockIdx.x, pair = blockIdx.y, W = (int)g.W;
+  if (outs[pair].path_len < 0) return;
+  const double* cells = cells_all + (int64_t)pair * g.cells;
+  const int* chain = reinterpret_cast<const int*>(cells + g.chain_off);
+  const int c = chain[2 * blk];
+  if (c < 0) return;  // the walk ended in an earlier block
+  const unsigned char* dirs = reinterpret_cast<const unsigned char*>(cells + g.dirs_off);
+  const int dtop = g.n + g.m - blk * kDtwBtDiags;
+  const int dbot = dtop - kDtwBtDiags + 1 > 0 ? dtop - kDtwBtDiags + 1 : 0;
+  bt_stage_block(dirs, g, dbot, dtop, bt_sm);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned char* sm = bt_sm + (((int64_t)dbot * W) & 3);
+    BtState st;
+    bt_state_cell(g, dtop, c, &st);
+    int steps;
+    bt_walk<true>(g, sm, dbot, st.i, st.j, &steps, path_q + (int64_t)pair * path_cap, path_r + (int64_t)pair * path_cap,
+                  path_cap - 1 - (int64_t)chain[2 * blk + 1]);
+  }
+}
+
+__global__ void dtw_bt_cost_kernel(const double* __restrict__ cells_all, DtwGeom g, const int32_t* __restrict__ path_q,
+                                   const int32_t* __restrict__ path_r, double* __restrict__ path_c, int64_t path_cap,
+                                   const DtwPairOut* __restrict__ outs) {
+  const int pair = blockIdx.y;
+  const int64_t len = outs[pair].path_len;
+  if (len < 0) return;
+  const double* cells = cells_all + (int64_t)pair * g.cells;
+  const int64_t take = len < path_cap ? len : path_cap;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < take; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pos = (int64_t)pair * path_cap + path_cap - 1 - e;
+    const int i = path_q[pos] + 1, j = path_r[pos] + 1;
+    path_c[pos] = cell_get(cells, g, i, j) - cell_get(cells, g, i - 1, j - 1);  // dtw.go:173-175
+  }
+}
+
 // CostMatrix = costMatrix[1:] (dtw.go:96): full[n][m+1]
 __global__ void dtw_expand_kernel(const double* __restrict__ cells, DtwGeom g, double* __restrict__ full) {
   const int64_t total = (int64_t)g.n * (g.m + 1);
@@ -573,6 +855,8 @@ __global__ void dtw_expand_kernel(const double* __restrict__ cells, DtwGeom g, d
 }  // namespace
 
 int dtw_geometry(int n, int m, int band, DtwGeom* g) {
+  g->dirs_off = g->tbl_off = g->chain_off = 0;
+  g->bt_nb = 0;
   g->n = n;
   g->m = m;
   g->band = band > 0 ? band : 0;
@@ -580,6 +864,13 @@ int dtw_geometry(int n, int m, int band, DtwGeom* g) {
     g->W = (int64_t)g->band + 1;  // cells per stored anti-diagonal
     g->n_off = 2 * g->band + 1;
     g->cells = ((int64_t)n + m + 1) * g->W;
+    if (2 * g->band + 3 <= 32 * 8) {  // the register wavefront applies (dim == 1): room for its side arrays
+      g->bt_nb = (n + m) / kDtwBtDiags + 1;
+      g->dirs_off = g->cells;
+      g->tbl_off = g->dirs_off + (g->cells + 7) / 8 + 2;                           // bytes -> doubles (+ slack for slot -1)
+      g->chain_off = g->tbl_off + ((int64_t)g->bt_nb * 2 * g->W + 1) / 2;          // int32 [bt_nb][2W]
+      g->cells = g->chain_off + (int64_t)g->bt_nb;                                 // int32 [bt_nb][2]
+    }
   } else {
     g->W = m;  // cells per stored row
     g->n_off = n + m + 1;
@@ -599,7 +890,8 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
   if (g.band > 0 && diag > g.band + 1) diag = g.band + 1;
   int threads = (diag + 31) & ~31;
   threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
-  if (dim == 1 && g.band > 0 && 2 * g.band + 1 <= 32 * 8) {
+  const bool warp_path = dim == 1 && g.band > 0 && g.dirs_off > 0;
+  if (warp_path) {
     // min(a, b) as (a < b ? a : b) equals fmin for the non-NaN values this recurrence produces
 #define SONAR_DTW_WARP(NPL)                                                                       \
   do {                                                                                            \
@@ -610,7 +902,7 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
     else                                                                                          \
       dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC1><<<n_pairs, 32, 0, st>>>(q, r, g, cells, qptr, rptr);   \
   } while (0)
-    const int offs = 2 * g.band + 1;
+    const int offs = 2 * g.band + 3;  // one never-valid slot on each side (see dtw_fill_warp_body)
     prof_begin("dtw_fill_warp_kernel", st);
     if (offs <= 64)
       SONAR_DTW_WARP(2);
@@ -619,6 +911,27 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
     else
       SONAR_DTW_WARP(8);
 #undef SONAR_DTW_WARP
+    prof_end();
+    SONAR_CUDA(cudaGetLastError());
+    // parallel backtrack: direction bytes from the finished cost store, then block exits / chain / emit / costs
+    prof_begin("dtw_dirs_kernel", st);
+    dtw_dirs_kernel<<<dim3(148 * 4, (unsigned)n_pairs), 256, 0, st>>>(cells, g);
+    prof_end();
+    const size_t bsm = (size_t)kDtwBtDiags * (size_t)g.W + 16;
+    const dim3 bgrid((unsigned)g.bt_nb, (unsigned)n_pairs);
+    prof_begin("dtw_bt_exits_kernel", st);
+    dtw_bt_exits_kernel<<<bgrid, kBtxThreads, bsm, st>>>(cells, g);
+    prof_end();
+    prof_begin("dtw_bt_chain_kernel", st);
+    dtw_bt_chain_kernel<<<(n_pairs + 31) / 32, 32, 0, st>>>(cells, g, n_pairs, out);
+    prof_end();
+    prof_begin("dtw_bt_emit_kernel", st);
+    dtw_bt_emit_kernel<<<bgrid, kBtxThreads, bsm, st>>>(cells, g, path_q, path_r, path_cap, out);
+    prof_end();
+    const int64_t max_len = (int64_t)g.n + g.m;
+    prof_begin("dtw_bt_cost_kernel", st);
+    dtw_bt_cost_kernel<<<dim3((unsigned)std::min<int64_t>((max_len + 255) / 256, 64), (unsigned)n_pairs), 256, 0, st>>>(
+        cells, g, path_q, path_r, path_c, path_cap, out);
     prof_end();
     SONAR_CUDA(cudaGetLastError());
   } else {
@@ -659,7 +972,7 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
                                     (int)(216 * 1024)));
     prof_begin("dtw_backtrack_banded_kernel", st);
     dtw_backtrack_banded_kernel<<<n_pairs, kBbThreads, bsm, st>>>(cells, g, nd, path_q, path_r, path_c, path_cap,
-                                                                  out);
+                                                                  out, warp_path ? 1 : 0);
     prof_end();
     SONAR_CUDA(cudaGetLastError());
     return SONAR_OK;
