@@ -171,7 +171,7 @@ struct DtwGeom {
   int64_t cells;    // doubles per pair: the cost store plus, for narrow bands, the backtrack side arrays below
   // narrow bands only (dirs_off > 0): one direction byte per cost cell (same diagonal-major indexing) and the
   // block tables of the parallel backtrack, as offsets in doubles from the start of the pair's region
-  int64_t dirs_off, tbl_off, chain_off;
+  int64_t dirs_off, tbl_off, chain_off, flag_off;
   int bt_nb;        // number of kDtwBtDiags-diagonal blocks covering diagonals n+m .. 0
 };
 constexpr int kDtwBtDiags = 256;

@@ -63,6 +63,12 @@ __device__ __forceinline__ double cell_get(const double* __restrict__ cells, con
 }
 
 constexpr int kRing = 2048;       // staged q / r window (power of two), doubles each
+constexpr int kRefill = 1024;     // diagonals between two refills of the register wavefront's rings
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
+}
 constexpr int kStageBytes = 48 * 1024;  // cost cells staged in shared memory between flushes
 
 // Two things keep the per-diagonal critical path short:
@@ -234,25 +240,22 @@ __device__ __forceinline__ unsigned dtw_dir(double cv, double ch, double cd) {
 
 // |x| of every non-zero element in [2^-458, 2^500] (and finite): then every difference a - b is either 0 or
 // has a square that is a normal number, so sqrt((a-b)^2) == |a - b| exactly and dist1's range test can go.
-__device__ __forceinline__ bool dtw_safe_range(const double* __restrict__ q, int n, const double* __restrict__ r, int m,
-                                               int lane) {
+// One CTA per pair screens both sequences and leaves the verdict in the pair's flag slot.
+__global__ void __launch_bounds__(1024) dtw_screen_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
+                                                          DtwGeom g, double* __restrict__ cells_all,
+                                                          const double* const* __restrict__ qptr,
+                                                          const double* const* __restrict__ rptr) {
+  const int pair = blockIdx.x;
+  const double* __restrict__ q = qptr ? qptr[pair] : qs + (int64_t)pair * g.n;
+  const double* __restrict__ r = rptr ? rptr[pair] : rs + (int64_t)pair * g.m;
   bool ok = true;
-  auto scan = [&](const double* __restrict__ x, int len) {
-    for (int e0 = lane; e0 < len; e0 += 128) {
-      unsigned ex[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + 32 * u;
-        const double v = e < len ? x[e] : 1.0;
-        ex[u] = (v == 0.0) ? 1023u : (((unsigned)__double2hiint(v) >> 20) & 0x7ffu);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) ok = ok && (ex[u] - 565u <= 958u);  // biased exponent in [1023-458, 1023+500]
-    }
-  };
-  scan(q, n);
-  scan(r, m);
-  return __all_sync(0xffffffffu, ok);
+  for (int e = threadIdx.x; e < g.n + g.m; e += blockDim.x) {
+    const double v = e < g.n ? q[e] : r[e - g.n];
+    const unsigned ex = (v == 0.0) ? 1023u : (((unsigned)__double2hiint(v) >> 20) & 0x7ffu);
+    ok = ok && (ex - 565u <= 958u);  // biased exponent in [1023-458, 1023+500]
+  }
+  const int all = __syncthreads_and(ok ? 1 : 0);
+  if (threadIdx.x == 0) cells_all[(int64_t)pair * g.cells + g.flag_off] = all ? 1.0 : 0.0;
 }
 
 template <int NPL, int STEP, bool FAST>
@@ -280,28 +283,29 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
     span[x] = any ? (unsigned)(hi - lo) : 0u;
   }
   const int last = n + m;
+  // q / r reach the rings through cp.async one refill period AHEAD of their use, so the warp never waits for
+  // a global load: the call at diagonal d first waits for the copies issued at d - kRefill (everything the
+  // diagonals [d, d + kRefill) read), then issues the elements of the following period.
   int loaded = 0;
-  auto refill = [&](int d) {
-    const int target = ((d + 262 + band) >> 1) + 4;
-    __syncwarp();
+  auto issue = [&](int target) {
     for (int e = loaded + lane; e < target; e += 32) {
-      if (e < n) ring_q[e & (kRing - 1)] = q[e];
-      if (e < m) ring_r[e & (kRing - 1)] = r[e];
+      if (e < n) cp_async8(&ring_q[e & (kRing - 1)], q + e);
+      if (e < m) cp_async8(&ring_r[e & (kRing - 1)], r + e);
     }
-    loaded = target;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    loaded = target > loaded ? target : loaded;
+  };
+  auto refill = [&](int d) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
+    issue(((d + 2 * kRefill + band) >> 1) + 8);
   };
   // The single warp is issue-bound (one instruction every ~2 cycles), so the loop body is kept minimal: the
   // invalid slots get their +Inf through the local distance, stores are predicated (no branches), the store
   // pointers advance incrementally, and the steady-state loop below takes the validity flags as invariants.
   auto local = [&](double a, double b, bool ok) -> double {
-    double df;
-    if (FAST) {
-      df = a - b;
-      df = ok ? df : inf;
-      return fabs(df);
-    }
-    df = dist1(a, b);
+    if (FAST) return fabs(a - b) + (ok ? 0.0 : inf);  // two DADDs; the penalty is loop-invariant in the steady state
+    const double df = dist1(a, b);
     return ok ? df : inf;
   };
   // odd slots (even offsets k = NPL*l + 2h) of a diagonal whose row starts at `row`; store slot (k >> 1) = half_l + h
@@ -338,8 +342,9 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
   };
   const int half_l = (NPL / 2) * lane;  // (NPL*lane) >> 1
   int d = 2;
+  issue(((d + kRefill + band) >> 1) + 8);
   refill(d);
-  int next_refill = d + 256;
+  int next_refill = d + kRefill;
   // Cells of an aligned iteration (d - band even): odd slots on d are (ib + h, jb - h), even slots on d + 1 are
   // (ib + h, jb - h + 1), with ib = (d - band + NPL*lane) / 2, jb = d - ib; Q[h] = q[ib + h - 1], R[u] = r[jb - u].
   double Q[H], R[H + 1];
@@ -369,7 +374,7 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
     constexpr bool STEADY = decltype(steady_tag)::value;
     if (d >= next_refill) {
       refill(d);
-      next_refill += 256;
+      next_refill += kRefill;
     }
     const double qn = ring_q[(ib + H - 1) & (kRing - 1)], rn = ring_r[(jb + 1) & (kRing - 1)];  // next iteration's
     bool okb[H], oka[H];
@@ -392,7 +397,11 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
     rowb += 2 * W;
   };
   while (d <= last && d < sd0) iterate(std::false_type{});
-  while (d + 1 < sd1) iterate(std::true_type{});
+  {
+    const int n_steady = d + 1 < sd1 ? (sd1 - d) / 2 : 0;  // iterations with d + 1 < sd1
+#pragma unroll 6  // the q / r register windows rotate with periods 2 and 3 (NPL = 4): no moves left after unrolling
+    for (int it = 0; it < n_steady; ++it) iterate(std::true_type{});
+  }
   while (d <= last) iterate(std::false_type{});
 }
 
@@ -406,7 +415,7 @@ __global__ void __launch_bounds__(32) dtw_fill_warp_kernel(const double* __restr
   const double* __restrict__ q = qptr ? qptr[pair] : qs + (int64_t)pair * g.n;
   const double* __restrict__ r = rptr ? rptr[pair] : rs + (int64_t)pair * g.m;
   double* cells = cells_all + (int64_t)pair * g.cells;
-  if (dtw_safe_range(q, g.n, r, g.m, threadIdx.x))
+  if (cells[g.flag_off] != 0.0)  // warp-uniform verdict of dtw_screen_kernel
     dtw_fill_warp_body<NPL, STEP, true>(q, r, g, cells, ring_q, ring_r);
   else
     dtw_fill_warp_body<NPL, STEP, false>(q, r, g, cells, ring_q, ring_r);
@@ -855,7 +864,7 @@ __global__ void dtw_expand_kernel(const double* __restrict__ cells, DtwGeom g, d
 }  // namespace
 
 int dtw_geometry(int n, int m, int band, DtwGeom* g) {
-  g->dirs_off = g->tbl_off = g->chain_off = 0;
+  g->dirs_off = g->tbl_off = g->chain_off = g->flag_off = 0;
   g->bt_nb = 0;
   g->n = n;
   g->m = m;
@@ -869,7 +878,8 @@ int dtw_geometry(int n, int m, int band, DtwGeom* g) {
       g->dirs_off = g->cells;
       g->tbl_off = g->dirs_off + (g->cells + 7) / 8 + 2;                           // bytes -> doubles (+ slack for slot -1)
       g->chain_off = g->tbl_off + ((int64_t)g->bt_nb * 2 * g->W + 1) / 2;          // int32 [bt_nb][2W]
-      g->cells = g->chain_off + (int64_t)g->bt_nb;                                 // int32 [bt_nb][2]
+      g->flag_off = g->chain_off + (int64_t)g->bt_nb;                              // int32 [bt_nb][2]
+      g->cells = g->flag_off + 1;                                                  // screening verdict
     }
   } else {
     g->W = m;  // cells per stored row
@@ -903,6 +913,9 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
       dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC1><<<n_pairs, 32, 0, st>>>(q, r, g, cells, qptr, rptr);   \
   } while (0)
     const int offs = 2 * g.band + 3;  // one never-valid slot on each side (see dtw_fill_warp_body)
+    prof_begin("dtw_screen_kernel", st);
+    dtw_screen_kernel<<<n_pairs, 1024, 0, st>>>(q, r, g, cells, qptr, rptr);
+    prof_end();
     prof_begin("dtw_fill_warp_kernel", st);
     if (offs <= 64)
       SONAR_DTW_WARP(2);
