@@ -63,6 +63,7 @@ struct FpPlan {  // immutable once built; cached per context keyed by the parame
   size_t blob_bytes = 0;
   size_t off_win2 = 0, off_tw1 = 0, off_wn = 0, off_xtab = 0, off_dct = 0, off_lift = 0, off_regions = 0,
          off_chunk_region = 0, off_hann = 0;
+  std::vector<MelRegion> h_regions;  // host copy of the mel region table (kernel eligibility checks)
   ~FpPlan();
 };
 
@@ -98,6 +99,9 @@ struct StftArgs {
 int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out);
 int launch_stft_features(const FpPlan& plan, StftArgs& a, bool spectrum_mode, cudaStream_t st);
 bool stft_supported(int window_size);
+// second-generation kernel (stft_v2.cu): N = 1024, aligned PCM, features mode
+bool stft_v2_eligible(const FpPlan& plan, const StftArgs& a);
+int launch_stft_v2(const FpPlan& plan, StftArgs& a, cudaStream_t st);
 
 // ---- fingerprint sequencing shared by the host-pointer, device-resident and pipeline entry points ----------
 struct FpShape {

@@ -306,6 +306,7 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
   std::memcpy(host.data() + plan->off_dct, dct.data(), sizeof(float) * dct.size());
   std::memcpy(host.data() + plan->off_lift, lift.data(), sizeof(float) * nc);
   std::memcpy(host.data() + plan->off_regions, reg.data(), sizeof(MelRegion) * reg.size());
+  plan->h_regions = reg;
   std::memcpy(host.data() + plan->off_chunk_region, chunk.data(), sizeof(int) * R1);
   {  // un-normalised symmetric Hann(1024) of the pitch detector (tonal/pitch_detection.go:318-324)
     double* h = reinterpret_cast<double*>(host.data() + plan->off_hann);
