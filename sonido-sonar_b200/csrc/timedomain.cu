@@ -164,6 +164,43 @@ __global__ void __launch_bounds__(256) rms_windows_kernel(const double* __restri
   if (lane == 0) out[(int64_t)s * out_stride + w] = sqrt(acc / (double)win);
 }
 
+// Same, for windows that are a whole number R of hops long (the 400 ms / 100 ms loudness windows and the 512 / 256
+// envelope): a CTA produces 16 consecutive windows from the 16 + R - 1 hop-sized block sums they share, so every
+// sample is squared ~1.2 times instead of R times.
+constexpr int kRbWin = 16;
+__global__ void __launch_bounds__(kRbWin * 32) rms_blocks_kernel(const double* __restrict__ pcm, int64_t stride,
+                                                                 double alpha, int win, int hop, int R, int64_t nw,
+                                                                 double* __restrict__ out, int64_t out_stride) {
+  __shared__ double part[kRbWin + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.y;
+  const double* __restrict__ x = pcm + (int64_t)s * stride;
+  const int64_t w0 = (int64_t)blockIdx.x * kRbWin;
+  const int64_t last_block = nw - 1 + R - 1;
+  for (int b = warp; b < kRbWin + R - 1; b += kRbWin) {
+    const int64_t blk = w0 + b;
+    double acc = 0.0;
+    if (blk <= last_block) {
+      const int64_t s0 = blk * hop;
+      double prev = (s0 + lane) > 0 ? x[s0 + lane - 1] : 0.0;
+      for (int j = lane; j < hop; j += 32) {
+        const double cur = x[s0 + j];
+        const double y = cur - alpha * prev;
+        acc += y * y;
+        if (j + 32 < hop) prev = x[s0 + j + 31];
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (lane == 0) part[b] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < kRbWin && w0 + threadIdx.x < nw) {
+    double acc = 0.0;
+    for (int k = 0; k < R; ++k) acc += part[threadIdx.x + k];
+    out[(int64_t)s * out_stride + w0 + threadIdx.x] = sqrt(acc / (double)win);
+  }
+}
+
 // loudness units + 10th/95th percentile range on <= 4096 values per stream (bitonic sort in smem)
 __global__ void __launch_bounds__(256) loudness_range_kernel(const double* __restrict__ rms, int64_t nw,
                                                              int64_t in_stride, double* __restrict__ out,
@@ -334,6 +371,14 @@ int launch_variance(const double* x, int64_t n, int64_t stride, int n_streams, d
 int launch_rms_windows(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int win,
                        int hop, int64_t nw, double* out, int64_t out_stride, cudaStream_t st) {
   if (nw <= 0 || n_streams <= 0) return SONAR_OK;
+  if (hop > 0 && win % hop == 0 && win / hop <= 8) {
+    dim3 bgrid((unsigned)((nw + kRbWin - 1) / kRbWin), (unsigned)n_streams);
+    prof_begin("rms_windows_kernel", st);
+    rms_blocks_kernel<<<bgrid, kRbWin * 32, 0, st>>>(pcm, stride, alpha, win, hop, win / hop, nw, out, out_stride);
+    prof_end();
+    SONAR_CUDA(cudaGetLastError());
+    return SONAR_OK;
+  }
   dim3 grid((unsigned)((nw + 7) / 8), (unsigned)n_streams);
   prof_begin("rms_windows_kernel", st);
   rms_windows_kernel<<<grid, 256, 0, st>>>(pcm, n, stride, alpha, win, hop, nw, out, out_stride);

@@ -50,6 +50,24 @@ __device__ __forceinline__ void yin_pick(const double* __restrict__ d, int64_t f
     if (lane >= o) incl += up;
   }
   const double base = incl - run;
+  // Screen before dividing: cmndf[tau] = d[tau] / (cum[tau] / tau) can only be below the 0.15 threshold when
+  // d[tau] * tau < 0.16 * cum[tau] (a 6 % margin against the few-ulp rounding of the two divisions).  A frame
+  // with no such lag has no pitch (pitch_detection.go:377-383 finds no dip) and skips the 1024 FP64 divisions.
+  {
+    bool cand = false;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int tau = lane * 16 + k;
+      cand = cand || (tau >= 1 && dv[k] * (double)tau < 0.16 * (base + loc[k]));
+    }
+    if (!__any_sync(0xffffffffu, cand)) {
+      if (lane == 0 && f < Tp) {
+        r[f] = 0.0;
+        r[Tp + f] = 0.0;
+      }
+      return;
+    }
+  }
   double cm[17];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
