@@ -365,7 +365,9 @@ def run_ours(args, rank, world, local_rank):
             tr = ncu_traffic()
             roof = {"kernel": "stft_features_kernel (fused framed STFT + MFCC + spectral descriptors)", "bound": "hbm",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": tr.get("dram_bytes_per_launch") if tr else None, "peak_source": peak_src,
+                    # ncu capture of the same kernel, scaled from its frames per launch to this run's
+                    "traffic": (tr["dram_bytes_per_launch"] / tr["frames_per_launch"] * frames_per_launch) if tr else None,
+                    "traffic_source": tr.get("source") if tr else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": frames_per_launch * ALGO_BYTES_PER_FRAME,
                     "avg_launch_ms": avg_ms, "launches_timed": k_n}
         total_k = sum(v[0] for v in kern.values()) or 1.0
@@ -409,7 +411,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=8, help="source/CDN pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=32, help="source/CDN pairs per GPU per step")
     ap.add_argument("--seconds", type=float, default=300.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks (diagnostic)")
