@@ -20,6 +20,7 @@
 //     then the peak-relative reductions (noise power outside +-5, side lobe outside +-10,
 //     second peak, neighbours of the peak).
 #include <cmath>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -106,6 +107,148 @@ __global__ void __launch_bounds__(kNccThreads) ncc_exact_kernel(const XcorrPair*
     c = den < 1e-10 ? 0.0 : sum / den;
   }
   p.corr[j - p.idx_lo] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiled form of the same sums (default).  ncc_exact_kernel issues two global loads per (lag, i) and is bound
+// by the L1 data path (ncu: l1tex 88 %, FP64 62 %).  Here a CTA owns kNtT * kNtR consecutive lags of one sign
+// and walks i in chunks staged in shared memory (cp.async, double buffered); a thread owns kNtR CONSECUTIVE
+// lags, so the shifted sequence slides through a register window: one conflict-free shared load (odd stride)
+// and one broadcast load per i feed kNtR products.  Sums stay sequential in i per lag, i.e. bit-identical:
+//   lag >= 0:  u = a, v = b;   lag < 0:  u = b, v = a, lag' = -lag   (a*b and q1*q2 commute exactly)
+//   c = sum_i u[i] v[lag'+i] / sqrt(sum_i u[i]^2 * sum_i v[lag'+i]^2),  i < len = min(nu, nv - lag')
+// sum_i u[i]^2 is one running sum per thread, sampled when each lag's overlap ends; squares of v are taken
+// once when a value enters the window.  The last (< 2 kNtR) terms of each lag are added from global memory.
+constexpr int kNtT = 64;                 // threads per CTA
+constexpr int kNtR = 5;                  // lags per thread (odd: stride-5 double loads are conflict free)
+constexpr int kNtLags = kNtT * kNtR;     // lags per CTA
+constexpr int kNtChunk = 640;            // i per staged chunk (multiple of kNtR)
+constexpr int kNtV = kNtChunk + kNtLags; // staged values of the shifted sequence
+
+__device__ __forceinline__ void ncc_cp8(double* smem_dst, const double* gmem_src, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int nbytes = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(nbytes));
+}
+
+__global__ void __launch_bounds__(kNtT) ncc_tiled_kernel(const XcorrPair* __restrict__ pairs, int blocks_per_sign) {
+  __shared__ double su[2][kNtChunk];
+  __shared__ double sv[2][kNtV];
+  const XcorrPair p = pairs[blockIdx.y];
+  const bool neg = (int)blockIdx.x >= blocks_per_sign;
+  const int blk = neg ? (int)blockIdx.x - blocks_per_sign : (int)blockIdx.x;
+  // lags (as l = |lag|) of this sign inside the shard [idx_lo, idx_hi): j = aml + lag
+  int64_t l_lo, l_hi;  // [l_lo, l_hi)
+  if (!neg) {
+    l_lo = p.idx_lo - p.aml > 0 ? p.idx_lo - p.aml : 0;
+    l_hi = p.idx_hi - p.aml;
+  } else {
+    l_lo = p.aml - p.idx_hi + 1 > 1 ? p.aml - p.idx_hi + 1 : 1;
+    l_hi = p.aml - p.idx_lo + 1;
+  }
+  const int64_t L0 = l_lo + (int64_t)blk * kNtLags;
+  if (L0 >= l_hi) return;
+  const double* __restrict__ u = neg ? p.zb : p.za;
+  const double* __restrict__ v = neg ? p.za : p.zb;
+  const int64_t nu = neg ? p.nb : p.na, nv = neg ? p.na : p.nb;
+  const int t = threadIdx.x;
+  int64_t len[kNtR];
+#pragma unroll
+  for (int r = 0; r < kNtR; ++r) {
+    const int64_t l = L0 + (int64_t)kNtR * t + r;
+    // lags past the end of the shard are computed like the others (the staged tiles are zero filled) and simply
+    // not stored: a thread that straddles the end must not fall back to the slow tail for its valid lags
+    const int64_t n = nu < nv - l ? nu : nv - l;
+    len[r] = n > 0 ? n : 0;
+  }
+  const int64_t i_main = (len[kNtR - 1] / kNtR) * kNtR;  // all kNtR lags of the thread overlap on [0, i_main)
+  int64_t cta_len = nu < nv - L0 ? nu : nv - L0;          // longest overlap in the CTA
+  if (cta_len < 0) cta_len = 0;
+  const int n_chunks = (int)((cta_len + kNtChunk - 1) / kNtChunk);
+  auto stage = [&](int c) {
+    const int64_t i0 = (int64_t)c * kNtChunk;
+    double* du = su[c & 1];
+    double* dv = sv[c & 1];
+    for (int e = t; e < kNtChunk; e += kNtT) ncc_cp8(du + e, u + (i0 + e < nu ? i0 + e : 0), i0 + e < nu);
+    for (int e = t; e < kNtV; e += kNtT) {
+      const int64_t g = L0 + i0 + e;
+      ncc_cp8(dv + e, v + (g < nv ? g : 0), g < nv);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  double sum[kNtR], qv[kNtR], qu[kNtR], run = 0.0;
+#pragma unroll
+  for (int r = 0; r < kNtR; ++r) sum[r] = qv[r] = qu[r] = 0.0;
+  if (n_chunks > 0) stage(0);
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + 1 < n_chunks) {
+      stage(c + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t i0 = (int64_t)c * kNtChunk;
+    const double* __restrict__ cu = su[c & 1];
+    const double* __restrict__ cv = sv[c & 1] + kNtR * t;
+    int64_t iend = i_main - i0;
+    if (iend > kNtChunk) iend = kNtChunk;
+    if (iend > 0) {
+      double w[kNtR], w2[kNtR];
+#pragma unroll
+      for (int r = 0; r < kNtR; ++r) {
+        w[r] = cv[r];
+        w2[r] = w[r] * w[r];
+      }
+      for (int ii = 0; ii < (int)iend; ii += kNtR) {
+#pragma unroll
+        for (int s5 = 0; s5 < kNtR; ++s5) {  // window slot (s5 + r) % kNtR holds v[l_r + i]
+          const double uv = cu[ii + s5];
+          const double nv1 = cv[ii + s5 + kNtR];
+          run += uv * uv;
+#pragma unroll
+          for (int r = 0; r < kNtR; ++r) {
+            sum[r] += uv * w[(s5 + r) % kNtR];
+            qv[r] += w2[(s5 + r) % kNtR];
+          }
+          w[s5] = nv1;  // the slot lag 0 just used now holds lag kNtR-1's next value
+          w2[s5] = nv1 * nv1;
+        }
+      }
+    }
+    __syncthreads();  // the buffer is restaged two chunks later
+  }
+  // ---- tails: i in [i_main, len_r), at most 2 kNtR - 2 terms per lag, straight from global memory ----
+  if (len[0] > 0) {
+#pragma unroll
+    for (int r = 0; r < kNtR; ++r)
+      if (len[r] == i_main) qu[r] = run;
+    for (int64_t i = i_main; i < len[0]; ++i) {
+      const double uv = u[i];
+      run += uv * uv;
+#pragma unroll
+      for (int r = 0; r < kNtR; ++r) {
+        if (i < len[r]) {
+          const double vv = v[L0 + (int64_t)kNtR * t + r + i];
+          sum[r] += uv * vv;
+          qv[r] += vv * vv;
+        }
+        if (i + 1 == len[r]) qu[r] = run;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kNtR; ++r) {
+    const int64_t l = L0 + (int64_t)kNtR * t + r;
+    if (l >= l_hi) continue;
+    double c = 0.0;
+    if (len[r] > 0) {
+      const double den = sqrt(qu[r] * qv[r]);
+      c = den < 1e-10 ? 0.0 : sum[r] / den;
+    }
+    const int64_t j = neg ? p.aml - l : p.aml + l;
+    p.corr[j - p.idx_lo] = c;
+  }
 }
 
 struct PeakKey {
@@ -261,9 +404,16 @@ int launch_znorm(const XcorrSeq* seqs_dev, int count, cudaStream_t st) {
 
 int launch_xcorr(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags, cudaStream_t st) {
   if (n_pairs <= 0 || max_shard_lags <= 0) return SONAR_OK;
-  dim3 grid((unsigned)((max_shard_lags + kNccThreads - 1) / kNccThreads), (unsigned)n_pairs);
+  static const bool direct = std::getenv("SONAR_NCC_DIRECT") != nullptr;  // diagnostic: one thread per lag
   prof_begin("ncc_exact_kernel", st);
-  ncc_exact_kernel<<<grid, kNccThreads, 0, st>>>(pairs_dev);
+  if (direct) {
+    dim3 grid((unsigned)((max_shard_lags + kNccThreads - 1) / kNccThreads), (unsigned)n_pairs);
+    ncc_exact_kernel<<<grid, kNccThreads, 0, st>>>(pairs_dev);
+  } else {
+    // a shard holds at most max_shard_lags lags of either sign
+    const int bps = (int)((max_shard_lags + kNtLags - 1) / kNtLags);
+    ncc_tiled_kernel<<<dim3((unsigned)(2 * bps), (unsigned)n_pairs), kNtT, 0, st>>>(pairs_dev, bps);
+  }
   prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
