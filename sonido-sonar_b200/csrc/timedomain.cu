@@ -55,14 +55,17 @@ __global__ void __launch_bounds__(kTdThreads) frame_walk_kernel(
   const double* __restrict__ x = pcm + (int64_t)s * stride;
   const int64_t g0 = f0 * hop - 1;                // global index of staged element 0
   const int count = (nf - 1) * hop + frame + 1;  // staged elements
-  // element e lives at e + e / hop
-  for (int e = threadIdx.x; e < count; e += kTdThreads) {
-    const int64_t gi = g0 + e;
-    double* dst = tile + e + e / hop;
-    if (gi >= 0)
-      cp_async8(dst, x + gi);
-    else
-      *dst = 0.0;  // x[-1] = 0 (pre_emphasis.go:135-155, lastSample starts at 0)
+  // element e lives at e + e / hop: one pad word per hop-sized block (no per-element division: blocks outside)
+  for (int blk = 0, e0 = 0; e0 < count; ++blk, e0 += hop) {
+    const int cnt_b = count - e0 < hop ? count - e0 : hop;
+    double* dst = tile + e0 + blk;
+    const int64_t gb = g0 + e0;
+    for (int o = threadIdx.x; o < cnt_b; o += kTdThreads) {
+      if (gb + o >= 0)
+        cp_async8(dst + o, x + gb + o);
+      else
+        dst[o] = 0.0;  // x[-1] = 0 (pre_emphasis.go:135-155, lastSample starts at 0)
+    }
   }
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -74,23 +77,45 @@ __global__ void __launch_bounds__(kTdThreads) frame_walk_kernel(
   double sum = 0.0;
   int crossings = 0;
   bool prev_neg = false;
+  // one sample of the walk; y < 0 is tested on the bit pattern (sign set and not -0.0) to keep the two
+  // comparisons per sample off the FP64 pipe, which the dependent sum chain needs
+  auto step = [&](double xv) {
+    const double y = xv - alpha * xprev;
+    xprev = xv;
+    if (ENERGY) sum += y * y;
+    if (ZCR) {
+      const bool neg = (unsigned long long)__double_as_longlong(y) > 0x8000000000000000ull;
+      crossings += (neg != prev_neg) ? 1 : 0;
+      prev_neg = neg;
+    }
+  };
   int u = 1, j = 0, b = 0;  // b = u / hop
   while (j < frame) {
     int cnt = (b + 1) * hop - u;
     if (cnt > frame - j) cnt = frame - j;
     const double* __restrict__ p = base + u + b;
-#pragma unroll 8
-    for (int c = 0; c < cnt; ++c) {
-      const double xv = p[c];
-      const double y = xv - alpha * xprev;
-      xprev = xv;
-      if (ENERGY) sum += y * y;
-      if (ZCR) {
-        const bool neg = y < 0.0;
-        crossings += (neg != prev_neg) ? 1 : 0;
-        prev_neg = neg;
+    // eight samples are in registers one block ahead of their use: the shared-memory latency stays off the chain
+    int c = 0;
+    double cur[8];
+    if (cnt >= 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cur[k] = p[k];
+    }
+    for (; c + 8 <= cnt; c += 8) {
+      double nxt[8];
+      const bool more = c + 16 <= cnt;
+      if (more) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nxt[k] = p[c + 8 + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) step(cur[k]);
+      if (more) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
       }
     }
+    for (; c < cnt; ++c) step(p[c]);
     u += cnt;
     j += cnt;
     if (u == (b + 1) * hop) ++b;
