@@ -58,13 +58,31 @@ __global__ void __launch_bounds__(kTdThreads) frame_walk_kernel(
   // element e lives at e + e / hop: one pad word per hop-sized block (no per-element division: blocks outside)
   for (int blk = 0, e0 = 0; e0 < count; ++blk, e0 += hop) {
     const int cnt_b = count - e0 < hop ? count - e0 : hop;
-    double* dst = tile + e0 + blk;
     const int64_t gb = g0 + e0;
-    for (int o = threadIdx.x; o < cnt_b; o += kTdThreads) {
-      if (gb + o >= 0)
-        cp_async8(dst + o, x + gb + o);
-      else
-        dst[o] = 0.0;  // x[-1] = 0 (pre_emphasis.go:135-155, lastSample starts at 0)
+    if (gb >= 0) {  // every block but the stream's very first: plain pointer walk, 16 bytes per request when aligned
+      const double* __restrict__ src = x + gb;
+      unsigned dst = (unsigned)__cvta_generic_to_shared(tile + e0 + blk);
+      if (((reinterpret_cast<uintptr_t>(src) | dst) & 15) == 0 && (cnt_b & 1) == 0) {
+        const double* sp = src + 2 * threadIdx.x;
+        unsigned dp = dst + 16 * threadIdx.x;
+#pragma unroll 4
+        for (int o = 2 * threadIdx.x; o < cnt_b; o += 2 * kTdThreads, sp += 2 * kTdThreads, dp += 16 * kTdThreads)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dp), "l"(sp));
+      } else {
+        const double* sp = src + threadIdx.x;
+        unsigned dp = dst + 8 * threadIdx.x;
+#pragma unroll 4
+        for (int o = threadIdx.x; o < cnt_b; o += kTdThreads, sp += kTdThreads, dp += 8 * kTdThreads)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dp), "l"(sp));
+      }
+    } else {
+      double* dst = tile + e0 + blk;
+      for (int o = threadIdx.x; o < cnt_b; o += kTdThreads) {
+        if (gb + o >= 0)
+          cp_async8(dst + o, x + gb + o);
+        else
+          dst[o] = 0.0;  // x[-1] = 0 (pre_emphasis.go:135-155, lastSample starts at 0)
+      }
     }
   }
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
