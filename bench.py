@@ -40,6 +40,7 @@ SR = 44100
 WIN, HOP = 1024, 256
 MAX_LAG_S = 60.0
 DTW_BAND = 50
+_OUT = sys.stdout
 METRIC = "audio-sec/s fingerprinted (1024/256 MFCC); 5-min pair alignments/s @60s lag"
 UNIT = "audio-s/s"
 ALGO_BYTES_PER_FRAME = HOP * 8 + 13 * 8  # every input sample read once, 13 MFCC written
@@ -219,7 +220,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "alignments_per_s": cores / (ms / 1e3),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------
@@ -399,10 +400,19 @@ def run_ours(args, rank, world, local_rank):
             "detected_lags_frames": lags,
             "lag_sharded": lag_sharded,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     lib.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _quiet_stdout():
+    """stdout must carry exactly ONE JSON line; libraries (NCCL's version banner) write to fd 1 directly.
+    Point fd 1 at stderr for the whole run and hand back a file object on the original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -421,6 +431,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    global _OUT
+    _OUT = _quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
