@@ -206,7 +206,8 @@ struct Slot {  // one in-flight unit of work on a device: its streams and buffer
   cudaStream_t st = nullptr;   // H2D + the kernels that saturate the GPU
   cudaStream_t st2 = nullptr;  // latency-bound tails (DTW) + D2H of the pair pipeline, so they overlap other slots
   cudaEvent_t done = nullptr;
-  cudaEvent_t mid = nullptr;   // hand-off st -> st2
+  cudaEvent_t mid = nullptr;   // hand-off st -> st2 (short-time energies ready)
+  cudaEvent_t fpdone = nullptr;  // the rest of the fingerprint (st) has finished: st2 may copy the features out
   Buf d_in, d_out, d_tmp, h_in, h_out;
 };
 struct DevCtx {
@@ -249,7 +250,8 @@ int fp_validate(const sonar_fp_params* p);
 int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s);
 // enqueues every kernel of one uniform batch of streams on `st` (fingerprint_api.cu)
 int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, const FpShape& sh, const double* pcm_dev,
-                        int64_t n, int64_t stride, int ns, double* feat_dev, double* tmp_dev, cudaStream_t st);
+                        int64_t n, int64_t stride, int ns, double* feat_dev, double* tmp_dev, cudaStream_t st,
+                        cudaEvent_t energy_ready = nullptr);  // recorded on st once the short-time energies exist
 void scatter_block(const double* f, const FpShape& sh, sonar_fp_out* o);
 void summarize_xcorr(const XcorrPairOut& o, int aml, int64_t na, int64_t nb, int64_t n_eval, sonar_xcorr_summary* s);
 void fill_align_from_xcorr(const sonar_xcorr_summary* xc, int64_t nq, int64_t nr, int max_lag, int hop, int sr,

@@ -146,11 +146,14 @@ int sonar_init(int n_devices, const int* device_ids, sonar_ctx** out) {
       delete ctx;
       return set_error(SONAR_ERR_CUDA, "libsonar.so is built for sm_100a (B200) only; device is older");
     }
+    int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (auto& s : d.slot) {
       if ((e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)) != cudaSuccess ||
-          (e = cudaStreamCreateWithFlags(&s.st2, cudaStreamNonBlocking)) != cudaSuccess ||
+          (e = cudaStreamCreateWithPriority(&s.st2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
           (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess ||
-          (e = cudaEventCreateWithFlags(&s.mid, cudaEventDisableTiming)) != cudaSuccess) {
+          (e = cudaEventCreateWithFlags(&s.mid, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s.fpdone, cudaEventDisableTiming)) != cudaSuccess) {
         delete ctx;
         return cuda_error(e, "cudaStreamCreate");
       }
@@ -176,6 +179,7 @@ void sonar_destroy(sonar_ctx* ctx) {
       if (s.h_out.p) cudaFreeHost(s.h_out.p);
       if (s.done) cudaEventDestroy(s.done);
       if (s.mid) cudaEventDestroy(s.mid);
+      if (s.fpdone) cudaEventDestroy(s.fpdone);
       if (s.st) cudaStreamDestroy(s.st);
       if (s.st2) cudaStreamDestroy(s.st2);
     }

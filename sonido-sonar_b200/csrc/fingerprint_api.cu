@@ -88,7 +88,7 @@ int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s) {
 // sh.tmp_doubles_per_stream doubles.
 int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, const FpShape& sh,
                         const double* pcm_dev, int64_t n, int64_t stride, int ns, double* feat_dev,
-                        double* tmp_dev, cudaStream_t st) {
+                        double* tmp_dev, cudaStream_t st, cudaEvent_t energy_ready) {
   std::shared_ptr<FpPlan> plan;
   int rc = get_plan(ctx, device, p, &plan);
   if (rc) return rc;
@@ -159,6 +159,9 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
                            p->algo_sample_rate, feat_dev, L.total, -1, -1, L.zero_crossing_rate, st);
     if (rc) return rc;
   }
+  // the alignment branch of the pair pipeline only needs the short-time energies: it may start on its own stream
+  // here, next to the rest of the fingerprint (loudness range, YIN)
+  if (energy_ready) SONAR_CUDA(cudaEventRecord(energy_ready, st));
   if (Te > T) {  // band ratios only exist where a magnitude frame does (speech.go:436-456)
     rc = launch_fill_strided(feat_dev + L.low_energy_ratio + T, Te - T, L.total, ns, 0.0, st);
     if (rc) return rc;

@@ -10,9 +10,10 @@
 // blocks, a tiny kernel turns the detected lag into the trimmed start pointers the DTW kernels consume
 // (TruncateToAlignmentPCM's sign convention, alignment.go:239-243).  Pairs travel in chunks (as many as fit a
 // 512 MB PCM staging buffer; all of them when the PCM is already resident), up to eight chunks in flight per
-// device: three staging buffers feed the GPU-filling front half (fingerprint, NCC) on their own streams, and each
-// chunk's latency-bound tail (one DTW warp per pair, then the D2H copy) runs on a second stream, so the PCIe copy
-// and the kernels of the following chunks overlap it and the host-side scatter of finished chunks.
+// device: three staging buffers feed the fingerprint kernels on their own streams, and each chunk's alignment
+// branch (z-score, NCC, one DTW warp per pair, then the D2H copy) is forked onto a second stream as soon as the
+// short-time energies exist, so its latency-bound kernels run beside the YIN kernels of the same chunk and the
+// PCIe copies, kernels and host-side scatter of the neighbouring chunks.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -111,13 +112,19 @@ const T* at(const void* base, size_t off) {
   return reinterpret_cast<const T*>(static_cast<const unsigned char*>(base) + off);
 }
 
-// Front half of a chunk of c pairs on `st`: fingerprint of the 2c streams -> NCC -> trim (these kernels fill the
-// GPU).  Stream 2i is pair i's query, 2i+1 its reference, `stride` apart starting at pcm_dev.
-int enqueue_front(sonar_ctx* ctx, int device, const sonar_fp_params* p, const PairGeom& G, const ChunkLayout& L, int c,
-                  const double* pcm_dev, void* d_tmp, void* d_out, cudaStream_t st) {
+// A chunk of c pairs: the fingerprint of the 2c streams on `st` (these kernels fill the GPU), and, forked off as
+// soon as the short-time energies exist, the alignment branch on `st2`: z-score, NCC, peak metrics, trim, banded
+// DTW.  Its z-score / DTW / backtrack-chain kernels are latency bound (one warp per sequence or pair), so they
+// hide under the YIN and loudness kernels that follow the energies on `st` instead of stalling one stream.
+// Stream 2i is pair i's query, 2i+1 its reference, `stride` apart starting at pcm_dev.
+int enqueue_chunk(sonar_ctx* ctx, int device, const sonar_fp_params* p, const PairGeom& G, const ChunkLayout& L, int c,
+                  const double* pcm_dev, void* d_tmp, void* d_out, cudaStream_t st, cudaStream_t st2, cudaEvent_t mid,
+                  cudaEvent_t fpdone) {
   double* feat = at<double>(d_out, L.o_feat);
-  int rc = enqueue_fingerprint(ctx, device, p, G.sh, pcm_dev, G.n, G.stride, 2 * c, feat, at<double>(d_tmp, L.t_fp), st);
+  int rc = enqueue_fingerprint(ctx, device, p, G.sh, pcm_dev, G.n, G.stride, 2 * c, feat, at<double>(d_tmp, L.t_fp), st, mid);
   if (rc) return rc;
+  SONAR_CUDA(cudaEventRecord(fpdone, st));
+  SONAR_CUDA(cudaStreamWaitEvent(st2, mid, 0));
   std::vector<XcorrSeq> seqs(2 * (size_t)c);
   std::vector<XcorrPair> pairs(c);
   double* z = at<double>(d_tmp, L.t_z);
@@ -135,22 +142,21 @@ int enqueue_front(sonar_ctx* ctx, int device, const sonar_fp_params* p, const Pa
   XcorrPair* d_pairs = at<XcorrPair>(d_out, L.o_pairs);
   XcorrPairOut* d_xo = at<XcorrPairOut>(d_out, L.o_xo);
   // pageable sources: staged by the runtime before these calls return
-  SONAR_CUDA(cudaMemcpyAsync(d_seqs, seqs.data(), sizeof(XcorrSeq) * seqs.size(), cudaMemcpyHostToDevice, st));
-  SONAR_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(XcorrPair) * pairs.size(), cudaMemcpyHostToDevice, st));
-  if ((rc = launch_znorm(d_seqs, 2 * c, st))) return rc;
-  if ((rc = launch_xcorr(d_pairs, c, G.nl, st))) return rc;
-  if ((rc = launch_xcorr_finalize(d_pairs, c, -1, d_xo, st))) return rc;
-  return launch_xcorr_trim(d_seqs, d_pairs, d_xo, c, at<const double*>(d_out, L.o_qptr), at<const double*>(d_out, L.o_rptr),
-                           st);
-}
-
-// Tail of the chunk on `st`: the banded DTWs are single latency-bound warps, so they run on the lane's second
-// stream where they overlap the front halves of the following chunks.
-int enqueue_tail(const PairGeom& G, const ChunkLayout& L, int c, void* d_tmp, void* d_out, cudaStream_t st) {
-  return launch_dtw(nullptr, nullptr, c, G.g, 1, SONAR_STEP_SYMMETRIC2, at<double>(d_tmp, L.t_cells), nullptr,
-                    at<int32_t>(d_out, L.o_pq), at<int32_t>(d_out, L.o_pr), at<double>(d_out, L.o_pc), G.path_cap,
-                    at<DtwPairOut>(d_out, L.o_dout), st, at<const double*>(d_out, L.o_qptr),
-                    at<const double*>(d_out, L.o_rptr));
+  SONAR_CUDA(cudaMemcpyAsync(d_seqs, seqs.data(), sizeof(XcorrSeq) * seqs.size(), cudaMemcpyHostToDevice, st2));
+  SONAR_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(XcorrPair) * pairs.size(), cudaMemcpyHostToDevice, st2));
+  if ((rc = launch_znorm(d_seqs, 2 * c, st2))) return rc;
+  if ((rc = launch_xcorr(d_pairs, c, G.nl, st2))) return rc;
+  if ((rc = launch_xcorr_finalize(d_pairs, c, -1, d_xo, st2))) return rc;
+  if ((rc = launch_xcorr_trim(d_seqs, d_pairs, d_xo, c, at<const double*>(d_out, L.o_qptr), at<const double*>(d_out, L.o_rptr),
+                              st2)))
+    return rc;
+  rc = launch_dtw(nullptr, nullptr, c, G.g, 1, SONAR_STEP_SYMMETRIC2, at<double>(d_tmp, L.t_cells), nullptr,
+                  at<int32_t>(d_out, L.o_pq), at<int32_t>(d_out, L.o_pr), at<double>(d_out, L.o_pc), G.path_cap,
+                  at<DtwPairOut>(d_out, L.o_dout), st2, at<const double*>(d_out, L.o_qptr),
+                  at<const double*>(d_out, L.o_rptr));
+  if (rc) return rc;
+  SONAR_CUDA(cudaStreamWaitEvent(st2, fpdone, 0));  // the result copy that follows on st2 also carries the features
+  return SONAR_OK;
 }
 
 // host side of pair i of a finished chunk: h = pinned copy of the chunk's result block
@@ -277,12 +283,8 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
     } else {
       pcm_dev = pcm_q[(*ids)[first]];
     }
-    rc = enqueue_front(ctx, dev->device, p, G, L, c, pcm_dev, lane.d_tmp.p, lane.d_out.p, stage.st);
-    if (rc) return fail(rc);
-    if ((e = cudaEventRecord(lane.mid, stage.st)) != cudaSuccess ||
-        (e = cudaStreamWaitEvent(lane.st2, lane.mid, 0)) != cudaSuccess)
-      return fail(cuda_error(e, "cudaEventRecord/cudaStreamWaitEvent"));
-    rc = enqueue_tail(G, L, c, lane.d_tmp.p, lane.d_out.p, lane.st2);
+    rc = enqueue_chunk(ctx, dev->device, p, G, L, c, pcm_dev, lane.d_tmp.p, lane.d_out.p, stage.st, lane.st2, lane.mid,
+                       lane.fpdone);
     if (rc) return fail(rc);
     bool feat = false;  // the feature blocks only travel when somebody asked for a feature array
     for (int i = 0; i < c && !feat; i++) {

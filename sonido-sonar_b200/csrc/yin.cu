@@ -701,7 +701,11 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = sizeof(double2) * (1024 + 64 + kFftFpb * kFBuf) + sizeof(double) * kFftFpb * kERow;
     SONAR_CUDA(cudaFuncSetAttribute(yin_frame_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned ctas = (unsigned)std::min<int64_t>(total, (int64_t)2 * sms);  // persistent: 2 CTAs per SM
+    // Not persistent: a CTA takes a bounded share of the groups (its twiddle tables cost ~1 % of that) and retires,
+    // so the latency-bound kernels of the alignment branch, which run beside this kernel on a higher-priority
+    // stream, get shared memory on an SM within ~100 us instead of after the whole launch.
+    const int64_t per_cta = 12;
+    const unsigned ctas = (unsigned)std::max<int64_t>(std::min<int64_t>(total, (int64_t)2 * sms), (total + per_cta - 1) / per_cta);
     prof_begin("yin_frame_kernel", st);
     yin_frame_fft_kernel<<<ctas, kFftThreads, smem, st>>>(pcm, stride, alpha, sr, Tp, gps, total, hann_dev, scratch,
                                                          scratch_stride);
