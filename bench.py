@@ -331,6 +331,34 @@ def run_ours(args, rank, world, local_rank):
     d2h = sum(a.nbytes for a in fps[0]["query"].arrays.values()) * NS + P * (2 * max_lag + 1) * 8 + \
         sum(len(pp["path_query"]) * 16 for pp in paths_e)
 
+    # ---- extra leg: the same step with int16 PCM (what the decoder holds before the reference widens it to float64;
+    #      sonar_align_pairs_pcm).  A quarter of the bytes cross PCIe; the samples are the float64 ones
+    #      quantised to 16 bits, so this is reported beside `e2e`, never instead of it.
+    s16 = None
+    if not args.no_s16:
+        host16 = torch.empty((NS, n), dtype=torch.int16).pin_memory()
+        h16 = host16.numpy()
+        for i in range(NS):
+            h16[i] = np.clip(np.rint(hv[i, :n] * 8192.0), -32768, 32767).astype(np.int16)
+        q16 = [h16[2 * i] for i in range(P)]
+        r16 = [h16[2 * i + 1] for i in range(P)]
+
+        def step_s16():
+            res = lib.align_pairs_pcm(q16, r16, prm, MAX_LAG_S, DTW_BAND, buffers=bufs_e2e)
+            return [x["xcorr"].peak_lag for x in res]
+
+        step_s16()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            lags16 = step_s16()
+        barrier()
+        s16_ms = reduce_max(1e3 * (time.perf_counter() - t0) / n_e2e)
+        s16 = {"value": audio_s / (s16_ms / 1e3), "unit": UNIT, "ms_per_step": s16_ms,
+               "h2d_bytes_per_step": int(NS * n * 2), "d2h_bytes_per_step": int(d2h),
+               "lags_equal_f64_leg": bool(lags16 == lags),
+               "note": "int16 host PCM through sonar_align_pairs_pcm (widened to float64 on the device)"}
+
     # ---- N > 1 only: ONE long correlation (10-min pair, +-60 s) split by lag range over the ranks, NCCL
     #      all-gather of the per-shard maxima.  Reported beside the main metric, not inside it.
     lag_sharded = None
@@ -392,6 +420,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": audio_s / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "timing": "wall clock around blocking C-ABI calls",
                     "alignments_per_s": world * P / (e2e_ms / 1e3)},
+            "e2e_s16_ingest": s16,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
@@ -424,6 +453,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=32, help="source/CDN pairs per GPU per step")
     ap.add_argument("--seconds", type=float, default=300.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-s16", action="store_true", help="skip the int16-ingest extra leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks (diagnostic)")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events (diagnostic)")
     args = ap.parse_args()

@@ -429,6 +429,17 @@ int sonar_align_pairs_f64(sonar_ctx* ctx, const double* const* query_pcm, const 
                           int64_t n, int n_pairs, const sonar_fp_params* p, double max_lag_seconds, int dtw_band,
                           sonar_pair_out* outs);
 
+/* The same with the PCM in the sample format the decoder holds BEFORE the reference widens it to float64
+ * (transcode/decoder.go:707-712 asks ffmpeg for "-f f64le" and :850-870 bytesToFloat64 reinterprets the bytes;
+ * ffmpeg's own s16 -> dbl conversion is x / 32768 and flt -> dbl is exact, so the float64 values the reference
+ * would see are reproduced bit for bit by widening on the device).  A quarter (s16) or half (f32) of the bytes
+ * cross PCIe, which is what bounds the host-pointer calls.  query_pcm[i] / reference_pcm[i] point
+ * at n samples of `sample_format`; results are identical to sonar_align_pairs_f64 on the widened samples. */
+enum { SONAR_PCM_F64 = 0, SONAR_PCM_F32 = 1, SONAR_PCM_S16 = 2 };
+int sonar_align_pairs_pcm(sonar_ctx* ctx, const void* const* query_pcm, const void* const* reference_pcm,
+                          int sample_format, int64_t n, int n_pairs, const sonar_fp_params* p,
+                          double max_lag_seconds, int dtw_band, sonar_pair_out* outs);
+
 /* Device-resident form: pair i = streams 2i (query) and 2i+1 (reference) of pcm_dev, `stride` (= n rounded up to
  * even) samples apart. */
 int sonar_align_pairs_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n, int64_t stride, int n_pairs,

@@ -179,7 +179,7 @@ EXPORTS = (
     "sonar_xcorr_shard_close", "sonar_xcorr_merge_peaks", "sonar_xcorr_merge_metrics",
     "sonar_align_xcorr_f64", "sonar_dtw_f64", "sonar_dtw_batch_f64", "sonar_align_dtw_scalars",
     "sonar_colstats_cosine_f64", "sonar_colstats_f64", "sonar_compare_f64",
-    "sonar_align_pairs_sizes", "sonar_align_pairs_f64", "sonar_align_pairs_dev",
+    "sonar_align_pairs_sizes", "sonar_align_pairs_f64", "sonar_align_pairs_pcm", "sonar_align_pairs_dev",
 )
 
 
@@ -281,6 +281,8 @@ class SonarLib:
         L.sonar_align_pairs_sizes.argtypes = [C.POINTER(FpParams), C.c_int64, C.c_double, c_int32_p, c_int32_p]
         L.sonar_align_pairs_f64.argtypes = [C.c_void_p, C.POINTER(c_double_p), C.POINTER(c_double_p), C.c_int64, C.c_int,
                                             C.POINTER(FpParams), C.c_double, C.c_int, C.POINTER(PairOut)]
+        L.sonar_align_pairs_pcm.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int64,
+                                            C.c_int, C.POINTER(FpParams), C.c_double, C.c_int, C.POINTER(PairOut)]
         L.sonar_align_pairs_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.POINTER(FpParams),
                                             C.c_double, C.c_int, C.POINTER(PairOut)]
         self.ctx = C.c_void_p()
@@ -592,6 +594,22 @@ class SonarLib:
         pq = (c_double_p * npairs)(*[_dp(x) for x in qs])
         pr = (c_double_p * npairs)(*[_dp(x) for x in rs])
         self._chk(self.lib.sonar_align_pairs_f64(self.ctx, pq, pr, n, npairs, C.byref(p), max_lag_seconds, dtw_band, outs))
+        return self._pair_results(outs, keep)
+
+    PCM_FORMATS = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int16): 2}
+
+    def align_pairs_pcm(self, queries, references, p: FpParams, max_lag_seconds: float, dtw_band: int, buffers=None):
+        """sonar_align_pairs_pcm: PCM as float64, float32 or int16 arrays (the decoder's own sample format)."""
+        fmt = self.PCM_FORMATS[np.asarray(queries[0]).dtype]
+        qs = [np.ascontiguousarray(x) for x in queries]
+        rs = [np.ascontiguousarray(x) for x in references]
+        assert all(x.dtype == qs[0].dtype for x in qs + rs)
+        npairs, n = len(qs), qs[0].size
+        outs, keep = buffers if buffers is not None else self.alloc_pair_outputs(npairs, n, p, max_lag_seconds)
+        pq = (C.c_void_p * npairs)(*[x.ctypes.data for x in qs])
+        pr = (C.c_void_p * npairs)(*[x.ctypes.data for x in rs])
+        self._chk(self.lib.sonar_align_pairs_pcm(self.ctx, pq, pr, fmt, n, npairs, C.byref(p), max_lag_seconds, dtw_band,
+                                                 outs))
         return self._pair_results(outs, keep)
 
     def align_pairs_dev(self, pcm_dev: int, n: int, stride: int, n_pairs: int, p: FpParams, max_lag_seconds: float,

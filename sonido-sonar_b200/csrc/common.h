@@ -209,6 +209,7 @@ struct Slot {  // one in-flight unit of work on a device: its streams and buffer
   cudaEvent_t mid = nullptr;   // hand-off st -> st2 (short-time energies ready)
   cudaEvent_t fpdone = nullptr;  // the rest of the fingerprint (st) has finished: st2 may copy the features out
   Buf d_in, d_out, d_tmp, h_in, h_out;
+  Buf d_raw;  // narrow (f32 / s16) PCM as it crossed PCIe, widened into d_in on the device
 };
 struct DevCtx {
   int device = 0;

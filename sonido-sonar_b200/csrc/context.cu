@@ -175,6 +175,7 @@ void sonar_destroy(sonar_ctx* ctx) {
       if (s.d_in.p) cudaFree(s.d_in.p);
       if (s.d_out.p) cudaFree(s.d_out.p);
       if (s.d_tmp.p) cudaFree(s.d_tmp.p);
+      if (s.d_raw.p) cudaFree(s.d_raw.p);
       if (s.h_in.p) cudaFreeHost(s.h_in.p);
       if (s.h_out.p) cudaFreeHost(s.h_out.p);
       if (s.done) cudaEventDestroy(s.done);

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <string>
 #include <thread>
 
 #include "common.h"
@@ -103,6 +104,22 @@ ChunkLayout chunk_layout(const PairGeom& G, int C) {
   return L;
 }
 
+// f32 / s16 samples -> the float64 the reference's decoder would have produced (exact in both cases)
+template <class T>
+__global__ void widen_pcm_kernel(const T* __restrict__ src, double* __restrict__ dst, int64_t n, int64_t src_stride,
+                                 int64_t dst_stride) {
+  const T* s = src + (int64_t)blockIdx.y * src_stride;
+  double* d = dst + (int64_t)blockIdx.y * dst_stride;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (sizeof(T) == 2)
+      d[i] = (double)s[i] * (1.0 / 32768.0);  // swresample's s16 -> dbl
+    else
+      d[i] = (double)s[i];
+  }
+}
+
+inline size_t sample_bytes(int fmt) { return fmt == SONAR_PCM_S16 ? 2 : (fmt == SONAR_PCM_F32 ? 4 : 8); }
+
 template <class T>
 T* at(void* base, size_t off) {
   return reinterpret_cast<T*>(static_cast<unsigned char*>(base) + off);
@@ -164,8 +181,9 @@ int finish_pair(const sonar_fp_params* p, const PairGeom& G, const ChunkLayout& 
                 sonar_pair_out* o) {
   if (feat) {
     const double* f = at<double>(h, L.o_feat) + (size_t)(2 * i) * G.sh.L.total;
+    std::thread ref_side([&] { scatter_block(f + G.sh.L.total, G.sh, &o->reference); });
     scatter_block(f, G.sh, &o->query);
-    scatter_block(f + G.sh.L.total, G.sh, &o->reference);
+    ref_side.join();
   }
   const double* corr = at<double>(h, L.o_corr) + (size_t)i * G.corr_pair;
   const double* pc = at<double>(h, L.o_pc) + (size_t)i * G.path_cap;
@@ -215,7 +233,7 @@ constexpr size_t kPairChunkBytes = (size_t)512 << 20;  // host PCM bytes staged 
 // pcm_q / pcm_r: host pointers (host_pcm) or, device-resident, pcm_q[i] = device pointer of pair i's query with the
 // reference `stride` behind it and consecutive pairs 2*stride apart.
 void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, const double* const* pcm_r,
-                      const std::vector<int>* ids, const sonar_fp_params* p, const PairGeom* Gp, bool host_pcm,
+                      const std::vector<int>* ids, const sonar_fp_params* p, const PairGeom* Gp, bool host_pcm, int fmt,
                       sonar_pair_out* outs, DevJob* job) {
   const PairGeom& G = *Gp;
   set_current_ctx(ctx);
@@ -243,10 +261,24 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
     SONAR_CUDA(cudaEventSynchronize(s.done));
     const Pending pd = pending[li];
     pending[li].first = -1;
-    for (int i = 0; i < pd.count; i++) {
-      int rc = finish_pair(p, G, L, s.h_out.p, i, pd.feat, &outs[(*ids)[pd.first + i]]);
-      if (rc) return rc;
+    // the scatter into the caller's arrays is plain memcpy at one core's bandwidth; with the feature blocks on
+    // board (~24 MB per pair) it would outlast the GPU work, so the pairs of a chunk go to worker threads
+    std::vector<int> rcs(pd.count, SONAR_OK);
+    std::vector<std::string> errs(pd.count);
+    auto one = [&](int i) {
+      rcs[i] = finish_pair(p, G, L, s.h_out.p, i, pd.feat, &outs[(*ids)[pd.first + i]]);
+      if (rcs[i]) errs[i] = sonar_last_error();
+    };
+    if (pd.feat && pd.count > 1) {
+      std::vector<std::thread> th;
+      for (int i = 1; i < pd.count; i++) th.emplace_back(one, i);
+      one(0);
+      for (auto& t : th) t.join();
+    } else {
+      for (int i = 0; i < pd.count; i++) one(i);
     }
+    for (int i = 0; i < pd.count; i++)
+      if (rcs[i]) return set_error(rcs[i], errs[i]);
     return SONAR_OK;
   };
   int k = 0;
@@ -271,13 +303,33 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
     if (host_pcm) {
       // the staging buffer's previous user (chunk k - NP) ran its fingerprint kernels on this same stream: ordered
       double* d_in = static_cast<double*>(stage.d_in.p);
+      const size_t sb = sample_bytes(fmt);
+      unsigned char* d_raw = nullptr;
+      const int64_t raw_stride = (G.n + 7) & ~(int64_t)7;  // samples; keeps every stream 16-byte aligned
+      if (fmt != SONAR_PCM_F64) {
+        if ((rc = dev->ensure_dev(stage.d_raw, sb * 2 * (size_t)C * (size_t)raw_stride))) return fail(rc);
+        d_raw = static_cast<unsigned char*>(stage.d_raw.p);
+      }
       for (int i = 0; i < c; i++) {
         const int id = (*ids)[first + i];
-        if ((e = cudaMemcpyAsync(d_in + (int64_t)(2 * i) * G.stride, pcm_q[id], sizeof(double) * (size_t)G.n,
-                                 cudaMemcpyHostToDevice, stage.st)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(d_in + (int64_t)(2 * i + 1) * G.stride, pcm_r[id], sizeof(double) * (size_t)G.n,
-                                 cudaMemcpyHostToDevice, stage.st)) != cudaSuccess)
+        const void* hq = pcm_q[id];
+        const void* hr = pcm_r[id];
+        void* dq = d_raw ? (void*)(d_raw + sb * (size_t)(2 * i) * raw_stride) : (void*)(d_in + (int64_t)(2 * i) * G.stride);
+        void* dr = d_raw ? (void*)(d_raw + sb * (size_t)(2 * i + 1) * raw_stride)
+                         : (void*)(d_in + (int64_t)(2 * i + 1) * G.stride);
+        if ((e = cudaMemcpyAsync(dq, hq, sb * (size_t)G.n, cudaMemcpyHostToDevice, stage.st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(dr, hr, sb * (size_t)G.n, cudaMemcpyHostToDevice, stage.st)) != cudaSuccess)
           return fail(cuda_error(e, "cudaMemcpyAsync(H2D pcm)"));
+      }
+      if (d_raw) {
+        const dim3 wg(296, (unsigned)(2 * c));
+        if (fmt == SONAR_PCM_S16)
+          widen_pcm_kernel<int16_t><<<wg, 256, 0, stage.st>>>(reinterpret_cast<const int16_t*>(d_raw), d_in, G.n, raw_stride,
+                                                            G.stride);
+        else
+          widen_pcm_kernel<float><<<wg, 256, 0, stage.st>>>(reinterpret_cast<const float*>(d_raw), d_in, G.n, raw_stride,
+                                                          G.stride);
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail(cuda_error(e, "widen_pcm_kernel"));
       }
       pcm_dev = d_in;
     } else {
@@ -309,7 +361,8 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
 }
 
 int align_pairs(sonar_ctx* ctx, const double* const* q, const double* const* r, int64_t n, int n_pairs,
-                const sonar_fp_params* p, double max_lag_seconds, int dtw_band, bool host_pcm, sonar_pair_out* outs) {
+                const sonar_fp_params* p, double max_lag_seconds, int dtw_band, bool host_pcm, int fmt,
+                sonar_pair_out* outs) {
   if (!ctx || !p || (n_pairs > 0 && (!q || !outs))) return set_error(SONAR_ERR_INVALID, "audio data cannot be nil");
   if (n_pairs <= 0) return SONAR_OK;
   std::lock_guard<std::mutex> call_lock(ctx->call_mu);
@@ -328,11 +381,11 @@ int align_pairs(sonar_ctx* ctx, const double* const* q, const double* const* r, 
   for (int i = 0; i < n_pairs; i++) ids[i % nd].push_back(i);
   std::vector<DevJob> res(nd);
   if (nd == 1) {
-    run_pairs_device(ctx, &ctx->devs[0], q, r, &ids[0], p, &G, host_pcm, outs, &res[0]);
+    run_pairs_device(ctx, &ctx->devs[0], q, r, &ids[0], p, &G, host_pcm, fmt, outs, &res[0]);
   } else {
     std::vector<std::thread> th;
     for (int d = 0; d < nd; d++)
-      th.emplace_back(run_pairs_device, ctx, &ctx->devs[d], q, r, &ids[d], p, &G, host_pcm, outs, &res[d]);
+      th.emplace_back(run_pairs_device, ctx, &ctx->devs[d], q, r, &ids[d], p, &G, host_pcm, fmt, outs, &res[d]);
     for (auto& t : th) t.join();
     cudaSetDevice(ctx->devs[0].device);
   }
@@ -362,7 +415,17 @@ int sonar_align_pairs_sizes(const sonar_fp_params* p, int64_t n, double max_lag_
 int sonar_align_pairs_f64(sonar_ctx* ctx, const double* const* query_pcm, const double* const* reference_pcm, int64_t n,
                           int n_pairs, const sonar_fp_params* p, double max_lag_seconds, int dtw_band,
                           sonar_pair_out* outs) {
-  return align_pairs(ctx, query_pcm, reference_pcm, n, n_pairs, p, max_lag_seconds, dtw_band, true, outs);
+  return align_pairs(ctx, query_pcm, reference_pcm, n, n_pairs, p, max_lag_seconds, dtw_band, true, SONAR_PCM_F64, outs);
+}
+
+int sonar_align_pairs_pcm(sonar_ctx* ctx, const void* const* query_pcm, const void* const* reference_pcm, int sample_format,
+                          int64_t n, int n_pairs, const sonar_fp_params* p, double max_lag_seconds, int dtw_band,
+                          sonar_pair_out* outs) {
+  if (sample_format != SONAR_PCM_F64 && sample_format != SONAR_PCM_F32 && sample_format != SONAR_PCM_S16)
+    return set_error(SONAR_ERR_INVALID, "unknown PCM sample format");
+  return align_pairs(ctx, reinterpret_cast<const double* const*>(query_pcm),
+                     reinterpret_cast<const double* const*>(reference_pcm), n, n_pairs, p, max_lag_seconds, dtw_band, true,
+                     sample_format, outs);
 }
 
 int sonar_align_pairs_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n, int64_t stride, int n_pairs,
@@ -371,7 +434,7 @@ int sonar_align_pairs_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n, int6
   if (stride != ((n + 1) & ~(int64_t)1)) return set_error(SONAR_ERR_INVALID, "stride must be n rounded up to even");
   std::vector<const double*> q(n_pairs > 0 ? n_pairs : 0);
   for (int i = 0; i < n_pairs; i++) q[i] = pcm_dev + (int64_t)2 * i * stride;
-  return align_pairs(ctx, q.data(), nullptr, n, n_pairs, p, max_lag_seconds, dtw_band, false, outs);
+  return align_pairs(ctx, q.data(), nullptr, n, n_pairs, p, max_lag_seconds, dtw_band, false, SONAR_PCM_F64, outs);
 }
 
 }  // extern "C"

@@ -162,3 +162,31 @@ def test_chained_pair_pipeline_equals_the_separate_calls(gpu, oracle, synth):
     for g, d in zip(got, got_dev):
         assert g["xcorr"].peak_lag == d["xcorr"].peak_lag and np.array_equal(g["corr"], d["corr"])
         assert np.array_equal(g["path_query"], d["path_query"]) and np.array_equal(g["path_ref"], d["path_ref"])
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.float32])
+def test_pair_pipeline_pcm_ingest_equals_the_widened_float64_call(gpu, oracle, synth, dtype):
+    """sonar_align_pairs_pcm: int16 / float32 PCM widened on the device must give exactly what the
+    float64 entry point gives on the samples the reference's decoder would have produced (x / 32768, exact
+    float -> double), and the oracle's own widening must agree bit for bit on the integer / exact outputs."""
+    p = gpu.default_params(algo_sample_rate=44100)
+    secs, max_lag_s, band = 8.0, 2.0, 50
+    pairs = [synth.aligned_pair(secs, offset_seconds=o, seed=70 + i) for i, o in enumerate((0.9, -0.4, 1.7))]
+    if dtype == np.int16:
+        narrow = [(np.clip(np.round(a * 20000.0), -32768, 32767).astype(np.int16),
+                   np.clip(np.round(b * 20000.0), -32768, 32767).astype(np.int16)) for a, b in pairs]
+        wide = [(a.astype(np.float64) / 32768.0, b.astype(np.float64) / 32768.0) for a, b in narrow]
+    else:
+        narrow = [(a.astype(np.float32), b.astype(np.float32)) for a, b in pairs]
+        wide = [(a.astype(np.float64), b.astype(np.float64)) for a, b in narrow]
+    got = gpu.align_pairs_pcm([a for a, _ in narrow], [b for _, b in narrow], p, max_lag_s, band)
+    ref = gpu.align_pairs([a for a, _ in wide], [b for _, b in wide], p, max_lag_s, band)
+    ora = oracle.align_pairs_pcm([a for a, _ in narrow], [b for _, b in narrow], p, max_lag_s, band)
+    for g, r, o in zip(got, ref, ora):
+        for k in r["query"].arrays:
+            assert np.array_equal(g["query"].arrays[k], r["query"].arrays[k]), k
+            assert np.array_equal(g["reference"].arrays[k], r["reference"].arrays[k]), k
+        assert np.array_equal(g["corr"], r["corr"]) and np.array_equal(g["corr"], o["corr"])
+        assert g["xcorr"].peak_lag == r["xcorr"].peak_lag == o["xcorr"].peak_lag
+        assert np.array_equal(g["path_query"], o["path_query"]) and np.array_equal(g["path_ref"], o["path_ref"])
+        assert np.array_equal(g["path_cost"], r["path_cost"], equal_nan=True)
