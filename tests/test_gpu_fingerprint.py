@@ -90,6 +90,16 @@ CASES = {
     "voiced_yin_16k": (lambda s: voiced(4.0, 16000, f0=200.0), dict(
         window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=16000,
         call_sample_rate=16000)),
+    # the second-generation STFT kernel's other hop instantiations (64 / 128 / 512) and a denser mel bank
+    "w1024_h64": (lambda s: s.sweep_noise(1.0, seed=11), dict(
+        window_size=1024, hop_size=64, energy_frame=1024, energy_hop=64, algo_sample_rate=44100)),
+    "w1024_h128": (lambda s: s.sweep_noise(1.5, seed=12), dict(
+        window_size=1024, hop_size=128, energy_frame=1024, energy_hop=128, algo_sample_rate=44100)),
+    "w1024_h512": (lambda s: s.sweep_noise(3.0, seed=13), dict(
+        window_size=1024, hop_size=512, energy_frame=1024, energy_hop=512, algo_sample_rate=44100)),
+    "w1024_40mel_22k": (lambda s: s.sweep_noise(2.0, seed=14), dict(
+        algo_sample_rate=22050, call_sample_rate=22050, n_mel=40)),
+    "run_boundaries": (lambda s: s.sweep_noise(1.0, seed=15)[:1024 + 256 * 62], dict(algo_sample_rate=44100)),
     "single_frame": (lambda s: s.sweep_noise(1.0, seed=10)[:1024], dict(algo_sample_rate=44100)),
     "silence": (lambda s: np.zeros(20000), dict(algo_sample_rate=44100)),
 }
