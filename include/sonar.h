@@ -252,6 +252,21 @@ int sonar_fp_dev_layout(const sonar_fp_params* p, int64_t n_samples, sonar_fp_de
 int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int hop, int window_type,
                    double* mag, double* phase, double* cplx);
 
+/* MusicFeatureExtractor's additions to the per-frame spectral block, computed on the same magnitude
+ * spectrogram ComputeSTFTWithWindow produces (fingerprint/extractors/music.go:261-302; the factory has the music
+ * extractor commented out, so this is reached by direct construction only):
+ *   contrast [T][n_bands]  SpectralContrast.Compute (algorithms/spectral/spectral_contrast.go:26-187): n_bands
+ *                          log-spaced bands from 200 Hz to Nyquist, 10*log10(mean of the top 20 % / mean of the
+ *                          bottom 20 % of the band's sorted power); music.go:111 uses 6 bands;
+ *   chroma   [T][12]       ChromaSTFT.convertSTFTToChroma (algorithms/chroma/chroma_stft.go:63-138): power folded by
+ *                          round(69 + 12 log2(f / 440)) mod 12 over 80..8000 Hz, then normalised to unit sum;
+ *   bark     [T][n_bark]   BarkScale.ComputeBarkSpectrum (algorithms/spectral/bark_scale.go:36-128): triangular
+ *                          Traunmueller filter bank between bark_low_hz and bark_high_hz applied to the power.
+ * Every output is optional (NULL = skipped; n_bands / n_bark may then be 0). */
+int sonar_music_spectral_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int hop, int window_type,
+                             int sample_rate, int n_bands, double* contrast, double* chroma, int n_bark,
+                             double bark_low_hz, double bark_high_hz, double* bark);
+
 /* ------------------------------------------------------------------------- */
 /* alignment: cross-correlation                                               */
 /* ------------------------------------------------------------------------- */

@@ -179,7 +179,7 @@ EXPORTS = (
     "sonar_xcorr_shard_close", "sonar_xcorr_merge_peaks", "sonar_xcorr_merge_metrics",
     "sonar_align_xcorr_f64", "sonar_dtw_f64", "sonar_dtw_batch_f64", "sonar_align_dtw_scalars",
     "sonar_colstats_cosine_f64", "sonar_colstats_f64", "sonar_compare_f64",
-    "sonar_align_pairs_sizes", "sonar_align_pairs_f64", "sonar_align_pairs_pcm", "sonar_align_pairs_dev",
+    "sonar_music_spectral_f64", "sonar_align_pairs_sizes", "sonar_align_pairs_f64", "sonar_align_pairs_pcm", "sonar_align_pairs_dev",
 )
 
 
@@ -281,6 +281,8 @@ class SonarLib:
         L.sonar_align_pairs_sizes.argtypes = [C.POINTER(FpParams), C.c_int64, C.c_double, c_int32_p, c_int32_p]
         L.sonar_align_pairs_f64.argtypes = [C.c_void_p, C.POINTER(c_double_p), C.POINTER(c_double_p), C.c_int64, C.c_int,
                                             C.POINTER(FpParams), C.c_double, C.c_int, C.POINTER(PairOut)]
+        L.sonar_music_spectral_f64.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               c_double_p, c_double_p, C.c_int, C.c_double, C.c_double, c_double_p]
         L.sonar_align_pairs_pcm.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int64,
                                             C.c_int, C.POINTER(FpParams), C.c_double, C.c_int, C.POINTER(PairOut)]
         L.sonar_align_pairs_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.POINTER(FpParams),
@@ -595,6 +597,20 @@ class SonarLib:
         pr = (c_double_p * npairs)(*[_dp(x) for x in rs])
         self._chk(self.lib.sonar_align_pairs_f64(self.ctx, pq, pr, n, npairs, C.byref(p), max_lag_seconds, dtw_band, outs))
         return self._pair_results(outs, keep)
+
+    def music_spectral(self, pcm, win=1024, hop=256, window_type="hann", sample_rate=44100, n_bands=6, n_bark=24,
+                       bark_low=0.0, bark_high=None):
+        """sonar_music_spectral_f64: (contrast [T][n_bands], chroma [T][12], bark [T][n_bark])."""
+        x = _f64(pcm)
+        T = (x.size - win) // hop + 1
+        if T <= 0:
+            T = 0
+        contrast, chroma, bark = np.zeros((T, n_bands)), np.zeros((T, 12)), np.zeros((T, n_bark))
+        wt = WINDOWS[window_type] if isinstance(window_type, str) else window_type
+        hi = float(sample_rate) / 2 if bark_high is None else bark_high
+        self._chk(self.lib.sonar_music_spectral_f64(self.ctx, _dp(x), x.size, win, hop, wt, sample_rate, n_bands,
+                                                    _dp(contrast), _dp(chroma), n_bark, bark_low, hi, _dp(bark)))
+        return contrast, chroma, bark
 
     PCM_FORMATS = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int16): 2}
 

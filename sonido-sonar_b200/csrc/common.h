@@ -194,6 +194,15 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
                const double* const* rptr = nullptr);
 int launch_dtw_expand(const double* cells, const DtwGeom& g, double* full, cudaStream_t st);
 
+// ---- music-extractor spectral additions (music_spectral.cu) -----------------
+int launch_music_spectral(const double* mag, int64_t T, int B, int n_bands, const int* edges, double* contrast,
+                          const signed char* cmap, double* chroma, int n_bark, const double* bank,
+                          const int2* bank_range, double* bark, cudaStream_t st);
+// host tables in float64 as the reference's constructors build them (host_tables.cpp)
+std::vector<int> host_contrast_edges(int n_bands, int num_bins, int sample_rate);
+std::vector<signed char> host_chroma_map(int freq_bins, double freq_resolution);
+std::vector<double> host_bark_bank(int n_filters, int fft_size, int sample_rate, double low, double high);
+
 // ---- column statistics (colstats.cu) ----------------------------------------
 int launch_colstats(const double* x, int64_t t, int dim, double* stats, cudaStream_t st);
 

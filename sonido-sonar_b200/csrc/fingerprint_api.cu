@@ -464,4 +464,103 @@ int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int ho
   return SONAR_OK;
 }
 
+int sonar_music_spectral_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int hop, int window_type,
+                             int sample_rate, int n_bands, double* contrast, double* chroma, int n_bark,
+                             double bark_low_hz, double bark_high_hz, double* bark) {
+  if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  if (!pcm || n <= 0) return set_error(SONAR_ERR_EMPTY, "empty signal");  // analyzers/spectral.go:387
+  if (win <= 0) return set_error(SONAR_ERR_INVALID, "window size must be positive");
+  if (hop <= 0) return set_error(SONAR_ERR_INVALID, "hop size must be positive");
+  if (sample_rate <= 0) return set_error(SONAR_ERR_INVALID, "sample rate must be positive");
+  if ((contrast && n_bands <= 0) || (bark && n_bark <= 0)) return set_error(SONAR_ERR_INVALID, "band count must be positive");
+  const int64_t T = (n - win) / hop + 1;
+  if (T <= 0) return set_error(SONAR_ERR_TOO_SHORT, "signal too short for given window size and hop size");
+  if (!stft_supported(win))
+    return set_error(SONAR_ERR_UNSUPPORTED, "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
+  std::lock_guard<std::mutex> call_lock(ctx->call_mu);
+  set_current_ctx(ctx);
+  sonar_fp_params p;
+  sonar_fp_params_default(&p);
+  p.window_size = win;
+  p.hop_size = hop;
+  p.window_type = window_type;
+  DevCtx& dev = ctx->devs[0];
+  SONAR_CUDA(cudaSetDevice(dev.device));
+  std::shared_ptr<FpPlan> plan;
+  int rc = get_plan(ctx, dev.device, &p, &plan);
+  if (rc) return rc;
+  Slot& s = dev.slot[0];
+  const int B = win / 2 + 1;
+  // host tables, float64, as the reference's constructors build them
+  std::vector<int> edges;
+  std::vector<signed char> cmap;
+  std::vector<double> bank;
+  std::vector<int2> ranges;
+  if (contrast) edges = host_contrast_edges(n_bands, B, sample_rate);
+  if (chroma) cmap = host_chroma_map(B, (double)sample_rate / (double)win);
+  if (bark) {
+    bank = host_bark_bank(n_bark, (B - 1) * 2, sample_rate, bark_low_hz, bark_high_hz);
+    ranges.resize((size_t)n_bark);
+    for (int i = 0; i < n_bark; i++) {
+      int lo = B, hi = 0;
+      for (int k = 0; k < B; k++)
+        if (bank[(size_t)i * B + k] != 0.0) {
+          lo = std::min(lo, k);
+          hi = k + 1;
+        }
+      ranges[(size_t)i] = make_int2(lo < hi ? lo : 0, lo < hi ? hi : 0);
+    }
+  }
+  auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const int64_t chunk = std::min<int64_t>(T, 4096);  // frames per materialised spectrogram chunk (~17 MB at B = 513)
+  const size_t o_mag = 0, o_con = o_mag + up256(sizeof(double) * (size_t)chunk * B),
+               o_chr = o_con + up256(sizeof(double) * (size_t)chunk * (size_t)std::max(n_bands, 1)),
+               o_brk = o_chr + up256(sizeof(double) * (size_t)chunk * 12),
+               o_edg = o_brk + up256(sizeof(double) * (size_t)chunk * (size_t)std::max(n_bark, 1)),
+               o_map = o_edg + up256(sizeof(int) * (edges.size() + 1)), o_bank = o_map + up256(cmap.size() + 1),
+               o_rng = o_bank + up256(sizeof(double) * (bank.size() + 1)),
+               total = o_rng + up256(sizeof(int2) * (ranges.size() + 1));
+  const int64_t stride = (n + 1) & ~(int64_t)1;
+  if ((rc = dev.ensure_dev(s.d_in, sizeof(double) * (size_t)stride)) || (rc = dev.ensure_dev(s.d_out, total))) return rc;
+  unsigned char* d = static_cast<unsigned char*>(s.d_out.p);
+  SONAR_CUDA(cudaMemcpyAsync(s.d_in.p, pcm, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s.st));
+  if (contrast) SONAR_CUDA(cudaMemcpyAsync(d + o_edg, edges.data(), sizeof(int) * edges.size(), cudaMemcpyHostToDevice, s.st));
+  if (chroma) SONAR_CUDA(cudaMemcpyAsync(d + o_map, cmap.data(), cmap.size(), cudaMemcpyHostToDevice, s.st));
+  if (bark) {
+    SONAR_CUDA(cudaMemcpyAsync(d + o_bank, bank.data(), sizeof(double) * bank.size(), cudaMemcpyHostToDevice, s.st));
+    SONAR_CUDA(cudaMemcpyAsync(d + o_rng, ranges.data(), sizeof(int2) * ranges.size(), cudaMemcpyHostToDevice, s.st));
+  }
+  const unsigned char* blob = static_cast<const unsigned char*>(plan->d_blob);
+  for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+    const int64_t tc = std::min<int64_t>(chunk, T - t0);
+    StftArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.pcm = static_cast<const double*>(s.d_in.p) + t0 * hop;
+    a.n = n - t0 * hop;
+    a.stride = stride;
+    a.n_streams = 1;
+    a.T = tc;
+    a.hop = hop;
+    a.win2 = reinterpret_cast<const float2*>(blob + plan->off_win2);
+    a.tw1 = reinterpret_cast<const float2*>(blob + plan->off_tw1);
+    a.wn = reinterpret_cast<const float2*>(blob + plan->off_wn);
+    a.mag = reinterpret_cast<double*>(d + o_mag);
+    if ((rc = launch_stft_features(*plan, a, true, s.st))) return rc;
+    double* dc = contrast ? reinterpret_cast<double*>(d + o_con) : nullptr;
+    double* dh = chroma ? reinterpret_cast<double*>(d + o_chr) : nullptr;
+    double* db = bark ? reinterpret_cast<double*>(d + o_brk) : nullptr;
+    rc = launch_music_spectral(a.mag, tc, B, n_bands, reinterpret_cast<const int*>(d + o_edg), dc,
+                               reinterpret_cast<const signed char*>(d + o_map), dh, n_bark,
+                               reinterpret_cast<const double*>(d + o_bank), reinterpret_cast<const int2*>(d + o_rng), db,
+                               s.st);
+    if (rc) return rc;
+    if (contrast)
+      SONAR_CUDA(cudaMemcpyAsync(contrast + t0 * n_bands, dc, sizeof(double) * (size_t)tc * n_bands, cudaMemcpyDeviceToHost, s.st));
+    if (chroma) SONAR_CUDA(cudaMemcpyAsync(chroma + t0 * 12, dh, sizeof(double) * (size_t)tc * 12, cudaMemcpyDeviceToHost, s.st));
+    if (bark) SONAR_CUDA(cudaMemcpyAsync(bark + t0 * n_bark, db, sizeof(double) * (size_t)tc * n_bark, cudaMemcpyDeviceToHost, s.st));
+    SONAR_CUDA(cudaStreamSynchronize(s.st));  // the chunk buffers are reused
+  }
+  return SONAR_OK;
+}
+
 }  // extern "C"

@@ -318,6 +318,69 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
   return SONAR_OK;
 }
 
+// ---- music-extractor tables --------------------------------------
+
+// spectral_contrast.go:131-187 initializeBands: log-spaced edges from 200 Hz to Nyquist, made strictly increasing
+std::vector<int> host_contrast_edges(int n_bands, int num_bins, int sample_rate) {
+  std::vector<int> edges((size_t)n_bands + 1);
+  const double nyquist = (double)sample_rate / 2.0;
+  const double min_freq = 200.0;
+  double max_freq = nyquist;
+  if (max_freq <= min_freq) max_freq = min_freq * 2;
+  const double log_min = std::log10(min_freq), log_max = std::log10(max_freq);
+  const double log_step = (log_max - log_min) / (double)n_bands;
+  for (int i = 0; i <= n_bands; i++) {
+    const double freq = std::pow(10.0, log_min + (double)i * log_step);
+    int bin = (int)(freq * (double)(num_bins - 1) / nyquist);
+    bin = std::min(bin, num_bins - 1);
+    bin = std::max(bin, 0);
+    edges[(size_t)i] = bin;
+  }
+  for (int i = 1; i <= n_bands; i++)
+    if (edges[(size_t)i] <= edges[(size_t)i - 1]) edges[(size_t)i] = edges[(size_t)i - 1] + 1;
+  return edges;
+}
+
+// chroma_stft.go:92-123: bins between 80 Hz and 8 kHz fold to round(69 + 12 log2(f / 440)) mod 12, others to -1
+std::vector<signed char> host_chroma_map(int freq_bins, double freq_resolution) {
+  std::vector<signed char> map((size_t)freq_bins);
+  for (int f = 0; f < freq_bins; f++) {
+    const double frequency = (double)f * freq_resolution;
+    if (frequency < 80.0 || frequency > 8000.0) {
+      map[(size_t)f] = -1;
+      continue;
+    }
+    const double midi = 69.0 + 12.0 * std::log2(frequency / 440.0);
+    map[(size_t)f] = (signed char)((int)std::round(midi) % 12);
+  }
+  return map;
+}
+
+// bark_scale.go:36-93 CreateBarkFilterBank (Traunmueller forward, the reference's own "inverse")
+std::vector<double> host_bark_bank(int n_filters, int fft_size, int sample_rate, double low, double high) {
+  auto hz2bark = [](double hz) { return (26.81 * hz / (1960.0 + hz)) - 0.53; };
+  auto bark2hz = [](double b) { return 1960.0 * (b + 0.53) / (26.28 - b); };
+  const int B = fft_size / 2 + 1;
+  std::vector<double> bank((size_t)n_filters * B, 0.0);
+  const double lo = hz2bark(low), hi = hz2bark(high);
+  const double step = (hi - lo) / (double)(n_filters + 1);
+  std::vector<int> bins((size_t)n_filters + 2);
+  for (int i = 0; i < n_filters + 2; i++) {
+    const double hz = bark2hz(lo + (double)i * step);
+    const int b = (int)std::floor(((double)fft_size + 1.0) * hz / (double)sample_rate + 0.5);
+    bins[(size_t)i] = std::min(b, fft_size / 2);
+  }
+  for (int m = 1; m <= n_filters; m++) {
+    const int left = bins[(size_t)m - 1], center = bins[(size_t)m], right = bins[(size_t)m + 1];
+    double* row = bank.data() + (size_t)(m - 1) * B;
+    for (int k = std::max(left, 0); k < center && k < B; k++)
+      if (center != left) row[k] = (double)(k - left) / (double)(center - left);
+    for (int k = std::max(center, 0); k < right && k < B; k++)
+      if (right != center) row[k] = (double)(right - k) / (double)(right - center);
+  }
+  return bank;
+}
+
 // ---- cross-correlation scalars ------------------------------------------------
 
 int actual_max_lag(int max_lag, int64_t l1, int64_t l2) {  // stats/correlation.go:452-461

@@ -225,3 +225,37 @@ def test_temporal_feature_group(gpu, oracle, synth, capi, algo_sr):
         assert a.scalars[k] == b.scalars[k], k
     for k in ("average_amplitude", "onset_density"):
         assert a.scalars[k] == pytest.approx(b.scalars[k], rel=1e-12), k
+
+
+@pytest.mark.parametrize("case", [
+    dict(make=lambda s: s.sweep_noise(2.0, seed=41), win=1024, hop=256, sr=44100, n_bands=6, n_bark=24, tol_db=1e-3),
+    dict(make=lambda s: s.speech_band_noise(3.0), win=512, hop=160, sr=16000, n_bands=6, n_bark=18, tol_db=1e-3),
+    dict(make=lambda s: voiced(2.0, 44100), win=2048, hop=512, sr=44100, n_bands=4, n_bark=24, tol_db=0.02),
+    dict(make=lambda s: s.sweep_noise(25.0, seed=42), win=1024, hop=256, sr=44100, n_bands=6, n_bark=24,
+         tol_db=1e-3),  # more than one 4096-frame chunk
+], ids=["music_1024", "speech_512", "voiced_2048", "chunked"])
+def test_music_spectral_matches_oracle(gpu, oracle, synth, case):
+    """spectral contrast, chroma folding and Bark-band energies of the music extractor on the GPU
+    spectrogram.  Chroma and Bark are linear in the FP32 power spectrum: 1e-4 of the array's scale.  The contrast is
+    10*log10(peak / valley) where the valley is the mean of the weakest 20 % of a band's bins, i.e. it sits at the
+    FP32 FFT's noise floor on frames with > 60 dB of dynamic range (the same effect as spectral flatness):
+    0.02 dB absolute there, 1e-3 dB on broadband frames."""
+    x = case["make"](synth)
+    kw = dict(win=case["win"], hop=case["hop"], sample_rate=case["sr"], n_bands=case["n_bands"], n_bark=case["n_bark"],
+              bark_low=50.0, bark_high=0.45 * case["sr"])
+    gc, gh, gb = gpu.music_spectral(x, **kw)
+    oc, oh, ob = oracle.music_spectral(x, **kw)
+    assert gc.shape == oc.shape and gh.shape == oh.shape and gb.shape == ob.shape
+    feature_close(gh, oh, tol=1e-4, name="chroma")
+    feature_close(gb, ob, tol=1e-4, name="bark")
+    assert np.max(np.abs(gc - oc)) <= case["tol_db"], np.max(np.abs(gc - oc))
+
+
+def test_music_spectral_edge_cases(gpu, oracle):
+    c, h, b = gpu.music_spectral(np.zeros(4096), sample_rate=44100)
+    assert not c.any() and not h.any() and not b.any()
+    for lib in (gpu, oracle):
+        with pytest.raises(Exception, match="signal too short"):
+            lib.music_spectral(np.zeros(100), sample_rate=44100)
+        with pytest.raises(Exception, match="sample rate must be positive"):
+            lib.music_spectral(np.zeros(4096), sample_rate=0)

@@ -376,3 +376,96 @@ def test_golden_alignment_fixture(oracle):
     assert np.array_equal(c, g["corr"]) and s.peak_lag == int(g["peak_lag"])
     d = oracle.dtw(g["dq"], g["dr"], band=int(g["band"]))
     assert np.array_equal(d["path_query"], g["path_query"]) and np.array_equal(d["path_ref"], g["path_ref"])
+
+
+# --------------------------------------------------------------------------------------
+# music-extractor spectral additions: independent numpy restatements of
+# spectral_contrast.go:26-187, chroma_stft.go:63-138 and bark_scale.go:36-128
+# --------------------------------------------------------------------------------------
+
+def _np_contrast(mag, sr, n_bands):
+    nb = mag.shape[1]
+    nyq = sr / 2.0
+    lo, hi = math.log10(200.0), math.log10(nyq if nyq > 200.0 else 400.0)
+    edges = []
+    for i in range(n_bands + 1):
+        f = 10.0 ** (lo + i * (hi - lo) / n_bands)
+        edges.append(min(max(int(f * (nb - 1) / nyq), 0), nb - 1))
+    for i in range(1, n_bands + 1):
+        if edges[i] <= edges[i - 1]:
+            edges[i] = edges[i - 1] + 1
+    out = np.zeros((mag.shape[0], n_bands))
+    for t in range(mag.shape[0]):
+        for b in range(n_bands):
+            s, e = edges[b], min(edges[b + 1], nb)
+            if s >= e:
+                continue
+            p = np.sort(mag[t, s:e] ** 2)
+            k = max(int(0.2 * p.size), 1)
+            valley, peak = p[:k].sum() / k, p[-k:].sum() / k
+            if valley <= 0:
+                valley = 1e-10
+            out[t, b] = 0.0 if peak <= 0 else 10.0 * math.log10(peak / valley)
+    return out, edges
+
+
+def _np_chroma(mag, sr, win):
+    res = sr / win
+    out = np.zeros((mag.shape[0], 12))
+    for f in range(mag.shape[1]):
+        fr = f * res
+        if fr < 80.0 or fr > 8000.0:
+            continue
+        midi = 69.0 + 12.0 * math.log2(fr / 440.0)
+        c = int(math.floor(abs(midi) + 0.5) * (1 if midi >= 0 else -1)) % 12  # Go's math.Round
+        out[:, c] += mag[:, f] ** 2
+    tot = out.sum(axis=1, keepdims=True)
+    return np.where(tot > 1e-10, out / np.where(tot > 1e-10, tot, 1.0), out)
+
+
+def _np_bark(mag, sr, n_filters, low, high):
+    nb = mag.shape[1]
+    fft = (nb - 1) * 2
+    h2b = lambda hz: 26.81 * hz / (1960.0 + hz) - 0.53
+    b2h = lambda b: 1960.0 * (b + 0.53) / (26.28 - b)
+    pts = [h2b(low) + i * (h2b(high) - h2b(low)) / (n_filters + 1) for i in range(n_filters + 2)]
+    bins = [min(int(math.floor((fft + 1.0) * b2h(b) / sr + 0.5)), fft // 2) for b in pts]
+    bank = np.zeros((n_filters, nb))
+    for m in range(1, n_filters + 1):
+        l, c, r = bins[m - 1], bins[m], bins[m + 1]
+        for k in range(max(l, 0), min(c, nb)):
+            if c != l:
+                bank[m - 1, k] = (k - l) / (c - l)
+        for k in range(max(c, 0), min(r, nb)):
+            if r != c:
+                bank[m - 1, k] = (r - k) / (r - c)
+    return (mag ** 2) @ bank.T
+
+
+def test_music_spectral_against_numpy(oracle, synth):
+    x = synth.sweep_noise(1.5, seed=31)
+    mag, _, _ = oracle.stft(x, 1024, 256)
+    contrast, chroma, bark = oracle.music_spectral(x, sample_rate=44100, n_bands=6, n_bark=24, bark_low=50.0,
+                                                   bark_high=15000.0)
+    ref_c, edges = _np_contrast(mag, 44100, 6)
+    assert edges == [4, 10, 22, 48, 106, 233, 512]  # 200 Hz * 110.25^(i/6) in 43.07 Hz bins
+    np.testing.assert_allclose(contrast, ref_c, rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(chroma, _np_chroma(mag, 44100, 1024), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(bark, _np_bark(mag, 44100, 24, 50.0, 15000.0), rtol=1e-11, atol=1e-12)
+    assert np.allclose(chroma.sum(axis=1), 1.0)
+
+
+def test_music_spectral_known_answers(oracle):
+    sr, n = 44100, 44100
+    t = np.arange(n) / sr
+    a440 = np.sin(2 * np.pi * 440.0 * t)
+    contrast, chroma, bark = oracle.music_spectral(a440, sample_rate=sr)
+    assert np.all(np.argmax(chroma, axis=1) == 9)          # A4 -> pitch class 9 (MIDI 69 mod 12)
+    assert np.all(chroma[:, 9] > 0.5)                       # 43 Hz bins: the Hann main lobe also touches G# and A#
+    assert np.all(contrast[:, 0] > 30.0)                    # the 200-438 Hz band holds the tone's skirt: peaky
+    # silence: no energy -> valley floored at 1e-10, peak 0 -> contrast 0; chroma stays all-zero (not normalised)
+    c0, h0, b0 = oracle.music_spectral(np.zeros(8192), sample_rate=sr)
+    assert not c0.any() and not h0.any() and not b0.any()
+    for bad in (dict(win=0), dict(hop=0), dict(sample_rate=0)):
+        with pytest.raises(Exception):
+            oracle.music_spectral(a440, **bad)
