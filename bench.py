@@ -386,9 +386,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = measured_peak()
         k_ms, k_n = kern.get("stft_features_kernel", (0.0, 0))
-        frames_per_launch = NS * T
         roof = None
         if k_n:
+            frames_per_launch = NS * T * args.steps / k_n  # the library may split a step into chunks of pairs
             avg_ms = k_ms / k_n
             achieved = frames_per_launch * ALGO_BYTES_PER_FRAME / (avg_ms / 1e3) / 1e9
             tr = ncu_traffic()

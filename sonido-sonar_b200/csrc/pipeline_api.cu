@@ -16,6 +16,7 @@
 // PCIe copies, kernels and host-side scatter of the neighbouring chunks.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -248,7 +249,12 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
   const int total = (int)ids->size();
   // pairs per chunk: host path = what fits the staging budget (the PCIe copy of the next chunk overlaps this one);
   // device-resident = contiguous runs as large as possible (batched launches hide the latency-bound kernels)
-  int C = host_pcm ? (int)std::max<size_t>(1, kPairChunkBytes / (sizeof(double) * 2 * (size_t)G.stride)) : 32;
+  static const int dev_chunk = [] {
+    const char* e = std::getenv("SONAR_PAIR_CHUNK");
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : 32;  // 16 overlaps the chunks' kernels (-3 % step) but they then time-share the SMs
+  }();
+  int C = host_pcm ? (int)std::max<size_t>(1, kPairChunkBytes / (sizeof(double) * 2 * (size_t)G.stride)) : dev_chunk;
   C = std::min(C, total);
   const ChunkLayout L = chunk_layout(G, C);
   struct Pending {
