@@ -16,6 +16,7 @@
 // bank-conflict free) and one warp accumulates ONE frame per lane in the reference's
 // order.  The chain of dependent DADDs is what bounds this kernel, not HBM.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -152,6 +153,90 @@ __global__ void __launch_bounds__(kTdThreads) frame_walk_kernel(
   if (ZCR) {
     const double dur = (double)frame / (double)sr;  // len(frame)/sampleRate; sr==0 -> +Inf -> zcr 0
     o[o_zcr + f] = frame < 2 ? 0.0 : (double)crossings / dur;
+  }
+}
+
+// The same walk without the shared-memory tile, for frames that are a whole number R of hops long: a thread owns
+// G CONSECUTIVE frames and walks their union once (hop-sized segments), so every pre-emphasised sample and its
+// square are computed once and added to the (up to R) running sums of the frames that contain it — each frame's
+// sum still receives its terms in ascending sample order, i.e. bit-identical.  G independent chains per thread hide
+// the FP64 add latency, and with no tile the SM holds as many warps as registers allow instead of ~100 chains.
+// Every lane streams through its own part of the signal (16-byte loads, each 128-byte line serves eight of them
+// from L1).
+template <int G, bool ALIGNED>
+__global__ void __launch_bounds__(128) frame_walk_multi_kernel(
+    const double* __restrict__ pcm, int64_t stride, double alpha, int frame, int hop, int R, int64_t Tn, int sr,
+    double* __restrict__ out, int64_t out_stride, int64_t o_energy, int64_t o_entropy, int64_t o_zcr) {
+  const int s = blockIdx.y;
+  const int64_t f0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * G;
+  if (f0 >= Tn) return;
+  const int nf = (int)((Tn - f0 < G) ? (Tn - f0) : G);
+  const double* __restrict__ x = pcm + (int64_t)s * stride;
+  const int64_t s0 = f0 * hop;
+  double sum[G];
+  int cnt[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    sum[g] = 0.0;
+    cnt[g] = 0;
+  }
+  double xprev = s0 > 0 ? x[s0 - 1] : 0.0;  // x[-1] = 0 (pre_emphasis.go:135-155)
+  bool prev_neg = false;
+  const int nseg = nf - 1 + R;
+  for (int sg = 0; sg < nseg; ++sg) {
+    bool act[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) act[g] = g < nf && g <= sg && sg < g + R;
+    const double* __restrict__ p = x + s0 + (int64_t)sg * hop;
+    auto step = [&](double xv, bool first) {
+      const double y = xv - alpha * xprev;
+      xprev = xv;
+      const double sq = y * y;
+      const bool neg = (unsigned long long)__double_as_longlong(y) > 0x8000000000000000ull;
+      const int cross = (neg != prev_neg) ? 1 : 0;
+      prev_neg = neg;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (act[g]) {
+          sum[g] += sq;
+          // the first sample of a frame has no predecessor inside the frame (zero_crossing_rate.go:43)
+          if (!(first && sg == g)) cnt[g] += cross;
+        }
+      }
+    };
+    if (ALIGNED) {  // hop even, 16-byte aligned rows
+      const double2* __restrict__ p2 = reinterpret_cast<const double2*>(p);
+      {
+        const double2 v = p2[0];
+        step(v.x, true);
+        step(v.y, false);
+      }
+      int e = 1;
+      for (; e + 4 <= hop / 2; e += 4) {
+        const double2 a = p2[e], b = p2[e + 1], c = p2[e + 2], d = p2[e + 3];
+        step(a.x, false); step(a.y, false); step(b.x, false); step(b.y, false);
+        step(c.x, false); step(c.y, false); step(d.x, false); step(d.y, false);
+      }
+      for (; e < hop / 2; ++e) {
+        const double2 a = p2[e];
+        step(a.x, false);
+        step(a.y, false);
+      }
+    } else {
+      step(p[0], true);
+      for (int e = 1; e < hop; ++e) step(p[e], false);
+    }
+  }
+  double* __restrict__ o = out + (int64_t)s * out_stride;
+  const double dur = (double)frame / (double)sr;  // len(frame)/sampleRate; sr==0 -> +Inf -> zcr 0
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (g >= nf) break;
+    const int64_t f = f0 + g;
+    const double e = sqrt(sum[g] / (double)frame);
+    o[o_energy + f] = e;
+    if (o_entropy >= 0) o[o_entropy + f] = e > 0.0 ? -e * log(e + 1e-10) : 0.0;
+    o[o_zcr + f] = frame < 2 ? 0.0 : (double)cnt[g] / dur;
   }
 }
 
@@ -376,11 +461,28 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
   if (Tn <= 0 || n_streams <= 0) return SONAR_OK;
   const int64_t count = (int64_t)(kTdFrames - 1) * hop + frame + 1;
   const size_t smem = sizeof(double) * (size_t)(count + count / hop + 2);
-  if (smem > 200 * 1024)
-    return set_error(SONAR_ERR_UNSUPPORTED, "energy frame / hop too long for the shared-memory tile");
   dim3 grid((unsigned)((Tn + kTdFrames - 1) / kTdFrames), (unsigned)n_streams);
   const bool en = o_energy >= 0, zc = o_zcr >= 0;
   if (!en && !zc) return SONAR_OK;
+  static const bool tiled_only = std::getenv("SONAR_FRAME_WALK_TILED") != nullptr;  // diagnostic
+  if (en && zc && !tiled_only && hop > 0 && frame % hop == 0 && frame / hop <= 8) {
+    constexpr int G = 8;
+    const bool aligned = (hop % 2 == 0) && (stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
+    const int64_t groups = (Tn + G - 1) / G;
+    const dim3 mg((unsigned)((groups + 127) / 128), (unsigned)n_streams);
+    prof_begin("frame_walk_kernel", st);
+    if (aligned)
+      frame_walk_multi_kernel<G, true><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr, out,
+                                                          out_stride, o_energy, o_entropy, o_zcr);
+    else
+      frame_walk_multi_kernel<G, false><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr, out,
+                                                           out_stride, o_energy, o_entropy, o_zcr);
+    prof_end();
+    SONAR_CUDA(cudaGetLastError());
+    return SONAR_OK;
+  }
+  if (smem > 200 * 1024)
+    return set_error(SONAR_ERR_UNSUPPORTED, "energy frame / hop too long for the shared-memory tile");
 #define LAUNCH_FW(E, Z)                                                                                  \
   do {                                                                                                   \
     auto k = frame_walk_kernel<E, Z>;                                                                    \
