@@ -310,13 +310,29 @@ __global__ void __launch_bounds__(kRbWin * 32) rms_blocks_kernel(const double* _
     double acc = 0.0;
     if (blk <= last_block) {
       const int64_t s0 = blk * hop;
-      double prev = (s0 + lane) > 0 ? x[s0 + lane - 1] : 0.0;
-      for (int j = lane; j < hop; j += 32) {
-        const double cur = x[s0 + j];
-        const double y = cur - alpha * prev;
-        acc += y * y;
-        if (j + 32 < hop) prev = x[s0 + j + 31];
+      // four independent strips per lane: eight loads in flight (this kernel waits on DRAM, not on arithmetic)
+      double a4[4] = {0.0, 0.0, 0.0, 0.0};
+      int j = lane;
+      for (; j + 96 < hop; j += 128) {
+        double cur[4], prv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t i = s0 + j + 32 * u;
+          cur[u] = x[i];
+          prv[u] = i > 0 ? x[i - 1] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double y = cur[u] - alpha * prv[u];
+          a4[u] += y * y;
+        }
       }
+      for (; j < hop; j += 32) {
+        const int64_t i = s0 + j;
+        const double y = x[i] - alpha * (i > 0 ? x[i - 1] : 0.0);
+        a4[0] += y * y;
+      }
+      acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     }
     if (lane == 0) part[b] = acc;
