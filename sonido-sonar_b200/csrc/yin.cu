@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(kYinThreads) yin_frame_kernel(const double* __
 //
 // r[tau] = sum_{j<512} p[j] p[j+tau] is the linear cross-correlation of a = p[0..512) (zero padded) with
 // b = p[0..1024), so r = IFFT(conj(A) B) with 1024-point transforms and no wrap-around (j + tau <= 1022).
-// Per frame: ONE complex forward FFT of z = a + i b (A and B fall out of the Hermitian split), and HALF an
+// Per frame: ONE complex forward FFT of z = u + i v, the two 512-sample halves of the frame (their zero-padded
+// spectra U, V fall out of the Hermitian split, A = U, B = U + (-1)^k V; half of z is zero, which prunes the first
+// pass), and HALF an
 // inverse FFT — the spectra conj(A)B of two frames are packed as Q = P0 + i P1, whose inverse carries r of
 // frame 0 in its real part and r of frame 1 in its imaginary part.  ~66 k FP64 operations per frame
 // instead of 262 k DFMA.
@@ -284,15 +286,44 @@ __device__ __forceinline__ void twiddle16(double2 (&v)[16], const double2* __res
 #undef SONAR_TW
 }
 
-// forward transform of the tile Z by the 64 threads tf of barrier `bar`; result in digit-reversed order
+template <int K>
+__device__ __forceinline__ void pre_tw16(double2 (&v)[8]) {  // v[n] *= W_16^n
+  if constexpr (K < 8) {
+    v[K] = dmul_tw<16, K>(v[K]);
+    pre_tw16<K + 1>(v);
+  }
+}
+
+// forward transform of the tile Z by the 64 threads tf of barrier `bar`; result in digit-reversed order.
+// HALF: only the first 512 points (rows 0..7 of the tile) are non-zero, so the 16-point transforms of pass 1
+// reduce to two 8-point transforms, X[2j] = DFT8(x)[j] and X[2j+1] = DFT8(x W_16^n)[j], and rows 8..15 are not read.
+template <bool HALF>
 __device__ __forceinline__ void fft1024_fwd(double2* __restrict__ Z, const double2* __restrict__ W,
                                             const double2* __restrict__ W64, int tf, int bar) {
   {
     double2 v[16];
-    ld16<0>(v, Z + tf + (tf >> 4), kFRow);
-    FftReg64<16>::run(v);
+    double2* col = Z + tf + (tf >> 4);
+    if (HALF) {
+      double2 e[8], o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        e[k] = col[k * kFRow];
+        o[k] = e[k];
+      }
+      pre_tw16<0>(o);
+      FftReg64<8>::run(e);
+      FftReg64<8>::run(o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[2 * k] = e[k];
+        v[2 * k + 1] = o[k];
+      }
+    } else {
+      ld16<0>(v, col, kFRow);
+      FftReg64<16>::run(v);
+    }
     twiddle16<false>(v, W, tf);
-    st16<0>(v, Z + tf + (tf >> 4), kFRow);
+    st16<0>(v, col, kFRow);
   }
   bar_sync(bar, 64);
   {
@@ -446,9 +477,12 @@ __global__ void __launch_bounds__(kFftThreads, 2)
     }
     __syncthreads();  // every window is in registers before the tiles are overwritten
     {
-      double2* zp = Z + (tf >> 2) * kFRow + 17 * (tf & 3);
+      // z[n] = p[n] + i p[n + 512], n < 512 (rows 0..7 of the tile; rows 8..15 are zeros the pruned first pass
+      // never reads): thread tf < 32 owns the real parts of n = 16 tf + k, thread tf + 32 their imaginary parts
+      const int th = tf & 31;
+      double* zp = reinterpret_cast<double*>(Z + (th >> 2) * kFRow + 17 * (th & 3)) + (tf >> 5);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) zp[k] = make_double2(tf < 32 ? v[k] : 0.0, v[k]);  // z = a + i b
+      for (int k = 0; k < 16; ++k) zp[2 * k] = v[k];
     }
     // ---- E(tau) = S[tau + 512] - S[tau]
     {
@@ -475,7 +509,7 @@ __global__ void __launch_bounds__(kFftThreads, 2)
         for (int k = 0; k < 16; ++k) E[17 * tf + k] -= base + ex[k];  // - S[tau]
       }
     }
-    fft1024_fwd(Z, sW, sW64, tf, 1 + fl);
+    fft1024_fwd<true>(Z, sW, sW64, tf, 1 + fl);
     // ---- P = conj(A) B per frame, Q = P0 + i P1 per pair, written over the pair's first tile
     bar_sync(5 + pr, 128);
     {
@@ -495,9 +529,12 @@ __global__ void __launch_bounds__(kFftThreads, 2)
         for (int h = 0; h < 2; ++h) {
           const double2* Zh = h ? Z1 : Z0;
           const double2 zk = Zh[pk], zn = Zh[pn];
-          // A = (zk + conj(zn))/2, B = -i (zk - conj(zn))/2, P = conj(A) B (the 1/4 is folded into the final scale)
+          // U = (zk + conj(zn))/2 and V = -i (zk - conj(zn))/2 are the spectra of the two zero-padded halves;
+          // A = U, B = U + (-1)^k V, P = conj(A) B = |U|^2 + (-1)^k conj(U) V (the 1/4 is folded into the final scale)
           const double sr_ = zk.x + zn.x, si = zk.y - zn.y, dr = zk.x - zn.x, di = zk.y + zn.y;
-          P[h] = make_double2(fma(sr_, di, -(si * dr)), -fma(sr_, dr, si * di));
+          const double cr = fma(sr_, di, -(si * dr)), ci = -fma(sr_, dr, si * di);
+          const double uu = fma(sr_, sr_, si * si);
+          P[h] = (k & 1) ? make_double2(uu - cr, -ci) : make_double2(uu + cr, ci);
         }
         Z0[pk] = make_double2(P[0].x - P[1].y, P[0].y + P[1].x);
         if (pn != pk) Z0[pn] = make_double2(P[0].x + P[1].y, P[1].x - P[0].y);
