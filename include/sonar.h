@@ -505,6 +505,14 @@ int sonar_compare_f64(sonar_ctx* ctx, const sonar_cmp_features* f1, const sonar_
                       const sonar_cmp_weights* weights, int enable_content_filter,
                       sonar_cmp_result* out);
 
+/* FingerprintComparator.BatchCompare / the comparison loop of FindBestMatches (comparison.go:1107-1151, 197-263):
+ * one query against n candidates, results[i] for candidates[i] (a NULL candidate is skipped: the reference drops
+ * it; its result is zeroed with n_features = -1).  Thresholding, sorting and ranking of FindBestMatches stay in
+ * the shim: they are O(n log n) on n scalars. */
+int sonar_compare_batch_f64(sonar_ctx* ctx, const sonar_cmp_features* query,
+                            const sonar_cmp_features* const* candidates, int n, const sonar_cmp_weights* weights,
+                            int enable_content_filter, sonar_cmp_result* results);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,7 +179,7 @@ EXPORTS = (
     "sonar_xcorr_shard_close", "sonar_xcorr_merge_peaks", "sonar_xcorr_merge_metrics",
     "sonar_align_xcorr_f64", "sonar_dtw_f64", "sonar_dtw_batch_f64", "sonar_align_dtw_scalars",
     "sonar_colstats_cosine_f64", "sonar_colstats_f64", "sonar_compare_f64",
-    "sonar_music_spectral_f64", "sonar_align_pairs_sizes", "sonar_align_pairs_f64", "sonar_align_pairs_pcm", "sonar_align_pairs_dev",
+    "sonar_music_spectral_f64", "sonar_compare_batch_f64", "sonar_align_pairs_sizes", "sonar_align_pairs_f64", "sonar_align_pairs_pcm", "sonar_align_pairs_dev",
 )
 
 
@@ -685,6 +685,21 @@ class SonarLib:
             f.silence_ratio = fp.scalars["silence_ratio"]
             f.onset_density = fp.scalars["onset_density"]
         return f, keep
+
+    def compare_batch(self, query: CmpFeatures, candidates, weights, content_filter=False):
+        """sonar_compare_batch_f64: FingerprintComparator.BatchCompare (None candidates are skipped)."""
+        w = CmpWeights()
+        for i, v in enumerate(weights):
+            w.w[i] = v
+        n = len(candidates)
+        ptrs = (C.POINTER(CmpFeatures) * n)(*[C.pointer(c) if c is not None else None for c in candidates])
+        res = (CmpResult * n)()
+        self.lib.sonar_compare_batch_f64.argtypes = [C.c_void_p, C.POINTER(CmpFeatures),
+                                                     C.POINTER(C.POINTER(CmpFeatures)), C.c_int, C.POINTER(CmpWeights),
+                                                     C.c_int, C.POINTER(CmpResult)]
+        self._chk(self.lib.sonar_compare_batch_f64(self.ctx, C.byref(query), ptrs, n, C.byref(w), int(content_filter),
+                                                   res))
+        return list(res)
 
     def compare(self, f1: CmpFeatures, f2: CmpFeatures, weights, content_filter=False) -> CmpResult:
         w = CmpWeights()

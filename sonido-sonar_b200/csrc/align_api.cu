@@ -667,12 +667,39 @@ int sonar_colstats_cosine_f64(sonar_ctx* ctx, const double* x, int64_t tx, const
   return SONAR_OK;
 }
 
+static int compare_locked(sonar_ctx* ctx, const sonar_cmp_features* f1, const sonar_cmp_features* f2,
+                          const sonar_cmp_weights* w, int content_filter, sonar_cmp_result* o);
+
 int sonar_compare_f64(sonar_ctx* ctx, const sonar_cmp_features* f1, const sonar_cmp_features* f2,
                       const sonar_cmp_weights* w, int content_filter, sonar_cmp_result* o) {
   if (!ctx || !f1 || !f2 || !w || !o) return set_error(SONAR_ERR_INVALID, "fingerprints cannot be nil");  // :135
   std::lock_guard<std::mutex> call_lock(ctx->call_mu);
   set_current_ctx(ctx);
   SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
+  return compare_locked(ctx, f1, f2, w, content_filter, o);
+}
+
+int sonar_compare_batch_f64(sonar_ctx* ctx, const sonar_cmp_features* query, const sonar_cmp_features* const* cands,
+                            int n, const sonar_cmp_weights* w, int content_filter, sonar_cmp_result* results) {
+  if (!ctx || !query || !w || (n > 0 && (!cands || !results)))
+    return set_error(SONAR_ERR_INVALID, "query fingerprint cannot be nil");  // comparison.go:1108-1110
+  std::lock_guard<std::mutex> call_lock(ctx->call_mu);
+  set_current_ctx(ctx);
+  SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
+  for (int i = 0; i < n; i++) {
+    if (!cands[i]) {  // comparison.go:1123-1125: nil candidates are skipped
+      std::memset(&results[i], 0, sizeof(results[i]));
+      results[i].n_features = -1;
+      continue;
+    }
+    int rc = compare_locked(ctx, query, cands[i], w, content_filter, &results[i]);
+    if (rc) return rc;
+  }
+  return SONAR_OK;
+}
+
+static int compare_locked(sonar_ctx* ctx, const sonar_cmp_features* f1, const sonar_cmp_features* f2,
+                          const sonar_cmp_weights* w, int content_filter, sonar_cmp_result* o) {
   std::memset(o, 0, sizeof(*o));
   o->dist_mfcc = o->dist_spectral = o->dist_temporal = o->dist_harmonic = kNaN;
   o->content_type_match = f1->content_type == f2->content_type;

@@ -36,3 +36,25 @@ def test_compare_fingerprints(gpu, oracle, synth):
     f2.content_type = 3
     r = gpu.compare(f1, f2, w, content_filter=True)
     assert r.overall_similarity == 0.0 and r.confidence == 0.25 and r.content_type_match == 0
+
+
+def test_batch_compare_equals_single_compares(gpu, oracle, synth):
+    """sonar_compare_batch_f64 (BatchCompare / FindBestMatches' loop, comparison.go:1107-1151,197-263)."""
+    p = gpu.default_params(algo_sample_rate=44100)
+    w = [0.5, 0.2, 0.0, 0.1, 0.0, 0.2, 0.0]
+    fps = [gpu.fingerprint(synth.sweep_noise(3.0, seed=50 + i, f1=3000.0 + 1500.0 * i), p) for i in range(4)]
+    feats = [gpu.cmp_features(f) for f in fps]  # (struct, keep-alive)
+    q = feats[0][0]
+    cands = [feats[1][0], None, feats[2][0], feats[3][0], feats[0][0]]
+    got = gpu.compare_batch(q, cands, w)
+    ref = oracle.compare_batch(q, cands, w)
+    assert got[1].n_features == -1 and ref[1].n_features == -1  # nil candidates are skipped
+    for i, c in enumerate(cands):
+        if c is None:
+            continue
+        one = gpu.compare(q, c, w).as_dict()
+        for k, v in got[i].as_dict().items():
+            assert v == pytest.approx(one[k], rel=0, abs=0, nan_ok=True), k       # same code path: identical
+            assert v == pytest.approx(ref[i].as_dict()[k], rel=1e-9, abs=1e-12, nan_ok=True), k
+    order = sorted((i for i, c in enumerate(cands) if c is not None), key=lambda i: -got[i].overall_similarity)
+    assert order[0] == 4  # the query itself is its own best match
