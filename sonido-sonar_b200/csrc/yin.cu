@@ -440,11 +440,14 @@ __global__ void __launch_bounds__(kFftThreads, 2)
     prefetch_pair(rawbuf, pcm + (grp / groups_per_stream) * stride, (grp % groups_per_stream) * kFftFpb + 2 * pr, limit, tf);
   }
 
+  __syncthreads();  // twiddle tables complete
   for (int64_t grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
     const int s = (int)(grp / groups_per_stream);
     const int64_t f0 = (grp % groups_per_stream) * kFftFpb;
+    // From here on the two pairs of a CTA never wait for each other: everything a pair touches (its two tiles, its
+    // raw-sample buffer, its E / d rows) is private to its 128 threads, so every barrier below is pair-wide at most.
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();  // raw samples landed; previous iteration's CMNDF is done with sE
+    bar_sync(5 + pr, 128);  // raw samples landed; previous iteration's CMNDF is done with sE
     // ---- stage: thread tf of frame fl owns samples [16 tf, 16 tf + 16): stream-level pre-emphasis (speech.go:161),
     //      the detector's own (pitch_detection.go:299-314), un-normalised Hann; exclusive prefix sums of p^2
     double v[16], ex[16], run = 0.0;
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(kFftThreads, 2)
         }
       }
     }
-    __syncthreads();  // every window is in registers before the tiles are overwritten
+    bar_sync(5 + pr, 128);  // every window is in registers before the pair's tiles are overwritten
     {
       // z[n] = p[n] + i p[n + 512], n < 512 (rows 0..7 of the tile; rows 8..15 are zeros the pruned first pass
       // never reads): thread tf < 32 owns the real parts of n = 16 tf + k, thread tf + 32 their imaginary parts
@@ -564,10 +567,9 @@ __global__ void __launch_bounds__(kFftThreads, 2)
         E1[ep] = d1 > 0.0 ? d1 : 0.0;
       }
     }
-    __syncthreads();
-    // ---- CMNDF + first dip below 0.15 (pitch_detection.go:363-383): one warp per frame, 16 lags per lane
-    const int wv = tid >> 5, lane = tid & 31;
-    if (wv < kFftFpb) yin_pick<17>(sE[wv], f0 + wv, Tp, sr, lane, raw + (int64_t)s * raw_stride);
+    bar_sync(5 + pr, 128);
+    // ---- CMNDF + first dip below 0.15 (pitch_detection.go:363-383): the first warp of each frame, 16 lags per lane
+    if (tf < 32) yin_pick<17>(sE[fl], f0 + fl, Tp, sr, tf, raw + (int64_t)s * raw_stride);
   }
 }
 
