@@ -224,7 +224,16 @@ int sonar_fingerprint_f64(sonar_ctx* ctx, const double* pcm, int64_t n,
  * applied to whole fingerprints): n_streams host buffers, one sonar_fp_out
  * each.  Streams are sharded round-robin over the context's devices and
  * pipelined (pinned double-buffered H2D) on each. */
+/* PCM sample formats of the *_pcm entry points */
+enum { SONAR_PCM_F64 = 0, SONAR_PCM_F32 = 1, SONAR_PCM_S16 = 2 };
+
 int sonar_fingerprint_batch_f64(sonar_ctx* ctx, const double* const* pcm, const int64_t* n,
+                                int n_streams, const sonar_fp_params* p, sonar_fp_out* outs);
+
+/* sonar_fingerprint_batch_f64 for PCM that has not been widened to float64 yet (SONAR_PCM_F32 / SONAR_PCM_S16, see
+ * sonar_align_pairs_pcm below): pcm[i] points at n[i] samples of `sample_format`; identical results to the float64
+ * call on the widened samples, a half / a quarter of the PCIe bytes. */
+int sonar_fingerprint_batch_pcm(sonar_ctx* ctx, const void* const* pcm, int sample_format, const int64_t* n,
                                 int n_streams, const sonar_fp_params* p, sonar_fp_out* outs);
 
 /* Device-resident batch: `pcm_dev` holds n_streams streams of `n` samples
@@ -450,7 +459,6 @@ int sonar_align_pairs_f64(sonar_ctx* ctx, const double* const* query_pcm, const 
  * would see are reproduced bit for bit by widening on the device).  A quarter (s16) or half (f32) of the bytes
  * cross PCIe, which is what bounds the host-pointer calls.  query_pcm[i] / reference_pcm[i] point
  * at n samples of `sample_format`; results are identical to sonar_align_pairs_f64 on the widened samples. */
-enum { SONAR_PCM_F64 = 0, SONAR_PCM_F32 = 1, SONAR_PCM_S16 = 2 };
 int sonar_align_pairs_pcm(sonar_ctx* ctx, const void* const* query_pcm, const void* const* reference_pcm,
                           int sample_format, int64_t n, int n_pairs, const sonar_fp_params* p,
                           double max_lag_seconds, int dtw_band, sonar_pair_out* outs);

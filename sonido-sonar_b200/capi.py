@@ -173,7 +173,7 @@ EXPORTS = (
     "sonar_memcpy_d2h", "sonar_synchronize", "sonar_kernel_launches", "sonar_stream",
     "sonar_profile_enable", "sonar_profile_read", "sonar_window_f64",
     "sonar_fp_params_default", "sonar_fp_sizes", "sonar_fingerprint_f64",
-    "sonar_fingerprint_batch_f64", "sonar_fingerprint_batch_dev", "sonar_fp_dev_layout",
+    "sonar_fingerprint_batch_f64", "sonar_fingerprint_batch_pcm", "sonar_fingerprint_batch_dev", "sonar_fp_dev_layout",
     "sonar_stft_f64", "sonar_xcorr_ncc_f64", "sonar_xcorr_batch_f64", "sonar_xcorr_batch_dev",
     "sonar_xcorr_shard_open", "sonar_xcorr_shard_metrics_f64", "sonar_xcorr_shard_corr",
     "sonar_xcorr_shard_close", "sonar_xcorr_merge_peaks", "sonar_xcorr_merge_metrics",
@@ -401,6 +401,20 @@ class SonarLib:
         lens = (C.c_int64 * ns)(*[x.size for x in pcms])
         outs, keep = buffers if buffers is not None else self.alloc_batch_outputs([x.size for x in pcms], p)
         self._chk(self.lib.sonar_fingerprint_batch_f64(self.ctx, ptrs, lens, ns, C.byref(p), outs))
+        return [self._finish_fp(k[0], dict(k[1]), outs[i]) for i, k in enumerate(keep)]
+
+    def fingerprint_batch_pcm(self, pcms, p: FpParams, buffers=None) -> list[Fingerprint]:
+        """sonar_fingerprint_batch_pcm: float64, float32 or int16 arrays (one dtype for the whole batch)."""
+        pcms = [np.ascontiguousarray(x) for x in pcms]
+        fmt = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int16): 2}[pcms[0].dtype]
+        assert all(x.dtype == pcms[0].dtype for x in pcms)
+        ns = len(pcms)
+        ptrs = (C.c_void_p * ns)(*[x.ctypes.data for x in pcms])
+        lens = (C.c_int64 * ns)(*[x.size for x in pcms])
+        outs, keep = buffers if buffers is not None else self.alloc_batch_outputs([x.size for x in pcms], p)
+        self.lib.sonar_fingerprint_batch_pcm.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, c_int64_p, C.c_int,
+                                                         C.POINTER(FpParams), C.POINTER(FpOut)]
+        self._chk(self.lib.sonar_fingerprint_batch_pcm(self.ctx, ptrs, fmt, lens, ns, C.byref(p), outs))
         return [self._finish_fp(k[0], dict(k[1]), outs[i]) for i, k in enumerate(keep)]
 
     def fp_dev_layout(self, p: FpParams, n: int) -> FpDevLayout:

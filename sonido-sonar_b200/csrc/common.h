@@ -263,6 +263,10 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
                         int64_t n, int64_t stride, int ns, double* feat_dev, double* tmp_dev, cudaStream_t st,
                         cudaEvent_t energy_ready = nullptr);  // recorded on st once the short-time energies exist
 void scatter_block(const double* f, const FpShape& sh, sonar_fp_out* o);
+// f32 / s16 PCM rows (src_stride samples apart) -> float64 rows (pipeline_api.cu); fmt = SONAR_PCM_*
+int launch_widen_pcm(const void* src, int fmt, double* dst, int64_t n, int64_t src_stride, int64_t dst_stride, int rows,
+                     cudaStream_t st);
+inline size_t pcm_sample_bytes(int fmt) { return fmt == SONAR_PCM_S16 ? 2 : (fmt == SONAR_PCM_F32 ? 4 : 8); }
 void summarize_xcorr(const XcorrPairOut& o, int aml, int64_t na, int64_t nb, int64_t n_eval, sonar_xcorr_summary* s);
 void fill_align_from_xcorr(const sonar_xcorr_summary* xc, int64_t nq, int64_t nr, int max_lag, int hop, int sr,
                            sonar_align_result* out);

@@ -270,7 +270,7 @@ struct DeviceJob {
 // the H2D copy of chunk k+1 and k+2 overlaps the kernels and the D2H of chunk k, and the host-side scatter of
 // a finished chunk into the caller's arrays overlaps the GPU work queued on the other slots.
 void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, const std::vector<Chunk>* chunks,
-                      const sonar_fp_params* p, sonar_fp_out* outs, DeviceJob* job) {
+                      const sonar_fp_params* p, int fmt, sonar_fp_out* outs, DeviceJob* job) {
   set_current_ctx(ctx);
   auto fail = [&](int rc) {
     job->rc = rc;
@@ -305,10 +305,23 @@ void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, con
         (rc = dev->ensure_host(s.h_out, out_bytes)))
       return fail(rc);
     double* d_in = static_cast<double*>(s.d_in.p);
-    for (int i = 0; i < ns; i++) {
-      e = cudaMemcpyAsync(d_in + (int64_t)i * stride, pcm[c.ids[i]], sizeof(double) * (size_t)c.n,
-                          cudaMemcpyHostToDevice, s.st);
-      if (e != cudaSuccess) return fail(cuda_error(e, "cudaMemcpyAsync(H2D pcm)"));
+    if (fmt == SONAR_PCM_F64) {
+      for (int i = 0; i < ns; i++) {
+        e = cudaMemcpyAsync(d_in + (int64_t)i * stride, pcm[c.ids[i]], sizeof(double) * (size_t)c.n,
+                            cudaMemcpyHostToDevice, s.st);
+        if (e != cudaSuccess) return fail(cuda_error(e, "cudaMemcpyAsync(H2D pcm)"));
+      }
+    } else {  // narrow samples cross PCIe and are widened on the device (sonar_fingerprint_batch_pcm)
+      const size_t sb = pcm_sample_bytes(fmt);
+      const int64_t raw_stride = (c.n + 7) & ~(int64_t)7;
+      if ((rc = dev->ensure_dev(s.d_raw, sb * (size_t)raw_stride * ns))) return fail(rc);
+      unsigned char* d_raw = static_cast<unsigned char*>(s.d_raw.p);
+      for (int i = 0; i < ns; i++) {
+        e = cudaMemcpyAsync(d_raw + sb * (size_t)i * raw_stride, pcm[c.ids[i]], sb * (size_t)c.n, cudaMemcpyHostToDevice,
+                            s.st);
+        if (e != cudaSuccess) return fail(cuda_error(e, "cudaMemcpyAsync(H2D pcm)"));
+      }
+      if ((rc = launch_widen_pcm(d_raw, fmt, d_in, c.n, raw_stride, stride, ns, s.st))) return fail(rc);
     }
     rc = enqueue_fingerprint(ctx, dev->device, p, c.sh, d_in, c.n, stride, ns, static_cast<double*>(s.d_out.p),
                              static_cast<double*>(s.d_tmp.p), s.st);
@@ -334,8 +347,23 @@ using namespace sonar;
 
 extern "C" {
 
+static int fingerprint_batch(sonar_ctx* ctx, const double* const* pcm, int fmt, const int64_t* n, int n_streams,
+                             const sonar_fp_params* p, sonar_fp_out* outs);
+
 int sonar_fingerprint_batch_f64(sonar_ctx* ctx, const double* const* pcm, const int64_t* n, int n_streams,
                                 const sonar_fp_params* p, sonar_fp_out* outs) {
+  return fingerprint_batch(ctx, pcm, SONAR_PCM_F64, n, n_streams, p, outs);
+}
+
+int sonar_fingerprint_batch_pcm(sonar_ctx* ctx, const void* const* pcm, int sample_format, const int64_t* n,
+                                int n_streams, const sonar_fp_params* p, sonar_fp_out* outs) {
+  if (sample_format != SONAR_PCM_F64 && sample_format != SONAR_PCM_F32 && sample_format != SONAR_PCM_S16)
+    return set_error(SONAR_ERR_INVALID, "unknown PCM sample format");
+  return fingerprint_batch(ctx, reinterpret_cast<const double* const*>(pcm), sample_format, n, n_streams, p, outs);
+}
+
+static int fingerprint_batch(sonar_ctx* ctx, const double* const* pcm, int fmt, const int64_t* n, int n_streams,
+                             const sonar_fp_params* p, sonar_fp_out* outs) {
   if (!ctx || !p || (n_streams > 0 && (!pcm || !n || !outs)))
     return set_error(SONAR_ERR_INVALID, "audio data cannot be nil");  // fingerprint.go:139
   if (n_streams <= 0) return SONAR_OK;
@@ -361,11 +389,11 @@ int sonar_fingerprint_batch_f64(sonar_ctx* ctx, const double* const* pcm, const 
   }
   std::vector<DeviceJob> jobs(nd);
   if (nd == 1) {
-    run_device_batch(ctx, &ctx->devs[0], pcm, &per_dev[0], p, outs, &jobs[0]);
+    run_device_batch(ctx, &ctx->devs[0], pcm, &per_dev[0], p, fmt, outs, &jobs[0]);
   } else {
     std::vector<std::thread> th;
     for (int d = 0; d < nd; d++)
-      th.emplace_back(run_device_batch, ctx, &ctx->devs[d], pcm, &per_dev[d], p, outs, &jobs[d]);
+      th.emplace_back(run_device_batch, ctx, &ctx->devs[d], pcm, &per_dev[d], p, fmt, outs, &jobs[d]);
     for (auto& t : th) t.join();
     cudaSetDevice(ctx->devs[0].device);
   }

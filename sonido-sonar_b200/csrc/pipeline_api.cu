@@ -41,6 +41,38 @@ struct PairGeom {
 
 inline size_t up(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// f32 / s16 samples -> the float64 the reference's decoder would have produced (exact in both cases)
+template <class T>
+__global__ void widen_pcm_kernel(const T* __restrict__ src, double* __restrict__ dst, int64_t n, int64_t src_stride,
+                                 int64_t dst_stride) {
+  const T* s = src + (int64_t)blockIdx.y * src_stride;
+  double* d = dst + (int64_t)blockIdx.y * dst_stride;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (sizeof(T) == 2)
+      d[i] = (double)s[i] * (1.0 / 32768.0);  // swresample's s16 -> dbl
+    else
+      d[i] = (double)s[i];
+  }
+}
+
+}  // namespace
+
+int launch_widen_pcm(const void* src, int fmt, double* dst, int64_t n, int64_t src_stride, int64_t dst_stride, int rows,
+                     cudaStream_t st) {
+  if (rows <= 0 || n <= 0) return SONAR_OK;
+  const dim3 wg(296, (unsigned)rows);
+  if (fmt == SONAR_PCM_S16)
+    widen_pcm_kernel<int16_t><<<wg, 256, 0, st>>>(static_cast<const int16_t*>(src), dst, n, src_stride, dst_stride);
+  else if (fmt == SONAR_PCM_F32)
+    widen_pcm_kernel<float><<<wg, 256, 0, st>>>(static_cast<const float*>(src), dst, n, src_stride, dst_stride);
+  else
+    return set_error(SONAR_ERR_INVALID, "unknown PCM sample format");
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
+namespace {
+
 int pair_geometry(const sonar_fp_params* p, int64_t n, double max_lag_seconds, int band, PairGeom* G) {
   int rc = fp_shape(p, n, &G->sh);
   if (rc) return rc;
@@ -105,21 +137,7 @@ ChunkLayout chunk_layout(const PairGeom& G, int C) {
   return L;
 }
 
-// f32 / s16 samples -> the float64 the reference's decoder would have produced (exact in both cases)
-template <class T>
-__global__ void widen_pcm_kernel(const T* __restrict__ src, double* __restrict__ dst, int64_t n, int64_t src_stride,
-                                 int64_t dst_stride) {
-  const T* s = src + (int64_t)blockIdx.y * src_stride;
-  double* d = dst + (int64_t)blockIdx.y * dst_stride;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    if (sizeof(T) == 2)
-      d[i] = (double)s[i] * (1.0 / 32768.0);  // swresample's s16 -> dbl
-    else
-      d[i] = (double)s[i];
-  }
-}
-
-inline size_t sample_bytes(int fmt) { return fmt == SONAR_PCM_S16 ? 2 : (fmt == SONAR_PCM_F32 ? 4 : 8); }
+inline size_t sample_bytes(int fmt) { return pcm_sample_bytes(fmt); }
 
 template <class T>
 T* at(void* base, size_t off) {
@@ -327,16 +345,7 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
             (e = cudaMemcpyAsync(dr, hr, sb * (size_t)G.n, cudaMemcpyHostToDevice, stage.st)) != cudaSuccess)
           return fail(cuda_error(e, "cudaMemcpyAsync(H2D pcm)"));
       }
-      if (d_raw) {
-        const dim3 wg(296, (unsigned)(2 * c));
-        if (fmt == SONAR_PCM_S16)
-          widen_pcm_kernel<int16_t><<<wg, 256, 0, stage.st>>>(reinterpret_cast<const int16_t*>(d_raw), d_in, G.n, raw_stride,
-                                                            G.stride);
-        else
-          widen_pcm_kernel<float><<<wg, 256, 0, stage.st>>>(reinterpret_cast<const float*>(d_raw), d_in, G.n, raw_stride,
-                                                          G.stride);
-        if ((e = cudaGetLastError()) != cudaSuccess) return fail(cuda_error(e, "widen_pcm_kernel"));
-      }
+      if (d_raw && (rc = launch_widen_pcm(d_raw, fmt, d_in, G.n, raw_stride, G.stride, 2 * c, stage.st))) return fail(rc);
       pcm_dev = d_in;
     } else {
       pcm_dev = pcm_q[(*ids)[first]];

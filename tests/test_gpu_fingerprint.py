@@ -259,3 +259,25 @@ def test_music_spectral_edge_cases(gpu, oracle):
             lib.music_spectral(np.zeros(100), sample_rate=44100)
         with pytest.raises(Exception, match="sample rate must be positive"):
             lib.music_spectral(np.zeros(4096), sample_rate=0)
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.float32])
+def test_batch_pcm_ingest_equals_the_widened_float64_call(gpu, oracle, synth, dtype):
+    """sonar_fingerprint_batch_pcm: ragged int16 / float32 batches widened on the device give exactly
+    the float64 call's results on the samples the reference's decoder would have produced."""
+    p = gpu.default_params(algo_sample_rate=44100)
+    raw = [synth.sweep_noise(s, seed=60 + i) for i, s in enumerate((1.0, 2.3, 1.0, 0.4))]
+    if dtype == np.int16:
+        narrow = [np.clip(np.round(x * 20000.0), -32768, 32767).astype(np.int16) for x in raw]
+        wide = [x.astype(np.float64) / 32768.0 for x in narrow]
+    else:
+        narrow = [x.astype(np.float32) for x in raw]
+        wide = [x.astype(np.float64) for x in narrow]
+    got = gpu.fingerprint_batch_pcm(narrow, p)
+    ref = gpu.fingerprint_batch(wide, p)
+    ora = oracle.fingerprint_batch_pcm(narrow, p)
+    for g, r, o in zip(got, ref, ora):
+        for k in r.arrays:
+            assert np.array_equal(g.arrays[k], r.arrays[k]), k
+        assert np.array_equal(g.short_time_energy, o.short_time_energy)  # bit-exact against the oracle's widening
+        assert g.energy_variance == r.energy_variance and g.loudness_range == r.loudness_range
