@@ -669,6 +669,57 @@ class FingerprintComparator {
     if (!std::isnan(r.dist_harmonic)) out->FeatureDistances["harmonic"] = r.dist_harmonic;
     return Result<SimilarityResult>{out, ""};
   }
+  // comparison.go:1107-1151: every non-nil candidate that is not the query itself (same ID) is compared; failures
+  // are skipped
+  std::vector<std::shared_ptr<SimilarityResult>> BatchCompare(const AudioFingerprint* query,
+                                                              const std::vector<const AudioFingerprint*>& candidates,
+                                                              std::string* err = nullptr) const {
+    std::vector<std::shared_ptr<SimilarityResult>> results;
+    if (!query) {
+      if (err) *err = "query fingerprint cannot be nil";
+      return results;
+    }
+    for (const AudioFingerprint* c : candidates) {
+      if (!c || c->ID == query->ID) continue;
+      auto r = Compare(query, c);
+      if (r.ok()) results.push_back(r.value);
+    }
+    return results;
+  }
+  struct Match {  // comparison.go:52-58
+    const AudioFingerprint* Fingerprint = nullptr;
+    std::shared_ptr<SimilarityResult> Similarity;
+    int Rank = 0;
+    std::string MatchType;
+  };
+  static std::string ClassifyMatch(const SimilarityResult& s) {  // comparison.go:1040-1052
+    if (s.OverallSimilarity >= 0.95) return "exact";
+    if (s.OverallSimilarity >= 0.85) return "very_similar";
+    if (s.OverallSimilarity >= 0.75) return "similar";
+    if (s.OverallSimilarity >= 0.6) return "somewhat_similar";
+    return "weak";
+  }
+  // comparison.go:197-263: compare, keep >= SimilarityThreshold, sort descending, cut to MaxCandidates, rank from 1
+  std::vector<Match> FindBestMatches(const AudioFingerprint* query, const std::vector<const AudioFingerprint*>& candidates,
+                                     std::string* err = nullptr) const {
+    std::vector<Match> matches;
+    if (!query) {
+      if (err) *err = "query fingerprint cannot be nil";
+      return matches;
+    }
+    for (const AudioFingerprint* c : candidates) {
+      if (!c || c->ID == query->ID) continue;
+      auto r = Compare(query, c);
+      if (!r.ok()) continue;
+      if (r->OverallSimilarity >= config_.SimilarityThreshold) matches.push_back(Match{c, r.value, 0, ClassifyMatch(*r.value)});
+    }
+    std::stable_sort(matches.begin(), matches.end(), [](const Match& a, const Match& b) {
+      return a.Similarity->OverallSimilarity > b.Similarity->OverallSimilarity;
+    });
+    if ((int)matches.size() > config_.MaxCandidates) matches.resize((size_t)config_.MaxCandidates);
+    for (size_t i = 0; i < matches.size(); i++) matches[i].Rank = (int)i + 1;
+    return matches;
+  }
   static std::map<std::string, double> EffectiveWeights(const AudioFingerprint& fp) {  // comparison.go:1055-1104
     if (!fp.FeatureWeights.empty()) return fp.FeatureWeights;
     if (fp.ContentType == config::ContentNews || fp.ContentType == config::ContentTalk)

@@ -146,6 +146,25 @@ int main() {
     CHECK(std::fabs(same->FeatureDistances["mfcc"]) < 1e-9);  // parity-mode MFCC rows are constant -> cosine 1
     CHECK(diff->OverallSimilarity > 0.5 && diff->OverallSimilarity <= 1.0 + 1e-12);
   }
+  {  // BatchCompare / FindBestMatches (comparison.go:1107-1151, 197-263)
+    fq.value->ID = "q";
+    fr.value->ID = "r";
+    fingerprint::AudioFingerprint twin = *fq.value;
+    twin.ID = "twin";
+    std::vector<const fingerprint::AudioFingerprint*> cands = {fr.value.get(), nullptr, fq.value.get(), &twin};
+    std::string berr;
+    CHECK(cmp->BatchCompare(nullptr, cands, &berr).empty() && berr == "query fingerprint cannot be nil");
+    auto batch = cmp->BatchCompare(fq.value.get(), cands);
+    CHECK(batch.size() == 2);  // nil and the query itself (same ID) are skipped
+    config::ComparisonConfig loose = cc;
+    loose.SimilarityThreshold = 0.0;
+    auto best = fingerprint::NewFingerprintComparator(&loose)->FindBestMatches(fq.value.get(), cands);
+    CHECK(best.size() == 2 && best[0].Fingerprint == &twin && best[0].Rank == 1 && best[1].Rank == 2);
+    CHECK(best[0].Similarity->OverallSimilarity >= best[1].Similarity->OverallSimilarity);
+    CHECK(best[0].MatchType == fingerprint::FingerprintComparator::ClassifyMatch(*best[0].Similarity));
+    loose.MaxCandidates = 1;
+    CHECK(fingerprint::NewFingerprintComparator(&loose)->FindBestMatches(fq.value.get(), cands).size() == 1);
+  }
   fr.value->ContentType = "news";
   cc.EnableContentFilter = true;
   auto filt = fingerprint::NewFingerprintComparator(&cc)->Compare(fq.value.get(), fr.value.get());
