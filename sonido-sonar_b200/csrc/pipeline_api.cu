@@ -272,7 +272,12 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
     const int v = e ? std::atoi(e) : 0;
     return v > 0 ? v : 32;  // 16 overlaps the chunks' kernels (-3 % step) but they then time-share the SMs
   }();
-  int C = host_pcm ? (int)std::max<size_t>(1, kPairChunkBytes / (sizeof(double) * 2 * (size_t)G.stride)) : dev_chunk;
+  static const size_t host_chunk_bytes = [] {
+    const char* e = std::getenv("SONAR_PAIR_CHUNK_MB");
+    const long v = e ? std::atol(e) : 0;
+    return v > 0 ? (size_t)v << 20 : kPairChunkBytes;
+  }();
+  int C = host_pcm ? (int)std::max<size_t>(1, host_chunk_bytes / (sizeof(double) * 2 * (size_t)G.stride)) : dev_chunk;
   C = std::min(C, total);
   const ChunkLayout L = chunk_layout(G, C);
   struct Pending {
