@@ -247,7 +247,7 @@ bool wants_features(const sonar_fp_out& o) {
   return false;
 }
 
-constexpr size_t kPairChunkBytes = (size_t)512 << 20;  // host PCM bytes staged per chunk
+constexpr size_t kPairChunkBytes = (size_t)256 << 20;  // host PCM bytes staged per chunk (measured: scripts/e2e_*_sweep.py)
 
 // pcm_q / pcm_r: host pointers (host_pcm) or, device-resident, pcm_q[i] = device pointer of pair i's query with the
 // reference `stride` behind it and consecutive pairs 2*stride apart.
@@ -277,7 +277,10 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
     const long v = e ? std::atol(e) : 0;
     return v > 0 ? (size_t)v << 20 : kPairChunkBytes;
   }();
-  int C = host_pcm ? (int)std::max<size_t>(1, host_chunk_bytes / (sizeof(double) * 2 * (size_t)G.stride)) : dev_chunk;
+  // host path: pairs per chunk by the bytes that cross PCIe (narrow formats travel in proportionally larger chunks:
+  // the kernels run better on bigger batches and the copy of a chunk costs the same)
+  int C = host_pcm ? (int)std::max<size_t>(1, host_chunk_bytes / (sample_bytes(fmt) * 2 * (size_t)G.stride)) : dev_chunk;
+  C = std::min(C, 4);  // deeper pipelines beat bigger batches here: 32 pairs of int16 take 63 ms at 4, 72 ms at 9 per chunk
   C = std::min(C, total);
   const ChunkLayout L = chunk_layout(G, C);
   struct Pending {
