@@ -9,7 +9,7 @@
 // without a host round trip: the z-score kernels read the short-time energies straight out of the feature
 // blocks, a tiny kernel turns the detected lag into the trimmed start pointers the DTW kernels consume
 // (TruncateToAlignmentPCM's sign convention, alignment.go:239-243).  Pairs travel in chunks (as many as fit a
-// 512 MB PCM staging buffer; all of them when the PCM is already resident), up to eight chunks in flight per
+// 256 MB PCM staging buffer, at most four; 32 when the PCM is already resident), up to eight chunks in flight per
 // device: three staging buffers feed the fingerprint kernels on their own streams, and each chunk's alignment
 // branch (z-score, NCC, one DTW warp per pair, then the D2H copy) is forked onto a second stream as soon as the
 // short-time energies exist, so its latency-bound kernels run beside the YIN kernels of the same chunk and the
@@ -280,7 +280,7 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
   // host path: pairs per chunk by the bytes that cross PCIe (narrow formats travel in proportionally larger chunks:
   // the kernels run better on bigger batches and the copy of a chunk costs the same)
   int C = host_pcm ? (int)std::max<size_t>(1, host_chunk_bytes / (sample_bytes(fmt) * 2 * (size_t)G.stride)) : dev_chunk;
-  C = std::min(C, 4);  // deeper pipelines beat bigger batches here: 32 pairs of int16 take 63 ms at 4, 72 ms at 9 per chunk
+  if (host_pcm) C = std::min(C, 4);  // deeper pipelines beat bigger batches: 32 pairs of int16 take 63 ms at 4, 72 ms at 9 per chunk
   C = std::min(C, total);
   const ChunkLayout L = chunk_layout(G, C);
   struct Pending {
