@@ -190,3 +190,24 @@ def test_pair_pipeline_pcm_ingest_equals_the_widened_float64_call(gpu, oracle, s
         assert g["xcorr"].peak_lag == r["xcorr"].peak_lag == o["xcorr"].peak_lag
         assert np.array_equal(g["path_query"], o["path_query"]) and np.array_equal(g["path_ref"], o["path_ref"])
         assert np.array_equal(g["path_cost"], r["path_cost"], equal_nan=True)
+
+
+def test_pcm_entry_points_reject_bad_arguments(gpu, oracle, synth):
+    """Error behaviour of the ingest entry points: unknown sample format, nil audio, too-short streams."""
+    import ctypes as C
+    p = gpu.default_params(algo_sample_rate=44100)
+    x = np.zeros(44100, np.int16)
+    for lib in (gpu, oracle):
+        outs, keep = lib.alloc_pair_outputs(1, x.size, p, 0.5)
+        ptr = (C.c_void_p * 1)(x.ctypes.data)
+        rc = lib.lib.sonar_align_pairs_pcm(lib.ctx, ptr, ptr, 7, x.size, 1, C.byref(p), 0.5, 50, outs)
+        assert rc != 0 and b"unknown PCM sample format" in lib.lib.sonar_last_error()
+        null = (C.c_void_p * 1)(None)
+        rc = lib.lib.sonar_align_pairs_pcm(lib.ctx, ptr, null, 2, x.size, 1, C.byref(p), 0.5, 50, outs)
+        assert rc != 0 and b"audio data cannot be nil" in lib.lib.sonar_last_error()
+        with pytest.raises(Exception, match="signal too short"):
+            lib.align_pairs_pcm([np.zeros(100, np.int16)], [np.zeros(100, np.int16)], p, 0.5, 50)
+    # silence in, silence out: all-zero int16 streams give zero energies and an all-zero correlation curve
+    res = gpu.align_pairs_pcm([x], [x], p, 0.5, 50)[0]
+    assert not res["query"].short_time_energy.any() and not res["corr"].any() and res["xcorr"].peak_lag == \
+        oracle.align_pairs_pcm([x], [x], p, 0.5, 50)[0]["xcorr"].peak_lag
