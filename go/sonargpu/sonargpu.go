@@ -219,3 +219,104 @@ func ColStatsCosine(x []float64, tx int, y []float64, ty, dim int) (float64, err
 	}
 	return float64(sim), nil
 }
+
+// PCM sample formats of the *_pcm entry points (include/sonar.h).
+const (
+	PCMF64 = C.SONAR_PCM_F64
+	PCMF32 = C.SONAR_PCM_F32
+	PCMS16 = C.SONAR_PCM_S16
+)
+
+// PairResult is what one source/CDN pair of AlignPairsS16 / AlignPairsF64 yields: the "corr_energy" lag and the
+// banded DTW path of the lag-trimmed short-time energies.
+type PairResult struct {
+	Xcorr              XcorrSummary
+	Align              AlignResult
+	PathQ, PathR       []int32
+	PathCost           []float64
+	Distance           float64
+}
+
+// alignPairs drives sonar_align_pairs_pcm: the whole CDN-latency loop of AlignmentExtractor.AlignAudioFiles
+// (fingerprint/extractors/alignment.go:489-560) for a batch of equally long pairs, chained on the device.
+// The per-pair sample pointers are copied into C memory (no Go pointer to Go pointer crosses the boundary) and
+// the sample slices themselves are pinned for the duration of the call.
+func alignPairs(q, r []unsafe.Pointer, format C.int, n int, p FpParams, maxLagSeconds float64, dtwBand int) ([]PairResult, error) {
+	c, err := Ctx()
+	if err != nil {
+		return nil, err
+	}
+	np := len(q)
+	if np == 0 || len(r) != np {
+		return nil, errors.New("feature sets cannot be nil")
+	}
+	var cp C.sonar_fp_params
+	C.sonar_fp_params_default(&cp)
+	cp.window_size, cp.hop_size, cp.window_type = C.int32_t(p.WindowSize), C.int32_t(p.HopSize), C.int32_t(p.WindowType)
+	cp.algo_sample_rate, cp.call_sample_rate = C.int32_t(p.AlgoSampleRate), C.int32_t(p.CallSampleRate)
+	cp.energy_frame, cp.energy_hop = C.int32_t(p.EnergyFrame), C.int32_t(p.EnergyHop)
+	var nLags, dtwLen C.int32_t
+	if rc := C.sonar_align_pairs_sizes(&cp, C.int64_t(n), C.double(maxLagSeconds), &nLags, &dtwLen); rc != C.SONAR_OK {
+		return nil, lastError()
+	}
+	ptrBytes := C.size_t(np) * C.size_t(unsafe.Sizeof(uintptr(0)))
+	cq := (*[1 << 28]unsafe.Pointer)(C.malloc(ptrBytes))
+	cr := (*[1 << 28]unsafe.Pointer)(C.malloc(ptrBytes))
+	outs := (*[1 << 20]C.sonar_pair_out)(C.calloc(C.size_t(np), C.size_t(unsafe.Sizeof(C.sonar_pair_out{}))))
+	defer C.free(unsafe.Pointer(cq))
+	defer C.free(unsafe.Pointer(cr))
+	defer C.free(unsafe.Pointer(outs))
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	res := make([]PairResult, np)
+	pcap := 2 * int(dtwLen)
+	for i := 0; i < np; i++ {
+		pin.Pin(q[i])
+		pin.Pin(r[i])
+		cq[i], cr[i] = q[i], r[i]
+		res[i].PathQ, res[i].PathR, res[i].PathCost = make([]int32, pcap), make([]int32, pcap), make([]float64, pcap)
+		pin.Pin(&res[i].PathQ[0])
+		pin.Pin(&res[i].PathR[0])
+		pin.Pin(&res[i].PathCost[0])
+		outs[i].dtw.path_query = (*C.int32_t)(unsafe.Pointer(&res[i].PathQ[0]))
+		outs[i].dtw.path_ref = (*C.int32_t)(unsafe.Pointer(&res[i].PathR[0]))
+		outs[i].dtw.path_cost = ptr(res[i].PathCost)
+		outs[i].dtw.path_cap = C.int64_t(pcap)
+	}
+	rc := C.sonar_align_pairs_pcm(c, (*unsafe.Pointer)(unsafe.Pointer(cq)), (*unsafe.Pointer)(unsafe.Pointer(cr)), format,
+		C.int64_t(n), C.int(np), &cp, C.double(maxLagSeconds), C.int(dtwBand), &outs[0])
+	if rc != C.SONAR_OK {
+		return nil, lastError()
+	}
+	for i := 0; i < np; i++ {
+		xs, ar, d := outs[i].xcorr, outs[i].corr_alignment, outs[i].dtw
+		res[i].Xcorr = XcorrSummary{float64(xs.peak_correlation), float64(xs.p_value), float64(xs.snr), float64(xs.sharpness),
+			float64(xs.second_peak), float64(xs.peak_to_sidelobe), int(xs.peak_lag), int(xs.peak_index),
+			int(xs.actual_max_lag), int(xs.overlap_length), xs.is_significant != 0}
+		res[i].Align = AlignResult{int(ar.offset), float64(ar.offset_seconds), float64(ar.confidence), float64(ar.similarity),
+			float64(ar.alignment_quality), float64(ar.noise_level)}
+		l := int(d.path_len)
+		res[i].PathQ, res[i].PathR, res[i].PathCost = res[i].PathQ[:l], res[i].PathR[:l], res[i].PathCost[:l]
+		res[i].Distance = float64(d.distance)
+	}
+	return res, nil
+}
+
+// AlignPairsF64 takes the []float64 PCM the reference's decoder produces (transcode/decoder.go:850-870).
+func AlignPairsF64(query, reference [][]float64, p FpParams, maxLagSeconds float64, dtwBand int) ([]PairResult, error) {
+	q, r := make([]unsafe.Pointer, len(query)), make([]unsafe.Pointer, len(reference))
+	for i := range query {
+		q[i], r[i] = unsafe.Pointer(&query[i][0]), unsafe.Pointer(&reference[i][0])
+	}
+	return alignPairs(q, r, PCMF64, len(query[0]), p, maxLagSeconds, dtwBand)
+}
+
+// AlignPairsS16 takes the s16le samples ffmpeg holds before the reference asks it for "-f f64le"
+// (transcode/decoder.go:707-712): a quarter of the PCIe bytes, bit-identical results (x / 32768 on the device).
+func AlignPairsS16(query, reference [][]int16, p FpParams, maxLagSeconds float64, dtwBand int) ([]PairResult, error) {
+	q, r := make([]unsafe.Pointer, len(query)), make([]unsafe.Pointer, len(reference))
+	for i := range query {
+		q[i], r[i] = unsafe.Pointer(&query[i][0]), unsafe.Pointer(&reference[i][0])
+	}
+	return alignPairs(q, r, PCMS16, len(query[0]), p, maxLagSeconds, dtwBand)
+}
