@@ -154,7 +154,7 @@ __device__ __forceinline__ void bin_step(BinAcc& s, bool flush, float dk, float 
   s.fl = fmaf(d, d, s.fl);
 }
 
-template <int NP>  // NP = hop / 64: new sample pairs per lane per frame
+template <int NP>  // NP = hop / 64: new sample pairs per lane per frame; NP = 0: any even hop <= 1024 (no register prefetch)
 __global__ void __launch_bounds__(kW * 32, 1) stft_v2_kernel(const StftArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const V2Smem L = v2_layout(a.n_mel, a.n_mfcc);
@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(kW * 32, 1) stft_v2_kernel(const StftArgs a) {
     wN[i] = make_float2((float)dcs, (float)dsn);
   }
   const int ka2 = lane >> 2, q4 = lane & 3;
-  constexpr int H = 64 * NP;
+  const int H = NP ? 64 * NP : a.hop;
+  constexpr int NPR = NP ? NP : 1;
   const int64_t T = a.T;
   const unsigned fmask = s_fmask[lane];
   const int lo_k = lane + 4 * (lane >> 4);           // bpos(lane + 32 i) = lo_k + 40 i
@@ -311,12 +312,12 @@ __global__ void __launch_bounds__(kW * 32, 1) stft_v2_kernel(const StftArgs a) {
       }
       // the next frame's H new samples start their trip from HBM now and are parked in the ring at the end
       // of this iteration (they replace the oldest H samples, which pass 1 above was the last to read)
-      double2 nx[NP];
+      double2 nx[NPR];
       const bool more = it + 1 < nfr;
-      if (more) {
+      if (NP && more) {
         const double2* __restrict__ src = reinterpret_cast<const double2*>(x + (t + 1) * H + (kN - H));
 #pragma unroll
-        for (int j = 0; j < NP; ++j) nx[j] = __ldg(src + lane + 32 * j);
+        for (int j = 0; j < NPR; ++j) nx[j] = __ldg(src + lane + 32 * j);
       }
       __syncwarp();
       // ================= pass 2a =================
@@ -519,8 +520,16 @@ __global__ void __launch_bounds__(kW * 32, 1) stft_v2_kernel(const StftArgs a) {
       // ---- ring: park the next frame's new samples over the oldest ones -----------------------------------
       if (more) {
         const int r2 = (int)((((t + 1) * H + (kN - H)) >> 1) & (kM - 1));
+        if (NP) {
 #pragma unroll
-        for (int j = 0; j < NP; ++j) ring2[(r2 + lane + 32 * j) & (kM - 1)] = make_float2((float)nx[j].x, (float)nx[j].y);
+          for (int j = 0; j < NPR; ++j) ring2[(r2 + lane + 32 * j) & (kM - 1)] = make_float2((float)nx[j].x, (float)nx[j].y);
+        } else {  // generic hop: straight from global memory (the latency is exposed once per frame)
+          const double2* __restrict__ src = reinterpret_cast<const double2*>(x + (t + 1) * H + (kN - H));
+          for (int j = lane; j < (H >> 1); j += 32) {
+            const double2 d = __ldg(src + j);
+            ring2[(r2 + j) & (kM - 1)] = make_float2((float)d.x, (float)d.y);
+          }
+        }
       }
       __syncwarp();  // tile / rows / macc / ring reused by the next frame
     }
@@ -581,7 +590,7 @@ bool stft_v2_eligible(const FpPlan& plan, const StftArgs& a) {
   static const bool off = std::getenv("SONAR_STFT_V1") != nullptr;  // diagnostic: force the first-generation kernel
   if (off || plan.N != kN) return false;
   if ((a.stride & 1) || (reinterpret_cast<uintptr_t>(a.pcm) & 15)) return false;
-  if (a.hop != 64 && a.hop != 128 && a.hop != 256 && a.hop != 512) return false;
+  if (a.hop <= 0 || a.hop > kN || (a.hop & 1)) return false;
   if (plan.h_regions.empty() || a.n_mel > kMaxMel || a.n_mfcc > kMaxMfcc || plan.split != 128) return false;
   auto region_of = [&](int k) {
     int r = 0;
@@ -624,7 +633,8 @@ int launch_stft_v2(const FpPlan& plan, StftArgs& a, cudaStream_t st) {
     case 64: SONAR_V2_LAUNCH(1); break;
     case 128: SONAR_V2_LAUNCH(2); break;
     case 256: SONAR_V2_LAUNCH(4); break;
-    default: SONAR_V2_LAUNCH(8); break;
+    case 512: SONAR_V2_LAUNCH(8); break;
+    default: SONAR_V2_LAUNCH(0); break;  // any other even hop
   }
 #undef SONAR_V2_LAUNCH
   prof_end();

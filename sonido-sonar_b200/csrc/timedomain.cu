@@ -47,12 +47,12 @@ template <bool ENERGY, bool ZCR>
 __global__ void __launch_bounds__(kTdThreads) frame_walk_kernel(
     const double* __restrict__ pcm, int64_t n, int64_t stride, double alpha, int frame, int hop, int64_t Tn,
     int sr, double* __restrict__ out, int64_t out_stride, int64_t o_energy, int64_t o_entropy,
-    int64_t o_zcr) {
+    int64_t o_zcr, int fpc) {  // fpc <= kTdFrames frames per CTA (fewer when a long hop would overflow the tile)
   extern __shared__ double tile[];
   const int s = blockIdx.y;
-  const int64_t f0 = (int64_t)blockIdx.x * kTdFrames;
+  const int64_t f0 = (int64_t)blockIdx.x * fpc;
   if (f0 >= Tn) return;
-  const int nf = (int)((Tn - f0 < kTdFrames) ? (Tn - f0) : kTdFrames);
+  const int nf = (int)((Tn - f0 < fpc) ? (Tn - f0) : fpc);
   const double* __restrict__ x = pcm + (int64_t)s * stride;
   const int64_t g0 = f0 * hop - 1;                // global index of staged element 0
   const int count = (nf - 1) * hop + frame + 1;  // staged elements
@@ -475,9 +475,11 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
                       int hop, int64_t Tn, int sr, double* out, int64_t out_stride, int64_t o_energy,
                       int64_t o_entropy, int64_t o_zcr, cudaStream_t st) {
   if (Tn <= 0 || n_streams <= 0) return SONAR_OK;
-  const int64_t count = (int64_t)(kTdFrames - 1) * hop + frame + 1;
+  int fpc = kTdFrames;  // frames per CTA: as many as keep the staged tile under 200 KB
+  while (fpc > 1 && sizeof(double) * (size_t)(((int64_t)(fpc - 1) * hop + frame + 1) * (hop + 1) / hop + 2) > 200 * 1024) --fpc;
+  const int64_t count = (int64_t)(fpc - 1) * hop + frame + 1;
   const size_t smem = sizeof(double) * (size_t)(count + count / hop + 2);
-  dim3 grid((unsigned)((Tn + kTdFrames - 1) / kTdFrames), (unsigned)n_streams);
+  dim3 grid((unsigned)((Tn + fpc - 1) / fpc), (unsigned)n_streams);
   const bool en = o_energy >= 0, zc = o_zcr >= 0;
   if (!en && !zc) return SONAR_OK;
   static const bool tiled_only = std::getenv("SONAR_FRAME_WALK_TILED") != nullptr;  // diagnostic
@@ -504,7 +506,7 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
     auto k = frame_walk_kernel<E, Z>;                                                                    \
     SONAR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     k<<<grid, kTdThreads, smem, st>>>(pcm, n, stride, alpha, frame, hop, Tn, sr, out, out_stride,       \
-                                      o_energy, o_entropy, o_zcr);                                      \
+                                      o_energy, o_entropy, o_zcr, fpc);                                 \
   } while (0)
   prof_begin("frame_walk_kernel", st);
   if (en && zc)

@@ -97,6 +97,10 @@ CASES = {
         window_size=1024, hop_size=128, energy_frame=1024, energy_hop=128, algo_sample_rate=44100)),
     "w1024_h512": (lambda s: s.sweep_noise(3.0, seed=13), dict(
         window_size=1024, hop_size=512, energy_frame=1024, energy_hop=512, algo_sample_rate=44100)),
+    "w1024_h882_generic_hop": (lambda s: s.sweep_noise(3.0, seed=16), dict(
+        window_size=1024, hop_size=882, energy_frame=1024, energy_hop=882, algo_sample_rate=44100)),
+    "w1024_h1024_no_overlap": (lambda s: s.sweep_noise(3.0, seed=17), dict(
+        window_size=1024, hop_size=1024, energy_frame=1024, energy_hop=1024, algo_sample_rate=44100)),
     "w1024_40mel_22k": (lambda s: s.sweep_noise(2.0, seed=14), dict(
         algo_sample_rate=22050, call_sample_rate=22050, n_mel=40)),
     "run_boundaries": (lambda s: s.sweep_noise(1.0, seed=15)[:1024 + 256 * 62], dict(algo_sample_rate=44100)),
