@@ -285,3 +285,19 @@ def test_batch_pcm_ingest_equals_the_widened_float64_call(gpu, oracle, synth, dt
             assert np.array_equal(g.arrays[k], r.arrays[k]), k
         assert np.array_equal(g.short_time_energy, o.short_time_energy)  # bit-exact against the oracle's widening
         assert g.energy_variance == r.energy_variance and g.loudness_range == r.loudness_range
+
+
+@pytest.mark.parametrize("sr,n_mel,n_mfcc,low,high", [
+    (8000, 20, 13, 0.0, 0.0), (8000, 64, 20, 50.0, 3800.0), (11025, 26, 13, 0.0, 0.0), (16000, 40, 13, 20.0, 7600.0),
+    (22050, 64, 32, 0.0, 0.0), (32000, 32, 12, 300.0, 3400.0), (44100, 64, 13, 0.0, 0.0), (44100, 13, 13, 1000.0, 2000.0),
+    (48000, 26, 13, 0.0, 0.0), (48000, 48, 24, 100.0, 20000.0), (96000, 26, 13, 0.0, 0.0), (44100, 26, 13, 21000.0, 22000.0),
+])
+def test_mel_bank_sweep_1024(gpu, oracle, synth, sr, n_mel, n_mfcc, low, high):
+    """Mel banks from very dense (64 filters at 8 kHz: zero-width regions, the first-generation kernel's job) to very
+    sparse / narrow ones, at N = 1024: whichever kernel the eligibility check picks must match the oracle."""
+    kw = dict(algo_sample_rate=sr, call_sample_rate=sr, n_mel=n_mel, n_mfcc=n_mfcc)
+    if low or high:
+        kw.update(low_hz=low, high_hz=high)
+    p = gpu.default_params(**kw)
+    x = synth.sweep_noise(1.0, seed=90 + n_mel)[: 1024 + 256 * 70]
+    check_fp(gpu.fingerprint(x, p), oracle.fingerprint(x, p))
