@@ -320,3 +320,24 @@ func AlignPairsS16(query, reference [][]int16, p FpParams, maxLagSeconds float64
 	}
 	return alignPairs(q, r, PCMS16, len(query[0]), p, maxLagSeconds, dtwBand)
 }
+
+// MusicSpectral replaces the three per-frame loops of MusicFeatureExtractor.extractSpectralFeatures
+// (fingerprint/extractors/music.go:261-302): SpectralContrast.Compute, the chroma folding of
+// ChromaSTFT.convertSTFTToChroma and BarkScale.ComputeBarkSpectrum.  Row-major [T][nBands], [T][12], [T][nBark].
+func MusicSpectral(pcm []float64, win, hop, windowType, sampleRate, nBands, nBark int, barkLow, barkHigh float64) (contrast, chroma, bark []float64, frames int, err error) {
+	c, err := Ctx()
+	if err != nil {
+		return nil, nil, nil, 0, err
+	}
+	if win <= 0 || hop <= 0 || len(pcm) < win {
+		return nil, nil, nil, 0, errors.New("signal too short for given window size and hop size")
+	}
+	frames = (len(pcm)-win)/hop + 1
+	contrast, chroma, bark = make([]float64, frames*nBands), make([]float64, frames*12), make([]float64, frames*nBark)
+	rc := C.sonar_music_spectral_f64(c, ptr(pcm), C.int64_t(len(pcm)), C.int(win), C.int(hop), C.int(windowType),
+		C.int(sampleRate), C.int(nBands), ptr(contrast), ptr(chroma), C.int(nBark), C.double(barkLow), C.double(barkHigh), ptr(bark))
+	if rc != C.SONAR_OK {
+		return nil, nil, nil, 0, lastError()
+	}
+	return contrast, chroma, bark, frames, nil
+}
