@@ -141,6 +141,7 @@ struct XcorrSeq {  // one sequence to z-score (population sigma, reference summa
   const double* in;
   double* out;
   int64_t n;
+  double* prefix = nullptr;  // optional: n + 2 doubles, running sum of squared deviations + scale (xcorr.cu znorm_kernel)
 };
 struct XcorrPair {  // one pair, or one lag shard [idx_lo, idx_hi) of a pair
   const double* za;
@@ -162,6 +163,23 @@ int launch_znorm(const XcorrSeq* seqs_dev, int count, cudaStream_t st);
 int launch_xcorr(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags, cudaStream_t st);
 int launch_xcorr_finalize(const XcorrPair* pairs_dev, int n_pairs, int64_t peak_override, XcorrPairOut* outs_dev,
                           cudaStream_t st);
+// lags per CTA of the flagged form of ncc_tiled_kernel (xcorr.cu); the screen (xcorr_fft.cu) flags CTAs in these units
+constexpr int kNccFlagLags = 64;
+// exact NCC only for the CTAs whose flag is set: need[pair * need_stride + blockIdx.x], grid.x = 2 * ceil(max_shard_lags / 64)
+int launch_xcorr_flagged(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags, const unsigned char* need_dev,
+                         int need_stride, cudaStream_t st);
+// Screened NCC (xcorr_fft.cu): FFT estimate of the whole curve, exact values wherever the peak or the second peak
+// can be.  The curve left in XcorrPair::corr is exact only there: callers that return the curve use launch_xcorr.
+struct XcorrScreen {
+  int log2n, bps, need_stride, n_pairs;
+  int64_t N, pre_stride;
+  size_t o_x, o_y, o_pre, o_need, bytes;
+};
+XcorrScreen xcorr_screen_geom(int64_t max_n, int aml_max, int64_t max_shard_lags, int n_pairs);
+// where znorm_kernel leaves sequence `seq`'s prefix sums (XcorrSeq::prefix) for launch_xcorr_screened
+double* xcorr_screen_prefix(const XcorrScreen& g, void* scratch, int seq);
+int launch_xcorr_screened(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags, const XcorrScreen& g,
+                          void* scratch, cudaStream_t st);
 // TruncateToAlignmentPCM's convention on the feature series (extractors/alignment.go:239-243): a positive lag skips
 // the start of the second sequence, a negative one the start of the first.  Writes the trimmed start pointers.
 int launch_xcorr_trim(const XcorrSeq* seqs_dev, const XcorrPair* pairs_dev, const XcorrPairOut* outs_dev, int n_pairs,

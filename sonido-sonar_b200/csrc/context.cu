@@ -1,6 +1,8 @@
 // Context, error plumbing, memory helpers and the host-arithmetic entry points of
 // the C ABI (include/sonar.h).  No kernels live here.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <sstream>
@@ -266,6 +268,15 @@ int sonar_profile_read(sonar_ctx* ctx, sonar_kernel_time* out, int cap, int* n_o
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(ctx->prof_mu);
   int n = 0;
+  if (std::getenv("SONAR_PROFILE_TIMELINE") && !ctx->prof.empty()) {  // diagnostic: when each launch ran
+    for (auto& r : ctx->prof) {
+      float t0 = 0.f, t1 = 0.f;
+      cudaEventElapsedTime(&t0, ctx->prof.front().a, r.a);
+      cudaEventElapsedTime(&t1, ctx->prof.front().a, r.b);
+      std::fprintf(stderr, "[timeline] %-32s %9.3f -> %9.3f ms\n", r.name, t0, t1);
+    }
+    cudaGetLastError();
+  }
   for (auto& r : ctx->prof) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) {

@@ -102,7 +102,8 @@ int pair_geometry(const sonar_fp_params* p, int64_t n, double max_lag_seconds, i
 struct ChunkLayout {
   int C = 0;
   // d_tmp
-  size_t t_fp = 0, t_z = 0, t_cells = 0, tmp_bytes = 0;
+  size_t t_fp = 0, t_z = 0, t_cells = 0, t_screen = 0, tmp_bytes = 0;
+  XcorrScreen xs{};  // scratch geometry of the screened cross-correlation
   // d_out / h_out
   size_t o_feat = 0, o_corr = 0, o_pc = 0, o_pq = 0, o_pr = 0, o_seqs = 0, o_pairs = 0, o_xo = 0, o_dout = 0, o_qptr = 0,
          o_rptr = 0, out_bytes = 0;
@@ -120,6 +121,8 @@ ChunkLayout chunk_layout(const PairGeom& G, int C) {
   L.t_fp = take(sizeof(double) * 2 * (size_t)C * G.sh.tmp_doubles_per_stream);
   L.t_z = take(sizeof(double) * (size_t)C * G.z_pair);
   L.t_cells = take(sizeof(double) * (size_t)C * (size_t)G.g.cells);
+  L.xs = xcorr_screen_geom(G.Te, G.aml, G.nl, C);
+  L.t_screen = take(L.xs.bytes);
   L.tmp_bytes = o;
   o = 0;
   L.o_feat = take(sizeof(double) * 2 * (size_t)C * (size_t)G.sh.L.total);
@@ -155,12 +158,16 @@ const T* at(const void* base, size_t off) {
 // Stream 2i is pair i's query, 2i+1 its reference, `stride` apart starting at pcm_dev.
 int enqueue_chunk(sonar_ctx* ctx, int device, const sonar_fp_params* p, const PairGeom& G, const ChunkLayout& L, int c,
                   const double* pcm_dev, void* d_tmp, void* d_out, cudaStream_t st, cudaStream_t st2, cudaEvent_t mid,
-                  cudaEvent_t fpdone) {
+                  cudaEvent_t fpdone, bool exact_curve, bool feat_travel) {
   double* feat = at<double>(d_out, L.o_feat);
   int rc = enqueue_fingerprint(ctx, device, p, G.sh, pcm_dev, G.n, G.stride, 2 * c, feat, at<double>(d_tmp, L.t_fp), st, mid);
   if (rc) return rc;
   SONAR_CUDA(cudaEventRecord(fpdone, st));
   SONAR_CUDA(cudaStreamWaitEvent(st2, mid, 0));
+  // a caller that takes the correlation curve home gets every lag in reference order; otherwise only the lags that
+  // can be the peak or the second peak are (xcorr_fft.cu)
+  static const bool full = std::getenv("SONAR_NCC_FULL") != nullptr;
+  const bool screen = !exact_curve && !full;
   std::vector<XcorrSeq> seqs(2 * (size_t)c);
   std::vector<XcorrPair> pairs(c);
   double* z = at<double>(d_tmp, L.t_z);
@@ -170,8 +177,9 @@ int enqueue_chunk(sonar_ctx* ctx, int device, const sonar_fp_params* p, const Pa
     const double* eb = feat + (size_t)(2 * i + 1) * G.sh.L.total + G.sh.L.short_time_energy;
     double* za = z + (size_t)i * G.z_pair;
     double* zb = za + G.z_pair / 2;
-    seqs[2 * i] = XcorrSeq{ea, za, G.Te};
-    seqs[2 * i + 1] = XcorrSeq{eb, zb, G.Te};
+    seqs[2 * i] = XcorrSeq{ea, za, G.Te, screen ? xcorr_screen_prefix(L.xs, at<unsigned char>(d_tmp, L.t_screen), 2 * i) : nullptr};
+    seqs[2 * i + 1] =
+        XcorrSeq{eb, zb, G.Te, screen ? xcorr_screen_prefix(L.xs, at<unsigned char>(d_tmp, L.t_screen), 2 * i + 1) : nullptr};
     pairs[i] = XcorrPair{za, zb, corr + (size_t)i * G.corr_pair, G.Te, G.Te, 0, G.nl, G.aml, 0};
   }
   XcorrSeq* d_seqs = at<XcorrSeq>(d_out, L.o_seqs);
@@ -181,7 +189,11 @@ int enqueue_chunk(sonar_ctx* ctx, int device, const sonar_fp_params* p, const Pa
   SONAR_CUDA(cudaMemcpyAsync(d_seqs, seqs.data(), sizeof(XcorrSeq) * seqs.size(), cudaMemcpyHostToDevice, st2));
   SONAR_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(XcorrPair) * pairs.size(), cudaMemcpyHostToDevice, st2));
   if ((rc = launch_znorm(d_seqs, 2 * c, st2))) return rc;
-  if ((rc = launch_xcorr(d_pairs, c, G.nl, st2))) return rc;
+  if (!screen)
+    rc = launch_xcorr(d_pairs, c, G.nl, st2);
+  else
+    rc = launch_xcorr_screened(d_pairs, c, G.nl, L.xs, at<unsigned char>(d_tmp, L.t_screen), st2);
+  if (rc) return rc;
   if ((rc = launch_xcorr_finalize(d_pairs, c, -1, d_xo, st2))) return rc;
   if ((rc = launch_xcorr_trim(d_seqs, d_pairs, d_xo, c, at<const double*>(d_out, L.o_qptr), at<const double*>(d_out, L.o_rptr),
                               st2)))
@@ -191,7 +203,9 @@ int enqueue_chunk(sonar_ctx* ctx, int device, const sonar_fp_params* p, const Pa
                   at<DtwPairOut>(d_out, L.o_dout), st2, at<const double*>(d_out, L.o_qptr),
                   at<const double*>(d_out, L.o_rptr));
   if (rc) return rc;
-  SONAR_CUDA(cudaStreamWaitEvent(st2, fpdone, 0));  // the result copy that follows on st2 also carries the features
+  // the result copy that follows on st2 carries the features only when somebody asked for a feature array; otherwise
+  // it (and the host-side scatter behind it) need not wait for the rest of the fingerprint
+  if (feat_travel) SONAR_CUDA(cudaStreamWaitEvent(st2, fpdone, 0));
   return SONAR_OK;
 }
 
@@ -309,6 +323,9 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
     } else {
       for (int i = 0; i < pd.count; i++) one(i);
     }
+    // without feature arrays the copy did not wait for the fingerprint kernels (the scatter above ran beside them);
+    // they still belong to the call, and the lane's buffers are theirs until they end
+    if (!pd.feat) SONAR_CUDA(cudaEventSynchronize(s.fpdone));
     for (int i = 0; i < pd.count; i++)
       if (rcs[i]) return set_error(rcs[i], errs[i]);
     return SONAR_OK;
@@ -358,15 +375,17 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
     } else {
       pcm_dev = pcm_q[(*ids)[first]];
     }
-    rc = enqueue_chunk(ctx, dev->device, p, G, L, c, pcm_dev, lane.d_tmp.p, lane.d_out.p, stage.st, lane.st2, lane.mid,
-                       lane.fpdone);
-    if (rc) return fail(rc);
+    bool curve = false;  // somebody in the chunk takes the correlation curve home
+    for (int i = 0; i < c && !curve; i++) curve = outs[(*ids)[first + i]].corr != nullptr;
     bool feat = false;  // the feature blocks only travel when somebody asked for a feature array
     for (int i = 0; i < c && !feat; i++) {
       const sonar_pair_out& o = outs[(*ids)[first + i]];
       feat = wants_features(o.query) || wants_features(o.reference);
     }
-    const size_t from = feat ? 0 : L.o_corr;
+    rc = enqueue_chunk(ctx, dev->device, p, G, L, c, pcm_dev, lane.d_tmp.p, lane.d_out.p, stage.st, lane.st2, lane.mid,
+                       lane.fpdone, curve, feat);
+    if (rc) return fail(rc);
+    const size_t from = feat ? 0 : (curve ? L.o_corr : L.o_pc);
     if ((e = cudaMemcpyAsync(static_cast<unsigned char*>(lane.h_out.p) + from,
                              static_cast<unsigned char*>(lane.d_out.p) + from, L.out_bytes - from,
                              cudaMemcpyDeviceToHost, lane.st2)) != cudaSuccess)

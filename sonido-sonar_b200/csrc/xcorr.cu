@@ -28,46 +28,104 @@ namespace sonar {
 namespace {
 
 constexpr int kZTile = 2048;
+constexpr int kZThreads = 128;
 
-__global__ void __launch_bounds__(32) znorm_kernel(const XcorrSeq* __restrict__ seqs) {
-  __shared__ double tile[kZTile];
+__device__ __forceinline__ void z_cp8(double* smem_dst, const double* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
+}
+
+// One CTA per sequence.  Thread 0 replays the reference's left-to-right sums; the other threads only move data:
+// tiles arrive by cp.async one tile ahead of the summation, so the kernel's length is the dependent-add chain.
+// With q.prefix set, the running sum of squared deviations (which the second pass forms anyway) is kept as
+// P[i + 1] = sum_{k <= i} (x[k] - mean)^2 with P[n + 1] = the factor that turns it into a prefix sum of z^2
+// (xcorr_fft.cu reads the denominators of the screened curve from it).
+__global__ void __launch_bounds__(kZThreads) znorm_kernel(const XcorrSeq* __restrict__ seqs) {
+  __shared__ double tile[2][kZTile];
+  __shared__ double s_val;
   const XcorrSeq q = seqs[blockIdx.x];
   const double* __restrict__ x = q.in;
   double* __restrict__ z = q.out;
+  double* __restrict__ P = q.prefix;
   const int64_t n = q.n;
-  const int lane = threadIdx.x;
+  const int t = threadIdx.x;
+  const int n_tiles = (int)((n + kZTile - 1) / kZTile);
+  auto count = [&](int k) { return (int)((n - (int64_t)k * kZTile < kZTile) ? (n - (int64_t)k * kZTile) : kZTile); };
+  auto stage = [&](int k) {
+    const int cnt = count(k);
+    double* dst = tile[k & 1];
+    const double* src = x + (int64_t)k * kZTile;
+    for (int e = t; e < cnt; e += kZThreads) z_cp8(dst + e, src + e);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto arrive = [&](int k) {  // tile k is in shared memory for everybody; tile k + 1 is on its way
+    if (k + 1 < n_tiles) {
+      stage(k + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+  };
   double acc = 0.0;
-  for (int64_t base = 0; base < n; base += kZTile) {
-    const int cnt = (int)((n - base < kZTile) ? (n - base) : kZTile);
-    for (int i = lane; i < cnt; i += 32) tile[i] = x[base + i];
-    __syncwarp();
-    if (lane == 0) {
+  if (n_tiles > 0) stage(0);
+  for (int k = 0; k < n_tiles; ++k) {
+    arrive(k);
+    if (t == 0) {
+      const double* c = tile[k & 1];
+      const int cnt = count(k);
 #pragma unroll 8
-      for (int i = 0; i < cnt; ++i) acc += tile[i];
+      for (int i = 0; i < cnt; ++i) acc += c[i];
     }
-    __syncwarp();
+    __syncthreads();  // the buffer is restaged in the next iteration
   }
-  const double mean = __shfl_sync(0xffffffffu, acc, 0) / (double)n;
+  if (t == 0) s_val = acc / (double)n;
+  __syncthreads();
+  const double mean = s_val;
   acc = 0.0;
-  for (int64_t base = 0; base < n; base += kZTile) {
-    const int cnt = (int)((n - base < kZTile) ? (n - base) : kZTile);
-    for (int i = lane; i < cnt; i += 32) {
-      const double d = x[base + i] - mean;
-      tile[i] = d * d;
+  if (n_tiles > 0) stage(0);
+  for (int k = 0; k < n_tiles; ++k) {
+    arrive(k);
+    double* c = tile[k & 1];
+    const int cnt = count(k);
+    for (int i = t; i < cnt; i += kZThreads) {
+      const double d = c[i] - mean;
+      c[i] = d * d;
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    if (t == 0) {
+      if (P) {
 #pragma unroll 8
-      for (int i = 0; i < cnt; ++i) acc += tile[i];
+        for (int i = 0; i < cnt; ++i) {
+          acc += c[i];
+          c[i] = acc;  // the tile turns into its own running sums
+        }
+      } else {
+#pragma unroll 8
+        for (int i = 0; i < cnt; ++i) acc += c[i];
+      }
     }
-    __syncwarp();
+    __syncthreads();
+    if (P) {
+      for (int i = t; i < cnt; i += kZThreads) P[(int64_t)k * kZTile + i + 1] = c[i];
+      __syncthreads();  // before the buffer is restaged
+    }
   }
-  const double var = __shfl_sync(0xffffffffu, acc, 0) / (double)n;
+  __syncthreads();
+  if (t == 0) s_val = acc / (double)n;
+  __syncthreads();
+  const double var = s_val;
   const double sd = sqrt(var);
   if (sd < 1e-10) {
-    for (int64_t i = lane; i < n; i += 32) z[i] = x[i] - mean;
+#pragma unroll 4
+    for (int64_t i = t; i < n; i += kZThreads) z[i] = x[i] - mean;
   } else {
-    for (int64_t i = lane; i < n; i += 32) z[i] = (x[i] - mean) / sd;
+#pragma unroll 4
+    for (int64_t i = t; i < n; i += kZThreads) z[i] = (x[i] - mean) / sd;
+  }
+  if (P && t == 0) {
+    P[0] = 0.0;
+    P[n + 1] = sd < 1e-10 ? 1.0 : 1.0 / var;
   }
 }
 
@@ -119,11 +177,10 @@ __global__ void __launch_bounds__(kNccThreads) ncc_exact_kernel(const XcorrPair*
 //   c = sum_i u[i] v[lag'+i] / sqrt(sum_i u[i]^2 * sum_i v[lag'+i]^2),  i < len = min(nu, nv - lag')
 // sum_i u[i]^2 is one running sum per thread, sampled when each lag's overlap ends; squares of v are taken
 // once when a value enters the window.  The last (< 2 kNtR) terms of each lag are added from global memory.
-constexpr int kNtT = 64;                 // threads per CTA
-constexpr int kNtR = 5;                  // lags per thread (odd: stride-5 double loads are conflict free)
-constexpr int kNtLags = kNtT * kNtR;     // lags per CTA
-constexpr int kNtChunk = 640;            // i per staged chunk (multiple of kNtR)
-constexpr int kNtV = kNtChunk + kNtLags; // staged values of the shifted sequence
+// Two shapes: <64, 5> (320 lags per CTA) evaluates whole curves at FP64-pipe throughput; <64, 1> (64 lags per CTA,
+// kNccFlagLags) evaluates the few blocks the screen (xcorr_fft.cu) flags, where only the length of the dependent
+// chain matters and a finer block wastes less work.
+constexpr int kNtChunk = 640;            // i per staged chunk (multiple of every R in use)
 
 __device__ __forceinline__ void ncc_cp8(double* smem_dst, const double* gmem_src, bool ok) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -131,9 +188,15 @@ __device__ __forceinline__ void ncc_cp8(double* smem_dst, const double* gmem_src
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(nbytes));
 }
 
-__global__ void __launch_bounds__(kNtT) ncc_tiled_kernel(const XcorrPair* __restrict__ pairs, int blocks_per_sign) {
+template <int kNtT /* threads per CTA */, int kNtR /* lags per thread; odd or 1: conflict-free strided loads */>
+__global__ void __launch_bounds__(kNtT) ncc_tiled_kernel(const XcorrPair* __restrict__ pairs, int blocks_per_sign,
+                                                         const unsigned char* __restrict__ need, int need_stride) {
+  constexpr int kNtLags = kNtT * kNtR;      // lags per CTA
+  constexpr int kNtV = kNtChunk + kNtLags;  // staged values of the shifted sequence
+  static_assert(kNtChunk % kNtR == 0, "chunk must hold whole window rotations");
   __shared__ double su[2][kNtChunk];
   __shared__ double sv[2][kNtV];
+  if (need && !need[(size_t)blockIdx.y * need_stride + blockIdx.x]) return;  // screened out (xcorr_fft.cu)
   const XcorrPair p = pairs[blockIdx.y];
   const bool neg = (int)blockIdx.x >= blocks_per_sign;
   const int blk = neg ? (int)blockIdx.x - blocks_per_sign : (int)blockIdx.x;
@@ -396,7 +459,7 @@ int launch_xcorr_trim(const XcorrSeq* seqs_dev, const XcorrPair* pairs_dev, cons
 int launch_znorm(const XcorrSeq* seqs_dev, int count, cudaStream_t st) {
   if (count <= 0) return SONAR_OK;
   prof_begin("znorm_kernel", st);
-  znorm_kernel<<<count, 32, 0, st>>>(seqs_dev);
+  znorm_kernel<<<count, kZThreads, 0, st>>>(seqs_dev);
   prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;
@@ -411,9 +474,20 @@ int launch_xcorr(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags
     ncc_exact_kernel<<<grid, kNccThreads, 0, st>>>(pairs_dev);
   } else {
     // a shard holds at most max_shard_lags lags of either sign
-    const int bps = (int)((max_shard_lags + kNtLags - 1) / kNtLags);
-    ncc_tiled_kernel<<<dim3((unsigned)(2 * bps), (unsigned)n_pairs), kNtT, 0, st>>>(pairs_dev, bps);
+    const int bps = (int)((max_shard_lags + 319) / 320);
+    ncc_tiled_kernel<64, 5><<<dim3((unsigned)(2 * bps), (unsigned)n_pairs), 64, 0, st>>>(pairs_dev, bps, nullptr, 0);
   }
+  prof_end();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
+int launch_xcorr_flagged(const XcorrPair* pairs_dev, int n_pairs, int64_t max_shard_lags, const unsigned char* need_dev,
+                         int need_stride, cudaStream_t st) {
+  if (n_pairs <= 0 || max_shard_lags <= 0) return SONAR_OK;
+  const int bps = (int)((max_shard_lags + kNccFlagLags - 1) / kNccFlagLags);
+  prof_begin("ncc_exact_kernel", st);
+  ncc_tiled_kernel<64, 1><<<dim3((unsigned)(2 * bps), (unsigned)n_pairs), 64, 0, st>>>(pairs_dev, bps, need_dev, need_stride);
   prof_end();
   SONAR_CUDA(cudaGetLastError());
   return SONAR_OK;

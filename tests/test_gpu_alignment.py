@@ -211,3 +211,48 @@ def test_pcm_entry_points_reject_bad_arguments(gpu, oracle, synth):
     res = gpu.align_pairs_pcm([x], [x], p, 0.5, 50)[0]
     assert not res["query"].short_time_energy.any() and not res["corr"].any() and res["xcorr"].peak_lag == \
         oracle.align_pairs_pcm([x], [x], p, 0.5, 50)[0]["xcorr"].peak_lag
+
+
+def _screen_cases(synth):
+    sr, secs = 44100, 12.0
+    n = int(secs * sr)
+    t = np.arange(n) / sr
+    rng = np.random.default_rng(7)
+    cases = {}
+    cases["offset"] = synth.aligned_pair(secs, offset_seconds=1.9, seed=51)
+    cases["negative"] = synth.aligned_pair(secs, offset_seconds=-2.2, seed=52)
+    q, _ = synth.aligned_pair(secs, offset_seconds=0.0, seed=53)
+    cases["identical"] = (q, q.copy())  # c(lag) == c(-lag) bit for bit: the first index must win every tie
+    tone = 0.4 * np.sin(2 * np.pi * 440.0 * t)
+    cases["steady_tone"] = (tone, 0.5 * tone)  # near-constant energies: flat, tie-ridden curve
+    am = (0.5 + 0.5 * np.sin(2 * np.pi * 1.0 * t)) * np.sin(2 * np.pi * 300.0 * t)
+    cases["periodic_envelope"] = (am, np.roll(am, 4410))  # one maximum per envelope period
+    cases["unrelated_noise"] = (rng.standard_normal(n) * 0.1, rng.standard_normal(n) * 0.1)
+    cases["silence"] = (np.zeros(n), np.zeros(n))
+    burst = np.zeros(n)
+    burst[1000:1400] = 0.8
+    cases["single_burst"] = (burst, np.roll(burst, 30000))
+    return cases
+
+
+def test_screened_pair_pipeline_matches_the_full_curve(gpu, oracle, synth):
+    """Without a correlation buffer the pipeline screens the lags with an FFT and evaluates only the candidate blocks
+    in reference order (csrc/xcorr_fft.cu).  Lag, peak value and DTW path must still be bit-identical to the oracle's
+    full evaluation; the reductions over the rest of the curve agree to 1e-9."""
+    p = gpu.default_params(algo_sample_rate=44100)
+    max_lag_s, band = 3.0, 50
+    cases = _screen_cases(synth)
+    qs, rs = [c[0] for c in cases.values()], [c[1] for c in cases.values()]
+    bufs = gpu.alloc_pair_outputs(len(qs), qs[0].size, p, max_lag_s, features=False, corr=False)
+    got = gpu.align_pairs(qs, rs, p, max_lag_s, band, buffers=bufs)
+    ref = oracle.align_pairs(qs, rs, p, max_lag_s, band)
+    full = gpu.align_pairs(qs, rs, p, max_lag_s, band)  # with curve: every lag exact
+    for name, g, o, f in zip(cases, got, ref, full):
+        assert g["corr"] is None
+        check_summary(g["xcorr"], o["xcorr"])
+        assert g["xcorr"].peak_correlation == f["xcorr"].peak_correlation, name
+        assert g["xcorr"].second_peak == f["xcorr"].second_peak, name  # second peak is verified exactly too
+        assert g["corr_alignment"].offset == o["corr_alignment"].offset, name
+        assert np.array_equal(g["path_query"], o["path_query"]) and np.array_equal(g["path_ref"], o["path_ref"]), name
+        assert np.array_equal(g["path_cost"], o["path_cost"], equal_nan=True), name
+        assert g["total_cost"] == o["total_cost"], name
