@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <cstdlib>
 #include <thread>
 
 #include "common.h"
@@ -98,9 +99,27 @@ int run_xcorr_chunk(DevCtx& dev, Slot& s, const PairJob* jobs, int np, int max_l
   }
   z_d = in_d;
   const size_t desc_bytes = sizeof(XcorrSeq) * 2 * np + sizeof(XcorrPair) * np + sizeof(XcorrPairOut) * np;
+  // Nobody takes the curve home: screen the lags with an FFT and evaluate only the candidate blocks in reference
+  // order (xcorr_fft.cu) -- same peak, same value, same second peak.
+  static const bool full_env = std::getenv("SONAR_NCC_FULL") != nullptr;
+  bool screen = !corr_dev_out && !full_env;
+  int64_t max_n = 0;
+  int aml_max = 0;
+  for (int p = 0; p < np && screen; p++) {
+    screen = jobs[p].corr == nullptr;
+    max_n = std::max<int64_t>(max_n, std::max(jobs[p].na, jobs[p].nb));
+    aml_max = std::max(aml_max, aml[p]);
+  }
+  XcorrScreen xs{};
+  if (screen) {
+    xs = xcorr_screen_geom(max_n, aml_max, max_lags, np);
+    if (xs.bytes > ((size_t)8 << 30)) screen = false;
+  }
+  const size_t screen_off = (sizeof(double) * z_d + desc_bytes + 64 + 255) & ~(size_t)255;
   int rc;
   if (host_inputs && (rc = dev.ensure_dev(s.d_in, sizeof(double) * in_d))) return rc;
-  if ((rc = dev.ensure_dev(s.d_tmp, sizeof(double) * z_d + desc_bytes + 64))) return rc;
+  if ((rc = dev.ensure_dev(s.d_tmp, screen ? screen_off + xs.bytes : sizeof(double) * z_d + desc_bytes + 64))) return rc;
+  unsigned char* d_screen = static_cast<unsigned char*>(s.d_tmp.p) + screen_off;
   if (!corr_dev_out && (rc = dev.ensure_dev(s.d_out, sizeof(double) * corr_d))) return rc;
 
   double* d_in = static_cast<double*>(s.d_in.p);
@@ -131,8 +150,8 @@ int run_xcorr_chunk(DevCtx& dev, Slot& s, const PairJob* jobs, int np, int max_l
       b_dev = j.b;
     }
     io += (size_t)(even(j.na) + even(j.nb));
-    seqs[2 * p] = XcorrSeq{a_dev, za, j.na};
-    seqs[2 * p + 1] = XcorrSeq{b_dev, zb, j.nb};
+    seqs[2 * p] = XcorrSeq{a_dev, za, j.na, screen ? xcorr_screen_prefix(xs, d_screen, 2 * p) : nullptr};
+    seqs[2 * p + 1] = XcorrSeq{b_dev, zb, j.nb, screen ? xcorr_screen_prefix(xs, d_screen, 2 * p + 1) : nullptr};
     const int64_t nl = 2 * (int64_t)aml[p] + 1;
     XcorrPair& pr = pairs[p];
     pr.za = za;
@@ -149,7 +168,8 @@ int run_xcorr_chunk(DevCtx& dev, Slot& s, const PairJob* jobs, int np, int max_l
   SONAR_CUDA(cudaMemcpyAsync(d_seqs, seqs.data(), sizeof(XcorrSeq) * seqs.size(), cudaMemcpyHostToDevice, s.st));
   SONAR_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(XcorrPair) * pairs.size(), cudaMemcpyHostToDevice, s.st));
   if ((rc = launch_znorm(d_seqs, 2 * np, s.st))) return rc;
-  if ((rc = launch_xcorr(d_pairs, np, max_lags, s.st))) return rc;
+  rc = screen ? launch_xcorr_screened(d_pairs, np, max_lags, xs, d_screen, s.st) : launch_xcorr(d_pairs, np, max_lags, s.st);
+  if (rc) return rc;
   if ((rc = launch_xcorr_finalize(d_pairs, np, -1, d_outs, s.st))) return rc;
   std::vector<XcorrPairOut> outs(np);
   SONAR_CUDA(cudaMemcpyAsync(outs.data(), d_outs, sizeof(XcorrPairOut) * np, cudaMemcpyDeviceToHost, s.st));

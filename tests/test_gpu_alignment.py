@@ -256,3 +256,36 @@ def test_screened_pair_pipeline_matches_the_full_curve(gpu, oracle, synth):
         assert np.array_equal(g["path_query"], o["path_query"]) and np.array_equal(g["path_ref"], o["path_ref"]), name
         assert np.array_equal(g["path_cost"], o["path_cost"], equal_nan=True), name
         assert g["total_cost"] == o["total_cost"], name
+
+
+def _xcorr_screen_inputs():
+    rng = np.random.default_rng(99)
+    t = np.arange(400)
+    square = np.sign(np.sin(2 * np.pi * t / 20.0) + 1e-9)
+    spike = np.zeros(5000)
+    spike[[100, 2500, 4100]] = [1e6, -3.0, 2.0]  # huge dynamic range, tiny overlap energies at the ends
+    smooth = np.cumsum(rng.standard_normal(30000))  # random walk: broad peak, neighbours within 1e-5
+    cases = [(rng.standard_normal(na), rng.standard_normal(nb), ml)
+             for na, nb, ml in [(500, 500, 100), (777, 512, 300), (64, 300, 1000), (3, 3, 5), (1, 9, 4), (2000, 2000, 0),
+                                (40000, 35000, 9000)]]
+    cases += [(np.full(300, 0.25), np.full(280, -1.5), 50), (square, square, 100), (square, -square, 150),
+              (spike, np.roll(spike, 37), 4000), (smooth, np.roll(smooth, -211), 3000),
+              (np.zeros(100), rng.standard_normal(100), 20)]
+    return cases
+
+
+def test_xcorr_without_curve_is_screened_and_keeps_the_peak_exact(gpu, oracle):
+    """want_corr=False: FFT screen + exact candidate blocks (csrc/xcorr_fft.cu) -- the summary must equal the one the
+    full reference-order evaluation gives: indices and the peak / second-peak values bit for bit."""
+    for a, b, ml in _xcorr_screen_inputs():
+        _, ss = gpu.xcorr(a, b, ml, want_corr=False)
+        _, sf = gpu.xcorr(a, b, ml, want_corr=True)
+        _, so = oracle.xcorr(a, b, ml)
+        check_summary(ss, so)
+        assert ss.peak_correlation == sf.peak_correlation and ss.second_peak == sf.second_peak, (a.size, b.size, ml)
+        assert same_float(ss.sharpness, sf.sharpness, rtol=1e-12), (ss.sharpness, sf.sharpness)
+    As, Bs = [c[0] for c in _xcorr_screen_inputs()[:3]], [c[1] for c in _xcorr_screen_inputs()[:3]]
+    _, sa = gpu.xcorr_batch(As, Bs, 128, want_corr=False)  # ragged batch through one screen geometry
+    _, sb = oracle.xcorr_batch(As, Bs, 128, want_corr=False)
+    for x, y in zip(sa, sb):
+        check_summary(x, y)
