@@ -267,7 +267,10 @@ def run_ours(args, rank, world, local_rank):
     # fingerprint both streams -> "corr_energy" NCC -> trim by the detected lag -> banded DTW, per pair, with
     # nothing returning to the host in between.  Result buffers are caller-owned and reused every step.
     bufs_dev = lib.alloc_pair_outputs(P, n, prm, MAX_LAG_S, features=False, corr=False)
-    bufs_e2e = lib.alloc_pair_outputs(P, n, prm, MAX_LAG_S, features=True, corr=True)
+    # e2e returns what GenerateFingerprint + ExtractAlignmentFeatures return: every feature array, the alignment scalars
+    # and the DTW path.  The correlation curve is internal to the reference (stats.CorrelationResult, never part of
+    # AlignmentFeatures), so it is not requested.
+    bufs_e2e = lib.alloc_pair_outputs(P, n, prm, MAX_LAG_S, features=True, corr=False)
     q_list = [hv[2 * i, :n] for i in range(P)]
     r_list = [hv[2 * i + 1, :n] for i in range(P)]
 
@@ -275,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
         res = lib.align_pairs_dev(pcm_dev.data_ptr(), n, stride, P, prm, MAX_LAG_S, DTW_BAND, buffers=bufs_dev)
         return [x["xcorr"].peak_lag for x in res], res
 
-    def step_e2e():  # host PCM in, every feature array + correlation curve + DTW path out
+    def step_e2e():  # host PCM in, every feature array + alignment scalars + DTW path out
         res = lib.align_pairs(q_list, r_list, prm, MAX_LAG_S, DTW_BAND, buffers=bufs_e2e)
         return [x["xcorr"].peak_lag for x in res], res, res
 
@@ -343,8 +346,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = reduce_max(1e3 * (time.perf_counter() - t0) / n_e2e)
     assert lags_e == lags, "host-pointer and device-resident legs disagree on the detected lags"
     h2d = NS * n * 8
-    d2h = sum(a.nbytes for a in fps[0]["query"].arrays.values()) * NS + P * (2 * max_lag + 1) * 8 + \
-        sum(len(pp["path_query"]) * 16 for pp in paths_e)
+    d2h = sum(a.nbytes for a in fps[0]["query"].arrays.values()) * NS + sum(len(pp["path_query"]) * 16 for pp in paths_e)
 
     # ---- extra leg: the same step with int16 PCM (what the decoder holds before the reference widens it to float64;
     #      sonar_align_pairs_pcm).  A quarter of the bytes cross PCIe; the samples are the float64 ones

@@ -14,10 +14,10 @@ q0, r0 = bench.make_pair(synth, seconds, 0)
 for i in range(P):
     hv[2 * i] = np.clip(np.rint(q0 * 8192.0), -32768, 32767).astype(np.int16)
     hv[2 * i + 1] = np.clip(np.rint(r0 * 8192.0), -32768, 32767).astype(np.int16)
-bufs = lib.alloc_pair_outputs(P, n, prm, 60.0, features=True, corr=True)
+bufs = lib.alloc_pair_outputs(P, n, prm, 60.0, features=True, corr=False)
 qs = [hv[2 * i] for i in range(P)]; rs = [hv[2 * i + 1] for i in range(P)]
 lib.align_pairs_pcm(qs, rs, prm, 60.0, 50, buffers=bufs)
 ts = []
 for _ in range(3):
     t0 = time.perf_counter(); lib.align_pairs_pcm(qs, rs, prm, 60.0, 50, buffers=bufs); ts.append(time.perf_counter() - t0)
-print(os.environ.get("SONAR_PAIR_CHUNK_MB", "default"), "ms", [round(1e3 * t, 1) for t in ts])
+print(os.environ.get("SONAR_PAIR_CHUNK_MB", "default"), os.environ.get("SONAR_PAIR_CHUNK_MAX", "4"), "ms", [round(1e3 * t, 1) for t in ts])

@@ -294,7 +294,12 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
   // host path: pairs per chunk by the bytes that cross PCIe (narrow formats travel in proportionally larger chunks:
   // the kernels run better on bigger batches and the copy of a chunk costs the same)
   int C = host_pcm ? (int)std::max<size_t>(1, host_chunk_bytes / (sample_bytes(fmt) * 2 * (size_t)G.stride)) : dev_chunk;
-  if (host_pcm) C = std::min(C, 4);  // deeper pipelines beat bigger batches: 32 pairs of int16 take 63 ms at 4, 72 ms at 9 per chunk
+  static const int host_cap = [] {
+    const char* e = std::getenv("SONAR_PAIR_CHUNK_MAX");
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : 4;
+  }();
+  if (host_pcm) C = std::min(C, host_cap);  // deeper pipelines beat bigger batches: 32 pairs of int16 take 63 ms at 4, 72 ms at 9 per chunk
   C = std::min(C, total);
   const ChunkLayout L = chunk_layout(G, C);
   struct Pending {
