@@ -296,7 +296,9 @@ __global__ void __launch_bounds__(256) rms_windows_kernel(const double* __restri
 // envelope): a CTA produces 16 consecutive windows from the 16 + R - 1 hop-sized block sums they share, so every
 // sample is squared ~1.2 times instead of R times.
 constexpr int kRbWin = 16;
-__global__ void __launch_bounds__(kRbWin * 32) rms_blocks_kernel(const double* __restrict__ pcm, int64_t stride,
+constexpr int kRbWarps = 16;
+// short hops (the 512 / 256 envelope): one warp per hop block
+__global__ void __launch_bounds__(kRbWin * 32) rms_blocks_warp_kernel(const double* __restrict__ pcm, int64_t stride,
                                                                  double alpha, int win, int hop, int R, int64_t nw,
                                                                  double* __restrict__ out, int64_t out_stride) {
   __shared__ double part[kRbWin + 8];
@@ -341,6 +343,68 @@ __global__ void __launch_bounds__(kRbWin * 32) rms_blocks_kernel(const double* _
   if (threadIdx.x < kRbWin && w0 + threadIdx.x < nw) {
     double acc = 0.0;
     for (int k = 0; k < R; ++k) acc += part[threadIdx.x + k];
+    out[(int64_t)s * out_stride + w0 + threadIdx.x] = sqrt(acc / (double)win);
+  }
+}
+
+// long hops (the 100 ms loudness hop): every warp takes a slice of every block
+__global__ void __launch_bounds__(kRbWarps * 32) rms_blocks_kernel(const double* __restrict__ pcm, int64_t stride,
+                                                                   double alpha, int win, int hop, int R, int64_t nw,
+                                                                   double* __restrict__ out, int64_t out_stride) {
+  __shared__ double part[kRbWin + 8][kRbWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.y;
+  const double* __restrict__ x = pcm + (int64_t)s * stride;
+  const int64_t w0 = (int64_t)blockIdx.x * kRbWin;
+  const int64_t last_block = nw - 1 + R - 1;
+  // every warp takes the same slice of every hop block (16 + R - 1 blocks do not divide over 16 warps); the slice
+  // sums meet in shared memory and are added in warp order, so the result does not depend on scheduling
+  const int per = (hop + kRbWarps - 1) / kRbWarps;
+  const int j0 = warp * per, j1 = (j0 + per < hop) ? j0 + per : hop;
+#pragma unroll 2
+  for (int b = 0; b < kRbWin + R - 1; ++b) {
+    const int64_t blk = w0 + b;
+    double acc = 0.0;
+    if (blk <= last_block) {
+      const int64_t s0 = blk * hop;
+      // independent strips per lane: this kernel waits on DRAM, not on arithmetic
+      double a4[4] = {0.0, 0.0, 0.0, 0.0};
+      int j = j0 + lane;
+      for (; j + 96 < j1; j += 128) {
+        double cur[4], prv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t i = s0 + j + 32 * u;
+          cur[u] = x[i];
+          prv[u] = i > 0 ? x[i - 1] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double y = cur[u] - alpha * prv[u];
+          a4[u] += y * y;
+        }
+      }
+      for (int u = 0; j < j1; j += 32, ++u) {
+        const int64_t i = s0 + j;
+        const double y = x[i] - alpha * (i > 0 ? x[i - 1] : 0.0);
+        a4[u & 3] += y * y;
+      }
+      acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (lane == 0) part[b][warp] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < kRbWin + R - 1) {  // block sums, slices in warp order
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRbWarps; ++k) t += part[threadIdx.x][k];
+    part[threadIdx.x][0] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < kRbWin && w0 + threadIdx.x < nw) {
+    double acc = 0.0;
+    for (int k = 0; k < R; ++k) acc += part[threadIdx.x + k][0];
     out[(int64_t)s * out_stride + w0 + threadIdx.x] = sqrt(acc / (double)win);
   }
 }
@@ -537,7 +601,10 @@ int launch_rms_windows(const double* pcm, int64_t n, int64_t stride, int n_strea
   if (hop > 0 && win % hop == 0 && win / hop <= 8) {
     dim3 bgrid((unsigned)((nw + kRbWin - 1) / kRbWin), (unsigned)n_streams);
     prof_begin("rms_windows_kernel", st);
-    rms_blocks_kernel<<<bgrid, kRbWin * 32, 0, st>>>(pcm, stride, alpha, win, hop, win / hop, nw, out, out_stride);
+    if (hop >= 32 * kRbWarps * 4)
+      rms_blocks_kernel<<<bgrid, kRbWarps * 32, 0, st>>>(pcm, stride, alpha, win, hop, win / hop, nw, out, out_stride);
+    else
+      rms_blocks_warp_kernel<<<bgrid, kRbWin * 32, 0, st>>>(pcm, stride, alpha, win, hop, win / hop, nw, out, out_stride);
     prof_end();
     SONAR_CUDA(cudaGetLastError());
     return SONAR_OK;
