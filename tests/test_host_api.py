@@ -27,3 +27,17 @@ def test_host_api_against_oracle(tmp_path):
 def test_host_api_against_cuda_library(tmp_path):
     r = build_and_run(tmp_path, os.path.join(ROOT, "sonido-sonar_b200"), "libsonar.so")
     assert r.returncode == 0 and "OK backend=cuda-sm100a" in r.stdout, r.stdout + r.stderr
+
+
+def test_xcorr_screen_fft_passes_on_the_cpu(tmp_path):
+    """The FP64 Stockham passes and the packed two-sequence correlation of csrc/xcorr_fft.cuh are __host__ __device__:
+    tests/cpp/xcorr_fft_selftest.cu replays them on the CPU against a naive DFT and direct correlation sums."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "xcorr_fft_selftest")
+    subprocess.check_call([nvcc, "-O2", "-Wno-deprecated-gpu-targets", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "xcorr_fft_selftest.cu")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
