@@ -207,7 +207,7 @@ void run_xcorr_device(sonar_ctx* ctx, DevCtx* dev, const std::vector<PairJob>* j
     size_t k = i, bytes = 0;
     while (k < jobs->size()) {
       const size_t b = sizeof(double) * (size_t)(2 * ((*jobs)[k].na + (*jobs)[k].nb) + 2 * (int64_t)max_lag + 8);
-      if (k > i && bytes + b > kXcorrChunkBytes) break;
+      if (k > i && (bytes + b > kXcorrChunkBytes || k - i >= 32768)) break;  // grid.y carries the pair index
       bytes += b;
       k++;
     }
