@@ -341,3 +341,47 @@ func MusicSpectral(pcm []float64, win, hop, windowType, sampleRate, nBands, nBar
 	}
 	return contrast, chroma, bark, frames, nil
 }
+
+// STFTStream replaces analyzers.STFTStreamer (fingerprint/analyzers/spectral.go:312-374): the buffer and its
+// advance/empty rule live behind sonar_stft_stream_*, the frames come from the same transform as ComputeSTFTWithWindow.
+type STFTStream struct {
+	h    *C.sonar_stft_stream
+	bins int
+}
+
+// NewSTFTStream is what SpectralAnalyzer.ComputeSTFTStreaming (spectral.go:289-310) calls.
+func NewSTFTStream(win, hop, windowType int) (*STFTStream, error) {
+	c, err := Ctx()
+	if err != nil {
+		return nil, err
+	}
+	var h *C.sonar_stft_stream
+	if rc := C.sonar_stft_stream_open(c, C.int(win), C.int(hop), C.int(windowType), &h); rc != C.SONAR_OK {
+		return nil, lastError()
+	}
+	return &STFTStream{h: h, bins: win/2 + 1}, nil
+}
+
+// ProcessChunk returns row-major magnitude / phase [T][bins] and complex [T][bins][2] for the T frames the chunk
+// completes (T may be 0; an empty chunk is not an error, spectral.go:324-326).
+func (s *STFTStream) ProcessChunk(chunk []float64) (mag, phase, cplx []float64, frames int, err error) {
+	if len(chunk) == 0 {
+		return nil, nil, nil, 0, nil
+	}
+	t := int(C.sonar_stft_stream_frames(s.h, C.int64_t(len(chunk))))
+	mag, phase, cplx = make([]float64, t*s.bins), make([]float64, t*s.bins), make([]float64, 2*t*s.bins)
+	var got C.int64_t
+	rc := C.sonar_stft_stream_process(s.h, ptr(chunk), C.int64_t(len(chunk)), ptr(mag), ptr(phase), ptr(cplx), C.int64_t(t), &got)
+	if rc != C.SONAR_OK {
+		return nil, nil, nil, 0, lastError()
+	}
+	return mag, phase, cplx, int(got), nil
+}
+
+// Close releases the native buffer (the reference's streamer is garbage collected; this one is not).
+func (s *STFTStream) Close() {
+	if s.h != nil {
+		C.sonar_stft_stream_close(s.h)
+		s.h = nil
+	}
+}

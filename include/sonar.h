@@ -261,6 +261,21 @@ int sonar_fp_dev_layout(const sonar_fp_params* p, int64_t n_samples, sonar_fp_de
 int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int hop, int window_type,
                    double* mag, double* phase, double* cplx);
 
+/* SpectralAnalyzer.ComputeSTFTStreaming + STFTStreamer.ProcessChunk (analyzers/spectral.go:289-374):
+ * samples are appended to the streamer's buffer; every complete window at the head of the buffer yields one frame
+ * (same window and transform as sonar_stft_f64) and the buffer advances by `hop` -- or is emptied when fewer than
+ * `hop` samples remain (spectral.go:364-369: with hop > win the samples a full hop would still skip are NOT skipped).
+ * sonar_stft_stream_frames tells how many frames a chunk of `chunk_len` samples would complete, so the caller can
+ * size mag [T][B] (required when T > 0), phase [T][B] and cplx [T][B][2] (optional, NULL = skipped), B = win/2 + 1.
+ * An empty chunk is not an error: 0 frames (spectral.go:324-326). */
+typedef struct sonar_stft_stream sonar_stft_stream;
+int sonar_stft_stream_open(sonar_ctx* ctx, int win, int hop, int window_type, sonar_stft_stream** out);
+int64_t sonar_stft_stream_frames(const sonar_stft_stream* s, int64_t chunk_len);
+int64_t sonar_stft_stream_buffered(const sonar_stft_stream* s);
+int sonar_stft_stream_process(sonar_stft_stream* s, const double* chunk, int64_t n, double* mag, double* phase,
+                              double* cplx, int64_t cap_frames, int64_t* n_frames);
+void sonar_stft_stream_close(sonar_stft_stream* s);
+
 /* MusicFeatureExtractor's additions to the per-frame spectral block, computed on the same magnitude
  * spectrogram ComputeSTFTWithWindow produces (fingerprint/extractors/music.go:261-302; the factory has the music
  * extractor commented out, so this is reached by direct construction only):

@@ -172,6 +172,8 @@ EXPORTS = (
     "sonar_host_alloc", "sonar_host_free", "sonar_dev_alloc", "sonar_dev_free", "sonar_memcpy_h2d",
     "sonar_memcpy_d2h", "sonar_synchronize", "sonar_kernel_launches", "sonar_stream",
     "sonar_profile_enable", "sonar_profile_read", "sonar_window_f64",
+    "sonar_stft_stream_open", "sonar_stft_stream_frames", "sonar_stft_stream_buffered", "sonar_stft_stream_process",
+    "sonar_stft_stream_close",
     "sonar_fp_params_default", "sonar_fp_sizes", "sonar_fingerprint_f64",
     "sonar_fingerprint_batch_f64", "sonar_fingerprint_batch_pcm", "sonar_fingerprint_batch_dev", "sonar_fp_dev_layout",
     "sonar_stft_f64", "sonar_xcorr_ncc_f64", "sonar_xcorr_batch_f64", "sonar_xcorr_batch_dev",
@@ -207,6 +209,34 @@ class Fingerprint:
         raise AttributeError(k)
 
 
+class StftStream:
+    """STFTStreamer (analyzers/spectral.go:312-374) over sonar_stft_stream_*."""
+
+    def __init__(self, lib, handle, win):
+        self.lib, self.h, self.bins = lib, handle, win // 2 + 1
+
+    def buffered(self) -> int:
+        return int(self.lib.lib.sonar_stft_stream_buffered(self.h))
+
+    def process_chunk(self, chunk, phase=True, cplx=True):
+        """-> (magnitude [T][B], phase [T][B] | None, complex [T][B][2] | None); T may be 0."""
+        chunk = _f64(chunk)
+        T = int(self.lib.lib.sonar_stft_stream_frames(self.h, chunk.size))
+        mag = np.zeros((T, self.bins))
+        ph = np.zeros((T, self.bins)) if phase else None
+        cx = np.zeros((T, self.bins, 2)) if cplx else None
+        n = C.c_int64()
+        self.lib._chk(self.lib.lib.sonar_stft_stream_process(self.h, _dp(chunk), chunk.size, _dp(mag), _dp(ph), _dp(cx), T,
+                                                             C.byref(n)))
+        assert n.value == T
+        return mag, ph, cx
+
+    def close(self):
+        if self.h:
+            self.lib.lib.sonar_stft_stream_close(self.h)
+            self.h = None
+
+
 class SonarLib:
     """One loaded implementation of include/sonar.h plus one sonar_ctx."""
 
@@ -231,6 +261,15 @@ class SonarLib:
         L.sonar_xcorr_shard_close.restype = None
         L.sonar_xcorr_shard_close.argtypes = [C.c_void_p]
         L.sonar_fp_params_default.restype = None
+        L.sonar_stft_stream_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.sonar_stft_stream_frames.restype = C.c_int64
+        L.sonar_stft_stream_frames.argtypes = [C.c_void_p, C.c_int64]
+        L.sonar_stft_stream_buffered.restype = C.c_int64
+        L.sonar_stft_stream_buffered.argtypes = [C.c_void_p]
+        L.sonar_stft_stream_process.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p,
+                                                C.c_int64, C.POINTER(C.c_int64)]
+        L.sonar_stft_stream_close.restype = None
+        L.sonar_stft_stream_close.argtypes = [C.c_void_p]
         L.sonar_init.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
         L.sonar_synchronize.argtypes = [C.c_void_p]
         L.sonar_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
@@ -438,6 +477,13 @@ class SonarLib:
         t = WINDOWS[wtype] if isinstance(wtype, str) else wtype
         self._chk(self.lib.sonar_stft_f64(self.ctx, _dp(pcm), pcm.size, win, hop, t, _dp(mag), _dp(ph), _dp(cx)))
         return mag, ph, cx
+
+    def stft_stream(self, win, hop, wtype="hann"):
+        """SpectralAnalyzer.ComputeSTFTStreaming (analyzers/spectral.go:289-310): returns an StftStream."""
+        t = WINDOWS[wtype] if isinstance(wtype, str) else wtype
+        h = C.c_void_p()
+        self._chk(self.lib.sonar_stft_stream_open(self.ctx, win, hop, t, C.byref(h)))
+        return StftStream(self, h, win)
 
     # -- cross-correlation -----------------------------------------------------
     def xcorr(self, a, b, max_lag, want_corr=True):

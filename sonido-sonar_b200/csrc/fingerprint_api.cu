@@ -592,3 +592,61 @@ int sonar_music_spectral_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int w
 }
 
 }  // extern "C"
+
+// ---- STFTStreamer (analyzers/spectral.go:289-374) -----------------------------------------------------------------
+struct sonar_stft_stream {
+  sonar_ctx* ctx;
+  int win, hop, wtype;
+  std::vector<double> buffer;
+};
+
+namespace {
+int64_t stream_frames_for(int64_t len, int win, int hop) { return len >= win ? (len - win) / hop + 1 : 0; }
+}  // namespace
+
+int sonar_stft_stream_open(sonar_ctx* ctx, int win, int hop, int window_type, sonar_stft_stream** out) {
+  if (!out) return set_error(SONAR_ERR_INVALID, "nil argument");
+  *out = nullptr;
+  if (win <= 0) return set_error(SONAR_ERR_INVALID, "window size must be positive");
+  if (hop <= 0) return set_error(SONAR_ERR_INVALID, "hop size must be positive");
+  if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  if (!stft_supported(win))
+    return set_error(SONAR_ERR_UNSUPPORTED, "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
+  *out = new sonar_stft_stream{ctx, win, hop, window_type, {}};
+  (*out)->buffer.reserve((size_t)win * 2);
+  return SONAR_OK;
+}
+
+int64_t sonar_stft_stream_frames(const sonar_stft_stream* s, int64_t chunk_len) {
+  if (!s || chunk_len <= 0) return 0;
+  return stream_frames_for((int64_t)s->buffer.size() + chunk_len, s->win, s->hop);
+}
+
+int64_t sonar_stft_stream_buffered(const sonar_stft_stream* s) { return s ? (int64_t)s->buffer.size() : 0; }
+
+int sonar_stft_stream_process(sonar_stft_stream* s, const double* chunk, int64_t n, double* mag, double* phase,
+                              double* cplx, int64_t cap_frames, int64_t* n_frames) {
+  if (!s || !n_frames) return set_error(SONAR_ERR_INVALID, "nil argument");
+  *n_frames = 0;
+  if (n <= 0) return SONAR_OK;  // spectral.go:324-326
+  if (!chunk) return set_error(SONAR_ERR_INVALID, "nil argument");
+  const int64_t len = (int64_t)s->buffer.size() + n;
+  const int64_t T = stream_frames_for(len, s->win, s->hop);
+  if (T > 0 && (!mag || cap_frames < T)) return set_error(SONAR_ERR_INVALID, "frame capacity too small");
+  s->buffer.insert(s->buffer.end(), chunk, chunk + n);
+  if (T == 0) return SONAR_OK;
+  // the frames the reference's loop extracts are those of the batch transform over the buffer: frame k starts k hops in
+  const int rc = sonar_stft_f64(s->ctx, s->buffer.data(), len, s->win, s->hop, s->wtype, mag, phase, cplx);
+  if (rc) {
+    s->buffer.resize((size_t)(len - n));  // nothing consumed
+    return rc;
+  }
+  // spectral.go:364-369: T - 1 plain advances, then the last one empties the buffer if a hop does not fit any more
+  const int64_t rem = len - (T - 1) * (int64_t)s->hop;
+  const int64_t keep = (int64_t)s->hop >= rem ? 0 : rem - s->hop;
+  s->buffer.erase(s->buffer.begin(), s->buffer.end() - keep);
+  *n_frames = T;
+  return SONAR_OK;
+}
+
+void sonar_stft_stream_close(sonar_stft_stream* s) { delete s; }

@@ -17,6 +17,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <complex>
 #include <vector>
 
 #include "../../include/sonar.h"
@@ -142,6 +143,66 @@ inline int WindowTypeId(const std::string& w) {  // analyzers/windowing.go:12-24
       {"welch", SONAR_WINDOW_WELCH}};
   auto it = ids.find(w);
   return it == ids.end() ? SONAR_WINDOW_HANN : it->second;
+}
+
+// analyzers/spectral.go:376-381
+struct SpectrogramFrame {
+  std::vector<double> Magnitude, Phase;
+  std::vector<std::complex<double>> Complex;
+};
+
+// STFTStreamer (analyzers/spectral.go:312-374) over sonar_stft_stream_*: same method, same results, same quirks
+// (an empty chunk yields no frames and no error; with hop > window an emptied buffer does not skip ahead).
+class STFTStreamer {
+ public:
+  ~STFTStreamer() {
+    if (h_) sonar_stft_stream_close(h_);
+  }
+  STFTStreamer(const STFTStreamer&) = delete;
+  STFTStreamer& operator=(const STFTStreamer&) = delete;
+
+  // ProcessChunk(chunk []float64) ([]*SpectrogramFrame, error); the error comes back in *err ("" == nil)
+  std::vector<std::shared_ptr<SpectrogramFrame>> ProcessChunk(const std::vector<double>& chunk, std::string* err) {
+    if (err) err->clear();
+    std::vector<std::shared_ptr<SpectrogramFrame>> frames;
+    if (chunk.empty()) return frames;  // :324-326
+    const int64_t T = sonar_stft_stream_frames(h_, (int64_t)chunk.size());
+    const size_t B = (size_t)freqBins_;
+    std::vector<double> mag((size_t)T * B), ph((size_t)T * B), cx((size_t)T * B * 2);
+    int64_t got = 0;
+    if (sonar_stft_stream_process(h_, chunk.data(), (int64_t)chunk.size(), mag.data(), ph.data(), cx.data(), T, &got) !=
+        SONAR_OK) {
+      if (err) *err = sonar_last_error();
+      return frames;
+    }
+    for (int64_t t = 0; t < got; t++) {
+      auto f = std::make_shared<SpectrogramFrame>();
+      f->Magnitude.assign(mag.begin() + t * B, mag.begin() + (t + 1) * B);
+      f->Phase.assign(ph.begin() + t * B, ph.begin() + (t + 1) * B);
+      f->Complex.resize(B);
+      for (size_t k = 0; k < B; k++) f->Complex[k] = {cx[(t * B + k) * 2], cx[(t * B + k) * 2 + 1]};
+      frames.push_back(std::move(f));
+    }
+    return frames;
+  }
+  int BufferedSamples() const { return (int)sonar_stft_stream_buffered(h_); }
+
+ private:
+  friend Result<STFTStreamer> ComputeSTFTStreaming(int, int, const std::string&);
+  STFTStreamer(sonar_stft_stream* h, int bins) : h_(h), freqBins_(bins) {}
+  sonar_stft_stream* h_ = nullptr;
+  int freqBins_ = 0;
+};
+
+// SpectralAnalyzer.ComputeSTFTStreaming(windowSize, hopSize, windowType) (*STFTStreamer, error)  (spectral.go:289-310)
+inline Result<STFTStreamer> ComputeSTFTStreaming(int windowSize, int hopSize, const std::string& windowType) {
+  std::string rerr;
+  sonar_ctx* ctx = Runtime::Ctx(&rerr);
+  if (!ctx) return Err<STFTStreamer>(rerr);
+  sonar_stft_stream* h = nullptr;
+  if (sonar_stft_stream_open(ctx, windowSize, hopSize, WindowTypeId(windowType), &h) != SONAR_OK)
+    return Err<STFTStreamer>(std::string("failed to generate window: ") + sonar_last_error());
+  return Result<STFTStreamer>{std::shared_ptr<STFTStreamer>(new STFTStreamer(h, windowSize / 2 + 1)), ""};
 }
 }  // namespace analyzers
 

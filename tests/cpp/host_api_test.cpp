@@ -170,6 +170,30 @@ int main() {
   auto filt = fingerprint::NewFingerprintComparator(&cc)->Compare(fq.value.get(), fr.value.get());
   CHECK(filt.ok() && filt->OverallSimilarity == 0.0 && filt->Confidence == 0.25 && !filt->ContentTypeMatch);
 
+  {  // ComputeSTFTStreaming / STFTStreamer.ProcessChunk (analyzers/spectral.go:289-374)
+    CHECK(!analyzers::ComputeSTFTStreaming(0, 256, "hann").ok());
+    auto st = analyzers::ComputeSTFTStreaming(1024, 256, "hann");
+    CHECK(st.ok());
+    std::string serr = "x";
+    CHECK(st->ProcessChunk({}, &serr).empty() && serr.empty());
+    std::vector<double> sig(5000);
+    for (size_t i = 0; i < sig.size(); i++) sig[i] = std::sin(0.05 * (double)i) + 0.25 * std::sin(0.31 * (double)i);
+    auto f1 = st->ProcessChunk(std::vector<double>(sig.begin(), sig.begin() + 1000), &serr);
+    CHECK(f1.empty() && serr.empty() && st->BufferedSamples() == 1000);
+    auto f2 = st->ProcessChunk(std::vector<double>(sig.begin() + 1000, sig.end()), &serr);
+    CHECK(serr.empty() && f2.size() == (5000 - 1024) / 256 + 1);  // 16 frames
+    CHECK(st->BufferedSamples() == 5000 - 16 * 256);
+    std::vector<double> mag(16 * 513);
+    CHECK(sonar_stft_f64(sonido::Runtime::Ctx(), sig.data(), (int64_t)sig.size(), 1024, 256, SONAR_WINDOW_HANN, mag.data(),
+                         nullptr, nullptr) == SONAR_OK);
+    bool same = f2.size() == 16;
+    for (size_t t = 0; same && t < 16; t++)
+      for (size_t k = 0; k < 513; k++) same = same && f2[t]->Magnitude[k] == mag[t * 513 + k];
+    CHECK(same);
+    CHECK(f2[3]->Complex.size() == 513 && std::fabs(std::abs(f2[3]->Complex[40]) - f2[3]->Magnitude[40]) <=
+                                              1e-5 * (1.0 + f2[3]->Magnitude[40]));
+  }
+
   std::printf("%s backend=%s failures=%d\n", failures ? "FAILED" : "OK", sonar_backend(), failures);
   return failures ? 1 : 0;
 }

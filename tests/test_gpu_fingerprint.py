@@ -301,3 +301,31 @@ def test_mel_bank_sweep_1024(gpu, oracle, synth, sr, n_mel, n_mfcc, low, high):
     p = gpu.default_params(**kw)
     x = synth.sweep_noise(1.0, seed=90 + n_mel)[: 1024 + 256 * 70]
     check_fp(gpu.fingerprint(x, p), oracle.fingerprint(x, p))
+
+
+@pytest.mark.parametrize("win,hop", [(512, 160), (1024, 256), (2048, 3000)])
+def test_stft_streamer_equals_the_batch_transform(gpu, oracle, win, hop):
+    """sonar_stft_stream_* (SURVEY §8 f3): chunked input gives the frames of the reference's streaming loop; each frame
+    equals the GPU batch STFT of the same samples bit for bit and the oracle within the STFT tolerance."""
+    from stream_model import frame_starts
+    rng = np.random.default_rng(win * 7 + hop)
+    x = rng.standard_normal(60000)
+    chunks = [5, win - 1, 1, 4000, 0, 17000, hop, 2 * win + 3]
+    chunks.append(x.size - sum(chunks))
+    starts, left = frame_starts(chunks, win, hop)
+    g, o = gpu.stft_stream(win, hop), oracle.stft_stream(win, hop)
+    pos = 0
+    for c, want in zip(chunks, starts):
+        mg, pg, cg = g.process_chunk(x[pos:pos + c])
+        mo, po, co = o.process_chunk(x[pos:pos + c])
+        pos += c
+        assert mg.shape == mo.shape and mg.shape[0] == len(want)
+        if want:
+            scale = np.max(np.abs(mo))
+            assert np.allclose(mg, mo, rtol=1e-4, atol=2e-6 * scale)
+            assert np.allclose(cg, co, rtol=1e-4, atol=2e-6 * scale)
+            m1, _, _ = gpu.stft(x[want[0]:want[0] + win], win, hop)
+            assert np.array_equal(mg[0], m1[0])
+    assert g.buffered() == o.buffered() == left
+    g.close()
+    o.close()

@@ -469,3 +469,43 @@ def test_music_spectral_known_answers(oracle):
     for bad in (dict(win=0), dict(hop=0), dict(sample_rate=0)):
         with pytest.raises(Exception):
             oracle.music_spectral(a440, **bad)
+
+
+@pytest.mark.parametrize("win,hop", [(512, 160), (1024, 256), (256, 256), (256, 700)])
+def test_stft_streamer_matches_the_reference_loop(oracle, win, hop):
+    """STFTStreamer.ProcessChunk (analyzers/spectral.go:323-374): every frame equals the batch transform of
+    the samples the reference's loop would have at the head of its buffer -- including hop > win, where an emptied buffer
+    does not skip the rest of the hop."""
+    from stream_model import frame_starts
+    rng = np.random.default_rng(win + hop)
+    x = rng.standard_normal(12000)
+    chunks = [1, 100, win - 1, 700, 0, 3000, 2 * win, hop, 37]
+    chunks.append(x.size - sum(chunks))
+    starts, left = frame_starts(chunks, win, hop)
+    st = oracle.stft_stream(win, hop)
+    pos = 0
+    for c, want in zip(chunks, starts):
+        mag, ph, cx = st.process_chunk(x[pos:pos + c])
+        pos += c
+        assert mag.shape[0] == len(want)
+        for k, s0 in enumerate(want):
+            m1, p1, c1 = oracle.stft(x[s0:s0 + win], win, hop, phase=True, cplx=True)
+            assert np.array_equal(mag[k], m1[0]) and np.array_equal(ph[k], p1[0]) and np.array_equal(cx[k], c1[0])
+    assert st.buffered() == left
+    st.close()
+
+
+def test_stft_streamer_arguments(oracle, capi):
+    with pytest.raises(capi.SonarError) as e:
+        oracle.stft_stream(0, 10)
+    assert "window size must be positive" in e.value.msg
+    with pytest.raises(capi.SonarError) as e:
+        oracle.stft_stream(512, 0)
+    assert "hop size must be positive" in e.value.msg
+    st = oracle.stft_stream(512, 128)
+    mag, _, _ = st.process_chunk(np.zeros(0))
+    assert mag.shape == (0, 257) and st.buffered() == 0
+    n = capi.C.c_int64()
+    rc = oracle.lib.sonar_stft_stream_process(st.h, capi._dp(np.zeros(2000)), 2000, None, None, None, 0, capi.C.byref(n))
+    assert rc != 0 and b"frame capacity too small" in oracle.lib.sonar_last_error() and st.buffered() == 0
+    st.close()
