@@ -134,7 +134,8 @@ int launch_fill_strided(double* p, int64_t count, int64_t stride, int n_streams,
 int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, int sr, int64_t Tp,
                const double* hann_dev, double* feat, int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
                int64_t o_voicing, int64_t o_hratio, int64_t o_inharm, int64_t o_tonal, double* scratch,
-               int64_t scratch_stride, cudaStream_t st);
+               int64_t scratch_stride, cudaStream_t st, cudaStream_t track_st = nullptr, cudaEvent_t fork = nullptr,
+               cudaEvent_t join = nullptr, bool* forked = nullptr);
 
 // ---- cross-correlation (xcorr.cu) ------------------------------------------
 struct XcorrSeq {  // one sequence to z-score (population sigma, reference summation order)
@@ -235,6 +236,8 @@ struct Slot {  // one in-flight unit of work on a device: its streams and buffer
   cudaEvent_t done = nullptr;
   cudaEvent_t mid = nullptr;   // hand-off st -> st2 (short-time energies ready)
   cudaEvent_t fpdone = nullptr;  // the rest of the fingerprint (st) has finished: st2 may copy the features out
+  cudaStream_t st3 = nullptr;    // the pitch tracker (one warp per stream) beside the DRAM-bound loudness kernels on st
+  cudaEvent_t fork = nullptr, join = nullptr;  // st -> st3 -> st
   Buf d_in, d_out, d_tmp, h_in, h_out;
   Buf d_raw;  // narrow (f32 / s16) PCM as it crossed PCIe, widened into d_in on the device
 };

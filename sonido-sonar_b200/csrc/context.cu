@@ -155,7 +155,10 @@ int sonar_init(int n_devices, const int* device_ids, sonar_ctx** out) {
           (e = cudaStreamCreateWithPriority(&s.st2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
           (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess ||
           (e = cudaEventCreateWithFlags(&s.mid, cudaEventDisableTiming)) != cudaSuccess ||
-          (e = cudaEventCreateWithFlags(&s.fpdone, cudaEventDisableTiming)) != cudaSuccess) {
+          (e = cudaEventCreateWithFlags(&s.fpdone, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaStreamCreateWithFlags(&s.st3, cudaStreamNonBlocking)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming)) != cudaSuccess) {
         delete ctx;
         return cuda_error(e, "cudaStreamCreate");
       }
@@ -185,6 +188,9 @@ void sonar_destroy(sonar_ctx* ctx) {
       if (s.fpdone) cudaEventDestroy(s.fpdone);
       if (s.st) cudaStreamDestroy(s.st);
       if (s.st2) cudaStreamDestroy(s.st2);
+      if (s.fork) cudaEventDestroy(s.fork);
+      if (s.join) cudaEventDestroy(s.join);
+      if (s.st3) cudaStreamDestroy(s.st3);
     }
   }
   if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].device);

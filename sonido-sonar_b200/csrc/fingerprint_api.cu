@@ -95,7 +95,19 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
   const auto& L = sh.L;
   const int64_t T = sh.sz.n_frames, Te = sh.sz.n_energy_frames, Tp = sh.sz.n_pitch_frames;
   const unsigned char* blob = static_cast<const unsigned char*>(plan->d_blob);
+  const int64_t tstride = (int64_t)sh.tmp_doubles_per_stream;
 
+  // The slot that owns `st` lends its side stream to the pitch tracker (one warp per stream), which then runs beside the
+  // kernels that follow the YIN kernel on `st`; `st` waits for the side stream at the end.  (Tried: the loudness kernels
+  // on the side stream beside the frame walk -- the two do not co-reside, either one fills the register file of an SM.)
+  Slot* side = nullptr;
+  for (auto& d : ctx->devs)
+    if (d.device == device)
+      for (auto& sl : d.slot)
+        if (sl.st == st) side = &sl;
+  // scalars: [0] energy variance (energy.go:97-118), [1] loudness range (energy.go:157-225), [2..] temporal block
+  rc = launch_fill_strided(feat_dev + L.scalars, L.total - L.scalars, L.total, ns, 0.0, st);
+  if (rc) return rc;
   StftArgs a;
   std::memset(&a, 0, sizeof(a));
   a.pcm = pcm_dev;
@@ -169,18 +181,26 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
     if (rc) return rc;
   }
 
-  // scalars: [0] energy variance (energy.go:97-118), [1] loudness range (energy.go:157-225)
-  rc = launch_fill_strided(feat_dev + L.scalars, L.total - L.scalars, L.total, ns, 0.0, st);
-  if (rc) return rc;
+  // harmonic block (speech.go:464-509).  Enqueued before the variance / temporal kernels so that its tracker, a
+  // sequential walk with one warp per stream, runs on the side stream beside them.
+  bool forked = false;
+  {
+    const double* hann = reinterpret_cast<const double*>(blob + plan->off_hann);
+    rc = launch_yin(pcm_dev, stride, ns, p->pre_emph_alpha, p->algo_sample_rate, Tp, hann, feat_dev, L.total,
+                    L.pitch_estimate, L.pitch_confidence, L.voicing_strength, L.harmonic_ratio, L.inharmonicity_ratio,
+                    L.tonal_centroid, tmp_dev, tstride, st, side ? side->st3 : nullptr, side ? side->fork : nullptr,
+                    side ? side->join : nullptr, &forked);
+    if (rc) return rc;
+  }
+
   if (Te >= 2) {
     rc = launch_variance(feat_dev + L.short_time_energy, Te, L.total, ns, feat_dev + L.scalars, L.total, st);
     if (rc) return rc;
   }
-  const int64_t tstride = (int64_t)sh.tmp_doubles_per_stream;
   if (sh.lr_nw > 0) {
     double* rms = tmp_dev + 2 * Tp;
-    rc = launch_rms_windows(pcm_dev, n, stride, ns, p->pre_emph_alpha, (int)sh.lr_win, (int)sh.lr_hop, sh.lr_nw,
-                            rms, tstride, st);
+    rc = launch_rms_windows(pcm_dev, n, stride, ns, p->pre_emph_alpha, (int)sh.lr_win, (int)sh.lr_hop, sh.lr_nw, rms,
+                            tstride, st);
     if (rc) return rc;
     rc = launch_loudness_range(rms, sh.lr_nw, tstride, ns, feat_dev + L.scalars + 1, L.total, st);
     if (rc) return rc;
@@ -199,12 +219,8 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
     if (rc) return rc;
   }
 
-  // harmonic block (speech.go:464-509)
-  const double* hann = reinterpret_cast<const double*>(blob + plan->off_hann);
-  rc = launch_yin(pcm_dev, stride, ns, p->pre_emph_alpha, p->algo_sample_rate, Tp, hann, feat_dev, L.total,
-                  L.pitch_estimate, L.pitch_confidence, L.voicing_strength, L.harmonic_ratio,
-                  L.inharmonicity_ratio, L.tonal_centroid, tmp_dev, tstride, st);
-  return rc;
+  if (side && forked) SONAR_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  return SONAR_OK;
 }
 
 void scatter_block(const double* f, const FpShape& sh, sonar_fp_out* o) {

@@ -710,7 +710,9 @@ __global__ void yin_zero_kernel(int n_streams, int64_t Tp, double* __restrict__ 
 int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, int sr, int64_t Tp,
                const double* hann_dev, double* feat, int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
                int64_t o_voicing, int64_t o_hratio, int64_t o_inharm, int64_t o_tonal, double* scratch,
-               int64_t scratch_stride, cudaStream_t st) {
+               int64_t scratch_stride, cudaStream_t st, cudaStream_t track_st, cudaEvent_t fork, cudaEvent_t join,
+               bool* forked) {
+  if (forked) *forked = false;
   if (Tp <= 0 || n_streams <= 0) return SONAR_OK;
   if (sr <= 0) {
     // frequency = sampleRate/period = 0 fails the [80,1000] Hz gate for every frame
@@ -751,12 +753,23 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
     prof_end();
   }
   SONAR_CUDA(cudaGetLastError());
-  prof_begin("yin_track_kernel", st);
-  yin_track_kernel<<<n_streams, 32, 0, st>>>(scratch, scratch_stride, n_streams, Tp, feat, feat_stride,
-                                                         o_pitch, o_conf, o_voicing, o_hratio, o_inharm,
-                                                         o_tonal);
+  // The tracker is a sequential walk, one warp per stream: with a side stream it runs beside whatever the caller
+  // enqueues next on `st` (the caller makes `st` wait for `join` before it is done with the features).
+  cudaStream_t ts = st;
+  if (track_st && fork && join) {
+    SONAR_CUDA(cudaEventRecord(fork, st));
+    SONAR_CUDA(cudaStreamWaitEvent(track_st, fork, 0));
+    ts = track_st;
+  }
+  prof_begin("yin_track_kernel", ts);
+  yin_track_kernel<<<n_streams, 32, 0, ts>>>(scratch, scratch_stride, n_streams, Tp, feat, feat_stride, o_pitch, o_conf,
+                                             o_voicing, o_hratio, o_inharm, o_tonal);
   prof_end();
   SONAR_CUDA(cudaGetLastError());
+  if (ts != st) {
+    SONAR_CUDA(cudaEventRecord(join, ts));
+    if (forked) *forked = true;
+  }
   return SONAR_OK;
 }
 
