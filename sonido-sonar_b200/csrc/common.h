@@ -113,13 +113,25 @@ struct FpShape {
   // bumped accordingly) and a partial-sum area in the scratch
   bool temporal = false;
   int64_t o_env = 0, o_att = 0, o_part = 0;
+  int64_t o_wpart = 0, wpart_doubles = 0;  // scratch of the frame walk's loudness block parts (timedomain.cu)
 };
 
 // ---- exact FP64 time-domain kernels (timedomain.cu) -------------------------
 // o_* are offsets (doubles) into each stream's output block; < 0 = not wanted.
+// Optional by-product of the frame walk: the RMS of the loudness windows (energy.go:157-179) from block sums of the
+// squared pre-emphasised samples the walk forms anyway, instead of a second pass over the PCM (launch_rms_windows).
+struct WalkLoudness {
+  int64_t win, hop, nw;            // window / hop in samples, windows per stream
+  double* part;                    // scratch: per stream 2 doubles per walk thread (ceil(Tn / 8) threads)
+  int64_t part_stride;
+  double* rms;                     // nw values per stream
+  int64_t rms_stride;
+};
+// *wl_done tells whether the by-product was produced (sizes permitting); otherwise the caller runs launch_rms_windows
 int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int frame,
                       int hop, int64_t Tn, int sr, double* out, int64_t out_stride, int64_t o_energy,
-                      int64_t o_entropy, int64_t o_zcr, cudaStream_t st);
+                      int64_t o_entropy, int64_t o_zcr, cudaStream_t st, const WalkLoudness* wl = nullptr,
+                      bool* wl_done = nullptr);
 int launch_variance(const double* x, int64_t n, int64_t stride, int n_streams, double* out, int64_t out_stride,
                     cudaStream_t st);
 int launch_rms_windows(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int win,

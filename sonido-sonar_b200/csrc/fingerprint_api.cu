@@ -72,6 +72,9 @@ int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s) {
     s->lr_nw = (n < s->lr_win || s->lr_win <= 0) ? 0 : (n - s->lr_win) / s->lr_hop + 1;
   }
   s->tmp_doubles_per_stream = (size_t)(2 * s->sz.n_pitch_frames + s->lr_nw + 2);
+  s->o_wpart = (int64_t)s->tmp_doubles_per_stream;
+  s->wpart_doubles = 2 * ((s->sz.n_frames + 7) / 8) + 2;
+  s->tmp_doubles_per_stream += (size_t)s->wpart_doubles;
   s->temporal = (p->enable & SONAR_FP_ENABLE_TEMPORAL) != 0;
   if (s->temporal) {
     s->o_env = s->L.total;
@@ -155,10 +158,12 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
 
   // exact FP64 walks over the pre-emphasised PCM: short-time energy (+entropy) and ZCR
   const bool same_grid = (Te == T) && p->energy_frame == p->window_size && p->energy_hop == p->hop_size;
+  bool loudness_done = false;  // the walk can leave the loudness windows' RMS behind (one pass over the PCM less)
   if (same_grid) {
+    WalkLoudness wl{sh.lr_win, sh.lr_hop, sh.lr_nw, tmp_dev + sh.o_wpart, tstride, tmp_dev + 2 * Tp, tstride};
     rc = launch_frame_walk(pcm_dev, n, stride, ns, p->pre_emph_alpha, p->window_size, p->hop_size, T,
                            p->algo_sample_rate, feat_dev, L.total, L.short_time_energy, L.energy_entropy,
-                           L.zero_crossing_rate, st);
+                           L.zero_crossing_rate, st, sh.lr_nw > 0 ? &wl : nullptr, &loudness_done);
     if (rc) return rc;
   } else {
     if (Te > 0) {
@@ -199,9 +204,11 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
   }
   if (sh.lr_nw > 0) {
     double* rms = tmp_dev + 2 * Tp;
-    rc = launch_rms_windows(pcm_dev, n, stride, ns, p->pre_emph_alpha, (int)sh.lr_win, (int)sh.lr_hop, sh.lr_nw, rms,
-                            tstride, st);
-    if (rc) return rc;
+    if (!loudness_done) {
+      rc = launch_rms_windows(pcm_dev, n, stride, ns, p->pre_emph_alpha, (int)sh.lr_win, (int)sh.lr_hop, sh.lr_nw, rms,
+                              tstride, st);
+      if (rc) return rc;
+    }
     rc = launch_loudness_range(rms, sh.lr_nw, tstride, ns, feat_dev + L.scalars + 1, L.total, st);
     if (rc) return rc;
   }

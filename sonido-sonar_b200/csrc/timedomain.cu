@@ -163,12 +163,25 @@ __global__ void __launch_bounds__(kTdThreads) frame_walk_kernel(
 // the FP64 add latency, and with no tile the SM holds as many warps as registers allow instead of ~100 chains.
 // Every lane streams through its own part of the signal (16-byte loads, each 128-byte line serves eight of them
 // from L1).
-template <int G, bool ALIGNED>
+// With BS the walk also leaves partial sums of y^2 over the hop-sized blocks of the loudness windows (energy.go:157-179:
+// 400 ms windows every 100 ms): every thread owns the samples of its G hops (the last thread of a stream everything
+// up to wb.limit), a block boundary falls inside that range at most once (the launcher checks the sizes), so a thread
+// writes two sums: the part of its range before the boundary and the part after it.  rms_from_parts_kernel adds the
+// 3-4 parts of each block in thread order.  This replaces a second pass over the PCM (rms_blocks_kernel).
+struct WalkBlocks {
+  double* part;         // per stream 2 doubles per walk thread, part_stride apart
+  int64_t part_stride;
+  int64_t hopL;         // block length
+  int64_t limit;        // samples [0, limit) belong to the blocks in use
+};
+
+template <int G, bool ALIGNED, bool BS>
 __global__ void __launch_bounds__(128) frame_walk_multi_kernel(
     const double* __restrict__ pcm, int64_t stride, double alpha, int frame, int hop, int R, int64_t Tn, int sr,
-    double* __restrict__ out, int64_t out_stride, int64_t o_energy, int64_t o_entropy, int64_t o_zcr) {
+    double* __restrict__ out, int64_t out_stride, int64_t o_energy, int64_t o_entropy, int64_t o_zcr, WalkBlocks wb) {
   const int s = blockIdx.y;
-  const int64_t f0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * G;
+  const int64_t tw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t f0 = tw * G;
   if (f0 >= Tn) return;
   const int nf = (int)((Tn - f0 < G) ? (Tn - f0) : G);
   const double* __restrict__ x = pcm + (int64_t)s * stride;
@@ -183,18 +196,35 @@ __global__ void __launch_bounds__(128) frame_walk_multi_kernel(
   double xprev = s0 > 0 ? x[s0 - 1] : 0.0;  // x[-1] = 0 (pre_emphasis.go:135-155)
   bool prev_neg = false;
   const int nseg = nf - 1 + R;
+  // block sums (BS): bcur collects the owned samples, p_first keeps what was collected before the boundary
+  const bool last_thread = f0 + G >= Tn;
+  const int64_t next_b = BS ? (s0 / wb.hopL + 1) * wb.hopL : 0;  // first sample of the next block
+  double bcur = 0.0, p_first = 0.0;
+  bool flushed = false;
   for (int sg = 0; sg < nseg; ++sg) {
     bool act[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) act[g] = g < nf && g <= sg && sg < g + R;
     const double* __restrict__ p = x + s0 + (int64_t)sg * hop;
-    auto step = [&](double xv, bool first) {
+    const bool own = BS && (last_thread || sg < G);
+    // offset of the block boundary inside this segment, -1 = none (no divergent path: lanes meet their boundary in
+    // different segments, a branch would make nearly every warp run both paths)
+    const int64_t seg0 = s0 + (int64_t)sg * hop;
+    const int rel_b = (own && next_b >= seg0 && next_b < seg0 + hop) ? (int)(next_b - seg0) : -1;
+    auto step = [&](double xv, bool first, int idx) {
       const double y = xv - alpha * xprev;
       xprev = xv;
       const double sq = y * y;
       const bool neg = (unsigned long long)__double_as_longlong(y) > 0x8000000000000000ull;
       const int cross = (neg != prev_neg) ? 1 : 0;
       prev_neg = neg;
+      if (BS) {
+        const bool hit = idx == rel_b;  // first sample of the next block: park what was collected so far
+        p_first = hit ? bcur : p_first;
+        flushed = flushed || hit;
+        const double add = own ? sq : 0.0;
+        bcur = hit ? add : bcur + add;
+      }
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         if (act[g]) {
@@ -208,24 +238,42 @@ __global__ void __launch_bounds__(128) frame_walk_multi_kernel(
       const double2* __restrict__ p2 = reinterpret_cast<const double2*>(p);
       {
         const double2 v = p2[0];
-        step(v.x, true);
-        step(v.y, false);
+        step(v.x, true, 0);
+        step(v.y, false, 1);
       }
       int e = 1;
       for (; e + 4 <= hop / 2; e += 4) {
         const double2 a = p2[e], b = p2[e + 1], c = p2[e + 2], d = p2[e + 3];
-        step(a.x, false); step(a.y, false); step(b.x, false); step(b.y, false);
-        step(c.x, false); step(c.y, false); step(d.x, false); step(d.y, false);
+        step(a.x, false, 2 * e); step(a.y, false, 2 * e + 1); step(b.x, false, 2 * e + 2); step(b.y, false, 2 * e + 3);
+        step(c.x, false, 2 * e + 4); step(c.y, false, 2 * e + 5); step(d.x, false, 2 * e + 6); step(d.y, false, 2 * e + 7);
       }
       for (; e < hop / 2; ++e) {
         const double2 a = p2[e];
-        step(a.x, false);
-        step(a.y, false);
+        step(a.x, false, 2 * e);
+        step(a.y, false, 2 * e + 1);
       }
     } else {
-      step(p[0], true);
-      for (int e = 1; e < hop; ++e) step(p[e], false);
+      step(p[0], true, 0);
+      for (int e = 1; e < hop; ++e) step(p[e], false, e);
     }
+  }
+  if (BS) {
+    if (last_thread) {  // the samples behind the last frame still belong to loudness blocks
+      for (int64_t i = s0 + (int64_t)nseg * hop; i < wb.limit; ++i) {
+        if (i == next_b) {
+          p_first = bcur;
+          bcur = 0.0;
+          flushed = true;
+        }
+        const double xv = x[i];
+        const double y = xv - alpha * xprev;
+        xprev = xv;
+        bcur += y * y;
+      }
+    }
+    double* part = wb.part + (int64_t)s * wb.part_stride + 2 * tw;
+    part[0] = flushed ? p_first : bcur;  // block s0 / hopL
+    part[1] = flushed ? bcur : 0.0;      // the block after it
   }
   double* __restrict__ o = out + (int64_t)s * out_stride;
   const double dur = (double)frame / (double)sr;  // len(frame)/sampleRate; sr==0 -> +Inf -> zcr 0
@@ -409,6 +457,35 @@ __global__ void __launch_bounds__(kRbWarps * 32) rms_blocks_kernel(const double*
   }
 }
 
+// RMS of the loudness windows from the block parts frame_walk_multi_kernel<.., BS = true> left: block b is covered by the
+// walk threads whose sample range [t U, (t + 1) U) (the last thread: to the end) meets [b hopL, (b + 1) hopL); their
+// parts are added in thread order, the R blocks of a window in block order.
+__global__ void __launch_bounds__(128) rms_from_parts_kernel(const double* __restrict__ part, int64_t part_stride,
+                                                            int64_t n_threads, int64_t U, int64_t hopL, int R, int win,
+                                                            int64_t nw, double* __restrict__ out, int64_t out_stride) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  const double* __restrict__ P = part + (int64_t)blockIdx.y * part_stride;
+  const int64_t last = n_threads - 1;
+  double acc = 0.0;
+  for (int k = 0; k < R; ++k) {
+    const int64_t b = w + k;
+    int64_t t_lo = (b * hopL) / U, t_hi = ((b + 1) * hopL - 1) / U;
+    if (t_lo > last) t_lo = last;
+    if (t_hi > last) t_hi = last;
+    double bs = 0.0;
+    for (int64_t t = t_lo; t <= t_hi; ++t) {
+      const int64_t b0 = (t * U) / hopL;
+      if (b0 == b)
+        bs += P[2 * t];
+      else if (b0 + 1 == b)
+        bs += P[2 * t + 1];
+    }
+    acc += bs;
+  }
+  out[(int64_t)blockIdx.y * out_stride + w] = sqrt(acc / (double)win);
+}
+
 // loudness units + 10th/95th percentile range on <= 4096 values per stream (bitonic sort in smem)
 __global__ void __launch_bounds__(256) loudness_range_kernel(const double* __restrict__ rms, int64_t nw,
                                                              int64_t in_stride, double* __restrict__ out,
@@ -537,7 +614,8 @@ __global__ void fill_strided_kernel(double* p, int64_t count, int64_t stride, do
 
 int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int frame,
                       int hop, int64_t Tn, int sr, double* out, int64_t out_stride, int64_t o_energy,
-                      int64_t o_entropy, int64_t o_zcr, cudaStream_t st) {
+                      int64_t o_entropy, int64_t o_zcr, cudaStream_t st, const WalkLoudness* wl, bool* wl_done) {
+  if (wl_done) *wl_done = false;
   if (Tn <= 0 || n_streams <= 0) return SONAR_OK;
   int fpc = kTdFrames;  // frames per CTA: as many as keep the staged tile under 200 KB
   while (fpc > 1 && sizeof(double) * (size_t)(((int64_t)(fpc - 1) * hop + frame + 1) * (hop + 1) / hop + 2) > 200 * 1024) --fpc;
@@ -552,15 +630,37 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
     const bool aligned = (hop % 2 == 0) && (stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
     const int64_t groups = (Tn + G - 1) / G;
     const dim3 mg((unsigned)((groups + 127) / 128), (unsigned)n_streams);
+    // loudness by-product: a thread's range (G hops, the last thread up to a frame and a hop more) must hold at most
+    // one block boundary, and the blocks in use must end inside the stream
+    WalkBlocks wb{nullptr, 0, 0, 0};
+    const bool fuse = wl && wl->nw > 0 && wl->hop > 0 && wl->win % wl->hop == 0 && wl->win / wl->hop <= 8 &&
+                      wl->hop > (int64_t)(G + 1) * hop + frame && (wl->nw - 1) * wl->hop + wl->win <= n &&
+                      wl->part_stride >= 2 * groups;
+    if (fuse) wb = WalkBlocks{wl->part, wl->part_stride, wl->hop, (wl->nw - 1) * wl->hop + wl->win};
     prof_begin("frame_walk_kernel", st);
-    if (aligned)
-      frame_walk_multi_kernel<G, true><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr, out,
-                                                          out_stride, o_energy, o_entropy, o_zcr);
+    if (aligned && fuse)
+      frame_walk_multi_kernel<G, true, true><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr, out,
+                                                                out_stride, o_energy, o_entropy, o_zcr, wb);
+    else if (aligned)
+      frame_walk_multi_kernel<G, true, false><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr, out,
+                                                                 out_stride, o_energy, o_entropy, o_zcr, wb);
+    else if (fuse)
+      frame_walk_multi_kernel<G, false, true><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr, out,
+                                                                 out_stride, o_energy, o_entropy, o_zcr, wb);
     else
-      frame_walk_multi_kernel<G, false><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr, out,
-                                                           out_stride, o_energy, o_entropy, o_zcr);
+      frame_walk_multi_kernel<G, false, false><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr,
+                                                                  out, out_stride, o_energy, o_entropy, o_zcr, wb);
     prof_end();
     SONAR_CUDA(cudaGetLastError());
+    if (fuse) {
+      prof_begin("rms_windows_kernel", st);
+      rms_from_parts_kernel<<<dim3((unsigned)((wl->nw + 127) / 128), (unsigned)n_streams), 128, 0, st>>>(
+          wl->part, wl->part_stride, groups, (int64_t)G * hop, wl->hop, (int)(wl->win / wl->hop), (int)wl->win, wl->nw,
+          wl->rms, wl->rms_stride);
+      prof_end();
+      SONAR_CUDA(cudaGetLastError());
+      if (wl_done) *wl_done = true;
+    }
     return SONAR_OK;
   }
   if (smem > 200 * 1024)
