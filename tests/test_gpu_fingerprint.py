@@ -329,3 +329,18 @@ def test_stft_streamer_equals_the_batch_transform(gpu, oracle, win, hop):
     assert g.buffered() == o.buffered() == left
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("n", [4410 * 1024 + 30000, 17640 + 4410 * 3, 17640 + 4410 * 3 + 255, 40001, 44100 * 3 + 1])
+def test_loudness_from_the_frame_walk_block_sums(gpu, oracle, synth, n):
+    """At 44.1 kHz the loudness windows' RMS comes from block sums the frame walk leaves behind (csrc/timedomain.cu,
+    WalkBlocks).  Lengths: one that contains sample 4410 * 1024 (a loudness block boundary that is also the first
+    sample of a walk thread), a stream that ends exactly with its last window, streams whose tail lies behind the last frame."""
+    rng = np.random.default_rng(n % 1000)
+    x = 0.3 * rng.standard_normal(n) * (1.0 + 0.8 * np.sin(np.arange(n) * 2e-4))
+    p = gpu.default_params(algo_sample_rate=44100)
+    a, b = gpu.fingerprint(x, p), oracle.fingerprint(x, p)
+    assert b.loudness_range >= 0.0
+    assert a.loudness_range == pytest.approx(b.loudness_range, rel=1e-9, abs=1e-12)
+    assert np.array_equal(a.short_time_energy, b.short_time_energy)
+    assert np.array_equal(a.zero_crossing_rate, b.zero_crossing_rate)
