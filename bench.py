@@ -136,6 +136,22 @@ class ClockSampler:
                 "how": self.how}
 
 
+def workload_config(P, seconds, T, max_lag, world):
+    """`config` of the JSON line: identical for both arms (--impl ours / reference), so that the driver's ratio is a
+    same-config ratio.  It names the WORKLOAD; how much of it a step of either arm processes is said in that arm's own
+    keys (`pairs_per_gpu` here is the GPU arm's batch, the reference arm states its per-step sample in `cpu_baseline`)."""
+    NS = 2 * P
+    n = int(round(seconds * SR))
+    return {
+        "workload": f"C2 pipeline: fingerprint both {int(seconds)} s 44.1 kHz streams of each source/CDN pair (1024/256 "
+                    "Hann, 26-mel/13-MFCC, fixed-sr mode; STFT/MFCC FP32, energy/ZCR FP64, YIN), NCC over "
+                    f"+-{int(MAX_LAG_S)} s ({2 * max_lag + 1} lags), banded DTW r={DTW_BAND}",
+        "pairs_per_gpu": P, "streams_per_gpu": NS, "frames_per_stream": int(T),
+        "l2": f"inputs {NS * n * 8 / 1e9:.2f} GB per step exceed the 126 MB L2; no flush needed",
+        "timing": "CUDA events on the library stream, max over ranks",
+    }
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -175,9 +191,9 @@ def cpu_baseline_single(capi, synth):
     seconds = 300.0
     q, r = make_pair(synth, seconds, 0)
     t0 = time.perf_counter()
-    cpu_pipeline(ora, q, r, seconds)
+    lag = cpu_pipeline(ora, q, r, seconds)
     dt = time.perf_counter() - t0
-    return {"value": 2 * seconds / dt, "unit": UNIT, "cores": 1, "kind": "port",
+    return {"value": 2 * seconds / dt, "unit": UNIT, "cores": 1, "kind": "port", "detected_lag_frames": int(lag),
             "sample": f"1 pair of 2x{int(seconds)} s streams (fingerprint both + NCC +-60 s + DTW r=50), "
                       f"C++ -O2 oracle port of the Go path, 1 thread, {dt:.1f} s; the Go toolchain is absent so the "
                       "reference itself cannot run here",
@@ -185,16 +201,24 @@ def cpu_baseline_single(capi, synth):
 
 
 def run_reference(args, rank):
-    """--impl reference: the CPU path with every host thread, on a bounded sample per step."""
+    """--impl reference: the CPU path on every host thread, SAME configuration as the GPU arm (5-min pairs, +-60 s lag,
+    DTW r=50); a step = one pair per host thread.  Rank 0 only."""
     if rank != 0:
         return
     p = pkg()
     capi, synth = p.capi, p.synth
-    cores = os.cpu_count() or 1
-    seconds = 60.0
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    seconds = float(args.seconds)
+    n = int(round(seconds * SR))
+    T = (n - WIN) // HOP + 1
+    max_lag = int(MAX_LAG_S * SR) // HOP
     from concurrent.futures import ThreadPoolExecutor
     oras = [capi.SonarLib(os.path.join(ROOT, "oracle", "libsonar_oracle.so")) for _ in range(cores)]
-    pairs = [make_pair(synth, seconds, i % 4) for i in range(cores)]
+    distinct = [make_pair(synth, seconds, i) for i in range(min(cores, 4))]
+    pairs = [distinct[i % len(distinct)] for i in range(cores)]
 
     def one(i):
         return cpu_pipeline(oras[i], pairs[i][0], pairs[i][1], seconds)
@@ -203,22 +227,23 @@ def run_reference(args, rank):
     with ThreadPoolExecutor(max_workers=cores) as ex:
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            list(ex.map(one, range(cores)))
+            lags = list(ex.map(one, range(cores)))
             if it >= args.warmup:
                 times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     value = cores * 2 * seconds / (ms / 1e3)
-    sample = (f"{cores} pairs of 2x{int(seconds)} s streams per step, one pair per host thread (ctypes releases the GIL), "
-              f"+-{MAX_LAG_S * seconds / 300:.0f} s lag, DTW r={DTW_BAND}; C++ -O2 oracle port (no Go toolchain on the box)")
+    sample = (f"{cores} pairs of 2x{int(seconds)} s streams per step, one pair per host thread ({cores} threads; ctypes "
+              f"releases the GIL), +-{int(MAX_LAG_S)} s lag ({2 * max_lag + 1} lags), DTW r={DTW_BAND}: the GPU arm's "
+              "configuration; C++ -O2 oracle port of the Go path (no Go toolchain on the box, so the reference itself "
+              "cannot run)")
+    cfg = workload_config(args.pairs, seconds, T, max_lag, 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 pipeline: fingerprint both streams of each source/CDN pair (1024/256, 26-mel/13-MFCC, "
-                               "fixed-sr mode), NCC over +-60 s, banded DTW r=50", "cpu_sample": sample},
+        "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "alignments_per_s": cores / (ms / 1e3),
+        "alignments_per_s": cores / (ms / 1e3), "detected_lags_frames": lags[:4],
     }
     print(json.dumps(line), file=_OUT, flush=True)
 
@@ -302,7 +327,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
     l0 = lib.kernel_launches()
-    lib.profile_enable(not args.no_profile)
+    lib.profile_enable(False)  # the headline is timed WITHOUT the per-kernel event pairs
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(ext)
     t0 = time.perf_counter()
@@ -312,10 +337,20 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     dev_ms = ev0.elapsed_time(ev1)
-    lib.profile_enable(False)
     launches = lib.kernel_launches() - l0
-    kern = lib.profile_read()
     clocks = sampler.stop() if sampler else None
+    # per-kernel table and the roofline kernel's launch duration: the same steps once more, now with every launch
+    # bracketed by a CUDA-event pair on its own stream (library side, sonar_profile_*), outside the headline timing
+    kern, prof_steps = {}, 0
+    if not args.no_profile:
+        prof_steps = max(1, min(args.steps, 5))
+        lib.profile_read()
+        lib.profile_enable(True)
+        for _ in range(prof_steps):
+            step_resident()
+        barrier()
+        lib.profile_enable(False)
+        kern = lib.profile_read()
     step_ms = reduce_max(dev_ms / args.steps)
     audio_s = world * NS * seconds
     value = audio_s / (step_ms / 1e3)
@@ -400,12 +435,29 @@ def run_ours(args, rank, world, local_rank):
                            "matches_unsharded": bool(sh_summ.peak_lag == whole.peak_lag and
                                                      sh_summ.peak_correlation == whole.peak_correlation),
                            "collectives": "all_gather(16 B/rank) + all_gather(72 B/rank) over NCCL"}
+    # ---- outside every timed region: the detected lags of the first pairs against the oracle.  The e2e leg returned
+    #      the short-time energies (bit-exact with the oracle's: tests/test_gpu_fullsize.py); the oracle's own
+    #      time-domain per-lag NCC over them must find the same lag index.  Pair 0 additionally runs the whole oracle
+    #      pipeline from the PCM in the cpu_baseline leg below.
+    lag_check = None
+    if rank == 0 and not args.no_cpu:
+        ora = capi.SonarLib(os.path.join(ROOT, "oracle", "libsonar_oracle.so"))
+        idx = list(range(min(4, P)))
+        ora_lags = []
+        for i in idx:
+            ea, eb = fps[i]["query"].short_time_energy, fps[i]["reference"].short_time_energy
+            _, xs, _ = ora.align_xcorr(ea, eb, max_lag, HOP, SR)
+            ora_lags.append(int(xs.peak_lag))
+        lag_check = {"pairs": idx, "oracle_lags_frames": ora_lags, "gpu_lags_frames": [int(lags[i]) for i in idx],
+                     "equal": bool(ora_lags == [int(lags[i]) for i in idx]),
+                     "method": "oracle time-domain NCC (correlation.go:373-449 restated) over the returned energies"}
+        assert lag_check["equal"], f"detected lags differ from the oracle: {lag_check}"
     if rank == 0:
         peak, peak_src = measured_peak()
         k_ms, k_n = kern.get("stft_features_kernel", (0.0, 0))
         roof = None
         if k_n:
-            frames_per_launch = NS * T * args.steps / k_n  # the library may split a step into chunks of pairs
+            frames_per_launch = NS * T * prof_steps / k_n  # the library may split a step into chunks of pairs
             avg_ms = k_ms / k_n
             achieved = frames_per_launch * ALGO_BYTES_PER_FRAME / (avg_ms / 1e3) / 1e9
             tr = ncu_traffic()
@@ -415,23 +467,22 @@ def run_ours(args, rank, world, local_rank):
                     "traffic": (tr["dram_bytes_per_launch"] / tr["frames_per_launch"] * frames_per_launch) if tr else None,
                     "traffic_source": tr.get("source") if tr else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": frames_per_launch * ALGO_BYTES_PER_FRAME,
-                    "avg_launch_ms": avg_ms, "launches_timed": k_n}
+                    "avg_launch_ms": avg_ms, "launches_timed": k_n,
+                    "timing": f"library-side CUDA-event pair around every launch on its own stream, over {prof_steps} "
+                              "profiled step(s) run right after the timed region (the headline is timed without them)"}
         total_k = sum(v[0] for v in kern.values()) or 1.0
-        shares = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+        shares = {k: {"ms_per_step": v[0] / max(prof_steps, 1), "launches_per_step": v[1] / max(prof_steps, 1),
                       "share": v[0] / total_k} for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
         cpu = cpu_baseline_single(capi, synth) if (world == 1 and not args.no_cpu) else None
+        if cpu is not None and rank * P == 0:  # pair 0 of rank 0 is the pair the cpu_baseline leg ran end to end
+            assert cpu["detected_lag_frames"] == int(lags[0]), (cpu["detected_lag_frames"], lags[0])
+            lag_check["pair0_full_oracle_pipeline_equal"] = True
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {
-                "workload": f"C2 pipeline x {P} pairs/GPU: fingerprint both {int(seconds)} s 44.1 kHz streams of each "
-                            "source/CDN pair (1024/256 Hann, 26-mel/13-MFCC, fixed-sr mode; STFT/MFCC FP32, "
-                            f"energy/ZCR/YIN FP64), NCC over +-{int(MAX_LAG_S)} s ({2 * max_lag + 1} lags), banded DTW r={DTW_BAND}",
-                "pairs_per_gpu": P, "streams_per_gpu": NS, "frames_per_stream": int(T), "parallelism": f"pair-sharded x{world}",
-                "l2": f"inputs {NS * n * 8 / 1e9:.2f} GB per step exceed the 126 MB L2; no flush needed",
-                "timing": "CUDA events on the library stream, max over ranks",
-            },
+            "config": workload_config(P, seconds, T, max_lag, world),
+            "parallelism": f"pair-sharded x{world} (one process per GPU, no data-path collective)",
             "alignments_per_s": world * P / (step_ms / 1e3),
             "wall_ms_per_step": wall_ms / args.steps,
             "e2e": {"value": audio_s / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -446,6 +497,7 @@ def run_ours(args, rank, world, local_rank):
             "kernels": shares,
             "cpu_baseline": cpu,
             "detected_lags_frames": lags,
+            "lags_checked_vs_oracle": lag_check,
             "lag_sharded": lag_sharded,
         }
         print(json.dumps(line), file=_OUT, flush=True)

@@ -468,7 +468,7 @@ class SonarLib:
 
     def stft(self, pcm, win, hop, wtype="hann", phase=False, cplx=False):
         pcm = _f64(pcm)
-        T = (pcm.size - win) // hop + 1 if (win > 0 and hop > 0) else 0
+        T = int((pcm.size - win) / hop) + 1 if (win > 0 and hop > 0) else 0  # Go's int division truncates toward zero
         B = win // 2 + 1
         T = max(T, 0)
         mag = np.zeros((T, B))
@@ -662,7 +662,7 @@ class SonarLib:
                        bark_low=0.0, bark_high=None):
         """sonar_music_spectral_f64: (contrast [T][n_bands], chroma [T][12], bark [T][n_bark])."""
         x = _f64(pcm)
-        T = (x.size - win) // hop + 1
+        T = int((x.size - win) / hop) + 1  # Go's int division truncates toward zero
         if T <= 0:
             T = 0
         contrast, chroma, bark = np.zeros((T, n_bands)), np.zeros((T, 12)), np.zeros((T, n_bark))

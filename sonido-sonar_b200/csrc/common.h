@@ -62,7 +62,7 @@ struct FpPlan {  // immutable once built; cached per context keyed by the parame
   void* d_blob = nullptr;
   size_t blob_bytes = 0;
   size_t off_win2 = 0, off_tw1 = 0, off_wn = 0, off_xtab = 0, off_dct = 0, off_lift = 0, off_regions = 0,
-         off_chunk_region = 0, off_hann = 0;
+         off_chunk_region = 0, off_hann = 0, off_zero = 0;
   std::vector<MelRegion> h_regions;  // host copy of the mel region table (kernel eligibility checks)
   ~FpPlan();
 };
@@ -132,6 +132,9 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
                       int hop, int64_t Tn, int sr, double* out, int64_t out_stride, int64_t o_energy,
                       int64_t o_entropy, int64_t o_zcr, cudaStream_t st, const WalkLoudness* wl = nullptr,
                       bool* wl_done = nullptr);
+// ZCR of the lone incomplete frame of a stream shorter than the window (n < W, T == 1)
+int launch_short_zcr(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int sr, double* out,
+                     int64_t out_stride, int64_t o_zcr, cudaStream_t st);
 int launch_variance(const double* x, int64_t n, int64_t stride, int n_streams, double* out, int64_t out_stride,
                     cudaStream_t st);
 int launch_rms_windows(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int win,

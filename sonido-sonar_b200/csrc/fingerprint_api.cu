@@ -111,11 +111,15 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
   // scalars: [0] energy variance (energy.go:97-118), [1] loudness range (energy.go:157-225), [2..] temporal block
   rc = launch_fill_strided(feat_dev + L.scalars, L.total - L.scalars, L.total, ns, 0.0, st);
   if (rc) return rc;
+  // n in (W - H, W): Go's truncating division still yields one frame, which the reference's worker then skips because
+  // it would end behind the signal (analyzers/spectral.go:409,472-474): its row stays zero.  The STFT kernel reads a
+  // frame of silence instead of running past the buffer; same for the lone pitch frame of n in (512, 1024).
+  const bool short_win = n < (int64_t)p->window_size;
   StftArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.pcm = pcm_dev;
-  a.n = n;
-  a.stride = stride;
+  a.pcm = short_win ? reinterpret_cast<const double*>(blob + plan->off_zero) : pcm_dev;
+  a.n = short_win ? (int64_t)p->window_size : n;
+  a.stride = short_win ? 0 : stride;
   a.n_streams = ns;
   a.T = T;
   a.Te = Te;
@@ -157,7 +161,7 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
   }
 
   // exact FP64 walks over the pre-emphasised PCM: short-time energy (+entropy) and ZCR
-  const bool same_grid = (Te == T) && p->energy_frame == p->window_size && p->energy_hop == p->hop_size;
+  const bool same_grid = !short_win && (Te == T) && p->energy_frame == p->window_size && p->energy_hop == p->hop_size;
   bool loudness_done = false;  // the walk can leave the loudness windows' RMS behind (one pass over the PCM less)
   if (same_grid) {
     WalkLoudness wl{sh.lr_win, sh.lr_hop, sh.lr_nw, tmp_dev + sh.o_wpart, tstride, tmp_dev + 2 * Tp, tstride};
@@ -172,8 +176,12 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
                              st);
       if (rc) return rc;
     }
-    rc = launch_frame_walk(pcm_dev, n, stride, ns, p->pre_emph_alpha, p->window_size, p->hop_size, T,
-                           p->algo_sample_rate, feat_dev, L.total, -1, -1, L.zero_crossing_rate, st);
+    if (short_win)  // the frame handed to the ZCR is pre[0 : min(W, N)] = the whole short stream (speech.go:351-357)
+      rc = launch_short_zcr(pcm_dev, n, stride, ns, p->pre_emph_alpha, p->algo_sample_rate, feat_dev, L.total,
+                            L.zero_crossing_rate, st);
+    else
+      rc = launch_frame_walk(pcm_dev, n, stride, ns, p->pre_emph_alpha, p->window_size, p->hop_size, T,
+                             p->algo_sample_rate, feat_dev, L.total, -1, -1, L.zero_crossing_rate, st);
     if (rc) return rc;
   }
   // the alignment branch of the pair pipeline only needs the short-time energies: it may start on its own stream
@@ -191,7 +199,9 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
   bool forked = false;
   {
     const double* hann = reinterpret_cast<const double*>(blob + plan->off_hann);
-    rc = launch_yin(pcm_dev, stride, ns, p->pre_emph_alpha, p->algo_sample_rate, Tp, hann, feat_dev, L.total,
+    // n in (512, 1024): one frame shorter than the detector's window -> DetectPitch errors, the zeros stay
+    // (speech.go:480-487, pitch_detection.go:226-228) = what the sample-rate-0 path writes
+    rc = launch_yin(pcm_dev, stride, ns, p->pre_emph_alpha, n < 1024 ? 0 : p->algo_sample_rate, Tp, hann, feat_dev, L.total,
                     L.pitch_estimate, L.pitch_confidence, L.voicing_strength, L.harmonic_ratio, L.inharmonicity_ratio,
                     L.tonal_centroid, tmp_dev, tstride, st, side ? side->st3 : nullptr, side ? side->fork : nullptr,
                     side ? side->join : nullptr, &forked);
@@ -481,6 +491,12 @@ int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int ho
   Slot& s = dev.slot[0];
   const int B = win / 2 + 1;
   const size_t per = sizeof(double) * (size_t)T * B;
+  if (n < win) {  // T == 1, the frame is skipped (analyzers/spectral.go:472-474): the rows stay as allocated
+    std::memset(mag, 0, per);
+    if (phase) std::memset(phase, 0, per);
+    if (cplx) std::memset(cplx, 0, 2 * per);
+    return SONAR_OK;
+  }
   const size_t out_bytes = per * (1 + (phase ? 1 : 0) + (cplx ? 2 : 0));
   const int64_t stride = (n + 1) & ~(int64_t)1;
   if ((rc = dev.ensure_dev(s.d_in, sizeof(double) * (size_t)stride)) || (rc = dev.ensure_dev(s.d_out, out_bytes)))
@@ -574,7 +590,13 @@ int sonar_music_spectral_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int w
   const int64_t stride = (n + 1) & ~(int64_t)1;
   if ((rc = dev.ensure_dev(s.d_in, sizeof(double) * (size_t)stride)) || (rc = dev.ensure_dev(s.d_out, total))) return rc;
   unsigned char* d = static_cast<unsigned char*>(s.d_out.p);
-  SONAR_CUDA(cudaMemcpyAsync(s.d_in.p, pcm, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s.st));
+  if (n < win) {  // the lone frame is skipped by the reference's STFT worker: a spectrogram row of zeros
+    if ((rc = dev.ensure_dev(s.d_in, sizeof(double) * (size_t)win))) return rc;
+    SONAR_CUDA(cudaMemsetAsync(s.d_in.p, 0, sizeof(double) * (size_t)win, s.st));
+    n = win;
+  } else {
+    SONAR_CUDA(cudaMemcpyAsync(s.d_in.p, pcm, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s.st));
+  }
   if (contrast) SONAR_CUDA(cudaMemcpyAsync(d + o_edg, edges.data(), sizeof(int) * edges.size(), cudaMemcpyHostToDevice, s.st));
   if (chroma) SONAR_CUDA(cudaMemcpyAsync(d + o_map, cmap.data(), cmap.size(), cudaMemcpyHostToDevice, s.st));
   if (bark) {

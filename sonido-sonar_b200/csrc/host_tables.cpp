@@ -297,6 +297,7 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
   plan->off_regions = take(sizeof(MelRegion) * reg.size());
   plan->off_chunk_region = take(sizeof(int) * R1);
   plan->off_hann = take(sizeof(double) * 1024);
+  plan->off_zero = take(sizeof(double) * N);  // one frame of silence: the lone incomplete frame of an input shorter than the window
   plan->blob_bytes = off;
   std::vector<unsigned char> host(off, 0);
   std::memcpy(host.data() + plan->off_win2, win2.data(), sizeof(float2) * M);

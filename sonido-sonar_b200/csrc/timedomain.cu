@@ -685,6 +685,40 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
   return SONAR_OK;
 }
 
+namespace {
+// Zero-crossing rate of the lone incomplete frame of a stream shorter than the window (speech.go:351-357 hands
+// pre[0 : min(W, N)] to zero_crossing_rate.go:37-53): one thread per stream, n < W samples, rate = crossings / (n / sr).
+__global__ void short_zcr_kernel(const double* __restrict__ pcm, int64_t n, int64_t stride, int n_streams, double alpha,
+                                 int sr, double* __restrict__ out, int64_t out_stride, int64_t o_zcr) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_streams) return;
+  const double* __restrict__ x = pcm + (int64_t)s * stride;
+  double xprev = 0.0;
+  int crossings = 0;
+  bool prev_neg = false;
+  for (int64_t i = 0; i < n; ++i) {
+    const double y = x[i] - alpha * xprev;
+    xprev = x[i];
+    const bool neg = y < 0.0;
+    if (i > 0 && neg != prev_neg) ++crossings;
+    prev_neg = neg;
+  }
+  double z = 0.0;
+  if (n >= 2) z = (double)crossings / ((double)n / (double)sr);  // sr == 0: x / +Inf = 0, as in Go
+  out[(int64_t)s * out_stride + o_zcr] = z;
+}
+}  // namespace
+
+int launch_short_zcr(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int sr, double* out,
+                     int64_t out_stride, int64_t o_zcr, cudaStream_t st) {
+  if (n_streams <= 0) return SONAR_OK;
+  prof_begin("frame_walk_kernel", st);
+  short_zcr_kernel<<<(n_streams + 63) / 64, 64, 0, st>>>(pcm, n, stride, n_streams, alpha, sr, out, out_stride, o_zcr);
+  prof_end();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
 int launch_variance(const double* x, int64_t n, int64_t stride, int n_streams, double* out, int64_t out_stride,
                     cudaStream_t st) {
   if (n_streams <= 0) return SONAR_OK;

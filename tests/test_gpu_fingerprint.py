@@ -106,6 +106,14 @@ CASES = {
     "run_boundaries": (lambda s: s.sweep_noise(1.0, seed=15)[:1024 + 256 * 62], dict(algo_sample_rate=44100)),
     "single_frame": (lambda s: s.sweep_noise(1.0, seed=10)[:1024], dict(algo_sample_rate=44100)),
     "silence": (lambda s: np.zeros(20000), dict(algo_sample_rate=44100)),
+    # n in (W - H, W): Go's truncating division yields ONE frame that the STFT worker then skips (spectral.go:409,
+    # 472-474) -> a zero spectrum row, ZCR over the n samples, no energy frame; n in (512, 1024): one pitch frame of zeros
+    "shorter_than_window_900": (lambda s: s.sweep_noise(1.0, seed=21)[:900], dict(algo_sample_rate=44100)),
+    "shorter_than_window_769": (lambda s: s.sweep_noise(1.0, seed=22)[:769], dict(algo_sample_rate=44100)),
+    "short_window_ok_pitch_short_700": (lambda s: s.sweep_noise(1.0, seed=23)[:700], dict(
+        window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=16000, call_sample_rate=16000)),
+    "shorter_than_window_energy_grid_fits": (lambda s: s.sweep_noise(1.0, seed=24)[:1000], dict(
+        algo_sample_rate=44100, energy_frame=256, energy_hop=128)),
 }
 
 
@@ -115,6 +123,41 @@ def test_fingerprint_matches_oracle(gpu, oracle, synth, name):
     pcm = make(synth)
     p = gpu.default_params(**kw)
     check_fp(gpu.fingerprint(pcm, p), oracle.fingerprint(pcm, p))
+
+
+ALL_WINDOWS = ("hann", "hamming", "blackman", "blackman_harris", "kaiser", "tukey", "rectangular", "bartlett", "welch")
+
+
+@pytest.mark.parametrize("wtype", ALL_WINDOWS)
+def test_every_window_type_matches_oracle(gpu, oracle, synth, capi, wtype):
+    """All nine analyzers.WindowType values (windowing.go:246-371) through the product library: the fused fingerprint
+    (1024/256 second-generation kernel and the 512/160 geometry) and the materialised spectrum."""
+    assert wtype in capi.WINDOWS
+    pcm = synth.sweep_noise(1.5, seed=40)
+    for kw in (dict(algo_sample_rate=44100, window_type=wtype),
+               dict(window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=44100,
+                    window_type=wtype)):
+        p = gpu.default_params(**kw)
+        check_fp(gpu.fingerprint(pcm, p), oracle.fingerprint(pcm, p))
+    mg, _, _ = gpu.stft(pcm[:20000], 1024, 256, wtype=wtype)
+    mr, _, _ = oracle.stft(pcm[:20000], 1024, 256, wtype=wtype)
+    assert np.max(np.abs(mg - mr)) <= 2e-6 * np.max(mr)
+
+
+def test_short_input_batch_does_not_read_the_neighbour(gpu, oracle, synth):
+    """with n in (W - H, W) the lone frame must not be read past the stream's end, i.e. into the next stream
+    of a batch.  The neighbour is loud, the short streams are quiet: any leak shows up in the spectral features."""
+    p = gpu.default_params(algo_sample_rate=44100)
+    quiet = 1e-3 * synth.sweep_noise(1.0, seed=50)[:900]
+    loud = 100.0 * synth.sweep_noise(1.0, seed=51)[:900]
+    batch = gpu.fingerprint_batch([quiet, loud, quiet], p)
+    ref = oracle.fingerprint(quiet, p)
+    for fb in (batch[0], batch[2]):
+        check_fp(fb, ref)
+        assert not fb.spectral_flatness.any() and not fb.spectral_crest.any()
+        assert fb.mfcc.shape == (1, 13) and fb.short_time_energy.size == 0 and fb.pitch_estimate.size == 0
+    mg, ph, cx = gpu.stft(quiet, 1024, 256, phase=True, cplx=True)
+    assert mg.shape == (1, 513) and not mg.any() and not ph.any() and not cx.any()
 
 
 @pytest.mark.gpu

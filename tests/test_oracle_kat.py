@@ -509,3 +509,42 @@ def test_stft_streamer_arguments(oracle, capi):
     rc = oracle.lib.sonar_stft_stream_process(st.h, capi._dp(np.zeros(2000)), 2000, None, None, None, 0, capi.C.byref(n))
     assert rc != 0 and b"frame capacity too small" in oracle.lib.sonar_last_error() and st.buffered() == 0
     st.close()
+
+
+# ---------------------------------------------------------------- inputs shorter than one window
+
+@pytest.mark.parametrize("n,win,hop", [(900, 1024, 256), (769, 1024, 256), (400, 512, 160)])
+def test_incomplete_single_frame_is_skipped_not_read(oracle, n, win, hop):
+    """analyzers/spectral.go:409: (n - W)/H + 1 with Go's truncating division is 1 for n in (W - H, W); the worker
+    then skips the job because it ends behind the signal (:472-474) and the row stays zero.  The samples behind the
+    buffer must never be read: a huge sentinel placed there would otherwise show up in the spectrum."""
+    rng = np.random.default_rng(n)
+    buf = np.full(n + 2048, 1e30)
+    buf[:n] = 0.1 * rng.standard_normal(n)
+    x = buf[:n]
+    mag, ph, cx = oracle.stft(x, win, hop, phase=True, cplx=True)
+    assert mag.shape == (1, win // 2 + 1) and not mag.any() and not ph.any() and not cx.any()
+    sr = 16000 if win == 512 else 44100
+    p = oracle.default_params(window_size=win, hop_size=hop, energy_frame=win, energy_hop=hop, algo_sample_rate=sr,
+                              call_sample_rate=sr)
+    fp = oracle.fingerprint(x, p)
+    assert fp.mfcc.shape == (1, 13) and np.isfinite(fp.mfcc).all()
+    assert fp.mfcc[0, 0] == pytest.approx(-117.40926320884498, rel=1e-12)  # every mel energy 0 -> ln(1e-10)
+    for k in ("spectral_centroid", "spectral_rolloff", "spectral_bandwidth", "spectral_flatness", "spectral_crest"):
+        assert fp.arrays[k].shape == (1,) and fp.arrays[k][0] == 0.0, k
+    assert fp.short_time_energy.size == 0  # energy.go:26-28
+    # ZCR over pre[0 : min(W, N)] (speech.go:351-357)
+    pre = x - 0.97 * np.concatenate(([0.0], x[:-1]))
+    crossings = int(np.sum((pre[:-1] >= 0) != (pre[1:] >= 0)))
+    assert fp.zero_crossing_rate[0] == crossings / (n / sr)
+    # pitch frames: (n - 1024)/512 + 1 truncates to 1 only for n in (512, 1024); DetectPitch rejects the short frame
+    tp = 1 if 512 < n < 1024 else 0
+    assert fp.pitch_estimate.size == tp
+    if tp:
+        assert fp.pitch_estimate[0] == 0.0 and fp.inharmonicity_ratio[0] == 1.0
+
+
+def test_too_short_still_errors(oracle, capi):
+    with pytest.raises(capi.SonarError) as e:
+        oracle.stft(np.zeros(768), 1024, 256)  # (768 - 1024)/256 + 1 = 0
+    assert "signal too short" in e.value.msg
