@@ -102,6 +102,9 @@ bool stft_supported(int window_size);
 // second-generation kernel (stft_v2.cu): N = 1024, aligned PCM, features mode
 bool stft_v2_eligible(const FpPlan& plan, const StftArgs& a);
 int launch_stft_v2(const FpPlan& plan, StftArgs& a, cudaStream_t st);
+// third generation (stft_v3.cu): 1024 / 256 and 512 / 160, two frames per complex FFT, register-resident sample ring
+bool stft_v3_eligible(const FpPlan& plan, const StftArgs& a);
+int launch_stft_v3(const FpPlan& plan, StftArgs& a, cudaStream_t st);
 
 // ---- fingerprint sequencing shared by the host-pointer, device-resident and pipeline entry points ----------
 struct FpShape {

@@ -532,6 +532,7 @@ int launch_geom(const FpPlan& plan, StftArgs& a, bool spectrum, cudaStream_t st)
 bool stft_supported(int w) { return w == 256 || w == 512 || w == 1024 || w == 2048; }
 
 int launch_stft_features(const FpPlan& plan, StftArgs& a, bool spectrum, cudaStream_t st) {
+  if (!spectrum && stft_v3_eligible(plan, a)) return launch_stft_v3(plan, a, st);
   if (!spectrum && stft_v2_eligible(plan, a)) return launch_stft_v2(plan, a, st);
   switch (plan.N) {
     case 256: return launch_geom<8, 16>(plan, a, spectrum, st);

@@ -1,0 +1,702 @@
+// Fused framed-STFT + MFCC + spectral-descriptor kernel, third generation (N = 1024 or 512, hop a multiple of 32;
+// FP32 arithmetic, f64 I/O).  Same outputs as stft_v2.cu / stft_features.cu, replacing
+//   analyzers.ComputeSTFTWithWindow        fingerprint/analyzers/spectral.go:385-545
+//   spectral.MFCC.Compute                  algorithms/spectral/mfcc.go:113-164
+//   MelScale.ApplyFilterBank               algorithms/spectral/mel_scale.go:89-105
+//   centroid/rolloff/bandwidth/flatness/crest/slope/flux   algorithms/spectral/spectral_*.go
+//   low/high band energy ratios            fingerprint/extractors/speech.go:436-456
+//
+// The second generation was bound by shared-memory wavefronts (575 per frame at 74 % of the pipe: three tile
+// exchanges of the 8 x 8 x 8 FFT, the ring, five table / row streams of the per-bin scan), not by FP32 issue or HBM
+// (profiles/r01_stft_v2_kernel_ncu_full.md; one SM moves 1 wavefront per clock but issues 4 FP32 warp instructions).
+// This generation is built around the wavefront count (scripts/proto/stft_v3_dataflow.py is the numpy model of it):
+//   * a warp transforms TWO consecutive frames at once as ONE complex FFT of c = a_w + i b_w (N = 512: two such
+//     packs, four frames).  Lane l owns the samples n = l + 32 j, so consecutive frames share their samples IN
+//     REGISTERS (the hop is a whole number of rows j): the sample ring costs no shared memory at all, and every new
+//     sample is loaded from HBM exactly once, converted to FP32 once;
+//   * 1024 = 32 x 32 (512 = 16 x 32): pass 1 is a radix-32 (radix-16) transform in registers, ONE transposition through
+//     a padded tile, pass 2 a radix-32 transform in registers that leaves Z[k1 + 32 k2] in lane k1;
+//   * the Hermitian split X_a = Z[k] + conj Z[N-k], X_b = (Z[k] - conj Z[N-k]) / i needs the partner bin from lane
+//     (32 - k1) & 31: 32 warp shuffles instead of a second trip through shared memory;
+//   * all complex arithmetic runs on the Blackwell packed-FP32 pipe instructions (FADD2 / FMUL2 / FFMA2, fft_packed.cuh):
+//     a radix-32 transform is 228 issue slots instead of ~510, and the scan processes (frame a, frame b) pairs;
+//   * magnitudes go to XOR-swizzled rows (conflict free for the stride-1 writes by bin AND for the 16-byte reads of
+//     the scan, no padding), the per-bin scan walks BOTH frames of a pack in one pass: the mel weights / slope
+//     abscissae are read once per two frames and frame b's predecessor is frame a (registers); the predecessor of the
+//     first frame of an iteration is kept in registers from the previous iteration.
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+
+#include "common.h"
+#include "fft_packed.cuh"
+
+namespace sonar {
+namespace {
+
+constexpr int kW3 = 12;               // warps per CTA (one CTA per SM)
+constexpr int kRun3 = 32;             // frames per segment: finished in FP64 one frame per lane
+constexpr int kSeg3 = 4;              // segments per run: a warp walks kSeg3 * 32 consecutive frames of one stream, the
+constexpr int kRunOut3 = kSeg3 * kRun3 - 1;  // first of which only warms the flux up (it has no predecessor at hand)
+constexpr unsigned kFull3 = 0xffffffffu;
+constexpr int kTileRow = 34;          // exchange tile row stride (float2): 16-byte rows, conflict-free LDS.128
+constexpr int kSlots3 = 24;           // lane-private mel slots (float2: both frames of a pack; alias the tile in the scan)
+constexpr int kRaw3 = 16;             // raw sums parked per frame
+constexpr int kMaxContrib3 = 12;      // lanes that may hold a part of one mel filter
+
+template <int LOGN, int HR_>
+struct V3G {
+  static constexpr int N = 1 << LOGN, M = N / 2, B = M + 1;
+  static constexpr int J = N / 32;            // samples per lane per frame = pass-1 radix
+  static constexpr int FR = 64 / J;           // frames per warp iteration (2 or 4)
+  static constexpr int PK = FR / 2;           // complex packs per iteration
+  static constexpr int HR = HR_, H = 32 * HR_;
+  static constexpr int RR = J + (FR - 1) * HR;  // ring rows per lane
+  static constexpr int NEW = FR * HR;           // new rows per iteration
+  static constexpr int BPL = M / 32;            // contiguous bins per lane in the scan (16 / 8)
+  static constexpr int KSTR = 32 / PK;          // bin stride of pass 2's outputs: k = k1 + KSTR k2
+  static constexpr int ROW = M + 4;             // floats per table row (xtab / wlo / whi), swizzled by spos
+  static constexpr int PROW = M + 4;            // float2 per magnitude pair row (|X_a|, |X_b|), swizzled by ppos
+  static_assert(LOGN == 10 || LOGN == 9, "N = 1024 or 512");
+  static_assert(NEW <= RR, "hop must not exceed the window");
+};
+
+// table rows (one float per bin): 16-byte chunk c = k >> 2 lives at c ^ ((c >> 3) & 7)
+__host__ __device__ __forceinline__ int spos(int k) { return ((((k >> 2) ^ ((k >> 5) & 7))) << 2) | (k & 3); }
+// magnitude pair rows (one float2 per bin): 16-byte chunk c = k >> 1 lives at c ^ ((c >> 3) & 7).  Conflict free both
+// for pass 2's 8-byte stores (32 consecutive bins per instruction) and for the scan's 16-byte loads (BPL contiguous bins
+// per lane).
+__host__ __device__ __forceinline__ int ppos(int k) { return ((((k >> 1) ^ ((k >> 4) & 7))) << 1) | (k & 1); }
+
+struct V3Smem {
+  size_t tw, win, xtab, wlo, whi, fmask, moff, dct, lift, r0, warp0, per_warp, total;
+  size_t w_tile, w_mag, w_raw, w_macc;
+};
+
+template <class G>
+__host__ __device__ inline V3Smem v3_layout(int n_mel, int n_mfcc) {
+  V3Smem L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += (bytes + 15) & ~(size_t)15;
+    return r;
+  };
+  L.tw = take(sizeof(float2) * G::J * 32);
+  L.win = take(sizeof(float) * G::N);
+  L.xtab = take(sizeof(float) * G::ROW);
+  L.wlo = take(sizeof(float) * G::ROW);
+  L.whi = take(sizeof(float) * G::ROW);
+  L.fmask = take(sizeof(unsigned) * 32);
+  L.moff = take(sizeof(unsigned short) * kMaxContrib3 * kMaxMel);
+  L.dct = take(sizeof(float) * (size_t)n_mfcc * (n_mel | 1));
+  L.lift = take(sizeof(float) * n_mfcc);
+  L.r0 = take(sizeof(int) * 33);
+  o = (o + 127) & ~(size_t)127;
+  L.warp0 = o;
+  size_t w = 0;
+  auto wtake = [&](size_t bytes) {
+    size_t r = w;
+    w += (bytes + 127) & ~(size_t)127;
+    return r;
+  };
+  L.w_tile = wtake(sizeof(float2) * 32 * kTileRow);
+  L.w_mag = wtake(sizeof(float2) * G::PK * G::PROW);
+  L.w_raw = wtake(sizeof(float) * kRaw3 * kRun3);
+  L.w_macc = wtake(sizeof(float2) * (kMaxMel + 4));
+  L.per_warp = w;
+  L.total = o + w * kW3;
+  return L;
+}
+
+__device__ __forceinline__ float warp_sum3(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull3, v, o);
+  return v;
+}
+__device__ __forceinline__ float2 warp_sum3(float2 v) {  // both frames of a pack at once
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1)
+    v = pk::add(v, make_float2(__shfl_xor_sync(kFull3, v.x, o), __shfl_xor_sync(kFull3, v.y, o)));
+  return v;
+}
+__device__ __forceinline__ float warp_max3(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull3, v, o));
+  return v;
+}
+__device__ __forceinline__ float sqrt_fast3(float x) {  // MUFU; sqrt(0) = 0
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_fast3(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Per-lane accumulators of the scan; every float2 is (frame a, frame b) of a pack.
+struct BinAcc3 {
+  float2 seg, sl, sxy, fl, s0, s1, s2, mlo, mhi, pend;
+  float mxa, mxb, mn;
+  float2* pp;  // next lane-private mel slot
+};
+__device__ __forceinline__ void acc_init(BinAcc3& s, float2* pp) {
+  const float2 z = make_float2(0.f, 0.f);
+  s.seg = s.sl = s.sxy = s.fl = s.s0 = s.s1 = s.s2 = s.mlo = s.mhi = s.pend = z;
+  s.mxa = s.mxb = 0.f;
+  s.mn = FLT_MAX;
+  s.pp = pp;
+}
+// One bin of the scan for both frames of a pack: m = (|X_a[k]|, |X_b[k]|), pv = |X[k]| of the frame before a.
+// `flush`: the bin opens a new mel region, i.e. the falling part of the filter being left joins its pending rising
+// part in the next private slot.  The centroid / bandwidth sums are taken relative to the lane's first bin (J = k -
+// k0 is a compile-time constant: sum m, sum J m, sum J^2 m), which also removes them from the split pass; bins below
+// 1e-10 (silence) are not tested here: the frame's smallest magnitude is tracked and the rare frame is redone exactly.
+__device__ __forceinline__ void bin_step3(BinAcc3& s, bool flux_a, int jj, bool flush, float2 m, float pv, float xv,
+                                          float wl, float wh) {
+  if (flush) {
+    *s.pp = pk::add(s.pend, s.mlo);
+    s.pend = s.mhi;
+    s.mlo = make_float2(0.f, 0.f);
+    s.mhi = make_float2(0.f, 0.f);
+    s.pp += 32;
+  }
+  const float2 p = __fmul2_rn(m, m);
+  s.mlo = pk::fma(p, wl, s.mlo);
+  s.mhi = pk::fma(p, wh, s.mhi);
+  s.seg = pk::add(s.seg, p);
+  s.s0 = pk::add(s.s0, m);
+  if (jj > 0) {  // jj is a compile-time constant after unrolling
+    s.s1 = pk::fma(m, (float)jj, s.s1);
+    s.s2 = pk::fma(m, (float)(jj * jj), s.s2);
+  }
+  s.mxa = fmaxf(s.mxa, m.x);
+  s.mxb = fmaxf(s.mxb, m.y);
+  s.mn = fminf(s.mn, fminf(m.x, m.y));
+  const float2 l2 = make_float2(lg2_fast3(m.x), lg2_fast3(m.y));
+  s.sl = pk::add(s.sl, l2);
+  s.sxy = pk::fma(l2, xv, s.sxy);  // xtab[0] == 0: bin 0 never enters the regression
+  // flux: frame b against frame a; frame a against its predecessor only when that one is at hand (flux_a, a compile-time constant after unrolling: packs after
+  // the first read it from the previous pack's row) -- the first pack's frame a is done in pass 2, see there
+  const float2 d = make_float2(flux_a ? fmaxf(m.x - pv, 0.f) : 0.f, fmaxf(m.y - m.x, 0.f));
+  s.fl = __ffma2_rn(d, d, s.fl);
+}
+
+template <int R, int K>
+__device__ __forceinline__ void tw_apply(float2 (&v)[R], const float2* __restrict__ tw) {
+  if constexpr (K < R) {
+    v[K] = pk::mul(v[K], tw[K * 32]);
+    tw_apply<R, K + 1>(v, tw);
+  }
+}
+
+// The frame's log-magnitude sums when some bin is <= 1e-10 (silence, digital zeros): bins below the threshold leave
+// the flatness mean and the slope regression (spectral_flatness.go:31-70, spectral_slope.go:42-51).  Rare and slow.
+template <class G>
+__device__ __noinline__ void slow_log_sums(const float* __restrict__ mrow2, const float* __restrict__ s_xtab, int lane,
+                                           float* __restrict__ out) {  // mrow2: the frame's component of the pair row
+  constexpr int BPL = G::BPL, M = G::M;
+  float sl = 0.f, sxy = 0.f, sxinv = 0.f, sxxinv = 0.f;
+  int ninv = 0;
+  for (int j = 0; j <= BPL; ++j) {
+    if (j == BPL && lane != 31) break;
+    const int k = BPL * lane + j;
+    const float m = mrow2[2 * ppos(k)], xv = s_xtab[spos(k)];
+    if (m > 1e-10f) {
+      const float l2 = lg2_fast3(m);
+      sl += l2;
+      sxy = fmaf(xv, l2, sxy);
+    } else if (k > 0) {
+      ++ninv;
+      sxinv += xv;
+      sxxinv = fmaf(xv, xv, sxxinv);
+    }
+  }
+  sl = warp_sum3(sl);
+  sxy = warp_sum3(sxy);
+  sxinv = warp_sum3(sxinv);
+  sxxinv = warp_sum3(sxxinv);
+  ninv = __reduce_add_sync(kFull3, ninv);
+  out[0] = sl, out[1] = sxy, out[2] = sxinv, out[3] = sxxinv, out[4] = __int_as_float(ninv);
+}
+
+// rolloff: first bin whose cumulative energy reaches 85 % (spectral_rolloff.go:19-55).  The lane whose range holds the
+// crossing is found from the prefix of the lanes' energies; its BPL (+1) bins are then scanned by the warp.
+template <class G>
+__device__ __forceinline__ int rolloff_bin(const float* __restrict__ mrow2, float pre, float seg, float etot, int lane) {
+  constexpr int BPL = G::BPL;
+  int rk = G::B - 1;
+  const float target = 0.85f * etot;
+  const float excl = pre - seg;
+  const unsigned cb = __ballot_sync(kFull3, (pre >= target) && (excl < target || lane == 0));
+  if (cb) {
+    const int cl = __ffs(cb) - 1;
+    const float ex0 = __shfl_sync(kFull3, excl, cl);
+    const int nbn = cl == 31 ? BPL + 1 : BPL;
+    const float mj = lane < nbn ? mrow2[2 * ppos(BPL * cl + lane)] : 0.f;
+    float cum = mj * mj;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_up_sync(kFull3, cum, o);
+      if (lane >= o) cum += up;
+    }
+    const unsigned hit = __ballot_sync(kFull3, lane < nbn && ex0 + cum >= target);
+    rk = BPL * cl + (hit ? __ffs(hit) - 1 : nbn - 1);
+  }
+  return rk;
+}
+
+template <int LOGN, int HR>
+__global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) {
+  using G = V3G<LOGN, HR>;
+  constexpr int N = G::N, M = G::M, B = G::B, J = G::J, FR = G::FR, PK = G::PK, RR = G::RR, NEW = G::NEW, BPL = G::BPL,
+                KSTR = G::KSTR, ROW = G::ROW, PROW = G::PROW, H = G::H;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const V3Smem L = v3_layout<G>(a.n_mel, a.n_mfcc);
+  float2* s_tw = reinterpret_cast<float2*>(smem + L.tw);
+  float* s_win = reinterpret_cast<float*>(smem + L.win);
+  float* s_xtab = reinterpret_cast<float*>(smem + L.xtab);
+  float* s_wlo = reinterpret_cast<float*>(smem + L.wlo);
+  float* s_whi = reinterpret_cast<float*>(smem + L.whi);
+  unsigned* s_fmask = reinterpret_cast<unsigned*>(smem + L.fmask);
+  unsigned short* s_moff = reinterpret_cast<unsigned short*>(smem + L.moff);
+  float* s_dct = reinterpret_cast<float*>(smem + L.dct);
+  float* s_lift = reinterpret_cast<float*>(smem + L.lift);
+  int* s_r0 = reinterpret_cast<int*>(smem + L.r0);
+  __shared__ int s_ncontrib;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* wb = smem + L.warp0 + (size_t)warp * L.per_warp;
+  float2* wbf2 = reinterpret_cast<float2*>(wb);
+  float2* tile = reinterpret_cast<float2*>(wb + L.w_tile);
+  float2* priv = tile;  // lane-private mel slots [slot][lane], (frame a, frame b)
+  float2* mag = reinterpret_cast<float2*>(wb + L.w_mag);
+  float* rawsum = reinterpret_cast<float*>(wb + L.w_raw);
+  float2* macc = reinterpret_cast<float2*>(wb + L.w_macc);
+  constexpr int kZeroSlot = kMaxMel + 2;  // macc[kZeroSlot] stays 0: padding target of the combine table
+
+  // ---- tables, once per CTA ------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < J * 32; i += blockDim.x) {
+    const int k1 = i / 32, l = i % 32;
+    double dsn, dcs;
+    sincospi(-2.0 * (double)((k1 * l) % N) / (double)N, &dsn, &dcs);
+    s_tw[i] = make_float2((float)dcs, (float)dsn);
+  }
+  {
+    const float* wsrc = reinterpret_cast<const float*>(a.win2);  // 0.5 w[n]: the 1/2 of the Hermitian split
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_win[i] = __ldg(wsrc + i);
+  }
+  for (int k = threadIdx.x; k < ROW; k += blockDim.x) {
+    s_xtab[k] = 0.f;
+    s_wlo[k] = 0.f;
+    s_whi[k] = 0.f;
+  }
+  if (threadIdx.x < 32) s_fmask[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) s_ncontrib = 0;
+  if (lane == 0) macc[kZeroSlot] = make_float2(0.f, 0.f);
+  __syncthreads();
+  for (int k = threadIdx.x; k < B; k += blockDim.x) {
+    s_xtab[spos(k)] = a.xtab[k];
+    int r = 0;
+    while (k >= a.regions[r].next_b) ++r;
+    const MelRegion reg = a.regions[r];
+    const float kf = (float)k;
+    s_wlo[spos(k)] = (reg.bhi - kf) * reg.inv_f;
+    s_whi[spos(k)] = (kf - reg.blo) * reg.inv_r;
+    int rp = 0;
+    if (k > 0)
+      while (k - 1 >= a.regions[rp].next_b) ++rp;
+    // bit j of a lane's mask: bin BPL lane + j opens a new region (a lane's first bin starts inside its region,
+    // nothing to close; the Nyquist bin is lane 31's extra one, bit BPL)
+    if (r != rp && ((k % BPL) || k == M)) atomicOr(&s_fmask[k == M ? 31 : (k / BPL)], 1u << (k == M ? BPL : (k % BPL)));
+    if ((k % BPL) == 0 && k < M) s_r0[k / BPL] = r;
+  }
+  {
+    const int nmp = a.n_mel | 1;
+    for (int i = threadIdx.x; i < a.n_mfcc * a.n_mel; i += blockDim.x)
+      s_dct[(i / a.n_mel) * nmp + (i % a.n_mel)] = a.dct[i];
+    for (int i = threadIdx.x; i < a.n_mfcc; i += blockDim.x) s_lift[i] = a.lift[i];
+  }
+  __syncthreads();
+  // combine table: the private slots (float2 offsets from the warp's base) that hold a part of filter f (absolute slot
+  // f + 1; lane j's slot q is r0[j] - 1 + q), padded with the zero slot to a uniform count
+  const unsigned short zero_off = (unsigned short)((macc + kZeroSlot) - wbf2);
+  const unsigned short priv_off = (unsigned short)(priv - wbf2);
+  for (int f = threadIdx.x; f < kMaxMel; f += blockDim.x) {
+    int cnt = 0;
+    if (f < a.n_mel) {
+      for (int j = 0; j < 32; ++j) {
+        int rl = 0;
+        const int kl = (j == 31) ? B - 1 : BPL * j + BPL - 1;
+        while (kl >= a.regions[rl].next_b) ++rl;
+        const int first = s_r0[j] - 1, last = rl;  // slots first .. last are written by lane j
+        if (f + 1 >= first && f + 1 <= last && cnt < kMaxContrib3)
+          s_moff[(cnt++) * kMaxMel + f] = (unsigned short)(priv_off + (f + 1 - first) * 32 + j);
+      }
+      atomicMax(&s_ncontrib, cnt);
+    }
+    for (int i = cnt; i < kMaxContrib3; ++i) s_moff[i * kMaxMel + f] = zero_off;
+  }
+  __syncthreads();
+  const int ncontrib = s_ncontrib;
+
+  // ---- per-lane constants ----------------------------------------------------------------------------
+  const int k1 = PK == 1 ? lane : (lane & 15);                               // pass-2 row of this lane
+  const int src = PK == 1 ? ((32 - lane) & 31) : ((lane & 16) | ((16 - k1) & 15));  // lane of the partner bins
+  const bool k1zero = k1 == 0;
+  const int64_t T = a.T;
+  const unsigned fmask = s_fmask[lane];
+  const int nyq = ppos(M);
+  const float k0f = (float)(BPL * lane);
+  // pass 2 stores bin k1 + KSTR k2 of the lane's pair row: ppos() of it is woff[k2 % NV] + KSTR k2 (the XOR of the swizzle
+  // only depends on k2 mod NV), so the 16 stores need no address arithmetic
+  constexpr int NV = PK == 1 ? 4 : 8;
+  int woff[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) woff[v] = ppos(k1 + KSTR * v) - KSTR * v;
+
+  for (int64_t run = (int64_t)blockIdx.x * kW3 + warp; run < a.total_runs; run += (int64_t)gridDim.x * kW3) {
+    const int s = (int)(run / a.runs_per_stream);
+    const int64_t t0 = (run % a.runs_per_stream) * (int64_t)kRunOut3;
+    const int64_t tend = (t0 + kRunOut3 < T) ? t0 + kRunOut3 : T;
+    const double* __restrict__ x = a.pcm + (int64_t)s * a.stride;
+    double* __restrict__ fo = a.feat + (int64_t)s * a.feat_stride;
+    const int64_t first = t0 - 1;                       // the run's first frame only warms the flux up (-1: none)
+    const int nfr = (int)(tend - first);                // frames first .. tend - 1
+    const int nit = (nfr + FR - 1) / FR;
+
+    // ---- ring: RR rows of the first iteration; samples outside [0, n) read as silence --------------------
+    // rows [jlo, jhi) of the lane's column lie inside the stream: two 32-bit compares per load instead of 64-bit ones
+    float ring[RR];
+    const double* __restrict__ xl = x + (first * H + lane);  // row j of the first iteration is xl[32 j]
+    int64_t rows_left;                                        // rows from xl's row 0 to the end of the stream
+    {
+      const int64_t g0 = first * H + lane;
+      rows_left = (a.n - g0 + 31) >> 5;
+      const int jlo = g0 < 0 ? (int)((-g0 + 31) >> 5) : 0;
+      const int jhi = rows_left < RR ? (int)(rows_left < 0 ? 0 : rows_left) : RR;
+#pragma unroll
+      for (int j = 0; j < RR; ++j) ring[j] = (j >= jlo && j < jhi) ? (float)__ldg(xl + 32 * j) : 0.f;
+    }
+
+    for (int it = 0; it < nit; ++it) {
+      const int64_t tf = first + (int64_t)FR * it;  // first frame of the iteration
+      // ================= pass 1: radix-J over the lane's own samples, both frames of a pack at once ==========
+#pragma unroll
+      for (int p = 0; p < PK; ++p) {
+        float2 c[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const float w = s_win[lane + 32 * j];
+          c[j] = make_float2(ring[j + 2 * p * HR] * w, ring[j + (2 * p + 1) * HR] * w);
+        }
+        pk::Fft<J>::run(c);
+        tw_apply<J, 1>(c, s_tw + lane);
+        float2* tp = tile + (p * J) * kTileRow + lane;
+#pragma unroll
+        for (int q = 0; q < J; ++q) tp[q * kTileRow] = c[q];
+      }
+      __syncwarp();
+      // ================= pass 2: radix-32 over the lanes of pass 1 ==========================================
+      float fla = 0.f;  // this lane's part of the first frame's flux
+      {
+        float2 z[32];
+        const float4* rp = reinterpret_cast<const float4*>(tile + lane * kTileRow);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 f = rp[i];
+          z[2 * i] = make_float2(f.x, f.y);
+          z[2 * i + 1] = make_float2(f.z, f.w);
+        }
+        pk::Fft<32>::run(z);
+        // Hermitian split + magnitudes: bins k = k1 + KSTR k2, k2 < 16; partner Z[N - k] = register 31 - k2 of lane
+        // `src` (k1 == 0: register (32 - k2) & 31 of this lane):  X_a = Z + conj P,  X_b = (Z - conj P) / i
+        // Flux of the iteration's FIRST frame: its predecessor is the previous iteration's last frame, whose magnitudes
+        // are still in the last pack's row (component .y) -- read bin k's old value right before the row is overwritten
+        // (the lanes of the last pack store to that row later in program order; shared memory is in order per warp).
+        float2* row = mag + (PK == 1 ? 0 : (lane >> 4)) * PROW;
+        const float* oldb = reinterpret_cast<const float*>(mag + (PK - 1) * PROW) + 1;
+        const bool first_pack = PK == 1 || lane < 16;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const float2 mine = k1zero ? z[(32 - k2) & 31] : z[31 - k2];
+          const float2 pz = make_float2(__shfl_sync(kFull3, mine.x, src), __shfl_sync(kFull3, mine.y, src));
+          const float2 zz = z[k2];
+          const float2 xa = __fadd2_rn(zz, make_float2(pz.x, -pz.y));
+          const float2 xb = __fadd2_rn(make_float2(zz.y, -zz.x), make_float2(pz.y, pz.x));
+          const float2 qa = __fmul2_rn(xa, xa), qb = __fmul2_rn(xb, xb);
+          const int e = woff[k2 % NV] + KSTR * k2;
+          const float ma = sqrt_fast3(qa.x + qa.y);
+          const float d = first_pack ? fmaxf(ma - oldb[2 * e], 0.f) : 0.f;
+          fla = fmaf(d, d, fla);
+          row[e] = make_float2(ma, sqrt_fast3(qb.x + qb.y));
+        }
+        if (k1zero) {  // Z[M] pairs with itself
+          const float ma = fabsf(2.f * z[16].x);
+          const float d = first_pack ? fmaxf(ma - oldb[2 * nyq], 0.f) : 0.f;
+          fla = fmaf(d, d, fla);
+          row[nyq] = make_float2(ma, fabsf(2.f * z[16].y));
+        }
+      }
+      // the next iteration's NEW rows start their trip from HBM now and join the ring at the end of the iteration
+      double nx[NEW];
+      const bool more = it + 1 < nit;
+      if (more) {
+        const int r0 = FR * HR * (it + 1) + (RR - NEW);  // first new row, counted from xl's row 0
+        const double* __restrict__ src_p = xl + 32 * (int64_t)r0;
+        const int64_t left = rows_left - r0;
+        const int jhi = left < NEW ? (int)(left < 0 ? 0 : left) : NEW;
+        const int jlo = (t0 == 0 && it == 0) ? ((H - lane + 31) >> 5) - r0 : 0;  // rows before the stream's first sample
+#pragma unroll
+        for (int j = 0; j < NEW; ++j) nx[j] = (j >= jlo && j < jhi) ? __ldg(src_p + 32 * j) : 0.0;
+      }
+      __syncwarp();  // magnitude rows complete; the tile becomes the private mel slots
+
+      // ================= scan: BPL contiguous bins per lane, both frames of a pack in one pass ===============
+#pragma unroll
+      for (int p = 0; p < PK; ++p) {
+        const float2* row = mag + p * PROW;
+        const float* rowf = reinterpret_cast<const float*>(row);
+        BinAcc3 ac;
+        acc_init(ac, priv + lane);
+#pragma unroll
+        for (int q = 0; q < BPL / 4; ++q) {  // four bins per step: two 16-byte pair chunks, one chunk of each table
+          const int tc = spos(BPL * lane + 4 * q);
+          const float4 xv = *reinterpret_cast<const float4*>(s_xtab + tc);
+          const float4 lv = *reinterpret_cast<const float4*>(s_wlo + tc);
+          const float4 hv = *reinterpret_cast<const float4*>(s_whi + tc);
+          const float4 m01 = *reinterpret_cast<const float4*>(row + ppos(BPL * lane + 4 * q));
+          const float4 m23 = *reinterpret_cast<const float4*>(row + ppos(BPL * lane + 4 * q + 2));
+          float pv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p > 0) {  // the frame before this pack's first one is the previous pack's second one
+            const float4 r01 = *reinterpret_cast<const float4*>(row - PROW + ppos(BPL * lane + 4 * q));
+            const float4 r23 = *reinterpret_cast<const float4*>(row - PROW + ppos(BPL * lane + 4 * q + 2));
+            pv[0] = r01.y, pv[1] = r01.w, pv[2] = r23.y, pv[3] = r23.w;
+          }
+          const float2 mm[4] = {make_float2(m01.x, m01.y), make_float2(m01.z, m01.w), make_float2(m23.x, m23.y),
+                                make_float2(m23.z, m23.w)};
+          const float xx[4] = {xv.x, xv.y, xv.z, xv.w}, ll[4] = {lv.x, lv.y, lv.z, lv.w}, hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            bin_step3(ac, p > 0, 4 * q + u, (fmask >> (4 * q + u)) & 1u, mm[u], pv[u], xx[u], ll[u], hh[u]);
+        }
+        if (lane == 31) {  // Nyquist bin
+          const float2 mq = row[nyq];
+          const float pv = p == 0 ? 0.f : row[nyq - PROW].y;
+          bin_step3(ac, p > 0, BPL, (fmask >> BPL) & 1u, mq, pv, s_xtab[spos(M)], s_wlo[spos(M)], s_whi[spos(M)]);
+        }
+        if (p == 0) ac.fl.x += fla;  // the first frame's flux was taken in pass 2
+        ac.pp[0] = pk::add(ac.pend, ac.mlo);
+        ac.pp[32] = ac.mhi;
+
+        // ---- the frames' sums: reductions over the warp, both frames at once --------------------------------
+        const int64_t ta = tf + 2 * p, tb = ta + 1;
+        const bool oka = ta >= t0 && ta < tend, okb = tb >= t0 && tb < tend;
+        float2 pre = ac.seg;  // inclusive prefix of the lanes' energies (bins ascend with the lane)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float2 up = make_float2(__shfl_up_sync(kFull3, pre.x, o), __shfl_up_sync(kFull3, pre.y, o));
+          if (lane >= o) pre = pk::add(pre, up);
+        }
+        const float2 etot = make_float2(__shfl_sync(kFull3, pre.x, 31), __shfl_sync(kFull3, pre.y, 31));
+        const float2 plow = make_float2(__shfl_sync(kFull3, pre.x, 7), __shfl_sync(kFull3, pre.y, 7));  // bins < B / 4
+        const float2 sm = warp_sum3(ac.s0);
+        const float2 skm = warp_sum3(pk::fma(ac.s0, k0f, ac.s1));
+        const float2 kc = make_float2(sm.x > 0.f ? __fdividef(skm.x, sm.x) : 0.f,
+                                      sm.y > 0.f ? __fdividef(skm.y, sm.y) : 0.f);  // centroids in bin units
+        // sum (k - kc)^2 m over the lane's bins = dk^2 S0 + 2 dk S1 + S2, dk = k0 - kc
+        const float2 dk = make_float2(k0f - kc.x, k0f - kc.y);
+        const float2 bw = warp_sum3(__ffma2_rn(__fmul2_rn(dk, dk), ac.s0, __ffma2_rn(pk::scale(dk, 2.f), ac.s1, ac.s2)));
+        float2 sl = warp_sum3(ac.sl), sxy = warp_sum3(ac.sxy);
+        const float2 fl = warp_sum3(ac.fl);
+        const float mxa = warp_max3(ac.mxa), mxb = warp_max3(ac.mxb);
+        const float2 m00 = row[0];
+        float l2k0a = lg2_fast3(m00.x), l2k0b = lg2_fast3(m00.y), v0a = 1.f, v0b = 1.f;
+        float sxinva = 0.f, sxxinva = 0.f, sxinvb = 0.f, sxxinvb = 0.f;
+        int ninva = 0, ninvb = 0;
+        if (__any_sync(kFull3, !(ac.mn > 1e-10f))) {  // rare: redo the log sums of both frames with the threshold test
+          float* tmp = reinterpret_cast<float*>(macc);
+          __syncwarp();
+          slow_log_sums<G>(rowf, s_xtab, lane, tmp);
+          slow_log_sums<G>(rowf + 1, s_xtab, lane, tmp + 8);
+          sl = make_float2(tmp[0], tmp[8]);
+          sxy = make_float2(tmp[1], tmp[9]);
+          sxinva = tmp[2], sxxinva = tmp[3], ninva = __float_as_int(tmp[4]);
+          sxinvb = tmp[10], sxxinvb = tmp[11], ninvb = __float_as_int(tmp[12]);
+          v0a = m00.x > 1e-10f ? 1.f : 0.f;
+          v0b = m00.y > 1e-10f ? 1.f : 0.f;
+          l2k0a = v0a != 0.f ? l2k0a : 0.f;
+          l2k0b = v0b != 0.f ? l2k0b : 0.f;
+          __syncwarp();
+        }
+        const int rka = rolloff_bin<G>(rowf, pre.x, ac.seg.x, etot.x, lane);
+        const int rkb = rolloff_bin<G>(rowf + 1, pre.y, ac.seg.y, etot.y, lane);
+
+        __syncwarp();  // private mel slots visible
+        // ---- ln + DCT-II + lifter (mfcc.go:136-157), both frames ----
+        if (a.mfcc_on) {
+          for (int f = lane; f < a.n_mel; f += 32) {
+            float2 v = make_float2(0.f, 0.f);
+            for (int i = 0; i < ncontrib; ++i) v = pk::add(v, wbf2[s_moff[i * kMaxMel + f]]);
+            macc[f] = make_float2(v.x > 0.f ? __logf(v.x) : -23.025850929940457f,
+                                  v.y > 0.f ? __logf(v.y) : -23.025850929940457f);  // ln(1e-10)
+          }
+          __syncwarp();
+          // coefficient c by the lane pair (2c, 2c+1): each half sums every other filter
+          const int nmp = a.n_mel | 1;
+          for (int c0 = 0; c0 < a.n_mfcc; c0 += 16) {
+            const int c = c0 + (lane >> 1);
+            float2 acc = make_float2(0.f, 0.f);
+            if (c < a.n_mfcc)
+              for (int f = lane & 1; f < a.n_mel; f += 2) acc = pk::fma(macc[f], s_dct[c * nmp + f], acc);
+            acc = pk::add(acc, make_float2(__shfl_xor_sync(kFull3, acc.x, 1), __shfl_xor_sync(kFull3, acc.y, 1)));
+            if (c < a.n_mfcc && !(lane & 1)) {
+              const float lf = s_lift[c];
+              if (oka) fo[a.o_mfcc + ta * a.n_mfcc + c] = (double)(acc.x * lf);
+              if (okb) fo[a.o_mfcc + tb * a.n_mfcc + c] = (double)(acc.y * lf);
+            }
+          }
+        }
+        // ---- park the raw sums of the two frames; finished in FP64 one frame per lane at the end of the run ----
+        if (lane == 0) {
+          const int slot = (int)(ta - first) & (kRun3 - 1);  // position inside the 32-frame segment
+          float4* rs = reinterpret_cast<float4*>(rawsum + slot * kRaw3);
+          rs[0] = make_float4(sm.x, kc.x, etot.x, __int_as_float(rka));
+          rs[1] = make_float4(bw.x, sl.x, __int_as_float(ninva), mxa);
+          rs[2] = make_float4(sxy.x, l2k0a, sxinva, sxxinva);
+          rs[3] = make_float4(fl.x, plow.x, v0a, 0.f);
+          if (slot + 1 < kRun3) {
+            rs[4] = make_float4(sm.y, kc.y, etot.y, __int_as_float(rkb));
+            rs[5] = make_float4(bw.y, sl.y, __int_as_float(ninvb), mxb);
+            rs[6] = make_float4(sxy.y, l2k0b, sxinvb, sxxinvb);
+            rs[7] = make_float4(fl.y, plow.y, v0b, 0.f);
+          }
+        }
+        __syncwarp();  // private slots / macc reused by the next pack
+      }
+      // ---- ring: drop the oldest NEW rows, append the prefetched ones ----------------------------------------
+      if (more) {
+#pragma unroll
+        for (int j = 0; j < RR - NEW; ++j) ring[j] = ring[j + NEW];
+#pragma unroll
+        for (int j = 0; j < NEW; ++j) ring[RR - NEW + j] = (float)nx[j];
+      }
+      __syncwarp();  // tile / rows / parked sums visible, reused by the next iteration
+
+      // ---- a 32-frame segment is complete: finish it in FP64, lane i <-> frame first + 32 seg + i ----------
+      if (((FR * (it + 1)) & (kRun3 - 1)) == 0 || !more) {
+        const int seg = (FR * it) / kRun3;
+        const int64_t t = first + (int64_t)kRun3 * seg + lane;
+        if (t >= t0 && t < tend) {
+          const float4* rs4 = reinterpret_cast<const float4*>(rawsum + lane * kRaw3);
+          const float4 r0 = rs4[0], r1 = rs4[1], r2 = rs4[2], r3 = rs4[3];
+          const float sm = r0.x, kc = r0.y, etot = r0.z, bw = r1.x, sl = r1.y, mx = r1.w, sxy = r2.x, l2k0 = r2.y,
+                      sxinv = r2.z, sxxinv = r2.w, fl = r3.x, plow = r3.y, val0 = r3.z;
+          const int rk = __float_as_int(r0.w), ninv = __float_as_int(r1.z);
+          const double fs = a.freq_scale;
+          const double dsm = (double)sm;
+          fo[a.o_centroid + t] = (double)kc * fs;
+          fo[a.o_rolloff + t] = etot > 0.f ? (double)rk * fs : 0.0;
+          fo[a.o_bandwidth + t] = sm > 0.f ? sqrt((double)bw / dsm) * fs : 0.0;
+          const float cnt = (float)(B - 1 - ninv) + val0;  // bins with m > 1e-10 (spectral_flatness.go:31-70)
+          double flat = 0.0;
+          if (cnt > 0.f) {
+            const double gm = exp2((double)sl / (double)cnt);
+            const double am = dsm / (double)B;
+            if (am > 1e-10) {
+              flat = gm / am;
+              if (flat > 1.0) flat = 1.0;
+            }
+          }
+          fo[a.o_flatness + t] = flat;
+          const double rms = sqrt((double)etot / (double)B);
+          fo[a.o_crest + t] = rms > 0.0 ? (double)mx / rms : 0.0;
+          double slope = 0.0;
+          if (a.slope_on) {
+            const double LG = 0.30102999566398120;  // log10(2)
+            const double n = a.slope_ntot - (double)ninv;
+            if (n >= 2.0) {
+              const double sx = -(double)sxinv, sxx = a.slope_xxtot - (double)sxxinv;
+              const double sy = LG * ((double)sl - (double)l2k0), sxyd = LG * (double)sxy;
+              const double den = n * sxx - sx * sx;
+              if (den != 0.0) slope = (n * sxyd - sx * sy) / den;
+            }
+          }
+          fo[a.o_slope + t] = slope;
+          if (t >= 1) fo[a.o_flux + t - 1] = sqrt((double)fl);
+          if (t < a.Te) {
+            fo[a.o_low + t] = etot > 0.f ? (double)plow / (double)etot : 0.0;
+            fo[a.o_high + t] = etot > 0.f ? ((double)etot - (double)plow) / (double)etot : 0.0;
+          }
+        }
+        __syncwarp();  // the parked sums are overwritten by the next segment
+      }
+    }
+  }
+}
+
+template <class G>
+bool v3_mel_eligible(const FpPlan& plan, const StftArgs& a) {
+  constexpr int BPL = G::BPL, B = G::B;
+  if (plan.h_regions.empty() || a.n_mel > kMaxMel || a.n_mfcc > kMaxMfcc || plan.split != G::M / 4) return false;
+  auto region_of = [&](int k) {
+    int r = 0;
+    while (k >= plan.h_regions[r].next_b) ++r;
+    return r;
+  };
+  int first[32], last[32];
+  for (int j = 0; j < 32; ++j) {
+    first[j] = region_of(BPL * j);
+    last[j] = region_of(j == 31 ? B - 1 : BPL * j + BPL - 1);
+    if (last[j] - first[j] + 2 > kSlots3) return false;
+  }
+  for (int k = 1; k < B; ++k)  // every mel region at least one bin wide (one private slot per boundary)
+    if (region_of(k) - region_of(k - 1) > 1) return false;
+  for (int f = 0; f < a.n_mel; ++f) {
+    int cnt = 0;
+    for (int j = 0; j < 32; ++j) cnt += (f + 1 >= first[j] - 1 && f + 1 <= last[j]);
+    if (cnt > kMaxContrib3) return false;
+  }
+  return true;
+}
+
+template <int LOGN, int HR>
+int v3_launch(StftArgs& a, cudaStream_t st) {
+  using G = V3G<LOGN, HR>;
+  a.runs_per_stream = (int)((a.T + kRunOut3 - 1) / kRunOut3);
+  a.total_runs = (int64_t)a.runs_per_stream * a.n_streams;
+  const V3Smem L = v3_layout<G>(a.n_mel, a.n_mfcc);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t ctas = (a.total_runs + kW3 - 1) / kW3;
+  if (ctas > sms) ctas = sms;  // persistent: one CTA per SM, warps stride over the runs
+  if (ctas < 1) ctas = 1;
+  prof_begin("stft_features_kernel", st);
+  SONAR_CUDA(cudaFuncSetAttribute(stft_v3_kernel<LOGN, HR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  stft_v3_kernel<LOGN, HR><<<(unsigned)ctas, kW3 * 32, L.total, st>>>(a);
+  prof_end();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
+}  // namespace
+
+// The third-generation kernel covers the two geometries the BASELINE configurations use (1024 / 256 and 512 / 160);
+// everything else stays with stft_v2.cu / stft_features.cu.
+bool stft_v3_eligible(const FpPlan& plan, const StftArgs& a) {
+  static const bool off = std::getenv("SONAR_STFT_V2") != nullptr || std::getenv("SONAR_STFT_V1") != nullptr;  // diagnostic
+  if (off) return false;
+  if (plan.N == 1024 && a.hop == 256) return v3_mel_eligible<V3G<10, 8>>(plan, a);
+  if (plan.N == 512 && a.hop == 160) return v3_mel_eligible<V3G<9, 5>>(plan, a);
+  return false;
+}
+
+int launch_stft_v3(const FpPlan& plan, StftArgs& a, cudaStream_t st) {
+  if (plan.N == 1024) return v3_launch<10, 8>(a, st);
+  return v3_launch<9, 5>(a, st);
+}
+
+}  // namespace sonar

@@ -43,10 +43,15 @@ def test_c2_full_size_known_offset_and_path_properties(gpu, oracle, synth):
     k = 30011
     tail = gpu.fingerprint(q[k * hop: k * hop + 12 * sr], p)
     m = tail.mfcc.shape[0] - 2
-    for name in ("mfcc", "spectral_centroid", "spectral_rolloff", "spectral_bandwidth", "spectral_flatness",
-                 "short_time_energy", "zero_crossing_rate"):
+    # (the FP64 walks are bit-identical; the FP32 features agree to rounding only: the third-generation kernel transforms
+    #  frames in pairs a + i b, so a frame's rounding depends on which neighbour it is paired with in a given run)
+    for name in ("short_time_energy", "zero_crossing_rate"):
         assert np.array_equal(fq.arrays[name][k + 1: k + m], tail.arrays[name][1:m]), name
-    assert np.array_equal(fq.spectral_flux[k + 1: k + m - 1], tail.spectral_flux[1: m - 1])
+    for name in ("mfcc", "spectral_centroid", "spectral_rolloff", "spectral_bandwidth", "spectral_flatness"):
+        x, y = fq.arrays[name][k + 1: k + m], tail.arrays[name][1:m]
+        assert np.all(np.abs(x - y) <= 1e-4 * np.maximum(np.abs(y), np.max(np.abs(y)))), name
+    x, y = fq.spectral_flux[k + 1: k + m - 1], tail.spectral_flux[1: m - 1]
+    assert np.all(np.abs(x - y) <= 1e-4 * np.max(np.abs(y)))
 
 
 def test_c3_full_size_one_hour_of_speech_band_noise(gpu, oracle, synth):
@@ -73,9 +78,9 @@ def test_c3_full_size_one_hour_of_speech_band_noise(gpu, oracle, synth):
     k = 200000
     tail = gpu.fingerprint(x[k * H: k * H + 20 * sr], p)
     m = tail.mfcc.shape[0] - 2
-    assert np.array_equal(fp.mfcc[k + 1: k + m], tail.mfcc[1:m])
     assert np.array_equal(fp.short_time_energy[k + 1: k + m], tail.short_time_energy[1:m])
-    assert np.array_equal(fp.spectral_centroid[k + 1: k + m], tail.spectral_centroid[1:m])
+    for x, y in ((fp.mfcc[k + 1: k + m], tail.mfcc[1:m]), (fp.spectral_centroid[k + 1: k + m], tail.spectral_centroid[1:m])):
+        assert np.all(np.abs(x - y) <= 1e-4 * np.maximum(np.abs(y), np.max(np.abs(y))))  # FP32: pairing differs per run
 
 
 def _trim_by_lag(ea, eb, lag, length):
@@ -146,8 +151,13 @@ def test_c1_thirty_seconds_both_sample_rate_modes(gpu, oracle, synth, algo_sr):
     g, o = gpu.fingerprint(pcm, p), oracle.fingerprint(pcm, p)
     assert g.mfcc.shape == (5164, 13) and g.sizes == o.sizes
     assert np.array_equal(g.short_time_energy, o.short_time_energy) and np.array_equal(g.zero_crossing_rate, o.zero_crossing_rate)
+    from test_gpu_fingerprint import log_feature_bound, log_features_close
+    bound = log_feature_bound(oracle, pcm, p)  # flatness / slope: 1e-4 + the stated per-input bound
     for k in FP32_KEYS:
         y, x = o.arrays[k], g.arrays[k]
+        if k in ("spectral_flatness", "spectral_slope"):
+            log_features_close(x, y, bound, k)
+            continue
         scale = np.max(np.abs(y))
         assert np.all(np.abs(x - y) <= 1e-4 * np.maximum(np.abs(y), scale)), k
     for k in ("pitch_estimate", "pitch_confidence", "voicing_strength", "harmonic_ratio", "inharmonicity_ratio", "tonal_centroid"):
