@@ -41,8 +41,21 @@ func Ctx() (*C.sonar_ctx, error) {
 	return ctx, ctxErr
 }
 
+// lastError fetches the thread-local message of the failing call.  The message lives in a thread_local of the C
+// library, and a goroutine may be moved to another OS thread between two cgo calls: every binding below therefore runs
+// its call AND this fetch between runtime.LockOSThread / UnlockOSThread (see locked()).
 func lastError() error {
 	return errors.New(C.GoString(C.sonar_last_error()))
+}
+
+// locked runs f (one sonar_* call) on a pinned OS thread and turns a non-zero status into the reference's error text.
+func locked(f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := f(); rc != C.SONAR_OK {
+		return lastError()
+	}
+	return nil
 }
 
 func ptr(s []float64) *C.double {
@@ -77,6 +90,8 @@ type Fingerprint struct {
 // GenerateFingerprint replaces ComputeSTFTWithWindow + SpeechFeatureExtractor.ExtractFeatures
 // (fingerprint/fingerprint.go:190-207).
 func GenerateFingerprint(pcm []float64, p FpParams) (*Fingerprint, error) {
+	runtime.LockOSThread() // the error message of a failing call is thread-local in the C library (see lastError)
+	defer runtime.UnlockOSThread()
 	c, err := Ctx()
 	if err != nil {
 		return nil, err
@@ -158,6 +173,8 @@ type AlignResult struct {
 // AlignCrossCorrelation replaces AlignmentAnalyzer.AlignFeatures(method = AlignmentCrossCorrelation) as
 // extractors.alignWithFeatures calls it for "corr_energy" (fingerprint/extractors/alignment.go:357-409).
 func AlignCrossCorrelation(query, reference []float64, maxLagFrames, hopSize, sampleRate int) ([]float64, *XcorrSummary, *AlignResult, error) {
+	runtime.LockOSThread() // the error message of a failing call is thread-local in the C library (see lastError)
+	defer runtime.UnlockOSThread()
 	c, err := Ctx()
 	if err != nil {
 		return nil, nil, nil, err
@@ -183,6 +200,8 @@ func AlignCrossCorrelation(query, reference []float64, maxLagFrames, hopSize, sa
 
 // DTW replaces DTWAlignment.Align (algorithms/stats/dtw.go:55-217).  q and r are row-major [n][dim].
 func DTW(q []float64, n int, r []float64, m, dim, band int) (pathQ, pathR []int32, pathCost []float64, distance float64, err error) {
+	runtime.LockOSThread() // the error message of a failing call is thread-local in the C library (see lastError)
+	defer runtime.UnlockOSThread()
 	c, err := Ctx()
 	if err != nil {
 		return nil, nil, nil, 0, err
@@ -209,6 +228,8 @@ func DTW(q []float64, n int, r []float64, m, dim, band int) (pathQ, pathR []int3
 
 // ColStatsCosine replaces extractMFCCStatistics x2 + cosineSimilarity (fingerprint/comparison.go:774-873).
 func ColStatsCosine(x []float64, tx int, y []float64, ty, dim int) (float64, error) {
+	runtime.LockOSThread() // the error message of a failing call is thread-local in the C library (see lastError)
+	defer runtime.UnlockOSThread()
 	c, err := Ctx()
 	if err != nil {
 		return 0, err
@@ -242,6 +263,8 @@ type PairResult struct {
 // The per-pair sample pointers are copied into C memory (no Go pointer to Go pointer crosses the boundary) and
 // the sample slices themselves are pinned for the duration of the call.
 func alignPairs(q, r []unsafe.Pointer, format C.int, n int, p FpParams, maxLagSeconds float64, dtwBand int) ([]PairResult, error) {
+	runtime.LockOSThread() // the error message of a failing call is thread-local in the C library (see lastError)
+	defer runtime.UnlockOSThread()
 	c, err := Ctx()
 	if err != nil {
 		return nil, err
@@ -325,6 +348,8 @@ func AlignPairsS16(query, reference [][]int16, p FpParams, maxLagSeconds float64
 // (fingerprint/extractors/music.go:261-302): SpectralContrast.Compute, the chroma folding of
 // ChromaSTFT.convertSTFTToChroma and BarkScale.ComputeBarkSpectrum.  Row-major [T][nBands], [T][12], [T][nBark].
 func MusicSpectral(pcm []float64, win, hop, windowType, sampleRate, nBands, nBark int, barkLow, barkHigh float64) (contrast, chroma, bark []float64, frames int, err error) {
+	runtime.LockOSThread() // the error message of a failing call is thread-local in the C library (see lastError)
+	defer runtime.UnlockOSThread()
 	c, err := Ctx()
 	if err != nil {
 		return nil, nil, nil, 0, err
@@ -351,6 +376,8 @@ type STFTStream struct {
 
 // NewSTFTStream is what SpectralAnalyzer.ComputeSTFTStreaming (spectral.go:289-310) calls.
 func NewSTFTStream(win, hop, windowType int) (*STFTStream, error) {
+	runtime.LockOSThread() // the error message of a failing call is thread-local in the C library (see lastError)
+	defer runtime.UnlockOSThread()
 	c, err := Ctx()
 	if err != nil {
 		return nil, err
@@ -365,6 +392,8 @@ func NewSTFTStream(win, hop, windowType int) (*STFTStream, error) {
 // ProcessChunk returns row-major magnitude / phase [T][bins] and complex [T][bins][2] for the T frames the chunk
 // completes (T may be 0; an empty chunk is not an error, spectral.go:324-326).
 func (s *STFTStream) ProcessChunk(chunk []float64) (mag, phase, cplx []float64, frames int, err error) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
 	if len(chunk) == 0 {
 		return nil, nil, nil, 0, nil
 	}
@@ -384,4 +413,177 @@ func (s *STFTStream) Close() {
 		C.sonar_stft_stream_close(s.h)
 		s.h = nil
 	}
+}
+
+// ---- FingerprintComparator.Compare (fingerprint/comparison.go:133-194) ---------------------------------------------
+
+// CmpFeatures is one side of a comparison: the feature arrays Compare reads (comparison.go:266-341, 646-771),
+// flattened (MFCC row-major [frames][dim]).  A nil / empty slice means "feature absent".
+type CmpFeatures struct {
+	MFCC                                       []float64
+	MFCCDim                                    int
+	ContentType                                int // index of config.ContentType in the order music, news, sports, talk, mixed, unknown
+	Centroid, Rolloff, Flux                    []float64
+	HasSpectral, HasHarmonic, HasTemporal      bool
+	HarmonicRatio, Pitch, RMSEnergy            []float64
+	DynamicRange, SilenceRatio, OnsetDensity   float64
+}
+
+// CmpResult mirrors the scalars of fingerprint.SimilarityResult (comparison.go:28-39); a NaN distance = not compared.
+type CmpResult struct {
+	OverallSimilarity, FeatureSimilarity, Confidence     float64
+	DistMFCC, DistSpectral, DistTemporal, DistHarmonic   float64
+	ContentTypeMatch                                     bool
+	NFeatures                                            int
+}
+
+// fill writes f into C memory (the struct holds pointers into Go slices, pinned for the duration of the call).
+func (f *CmpFeatures) fill(c *C.sonar_cmp_features, pin *runtime.Pinner) {
+	set := func(dst **C.double, n *C.int64_t, s []float64, div int) {
+		if len(s) > 0 {
+			pin.Pin(&s[0])
+			*dst = ptr(s)
+			*n = C.int64_t(len(s) / div)
+		}
+	}
+	dim := f.MFCCDim
+	if dim <= 0 {
+		dim = 1
+	}
+	set(&c.mfcc, &c.mfcc_frames, f.MFCC, dim)
+	c.mfcc_dim, c.content_type = C.int32_t(dim), C.int32_t(f.ContentType)
+	set(&c.spectral_centroid, &c.n_centroid, f.Centroid, 1)
+	set(&c.spectral_rolloff, &c.n_rolloff, f.Rolloff, 1)
+	set(&c.spectral_flux, &c.n_flux, f.Flux, 1)
+	set(&c.harmonic_ratio, &c.n_harmonic_ratio, f.HarmonicRatio, 1)
+	set(&c.pitch_estimate, &c.n_pitch, f.Pitch, 1)
+	set(&c.rms_energy, &c.n_rms, f.RMSEnergy, 1)
+	b := func(v bool) C.int32_t {
+		if v {
+			return 1
+		}
+		return 0
+	}
+	c.has_spectral, c.has_harmonic, c.has_temporal = b(f.HasSpectral), b(f.HasHarmonic), b(f.HasTemporal)
+	c.dynamic_range, c.silence_ratio, c.onset_density = C.double(f.DynamicRange), C.double(f.SilenceRatio), C.double(f.OnsetDensity)
+}
+
+func cmpResult(r *C.sonar_cmp_result) CmpResult {
+	return CmpResult{
+		OverallSimilarity: float64(r.overall_similarity), FeatureSimilarity: float64(r.feature_similarity),
+		Confidence: float64(r.confidence), DistMFCC: float64(r.dist_mfcc), DistSpectral: float64(r.dist_spectral),
+		DistTemporal: float64(r.dist_temporal), DistHarmonic: float64(r.dist_harmonic),
+		ContentTypeMatch: r.content_type_match != 0, NFeatures: int(r.n_features),
+	}
+}
+
+// Compare replaces the arithmetic of FingerprintComparator.Compare (comparison.go:133-194): weights in the order mfcc,
+// spectral, chroma, temporal, speech, harmonic, energy (getEffectiveWeights, comparison.go:1055-1104).
+func Compare(f1, f2 *CmpFeatures, weights [7]float64, enableContentFilter bool) (*CmpResult, error) {
+	if f1 == nil || f2 == nil {
+		return nil, errors.New("fingerprints cannot be nil") // comparison.go:135
+	}
+	c, err := Ctx()
+	if err != nil {
+		return nil, err
+	}
+	mem := (*[2]C.sonar_cmp_features)(C.calloc(2, C.size_t(unsafe.Sizeof(C.sonar_cmp_features{}))))
+	defer C.free(unsafe.Pointer(mem))
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	f1.fill(&mem[0], &pin)
+	f2.fill(&mem[1], &pin)
+	var w C.sonar_cmp_weights
+	for i, v := range weights {
+		w.w[i] = C.double(v)
+	}
+	filter := C.int(0)
+	if enableContentFilter {
+		filter = 1
+	}
+	var out C.sonar_cmp_result
+	if err := locked(func() C.int { return C.sonar_compare_f64(c, &mem[0], &mem[1], &w, filter, &out) }); err != nil {
+		return nil, err
+	}
+	r := cmpResult(&out)
+	return &r, nil
+}
+
+// CompareBatch replaces the comparison loop of BatchCompare / FindBestMatches (comparison.go:1107-1151, 197-263): one
+// query against n candidates (a nil candidate is skipped as in the reference: NFeatures = -1).
+func CompareBatch(query *CmpFeatures, candidates []*CmpFeatures, weights [7]float64, enableContentFilter bool) ([]CmpResult, error) {
+	if query == nil {
+		return nil, errors.New("fingerprints cannot be nil")
+	}
+	c, err := Ctx()
+	if err != nil {
+		return nil, err
+	}
+	n := len(candidates)
+	if n == 0 {
+		return nil, nil
+	}
+	sz := C.size_t(unsafe.Sizeof(C.sonar_cmp_features{}))
+	mem := C.calloc(C.size_t(n+1), sz)
+	defer C.free(mem)
+	at := func(i int) *C.sonar_cmp_features { return (*C.sonar_cmp_features)(unsafe.Add(mem, uintptr(i)*uintptr(sz))) }
+	ptrs := (*[1 << 28]*C.sonar_cmp_features)(C.calloc(C.size_t(n), C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(ptrs))
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	query.fill(at(0), &pin)
+	for i, cand := range candidates {
+		if cand != nil {
+			cand.fill(at(i+1), &pin)
+			ptrs[i] = at(i + 1)
+		}
+	}
+	var w C.sonar_cmp_weights
+	for i, v := range weights {
+		w.w[i] = C.double(v)
+	}
+	filter := C.int(0)
+	if enableContentFilter {
+		filter = 1
+	}
+	res := make([]C.sonar_cmp_result, n)
+	if err := locked(func() C.int {
+		return C.sonar_compare_batch_f64(c, at(0), (**C.sonar_cmp_features)(unsafe.Pointer(ptrs)), C.int(n), &w, filter, &res[0])
+	}); err != nil {
+		return nil, err
+	}
+	out := make([]CmpResult, n)
+	for i := range res {
+		out[i] = cmpResult(&res[i])
+	}
+	return out, nil
+}
+
+// ---- pinned host memory for Go slices ---------------------------------------------------------------------------------
+
+// RegisterPCM page-locks the backing array of a Go slice for the duration of a batch of calls (cudaHostRegister behind
+// sonar_host_register): the H2D copies of the *_f64 entry points then run at full PCIe rate instead of through the
+// driver's pageable staging.  The slice must stay alive and must not be resized until UnregisterPCM.
+func RegisterPCM(pcm []float64, pin *runtime.Pinner) error {
+	if len(pcm) == 0 {
+		return nil
+	}
+	c, err := Ctx()
+	if err != nil {
+		return err
+	}
+	pin.Pin(&pcm[0])
+	return locked(func() C.int { return C.sonar_host_register(c, unsafe.Pointer(&pcm[0]), C.uint64_t(8*len(pcm))) })
+}
+
+// UnregisterPCM undoes RegisterPCM.
+func UnregisterPCM(pcm []float64) error {
+	if len(pcm) == 0 {
+		return nil
+	}
+	c, err := Ctx()
+	if err != nil {
+		return err
+	}
+	return locked(func() C.int { return C.sonar_host_unregister(c, unsafe.Pointer(&pcm[0])) })
 }

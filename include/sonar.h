@@ -90,6 +90,12 @@ const char* sonar_backend(void);
 /* Pinned host memory for callers that want full PCIe rate (optional). */
 int sonar_host_alloc(sonar_ctx* ctx, uint64_t bytes, void** out);
 int sonar_host_free(sonar_ctx* ctx, void* p);
+/* Page-locks caller-owned memory in place (cudaHostRegister) so that the H2D copies of the host-pointer entry points
+ * run at full PCIe rate from it: the route for a Go []float64 or a decoder's own buffer (transcode/decoder.go:850-870
+ * bytesToFloat64 output), which sonar_host_alloc cannot replace.  Pageable memory is accepted everywhere too; it is
+ * staged by the driver at a fraction of the rate.  `p` need not be page aligned. */
+int sonar_host_register(sonar_ctx* ctx, void* p, uint64_t bytes);
+int sonar_host_unregister(sonar_ctx* ctx, void* p);
 /* Device memory on the context's first device (for `_dev` entry points). */
 int sonar_dev_alloc(sonar_ctx* ctx, uint64_t bytes, void** out);
 int sonar_dev_free(sonar_ctx* ctx, void* p);

@@ -169,7 +169,7 @@ class CmpResult(C.Structure):
 # every symbol include/sonar.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "sonar_init", "sonar_destroy", "sonar_last_error", "sonar_abi_version", "sonar_backend",
-    "sonar_host_alloc", "sonar_host_free", "sonar_dev_alloc", "sonar_dev_free", "sonar_memcpy_h2d",
+    "sonar_host_alloc", "sonar_host_free", "sonar_host_register", "sonar_host_unregister", "sonar_dev_alloc", "sonar_dev_free", "sonar_memcpy_h2d",
     "sonar_memcpy_d2h", "sonar_synchronize", "sonar_kernel_launches", "sonar_stream",
     "sonar_profile_enable", "sonar_profile_read", "sonar_window_f64",
     "sonar_stft_stream_open", "sonar_stft_stream_frames", "sonar_stft_stream_buffered", "sonar_stft_stream_process",
@@ -274,6 +274,8 @@ class SonarLib:
         L.sonar_synchronize.argtypes = [C.c_void_p]
         L.sonar_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
         L.sonar_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.sonar_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.sonar_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
         L.sonar_dev_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
         L.sonar_dev_free.argtypes = [C.c_void_p, C.c_void_p]
         L.sonar_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -362,6 +364,13 @@ class SonarLib:
 
     def synchronize(self):
         self._chk(self.lib.sonar_synchronize(self.ctx))
+
+    def host_register(self, arr: np.ndarray):
+        """sonar_host_register: page-locks a caller-owned (pageable) numpy array in place."""
+        self._chk(self.lib.sonar_host_register(self.ctx, arr.ctypes.data, arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray):
+        self._chk(self.lib.sonar_host_unregister(self.ctx, arr.ctypes.data))
 
     def default_params(self, **kw) -> FpParams:
         p = FpParams()

@@ -117,6 +117,7 @@ struct FpShape {
   bool temporal = false;
   int64_t o_env = 0, o_att = 0, o_part = 0;
   int64_t o_wpart = 0, wpart_doubles = 0;  // scratch of the frame walk's loudness block parts (timedomain.cu)
+  int64_t o_ylist = 0;  // scratch of the pitch detector: 1 + Tp ints (count, frames re-evaluated exactly; yin32.cu)
 };
 
 // ---- exact FP64 time-domain kernels (timedomain.cu) -------------------------
@@ -153,7 +154,11 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
                const double* hann_dev, double* feat, int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
                int64_t o_voicing, int64_t o_hratio, int64_t o_inharm, int64_t o_tonal, double* scratch,
                int64_t scratch_stride, cudaStream_t st, cudaStream_t track_st = nullptr, cudaEvent_t fork = nullptr,
-               cudaEvent_t join = nullptr, bool* forked = nullptr);
+               cudaEvent_t join = nullptr, bool* forked = nullptr, int* lists = nullptr, int64_t list_stride = 0);
+// FP32 difference function on the packed pipe + exact float64 re-evaluation of the borderline frames (yin32.cu);
+// lists: per stream 1 + Tp ints, list_stride ints apart, counts zeroed by the caller
+int launch_yin32(const double* pcm, int64_t stride, int n_streams, double alpha, int sr, int64_t Tp, const double* hann_dev,
+                 double* scratch, int64_t scratch_stride, int* lists, int64_t list_stride, cudaStream_t st);
 
 // ---- cross-correlation (xcorr.cu) ------------------------------------------
 struct XcorrSeq {  // one sequence to z-score (population sigma, reference summation order)

@@ -212,6 +212,17 @@ int sonar_host_free(sonar_ctx*, void* p) {
   if (p) SONAR_CUDA(cudaFreeHost(p));
   return SONAR_OK;
 }
+int sonar_host_register(sonar_ctx* ctx, void* p, uint64_t bytes) {
+  if (!ctx || !p) return set_error(SONAR_ERR_INVALID, "nil argument");
+  if (bytes == 0) return SONAR_OK;
+  SONAR_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return SONAR_OK;
+}
+int sonar_host_unregister(sonar_ctx* ctx, void* p) {
+  if (!ctx || !p) return set_error(SONAR_ERR_INVALID, "nil argument");
+  SONAR_CUDA(cudaHostUnregister(p));
+  return SONAR_OK;
+}
 int sonar_dev_alloc(sonar_ctx* ctx, uint64_t bytes, void** out) {
   if (!ctx || !out) return set_error(SONAR_ERR_INVALID, "nil argument");
   SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));

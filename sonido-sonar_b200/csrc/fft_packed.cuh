@@ -14,6 +14,16 @@
 #include "fft_regs.cuh"
 
 namespace sonar {
+
+// XOR-swizzled shared-memory rows read 16 bytes at a time by lanes that each own a run of consecutive elements, and
+// written 4 / 8 bytes at a time by lanes that own consecutive elements (both conflict free, no padding):
+// table rows (one float per bin): 16-byte chunk c = k >> 2 lives at c ^ ((c >> 3) & 7)
+__host__ __device__ __forceinline__ int spos(int k) { return ((((k >> 2) ^ ((k >> 5) & 7))) << 2) | (k & 3); }
+// magnitude pair rows (one float2 per bin): 16-byte chunk c = k >> 1 lives at c ^ ((c >> 3) & 7).  Conflict free both
+// for pass 2's 8-byte stores (32 consecutive bins per instruction) and for the scan's 16-byte loads (BPL contiguous bins
+// per lane).
+__host__ __device__ __forceinline__ int ppos(int k) { return ((((k >> 1) ^ ((k >> 4) & 7))) << 1) | (k & 1); }
+
 namespace pk {
 
 __device__ __forceinline__ float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }

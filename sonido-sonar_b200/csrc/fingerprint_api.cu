@@ -75,6 +75,8 @@ int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s) {
   s->o_wpart = (int64_t)s->tmp_doubles_per_stream;
   s->wpart_doubles = 2 * ((s->sz.n_frames + 7) / 8) + 2;
   s->tmp_doubles_per_stream += (size_t)s->wpart_doubles;
+  s->o_ylist = (int64_t)s->tmp_doubles_per_stream;
+  s->tmp_doubles_per_stream += (size_t)((s->sz.n_pitch_frames + 2) / 2 + 1);
   s->temporal = (p->enable & SONAR_FP_ENABLE_TEMPORAL) != 0;
   if (s->temporal) {
     s->o_env = s->L.total;
@@ -204,7 +206,7 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
     rc = launch_yin(pcm_dev, stride, ns, p->pre_emph_alpha, n < 1024 ? 0 : p->algo_sample_rate, Tp, hann, feat_dev, L.total,
                     L.pitch_estimate, L.pitch_confidence, L.voicing_strength, L.harmonic_ratio, L.inharmonicity_ratio,
                     L.tonal_centroid, tmp_dev, tstride, st, side ? side->st3 : nullptr, side ? side->fork : nullptr,
-                    side ? side->join : nullptr, &forked);
+                    side ? side->join : nullptr, &forked, reinterpret_cast<int*>(tmp_dev + sh.o_ylist), 2 * tstride);
     if (rc) return rc;
   }
 

@@ -61,13 +61,6 @@ struct V3G {
   static_assert(NEW <= RR, "hop must not exceed the window");
 };
 
-// table rows (one float per bin): 16-byte chunk c = k >> 2 lives at c ^ ((c >> 3) & 7)
-__host__ __device__ __forceinline__ int spos(int k) { return ((((k >> 2) ^ ((k >> 5) & 7))) << 2) | (k & 3); }
-// magnitude pair rows (one float2 per bin): 16-byte chunk c = k >> 1 lives at c ^ ((c >> 3) & 7).  Conflict free both
-// for pass 2's 8-byte stores (32 consecutive bins per instruction) and for the scan's 16-byte loads (BPL contiguous bins
-// per lane).
-__host__ __device__ __forceinline__ int ppos(int k) { return ((((k >> 1) ^ ((k >> 4) & 7))) << 1) | (k & 1); }
-
 struct V3Smem {
   size_t tw, win, xtab, wlo, whi, fmask, moff, dct, lift, r0, warp0, per_warp, total;
   size_t w_tile, w_mag, w_raw, w_macc;

@@ -711,7 +711,7 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
                const double* hann_dev, double* feat, int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
                int64_t o_voicing, int64_t o_hratio, int64_t o_inharm, int64_t o_tonal, double* scratch,
                int64_t scratch_stride, cudaStream_t st, cudaStream_t track_st, cudaEvent_t fork, cudaEvent_t join,
-               bool* forked) {
+               bool* forked, int* lists, int64_t list_stride) {
   if (forked) *forked = false;
   if (Tp <= 0 || n_streams <= 0) return SONAR_OK;
   if (sr <= 0) {
@@ -727,7 +727,12 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
   }
   if (Tp > 0x7fffffffLL) return set_error(SONAR_ERR_UNSUPPORTED, "too many pitch frames");
   static const bool direct = std::getenv("SONAR_YIN_DIRECT") != nullptr;  // diagnostic: the O(W^2) form
-  if (direct) {
+  static const bool fp64 = std::getenv("SONAR_YIN_FP64") != nullptr;      // diagnostic: the float64 FFT kernel below
+  if (!direct && !fp64 && lists) {  // default: packed-FP32 transforms + exact re-evaluation of borderline frames (yin32.cu)
+    SONAR_CUDA(cudaMemset2DAsync(lists, sizeof(int) * (size_t)list_stride, 0, sizeof(int), (size_t)n_streams, st));
+    int rc = launch_yin32(pcm, stride, n_streams, alpha, sr, Tp, hann_dev, scratch, scratch_stride, lists, list_stride, st);
+    if (rc) return rc;
+  } else if (direct) {
     dim3 grid((unsigned)((Tp + kYinFpb - 1) / kYinFpb), (unsigned)n_streams);
     const size_t smem = sizeof(double) * kYinFpb * (kYinPad + kYinFrame + 2 + kYinHalf);
     SONAR_CUDA(cudaFuncSetAttribute(yin_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -6,8 +6,8 @@ spectral kernels compute in FP32, so for every feature array
     |gpu - oracle| <= 1e-4 * max(|oracle|, max|oracle array|)
 i.e. 1e-4 relative, floored at 1e-4 of the array's own scale for near-zero entries.  Outputs computed
 in FP64 in the reference's summation order (short-time energy, ZCR) must be bit-exact: they feed the
-cross-correlation arg-max and the DTW path.  The FP64 pitch track agrees to 1e-7 relative (its difference
-function is evaluated through the autocorrelation identity, which reorders the float64 sums).
+cross-correlation arg-max and the DTW path.  The pitch track's voiced pattern is identical and its values agree to 1e-4
+(FP32 transforms for the difference function, float64 re-evaluation in the reference's order of every borderline frame).
 """
 import numpy as np
 import pytest
@@ -68,8 +68,12 @@ def check_fp(a, b, bound=None):
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
     for k in FP64_CLOSE:
         np.testing.assert_allclose(a.arrays[k], b.arrays[k], rtol=1e-12, atol=1e-15)
-    for k in PITCH:  # FP64, but the YIN difference function uses the autocorrelation identity (yin.cu): ~1e-12
-        np.testing.assert_allclose(a.arrays[k], b.arrays[k], rtol=1e-7, atol=1e-9, err_msg=k)
+    # The pitch track: the difference function runs on FP32 transforms (yin32.cu, values ~1e-6) while every DECISION
+    # (voiced or not, which lag) is either outside the FP32 error bound or re-taken in float64 in the reference's order:
+    # the voiced pattern must be identical, the values hold the north star's 1e-4.
+    assert np.array_equal(a.pitch_estimate > 0, b.pitch_estimate > 0), "voiced / unvoiced pattern"
+    for k in PITCH:
+        np.testing.assert_allclose(a.arrays[k], b.arrays[k], rtol=1e-4, atol=1e-6, err_msg=k)
     assert a.energy_variance == pytest.approx(b.energy_variance, rel=1e-10)
     assert a.loudness_range == pytest.approx(b.loudness_range, rel=1e-9, abs=1e-12)
     assert a.sizes == b.sizes
@@ -413,3 +417,55 @@ def test_loudness_from_the_frame_walk_block_sums(gpu, oracle, synth, n):
     assert a.loudness_range == pytest.approx(b.loudness_range, rel=1e-9, abs=1e-12)
     assert np.array_equal(a.short_time_energy, b.short_time_energy)
     assert np.array_equal(a.zero_crossing_rate, b.zero_crossing_rate)
+
+
+def test_yin_threshold_bisection_decisions_match_the_oracle(gpu, oracle):
+    """Adversarial for the 0.15 threshold.  A 440 Hz tone plus a fixed noise realisation scaled by
+    `amp`: the oracle's voiced / unvoiced decision for the frame flips at some amplitude, and a bisection on `amp` drives
+    the CMNDF dip to within rounding of the threshold (the last iterations differ by single float64 ulps of amp).  At
+    EVERY amplitude visited the GPU must take the oracle's decision and reproduce its values: frames whose comparison is
+    inside the FP32 error bound are re-evaluated in float64 in the reference's summation order (yin32.cu)."""
+    sr, n = 44100, 1024 + 512
+    t = np.arange(n) / sr
+    tone = 0.5 * np.sin(2 * np.pi * 440.0 * t)
+    noise = np.random.default_rng(5).standard_normal(n)
+    p = gpu.default_params(algo_sample_rate=sr)
+
+    def both(amp):
+        x = tone + amp * noise
+        a, b = gpu.fingerprint(x, p), oracle.fingerprint(x, p)
+        assert np.array_equal(a.pitch_confidence > 0, b.pitch_confidence > 0), amp
+        np.testing.assert_allclose(a.pitch_confidence, b.pitch_confidence, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(a.pitch_estimate, b.pitch_estimate, rtol=1e-4, atol=1e-6)
+        return bool(b.pitch_confidence[0] > 0)
+
+    lo, hi = 1e-5, 5e-3
+    assert both(lo) and not both(hi)  # voiced with little noise, unvoiced with more
+    for _ in range(70):
+        mid = 0.5 * (lo + hi)
+        if mid == lo or mid == hi:
+            break
+        if both(mid):
+            lo = mid
+        else:
+            hi = mid
+    assert hi - lo <= 4 * np.spacing(lo)  # the search really ended at float64 resolution
+
+
+def test_yin_noise_sweep_decisions_match_the_oracle(gpu, oracle):
+    """The same statistically: 40 s of a 440 Hz tone whose noise level creeps through the range where the dip crosses
+    0.15, 3,444 frames; the voiced pattern must equal the oracle's exactly."""
+    sr, secs = 44100, 40.0
+    n = int(sr * secs)
+    t = np.arange(n) / sr
+    rng = np.random.default_rng(5)
+    amp = np.linspace(1.0e-4, 4.5e-4, n)
+    x = 0.5 * np.sin(2 * np.pi * 440.0 * t) + amp * rng.standard_normal(n)
+    p = gpu.default_params(algo_sample_rate=sr)
+    a, b = gpu.fingerprint(x, p), oracle.fingerprint(x, p)
+    va, vb = a.pitch_confidence > 0, b.pitch_confidence > 0
+    assert 0.05 < vb.mean() < 0.95  # the sweep really crosses the threshold
+    assert np.array_equal(va, vb)
+    assert np.array_equal(a.pitch_estimate > 0, b.pitch_estimate > 0)
+    np.testing.assert_allclose(a.pitch_confidence, b.pitch_confidence, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(a.pitch_estimate, b.pitch_estimate, rtol=1e-4, atol=1e-6)

@@ -36,7 +36,7 @@ def test_c2_full_size_known_offset_and_path_properties(gpu, oracle, synth):
     scale = np.max(np.abs(oq.mfcc))
     assert np.allclose(fq.mfcc[:t], oq.mfcc[:t], rtol=1e-4, atol=1e-4 * scale)
     tp = oq.pitch_estimate.size - 25  # the pitch tracker looks 20 frames back only
-    assert np.allclose(fq.pitch_estimate[:tp], oq.pitch_estimate[:tp], rtol=1e-7, atol=1e-9)
+    assert np.allclose(fq.pitch_estimate[:tp], oq.pitch_estimate[:tp], rtol=1e-4, atol=1e-6)
     # frames are also independent of how the kernel cuts the stream into runs of 31 frames / rings of 1024 samples:
     # a fresh fingerprint of the PCM from frame 30,011 on reproduces the long run's frames bit for bit (except the
     # first one, whose pre-emphasis sees x[-1] = 0 in the fresh run; flux additionally needs its predecessor)
