@@ -249,6 +249,173 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------
+# Extra legs: the other BASELINE.json configurations (C1, C3, C4, C5) at their named sizes
+# --------------------------------------------------------------------------------------
+
+def _roof_from_profile(kern, frames, bytes_per_frame, peak):
+    k_ms, k_n = kern.get("stft_features_kernel", (0.0, 0))
+    if not k_n:
+        return None
+    achieved = frames * bytes_per_frame / (k_ms / 1e3) / 1e9
+    return {"kernel": "stft_features_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "algorithmic_bytes_per_frame": bytes_per_frame, "kernel_ms_total": k_ms,
+            "launches_timed": k_n}
+
+
+def extra_legs(lib, capi, synth, torch, ext, barrier, reduce_max, rank, world, peak):
+    """C1 (30 s, 1024/256), C3 (1 h @16 kHz, 512/160, 40 mel), C4 (4,096 x 60 s sharded over the ranks) and C5
+    (1,024 x 10-min pairs sharded over the ranks), each with the PCM resident in HBM (CUDA events) and, where the bytes
+    fit the time budget, through the host-pointer C ABI.  Inputs are replicated synthetic streams: C4 / C5 re-use one
+    resident chunk (their 86.7 GB / 433 GB of float64 PCM do not fit HBM at once), every stream of a chunk is distinct."""
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            fn()
+        e1.record(ext)
+        barrier()
+        return reduce_max(e0.elapsed_time(e1) / reps)
+
+    def profiled(fn):
+        lib.profile_read()
+        lib.profile_enable(True)
+        fn()
+        barrier()
+        lib.profile_enable(False)
+        return lib.profile_read()
+
+    # ---- C1: one 30 s stream (latency of a single GenerateFingerprint) and 64 of them resident ----
+    sr = 44100
+    x1 = synth.sweep_noise(30.0, seed=1)
+    n1 = x1.size
+    p1 = lib.default_params(algo_sample_rate=sr, call_sample_rate=sr)
+    L1 = lib.fp_dev_layout(p1, n1)
+    S1 = 64
+    st1 = (n1 + 1) & ~1
+    d1 = torch.zeros((S1, st1), dtype=torch.float64, device="cuda")
+    d1[:, :n1] = torch.from_numpy(x1).cuda()
+    f1 = torch.empty(S1 * L1.total, dtype=torch.float64, device="cuda")
+    ms = timed(lambda: lib.fingerprint_batch_dev(d1.data_ptr(), n1, st1, S1, p1, f1.data_ptr()), 5)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        lib.fingerprint(x1, p1)
+    one_ms = 1e3 * (time.perf_counter() - t0) / 3
+    out["c1"] = {"workload": "GenerateFingerprint, 30 s 44.1 kHz sweep+noise, 1024/256, music, fixed-sr mode",
+                 "resident_64_streams": {"value": world * S1 * 30.0 / (ms / 1e3), "unit": UNIT, "ms": ms},
+                 "single_stream_host_call": {"value": 30.0 / (one_ms / 1e3), "unit": UNIT, "ms": one_ms,
+                                             "note": "one blocking sonar_fingerprint_f64 call from pageable host memory"}}
+    del d1, f1
+
+    # ---- C3: 1 h @ 16 kHz, 512/160, 40 mel / 13 MFCC ----
+    sr3 = 16000
+    x3 = synth.speech_band_noise(600.0, sr=sr3)          # 10 min generated, tiled to the hour
+    x3 = np.tile(x3, 6)
+    n3 = x3.size
+    p3 = lib.default_params(window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=sr3,
+                            call_sample_rate=sr3, n_mel=40)
+    L3 = lib.fp_dev_layout(p3, n3)
+    S3 = 4
+    st3 = (n3 + 1) & ~1
+    d3 = torch.zeros((S3, st3), dtype=torch.float64, device="cuda")
+    d3[:, :n3] = torch.from_numpy(x3).cuda()
+    f3 = torch.empty(S3 * L3.total, dtype=torch.float64, device="cuda")
+    run3 = lambda: lib.fingerprint_batch_dev(d3.data_ptr(), n3, st3, S3, p3, f3.data_ptr())
+    ms = timed(run3, 3)
+    T3 = (n3 - 512) // 160 + 1
+    k3 = profiled(run3)
+    t0 = time.perf_counter()
+    lib.fingerprint(x3, p3)
+    h_ms = 1e3 * (time.perf_counter() - t0)
+    out["c3"] = {"workload": "speech/news fingerprint, 1 h 16 kHz speech-band noise, 512/160, 40-mel / 13-MFCC + flux",
+                 "frames_per_stream": int(T3),
+                 "resident_4_streams": {"value": world * S3 * 3600.0 / (ms / 1e3), "unit": UNIT, "ms": ms},
+                 "single_stream_host_call": {"value": 3600.0 / (h_ms / 1e3), "unit": UNIT, "ms": h_ms},
+                 "roofline": _roof_from_profile(k3, S3 * T3, 160 * 8 + 13 * 8, peak),
+                 "kernels_ms": {k: v[0] for k, v in sorted(k3.items(), key=lambda kv: -kv[1][0])[:6]}}
+    del d3, f3
+
+    # ---- C4: 4,096 x 60 s streams, sharded round-robin over the ranks; chunks of 256 streams through HBM ----
+    n4 = 60 * sr
+    st4 = (n4 + 1) & ~1
+    per_rank = 4096 // world
+    CH = 256
+    base = synth.sweep_noise(60.0, seed=100 + rank)
+    d4 = torch.empty((CH, st4), dtype=torch.float64, device="cuda")
+    row = torch.from_numpy(base).cuda()
+    for i in range(CH):  # distinct streams: a different gain and a circular shift per stream
+        d4[i, :n4] = torch.roll(row, 997 * i) * (0.5 + 0.5 * (i % 7) / 7.0)
+    L4 = lib.fp_dev_layout(p1, n4)
+    f4 = torch.empty(CH * L4.total, dtype=torch.float64, device="cuda")
+    chunks = per_rank // CH
+
+    def run4():
+        for _ in range(chunks):
+            lib.fingerprint_batch_dev(d4.data_ptr(), n4, st4, CH, p1, f4.data_ptr())
+    ms = timed(run4, 1)
+    T4 = (n4 - WIN) // HOP + 1
+    k4 = profiled(lambda: lib.fingerprint_batch_dev(d4.data_ptr(), n4, st4, CH, p1, f4.data_ptr()))
+    # host leg: the same chunk count from pinned host memory through sonar_fingerprint_batch_f64 (H2D + D2H inside)
+    hostbuf = torch.empty((64, st4), dtype=torch.float64).pin_memory()
+    hostbuf.copy_(d4[:64].cpu())
+    hv = hostbuf.numpy()
+    streams = [hv[i, :n4] for i in range(64)]
+    bufs = lib.alloc_batch_outputs([n4] * 64, p1)
+    lib.fingerprint_batch(streams, p1, buffers=bufs)
+    barrier()
+    t0 = time.perf_counter()
+    reps4 = 4
+    for _ in range(reps4):
+        lib.fingerprint_batch(streams, p1, buffers=bufs)
+    barrier()
+    e_ms = reduce_max(1e3 * (time.perf_counter() - t0) / reps4)
+    out["c4"] = {"workload": "batch fingerprinting of 4,096 x 60 s 44.1 kHz streams, sharded over the ranks (no collective)",
+                 "streams_total": 4096, "streams_per_rank": per_rank, "chunk_streams": CH,
+                 "resident": {"value": 4096 * 60.0 / (ms / 1e3), "unit": UNIT, "ms_whole_job": ms,
+                              "note": "every rank fingerprints its 4096/N streams, 256 resident streams per chunk"},
+                 "e2e_sample": {"value": world * 64 * 60.0 / (e_ms / 1e3), "unit": UNIT, "ms_per_64_streams": e_ms,
+                                "h2d_bytes": int(64 * n4 * 8), "note": "64 streams per rank per call from pinned host memory "
+                                "through sonar_fingerprint_batch_f64 (PCIe bound); the whole job moves 86.7 GB"},
+                 "roofline": _roof_from_profile(k4, CH * T4, ALGO_BYTES_PER_FRAME, peak)}
+    del d4, f4, hostbuf
+
+    # ---- C5: 1,024 x 10-min pairs, +-60 s, DTW r=50, sharded by pair over the ranks; 8 resident pairs per chunk ----
+    n5 = 600 * sr
+    st5 = (n5 + 1) & ~1
+    P5 = 32
+    pairs_rank = 1024 // world
+    d5 = torch.empty((2 * P5, st5), dtype=torch.float64, device="cuda")
+    true_lags = []
+    for i in range(P5):
+        rng = np.random.default_rng(200 + rank * P5 + i)
+        off = float(rng.uniform(-55.0, 55.0))
+        q, r = synth.aligned_pair(600.0, offset_seconds=off, sr=sr, seed=300 + 2 * (rank * P5 + i))
+        d5[2 * i, :n5] = torch.from_numpy(q).cuda()
+        d5[2 * i + 1, :n5] = torch.from_numpy(r).cuda()
+        true_lags.append(off * sr / HOP)
+    bufs5 = lib.alloc_pair_outputs(P5, n5, p1, MAX_LAG_S, features=False, corr=False)
+    res5 = [None]
+
+    def run5():
+        for _ in range(pairs_rank // P5):
+            res5[0] = lib.align_pairs_dev(d5.data_ptr(), n5, st5, P5, p1, MAX_LAG_S, DTW_BAND, buffers=bufs5)
+    ms = timed(run5, 1)
+    lags5 = [int(x["xcorr"].peak_lag) for x in res5[0]]
+    out["c5"] = {"workload": "batched alignment of 1,024 source/CDN pairs (10 min each, +-60 s lag, banded DTW r=50), "
+                             "sharded by pair over the ranks (no collective)",
+                 "pairs_total": 1024, "pairs_per_rank": pairs_rank, "chunk_pairs": P5,
+                 "resident": {"alignments_per_s": 1024 / (ms / 1e3), "value": 1024 * 1200.0 / (ms / 1e3), "unit": UNIT,
+                              "ms_whole_job": ms},
+                 "detected_lags_frames": lags5, "true_offsets_frames": [round(v, 1) for v in true_lags],
+                 "lags_within_one_frame_of_truth": bool(all(abs(a - b) <= 1.0 for a, b in zip(lags5, true_lags)))}
+    del d5
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
 
@@ -452,6 +619,9 @@ def run_ours(args, rank, world, local_rank):
                      "equal": bool(ora_lags == [int(lags[i]) for i in idx]),
                      "method": "oracle time-domain NCC (correlation.go:373-449 restated) over the returned energies"}
         assert lag_check["equal"], f"detected lags differ from the oracle: {lag_check}"
+    legs = None
+    if not args.no_legs:
+        legs = extra_legs(lib, capi, synth, torch, ext, barrier, reduce_max, rank, world, measured_peak()[0])
     if rank == 0:
         peak, peak_src = measured_peak()
         k_ms, k_n = kern.get("stft_features_kernel", (0.0, 0))
@@ -499,6 +669,7 @@ def run_ours(args, rank, world, local_rank):
             "detected_lags_frames": lags,
             "lags_checked_vs_oracle": lag_check,
             "lag_sharded": lag_sharded,
+            "legs": legs,
         }
         print(json.dumps(line), file=_OUT, flush=True)
     lib.close()
@@ -527,6 +698,7 @@ def main():
     ap.add_argument("--no-s16", action="store_true", help="skip the int16-ingest extra leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks (diagnostic)")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events (diagnostic)")
+    ap.add_argument("--no-legs", action="store_true", help="skip the extra C1 / C3 / C4 / C5 legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
