@@ -425,6 +425,7 @@ def run_ours(args, rank, world, local_rank):
 
     p = pkg()
     capi, synth = p.capi, p.synth
+    numa = None if args.no_numa else bind_to_gpu_numa(local_rank)  # before any pinned allocation (first touch)
     torch.cuda.set_device(local_rank)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
     if world > 1:
@@ -550,6 +551,43 @@ def run_ours(args, rank, world, local_rank):
     h2d = NS * n * 8
     d2h = sum(a.nbytes for a in fps[0]["query"].arrays.values()) * NS + sum(len(pp["path_query"]) * 16 for pp in paths_e)
 
+    # ---- extra legs: the SAME call from memory a Go caller actually holds.  `pageable`: ordinary heap
+    #      arrays (a Go []float64): the runtime stages every copy through its own bounce buffer.  `registered`: the same
+    #      arrays page-locked in place once with sonar_host_register (what go/sonargpu does for long-lived buffers), the
+    #      registration itself outside the timed region.
+    mem_legs = None
+    if not args.no_s16:
+        heap = np.empty((NS, n), dtype=np.float64)
+        heap[:] = hv[:, :n]
+        qh = [heap[2 * i] for i in range(P)]
+        rh = [heap[2 * i + 1] for i in range(P)]
+
+        def timed_heap():
+            lib.align_pairs(qh, rh, prm, MAX_LAG_S, DTW_BAND, buffers=bufs_e2e)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                res = lib.align_pairs(qh, rh, prm, MAX_LAG_S, DTW_BAND, buffers=bufs_e2e)
+            barrier()
+            return reduce_max(1e3 * (time.perf_counter() - t0) / n_e2e), [x["xcorr"].peak_lag for x in res]
+
+        pg_ms, pg_lags = timed_heap()
+        t0 = time.perf_counter()
+        lib.host_register(heap)
+        reg_cost_ms = 1e3 * (time.perf_counter() - t0)
+        try:
+            rg_ms, rg_lags = timed_heap()
+        finally:
+            lib.host_unregister(heap)
+        mem_legs = {"pageable": {"value": audio_s / (pg_ms / 1e3), "unit": UNIT, "ms_per_step": pg_ms,
+                                 "lags_equal": bool(pg_lags == lags)},
+                    "registered": {"value": audio_s / (rg_ms / 1e3), "unit": UNIT, "ms_per_step": rg_ms,
+                                   "lags_equal": bool(rg_lags == lags), "one_time_register_ms": reg_cost_ms,
+                                   "bytes_registered": int(heap.nbytes)},
+                    "note": "e2e (the headline) reads pinned memory from sonar_host_alloc / torch pin_memory; these two "
+                            "legs read a plain heap array, as a Go []float64 is, without and with sonar_host_register"}
+        del heap, qh, rh
+
     # ---- extra leg: the same step with int16 PCM (what the decoder holds before the reference widens it to float64;
     #      sonar_align_pairs_pcm).  A quarter of the bytes cross PCIe; the samples are the float64 ones
     #      quantised to 16 bits, so this is reported beside `e2e`, never instead of it.
@@ -578,30 +616,60 @@ def run_ours(args, rank, world, local_rank):
                "lags_equal_f64_leg": bool(lags16 == lags),
                "note": "int16 host PCM through sonar_align_pairs_pcm (widened to float64 on the device)"}
 
-    # ---- N > 1 only: ONE long correlation (10-min pair, +-60 s) split by lag range over the ranks, NCCL
-    #      all-gather of the per-shard maxima.  Reported beside the main metric, not inside it.
+    # ---- N > 1 only: ONE long correlation (+-60 s) split by lag range over the ranks INSIDE the library: every rank
+    #      z-scores, evaluates its lags in reference order, one ncclAllGather of the curve shards on the library's stream,
+    #      peak analysis on every rank (csrc/nccl_shard.cu).  Reported beside the main metric, not inside it.
     lag_sharded = None
     if world > 1:
-        rng = np.random.default_rng(7)  # identical on every rank: both sequences are replicated
-        t10 = (int(600 * SR) - WIN) // HOP + 1
-        base = np.convolve(rng.standard_normal(t10 + 6000), np.ones(32) / 32, mode="same") + 1.0
-        qa, rb = base[3000:3000 + t10].copy(), base[3000 - 2345:3000 - 2345 + t10] + 0.01 * rng.standard_normal(t10)
         dev = torch.device("cuda", local_rank)
-        p.sharding.xcorr_lag_sharded(lib, qa, rb, max_lag, device=dev)  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        sh_summ, (lo, hi), _ = p.sharding.xcorr_lag_sharded(lib, qa, rb, max_lag, device=dev)
-        barrier()
-        sh_ms = reduce_max(1e3 * (time.perf_counter() - t0))
-        if rank == 0:
+        p.sharding.nccl_setup(lib, device=dev)
+        rng = np.random.default_rng(7)  # identical on every rank: both sequences are replicated
+        sweep = []
+        for minutes in (2.5, 5, 10, 20, 40):
+            tn = (int(minutes * 60 * SR) - WIN) // HOP + 1
+            base = np.convolve(rng.standard_normal(tn + 6000), np.ones(32) / 32, mode="same") + 1.0
+            qa, rb = base[3000:3000 + tn].copy(), base[3000 - 2345:3000 - 2345 + tn] + 0.01 * rng.standard_normal(tn)
+            lib.xcorr_lag_sharded(qa, rb, max_lag)  # warm-up
+            barrier()
             t0 = time.perf_counter()
-            _, whole = lib.xcorr(qa, rb, max_lag, want_corr=False)
-            one_ms = 1e3 * (time.perf_counter() - t0)
-            lag_sharded = {"frames": int(t10), "lags": 2 * max_lag + 1, "ranks": world, "ms": sh_ms,
-                           "single_gpu_ms": one_ms, "peak_lag": sh_summ.peak_lag,
-                           "matches_unsharded": bool(sh_summ.peak_lag == whole.peak_lag and
-                                                     sh_summ.peak_correlation == whole.peak_correlation),
-                           "collectives": "all_gather(16 B/rank) + all_gather(72 B/rank) over NCCL"}
+            reps = 5
+            for _ in range(reps):
+                sh_summ, _ = lib.xcorr_lag_sharded(qa, rb, max_lag)
+            barrier()
+            sh_ms = reduce_max(1e3 * (time.perf_counter() - t0) / reps)
+            row = None
+            if rank == 0:
+                lib.xcorr(qa, rb, max_lag, want_corr=True)
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    _, whole = lib.xcorr(qa, rb, max_lag, want_corr=True)
+                exact_ms = 1e3 * (time.perf_counter() - t0) / reps
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    _, scr = lib.xcorr(qa, rb, max_lag, want_corr=False)
+                scr_ms = 1e3 * (time.perf_counter() - t0) / reps
+                row = {"minutes": minutes, "frames": int(tn), "lags": 2 * max_lag + 1, "sharded_ms": sh_ms,
+                       "single_gpu_exact_curve_ms": exact_ms, "single_gpu_screened_ms": scr_ms,
+                       "peak_lag": int(sh_summ.peak_lag),
+                       "matches_unsharded": bool(sh_summ.peak_lag == whole.peak_lag and
+                                                 sh_summ.peak_correlation == whole.peak_correlation and
+                                                 sh_summ.second_peak == whole.second_peak and sh_summ.snr == whole.snr)}
+            sweep.append(row)
+        if rank == 0:
+            ten = [r for r in sweep if r["minutes"] == 10][0]
+            cross = [r["minutes"] for r in sweep if r["sharded_ms"] < r["single_gpu_exact_curve_ms"]]
+            lag_sharded = {"frames": ten["frames"], "lags": ten["lags"], "ranks": world, "ms": ten["sharded_ms"],
+                           "single_gpu_ms": ten["single_gpu_exact_curve_ms"],
+                           "single_gpu_screened_ms": ten["single_gpu_screened_ms"], "peak_lag": ten["peak_lag"],
+                           "matches_unsharded": bool(all(r["matches_unsharded"] for r in sweep)),
+                           "collectives": "one ncclAllGather of the curve shards (%d doubles per rank) on the library stream"
+                                          % (-(-ten["lags"] // world)),
+                           "sweep": sweep,
+                           "shortest_length_where_sharding_wins_minutes": (min(cross) if cross else None),
+                           "note": "every rank z-scores both sequences itself (a dependent-add chain in the reference's "
+                                   "order: it does not shard and bounds the speed-up); the screened single-GPU form skips "
+                                   "most exact lags and is what the pair pipeline uses"}
+        lib.nccl_shutdown()
     # ---- outside every timed region: the detected lags of the first pairs against the oracle.  The e2e leg returned
     #      the short-time energies (bit-exact with the oracle's: tests/test_gpu_fullsize.py); the oracle's own
     #      time-domain per-lag NCC over them must find the same lag index.  Pair 0 additionally runs the whole oracle
@@ -669,6 +737,8 @@ def run_ours(args, rank, world, local_rank):
             "detected_lags_frames": lags,
             "lags_checked_vs_oracle": lag_check,
             "lag_sharded": lag_sharded,
+            "e2e_host_memory": mem_legs,
+            "numa_binding": numa,
             "legs": legs,
         }
         print(json.dumps(line), file=_OUT, flush=True)
@@ -686,6 +756,36 @@ def _quiet_stdout():
     return real
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pins this process (and the threads the library starts from it) to the CPUs of the NUMA node its GPU hangs off, so
+    that the pinned staging buffers are first-touched on that node and the H2D copies do not cross the socket
+    interconnect (all ranks sat on node 0).  Returns {"node": n, "cpus": k} or None when the topology
+    is not exposed (single-socket box, container without sysfs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -699,6 +799,7 @@ def main():
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks (diagnostic)")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events (diagnostic)")
     ap.add_argument("--no-legs", action="store_true", help="skip the extra C1 / C3 / C4 / C5 legs")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

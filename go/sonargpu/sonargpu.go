@@ -74,6 +74,17 @@ type FpParams struct {
 	EnableMFCC                       bool
 }
 
+// SpeechFeatures mirrors the frame-level part of extractors.SpeechFeatures (fingerprint/extractors/features.go:45-65) that
+// sonar_fingerprint_speech_f64 produces.  FormantFrequencies, VocalTractLength, Jitter and Shimmer stay with the
+// reference's host-side analyzers (algorithms/speech): extractSpeechFeatures keeps calling them for those four fields.
+type SpeechFeatures struct {
+	IsSpeech           bool
+	VoicingProbability []float64
+	SpectralTilt       []float64
+	PauseDuration      []float64
+	SpeechRate         float64
+}
+
 // Fingerprint holds the flat outputs of sonar_fingerprint_f64 (row-major MFCC).
 type Fingerprint struct {
 	Frames, EnergyFrames, PitchFrames, NMFCC int
@@ -90,11 +101,22 @@ type Fingerprint struct {
 // GenerateFingerprint replaces ComputeSTFTWithWindow + SpeechFeatureExtractor.ExtractFeatures
 // (fingerprint/fingerprint.go:190-207).
 func GenerateFingerprint(pcm []float64, p FpParams) (*Fingerprint, error) {
+	f, _, err := generate(pcm, p, false)
+	return f, err
+}
+
+// GenerateFingerprintSpeech is GenerateFingerprint with FeatureConfig.EnableSpeechFeatures (news / talk): the speech
+// group runs before the harmonic block on the shared pitch detector, exactly as extractors/speech.go:194-205 orders it.
+func GenerateFingerprintSpeech(pcm []float64, p FpParams) (*Fingerprint, *SpeechFeatures, error) {
+	return generate(pcm, p, true)
+}
+
+func generate(pcm []float64, p FpParams, speech bool) (*Fingerprint, *SpeechFeatures, error) {
 	runtime.LockOSThread() // the error message of a failing call is thread-local in the C library (see lastError)
 	defer runtime.UnlockOSThread()
 	c, err := Ctx()
 	if err != nil {
-		return nil, err
+		return nil, nil, err
 	}
 	var cp C.sonar_fp_params
 	C.sonar_fp_params_default(&cp)
@@ -108,7 +130,7 @@ func GenerateFingerprint(pcm []float64, p FpParams) (*Fingerprint, error) {
 	}
 	var sz C.sonar_fp_sizes_t
 	if rc := C.sonar_fp_sizes(&cp, C.int64_t(len(pcm)), &sz); rc != C.SONAR_OK {
-		return nil, lastError() // "empty signal", "signal too short for given window size and hop size", ...
+		return nil, nil, lastError() // "empty signal", "signal too short for given window size and hop size", ...
 	}
 	T, Te, Tp, K := int(sz.n_frames), int(sz.n_energy_frames), int(sz.n_pitch_frames), int(sz.n_mfcc)
 	f := &Fingerprint{Frames: T, EnergyFrames: Te, PitchFrames: Tp, NMFCC: K}
@@ -150,11 +172,79 @@ func GenerateFingerprint(pcm []float64, p FpParams) (*Fingerprint, error) {
 	set(&out.harmonic_ratio, f.HarmonicRatio)
 	set(&out.inharmonicity_ratio, f.Inharmonicity)
 	set(&out.tonal_centroid, f.TonalCentroid)
-	if rc := C.sonar_fingerprint_f64(c, ptr(pcm), C.int64_t(len(pcm)), &cp, out); rc != C.SONAR_OK {
-		return nil, lastError()
+	var sf *SpeechFeatures
+	if speech {
+		so := (*C.sonar_speech_out)(C.calloc(1, C.size_t(unsafe.Sizeof(C.sonar_speech_out{}))))
+		defer C.free(unsafe.Pointer(so))
+		voi, tilt, pauses := mk(Tp), mk(Tp), mk(Te/2+1)
+		set(&so.voicing_probability, voi)
+		set(&so.spectral_tilt, tilt)
+		set(&so.pause_duration, pauses)
+		so.pause_cap = C.int64_t(len(pauses))
+		if rc := C.sonar_fingerprint_speech_f64(c, ptr(pcm), C.int64_t(len(pcm)), &cp, out, so); rc != C.SONAR_OK {
+			return nil, nil, lastError()
+		}
+		nf, np := int(so.n_frames), int(so.n_pause)
+		if np > len(pauses) {
+			np = len(pauses)
+		}
+		sf = &SpeechFeatures{IsSpeech: so.is_speech != 0, VoicingProbability: voi[:nf], SpectralTilt: tilt[:nf],
+			PauseDuration: pauses[:np], SpeechRate: float64(so.speech_rate)}
+	} else if rc := C.sonar_fingerprint_f64(c, ptr(pcm), C.int64_t(len(pcm)), &cp, out); rc != C.SONAR_OK {
+		return nil, nil, lastError()
 	}
 	f.EnergyVariance, f.LoudnessRange = float64(out.energy_variance), float64(out.loudness_range)
-	return f, nil
+	return f, sf, nil
+}
+
+// ExactFrameCounts reports how many frames of the last fingerprint batch were re-evaluated in float64 in the reference's
+// order instead of taking the FP32 kernels' values (sonar_fp_exact_counts; diagnostic).
+func ExactFrameCounts() (spectral, pitch int64, err error) {
+	c, err := Ctx()
+	if err != nil {
+		return 0, 0, err
+	}
+	var a, b C.int64_t
+	err = locked(func() C.int { return C.sonar_fp_exact_counts(c, &a, &b) })
+	return int64(a), int64(b), err
+}
+
+// NCCLUniqueID / NCCLInit give the library its own communicator over the ranks of a multi-process job (one process per
+// GPU): rank 0 draws the id, the host distributes the 128 bytes by any means, every rank calls NCCLInit.
+func NCCLUniqueID() ([]byte, error) {
+	id := make([]byte, C.SONAR_NCCL_ID_BYTES)
+	err := locked(func() C.int { return C.sonar_nccl_unique_id((*C.uchar)(unsafe.Pointer(&id[0])), C.int(len(id))) })
+	return id, err
+}
+
+func NCCLInit(world, rank int, id []byte) error {
+	c, err := Ctx()
+	if err != nil {
+		return err
+	}
+	return locked(func() C.int {
+		return C.sonar_nccl_init(c, C.int(world), C.int(rank), (*C.uchar)(unsafe.Pointer(&id[0])))
+	})
+}
+
+// CrossCorrelationSharded is CrossCorrelation.Compute of ONE long pair with the lag range split over the ranks of the
+// communicator (every rank calls it with the same sequences and receives the identical result): sonar_xcorr_lag_sharded.
+func CrossCorrelationSharded(a, b []float64, maxLag int) (*XcorrSummary, error) {
+	c, err := Ctx()
+	if err != nil {
+		return nil, err
+	}
+	var s C.sonar_xcorr_summary
+	err = locked(func() C.int {
+		return C.sonar_xcorr_lag_sharded(c, ptr(a), C.int64_t(len(a)), ptr(b), C.int64_t(len(b)), C.int(maxLag), 0, nil, &s)
+	})
+	if err != nil {
+		return nil, err
+	}
+	return &XcorrSummary{PeakCorrelation: float64(s.peak_correlation), PValue: float64(s.p_value), SNR: float64(s.snr),
+		Sharpness: float64(s.sharpness), SecondPeak: float64(s.second_peak), PeakToSidelobe: float64(s.peak_to_sidelobe),
+		PeakLag: int(s.peak_lag), PeakIndex: int(s.peak_index), MaxLag: int(s.actual_max_lag),
+		OverlapLength: int(s.overlap_length), IsSignificant: s.is_significant != 0}, nil
 }
 
 // XcorrSummary mirrors stats.CorrelationResult without the arrays (algorithms/stats/correlation.go:44-71).

@@ -70,7 +70,7 @@ typedef enum sonar_window {
  * harmonic groups are unconditional in the reference (speech.go:193,215,224). */
 #define SONAR_FP_ENABLE_MFCC      0x1u
 #define SONAR_FP_ENABLE_TEMPORAL  0x2u   /* speech.go:370-408            */
-#define SONAR_FP_ENABLE_SPEECH    0x4u   /* speech.go:271-317 — out of scope: UNSUPPORTED */
+#define SONAR_FP_ENABLE_SPEECH    0x4u   /* speech.go:194-205,271-317: see sonar_speech_out */
 
 /* ------------------------------------------------------------------------- */
 /* context                                                                    */
@@ -120,6 +120,12 @@ typedef struct sonar_kernel_time {
 } sonar_kernel_time;
 int sonar_profile_enable(sonar_ctx* ctx, int on);
 int sonar_profile_read(sonar_ctx* ctx, sonar_kernel_time* out, int cap, int* n_out);
+
+/* Diagnostic: how many frames of the most recently enqueued fingerprint batch took the float64 re-evaluation instead
+ * of the FP32 kernels' results -- *spectral: STFT frames whose rolloff bin, log-magnitude means or mel bands are not safe
+ * in FP32 (spectral_rolloff.go:19-55, spectral_flatness.go:31-70, mfcc.go:136-145); *pitch: YIN frames with a
+ * borderline threshold / dip decision (pitch_detection.go:363-383).  Synchronises the library stream. */
+int sonar_fp_exact_counts(sonar_ctx* ctx, int64_t* spectral, int64_t* pitch);
 
 /* ------------------------------------------------------------------------- */
 /* windows                                                                    */
@@ -211,6 +217,24 @@ typedef struct sonar_fp_out {
   int64_t n_attack_time;     /* number of onsets (speech.go:402) */
 } sonar_fp_out;
 
+/* The frame-level part of SpeechFeatures (features.go:45-65; extractSpeechFeatures, speech.go:271-317), produced with
+ * SONAR_FP_ENABLE_SPEECH by sonar_fingerprint_speech_f64.  The group runs on the pre-emphasised PCM BEFORE the harmonic
+ * block and on the same pitch detector: when the signal is judged to be speech, the detector's 20-frame history carries
+ * over, so the FIRST frames of pitch_estimate / tonal_centroid differ from a run without the group -- reproduced here.
+ * Not computed on this path (host-side LPC / voice-quality analyzers of algorithms/speech, no data-parallel work):
+ * FormantFrequencies, VocalTractLength, Jitter, Shimmer. */
+typedef struct sonar_speech_out {
+  double* voicing_probability;  /* [n_frames] extractVoicingProbability (speech.go:529-549)                     */
+  double* spectral_tilt;        /* [n_frames] extractSpectralTilt (speech.go:551-584)                           */
+  double* pause_duration;       /* [pause_cap] extractPauseDurations (speech.go:586-641); n_pause found in all  */
+  int64_t pause_cap;
+  int64_t n_pause;              /* written by the call                                                          */
+  int64_t n_frames;             /* (N-1024)/512+1, or 0 when the signal is not speech (speech.go:281-291)       */
+  int32_t is_speech;            /* SpeechAnalyzer.detectSpeech (algorithms/speech/speech_analysis.go:113-207)   */
+  int32_t reserved;
+  double speech_rate;           /* estimateSpeechRate (speech.go:779-797)                                       */
+} sonar_speech_out;
+
 void sonar_fp_params_default(sonar_fp_params* p);
 
 /* Replaces the size arithmetic of ComputeSTFTWithWindow / ComputeShortTimeEnergy
@@ -225,6 +249,13 @@ int sonar_fp_sizes(const sonar_fp_params* p, int64_t n_samples, sonar_fp_sizes_t
  * materialised. `pcm` is a host pointer to n float64 samples. */
 int sonar_fingerprint_f64(sonar_ctx* ctx, const double* pcm, int64_t n,
                           const sonar_fp_params* p, sonar_fp_out* out);
+
+/* sonar_fingerprint_f64 with the speech-specific group (EnableSpeechFeatures: what the news / talk configurations
+ * turn on, config.go): `speech` receives the frame-level SpeechFeatures, `out` the fingerprint whose harmonic block saw
+ * the shared detector history (see sonar_speech_out).  The voicing / tilt arrays hold sonar_fp_sizes_t.n_pitch_frames
+ * entries at most. */
+int sonar_fingerprint_speech_f64(sonar_ctx* ctx, const double* pcm, int64_t n, const sonar_fp_params* p,
+                                 sonar_fp_out* out, sonar_speech_out* speech);
 
 /* Batch form (the analogue of ComputeSTFTBatch, analyzers/spectral.go:234-285,
  * applied to whole fingerprints): n_streams host buffers, one sonar_fp_out
@@ -371,6 +402,22 @@ int sonar_xcorr_shard_metrics_f64(sonar_xcorr_shard* sh, int64_t global_peak_ind
 /* copies this shard's correlations (idx_hi-idx_lo doubles) to the host */
 int sonar_xcorr_shard_corr(sonar_xcorr_shard* sh, double* corr);
 void sonar_xcorr_shard_close(sonar_xcorr_shard* sh);
+/* The same sharding done inside the library (one call per rank, no host round trip between the phases): every rank
+ * z-scores both sequences, evaluates its ceil((2L+1)/world) lags in reference order (correlation.go:373-449), ONE
+ * ncclAllGather of the curve shards (device buffers, the library's stream) assembles the curve on every rank, and
+ * findPeak / SNR / sharpness / second peak / side lobe (correlation.go:526-661) run over it: every rank returns the
+ * identical summary, bit-identical to sonar_xcorr_ncc_f64.  The communicator is the library's own: rank 0 calls
+ * sonar_nccl_unique_id, the host distributes the 128 bytes by any means (torch.distributed broadcast, MPI, a file),
+ * every rank calls sonar_nccl_init.  NCCL is bound with dlopen("libnccl.so.2") at the first call; without a
+ * communicator the call degenerates to one shard = the unsharded evaluation.  inputs_on_device != 0: a / b are device
+ * pointers on the context's device 0.  corr_host (nullable) receives the 2L+1 values. */
+#define SONAR_NCCL_ID_BYTES 128
+int sonar_nccl_unique_id(unsigned char* id, int cap);
+int sonar_nccl_init(sonar_ctx* ctx, int world, int rank, const unsigned char* id);
+int sonar_nccl_shutdown(sonar_ctx* ctx);
+int sonar_xcorr_lag_sharded(sonar_ctx* ctx, const double* a, int64_t na, const double* b, int64_t nb, int max_lag,
+                            int inputs_on_device, double* corr_host, sonar_xcorr_summary* out);
+
 /* pure host arithmetic over the gathered partials (same tie rules as findPeak) */
 int sonar_xcorr_merge_peaks(const sonar_xcorr_shard_peak* peaks, int n, int64_t* global_index);
 int sonar_xcorr_merge_metrics(const sonar_xcorr_shard_metrics* parts, int n, int64_t na,

@@ -95,6 +95,13 @@ class XcorrSummary(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class SpeechOut(C.Structure):
+    """sonar_speech_out (include/sonar.h)."""
+    _fields_ = [("voicing_probability", c_double_p), ("spectral_tilt", c_double_p), ("pause_duration", c_double_p),
+                ("pause_cap", C.c_int64), ("n_pause", C.c_int64), ("n_frames", C.c_int64), ("is_speech", C.c_int32),
+                ("reserved", C.c_int32), ("speech_rate", C.c_double)]
+
+
 class XcorrShardPeak(C.Structure):
     _fields_ = [("abs_peak", C.c_double), ("index", C.c_int64)]
 
@@ -171,14 +178,15 @@ EXPORTS = (
     "sonar_init", "sonar_destroy", "sonar_last_error", "sonar_abi_version", "sonar_backend",
     "sonar_host_alloc", "sonar_host_free", "sonar_host_register", "sonar_host_unregister", "sonar_dev_alloc", "sonar_dev_free", "sonar_memcpy_h2d",
     "sonar_memcpy_d2h", "sonar_synchronize", "sonar_kernel_launches", "sonar_stream",
-    "sonar_profile_enable", "sonar_profile_read", "sonar_window_f64",
+    "sonar_profile_enable", "sonar_profile_read", "sonar_fp_exact_counts", "sonar_window_f64",
     "sonar_stft_stream_open", "sonar_stft_stream_frames", "sonar_stft_stream_buffered", "sonar_stft_stream_process",
     "sonar_stft_stream_close",
-    "sonar_fp_params_default", "sonar_fp_sizes", "sonar_fingerprint_f64",
+    "sonar_fp_params_default", "sonar_fp_sizes", "sonar_fingerprint_f64", "sonar_fingerprint_speech_f64",
     "sonar_fingerprint_batch_f64", "sonar_fingerprint_batch_pcm", "sonar_fingerprint_batch_dev", "sonar_fp_dev_layout",
     "sonar_stft_f64", "sonar_xcorr_ncc_f64", "sonar_xcorr_batch_f64", "sonar_xcorr_batch_dev",
     "sonar_xcorr_shard_open", "sonar_xcorr_shard_metrics_f64", "sonar_xcorr_shard_corr",
     "sonar_xcorr_shard_close", "sonar_xcorr_merge_peaks", "sonar_xcorr_merge_metrics",
+    "sonar_nccl_unique_id", "sonar_nccl_init", "sonar_nccl_shutdown", "sonar_xcorr_lag_sharded",
     "sonar_align_xcorr_f64", "sonar_dtw_f64", "sonar_dtw_batch_f64", "sonar_align_dtw_scalars",
     "sonar_colstats_cosine_f64", "sonar_colstats_f64", "sonar_compare_f64",
     "sonar_music_spectral_f64", "sonar_compare_batch_f64", "sonar_align_pairs_sizes", "sonar_align_pairs_f64", "sonar_align_pairs_pcm", "sonar_align_pairs_dev",
@@ -256,6 +264,8 @@ class SonarLib:
         L.sonar_stream.argtypes = [C.c_void_p]
         L.sonar_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.sonar_profile_read.argtypes = [C.c_void_p, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]
+        if hasattr(L, "sonar_fp_exact_counts"):
+            L.sonar_fp_exact_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.sonar_destroy.restype = None
         L.sonar_destroy.argtypes = [C.c_void_p]
         L.sonar_xcorr_shard_close.restype = None
@@ -303,6 +313,11 @@ class SonarLib:
         L.sonar_xcorr_shard_metrics_f64.argtypes = [C.c_void_p, C.c_int64, C.POINTER(XcorrShardMetrics)]
         L.sonar_xcorr_shard_corr.argtypes = [C.c_void_p, c_double_p]
         L.sonar_xcorr_merge_peaks.argtypes = [C.POINTER(XcorrShardPeak), C.c_int, c_int64_p]
+        L.sonar_nccl_unique_id.argtypes = [C.c_char_p, C.c_int]
+        L.sonar_nccl_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        L.sonar_nccl_shutdown.argtypes = [C.c_void_p]
+        L.sonar_xcorr_lag_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                              c_double_p, C.POINTER(XcorrSummary)]
         L.sonar_xcorr_merge_metrics.argtypes = [C.POINTER(XcorrShardMetrics), C.c_int, C.c_int64, C.c_int64,
                                                 C.c_int, C.c_int64, C.POINTER(XcorrSummary)]
         L.sonar_align_xcorr_f64.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int,
@@ -361,6 +376,12 @@ class SonarLib:
         n = C.c_int()
         self._chk(self.lib.sonar_profile_read(self.ctx, buf, 64, C.byref(n)))
         return {buf[i].kernel.decode(): (buf[i].total_ms, int(buf[i].launches)) for i in range(n.value)}
+
+    def exact_counts(self) -> tuple[int, int]:
+        """(STFT frames, YIN frames) of the last fingerprint batch that took the float64 re-evaluation; synchronises."""
+        a, b = C.c_int64(), C.c_int64()
+        self._chk(self.lib.sonar_fp_exact_counts(self.ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def synchronize(self):
         self._chk(self.lib.sonar_synchronize(self.ctx))
@@ -430,6 +451,23 @@ class SonarLib:
         sizes, arrays, out = self._alloc_fp(p, pcm.size)
         self._chk(self.lib.sonar_fingerprint_f64(self.ctx, _dp(pcm), pcm.size, C.byref(p), C.byref(out)))
         return self._finish_fp(sizes, arrays, out)
+
+    def fingerprint_speech(self, pcm, p: FpParams):
+        """sonar_fingerprint_speech_f64: (Fingerprint, speech dict) with the speech-specific group enabled."""
+        pcm = _f64(pcm)
+        sizes, arrays, out = self._alloc_fp(p, pcm.size)
+        tp = max(int(sizes["n_pitch_frames"]), 0)
+        cap = max(int(sizes["n_energy_frames"]) // 2 + 1, 1)
+        voi, tilt, pauses = np.zeros(tp), np.zeros(tp), np.zeros(cap)
+        sp = SpeechOut(_dp(voi), _dp(tilt), _dp(pauses), cap, 0, 0, 0, 0, 0.0)
+        self.lib.sonar_fingerprint_speech_f64.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.POINTER(FpParams),
+                                                          C.POINTER(FpOut), C.POINTER(SpeechOut)]
+        self._chk(self.lib.sonar_fingerprint_speech_f64(self.ctx, _dp(pcm), pcm.size, C.byref(p), C.byref(out), C.byref(sp)))
+        nf, npause = int(sp.n_frames), int(sp.n_pause)
+        speech = {"is_speech": bool(sp.is_speech), "speech_rate": float(sp.speech_rate),
+                  "voicing_probability": voi[:nf].copy(), "spectral_tilt": tilt[:nf].copy(),
+                  "pause_duration": pauses[:min(npause, cap)].copy(), "n_pause": npause}
+        return self._finish_fp(sizes, arrays, out), speech
 
     def alloc_batch_outputs(self, lengths, p: FpParams):
         """Caller-owned output buffers for fingerprint_batch (reusable across calls, like the Go shim's slices)."""
@@ -517,6 +555,36 @@ class SonarLib:
         outs = (XcorrSummary * n)()
         self._chk(self.lib.sonar_xcorr_batch_f64(self.ctx, pa, la, pb, lb, n, max_lag, pc, outs))
         return corrs, list(outs)
+
+    def nccl_unique_id(self) -> bytes:
+        """sonar_nccl_unique_id: 128 bytes rank 0 hands to every rank (any transport)."""
+        buf = C.create_string_buffer(128)
+        self._chk(self.lib.sonar_nccl_unique_id(buf, 128))
+        return buf.raw
+
+    def nccl_init(self, world: int, rank: int, uid: bytes):
+        self._chk(self.lib.sonar_nccl_init(self.ctx, world, rank, uid))
+
+    def nccl_shutdown(self):
+        self._chk(self.lib.sonar_nccl_shutdown(self.ctx))
+
+    def xcorr_lag_sharded(self, a, b, max_lag, want_corr=False, dev_ptrs=None):
+        """sonar_xcorr_lag_sharded: this rank's lags + one ncclAllGather + the peak analysis, inside the library.
+        dev_ptrs = (a_ptr, na, b_ptr, nb): the sequences are already on the device."""
+        s = XcorrSummary()
+        corr = None
+        if dev_ptrs is not None:
+            pa, na, pb, nb = dev_ptrs
+            if want_corr:
+                corr = np.zeros(2 * max(0, min(max_lag, na - 1, nb - 1)) + 1)
+            self._chk(self.lib.sonar_xcorr_lag_sharded(self.ctx, pa, na, pb, nb, max_lag, 1, _dp(corr), C.byref(s)))
+        else:
+            a, b = _f64(a), _f64(b)
+            if want_corr:
+                corr = np.zeros(2 * max(0, min(max_lag, a.size - 1, b.size - 1)) + 1)
+            self._chk(self.lib.sonar_xcorr_lag_sharded(self.ctx, a.ctypes.data, a.size, b.ctypes.data, b.size, max_lag, 0,
+                                                       _dp(corr), C.byref(s)))
+        return s, corr
 
     def xcorr_shard(self, a, b, max_lag, lo, hi):
         a, b = _f64(a), _f64(b)

@@ -63,6 +63,9 @@ struct FpPlan {  // immutable once built; cached per context keyed by the parame
   size_t blob_bytes = 0;
   size_t off_win2 = 0, off_tw1 = 0, off_wn = 0, off_xtab = 0, off_dct = 0, off_lift = 0, off_regions = 0,
          off_chunk_region = 0, off_hann = 0, off_zero = 0;
+  // float64 tables of the exact re-evaluation (spectral_exact.cu): window, go-dsp radix-2 factors, mel bin points,
+  // DCT-II, lifter; float32 1 / (sum of a filter's weights) for the fused kernel's weak-band test
+  size_t off_win64 = 0, off_fac64 = 0, off_melbins = 0, off_dct64 = 0, off_lift64 = 0, off_melinvw = 0;
   std::vector<MelRegion> h_regions;  // host copy of the mel region table (kernel eligibility checks)
   ~FpPlan();
 };
@@ -94,7 +97,23 @@ struct StftArgs {
   double* mag;
   double* phase;
   double* cplx;
+  // frames whose discrete or ill-conditioned results need float64 (rolloff bin within the FP32 error of the 85 %
+  // threshold, bins or mel bands at the FP32 transform's noise floor, silence): per stream a list [count, t...] of
+  // ints, `xlist_stride` ints apart, re-evaluated in the reference's order by spectral_exact.cu.  nullptr: no lists.
+  int* xlist;
+  int64_t xlist_stride;
+  unsigned* work_counter;  // zeroed before the launch: the persistent kernel's warps draw their runs from it (stft_v3.cu)
+  const double* win64;
+  const double2* fac64;
+  const int* melbins;
+  const double* dct64;
+  const double* lift64;
+  const float* mel_invw;
+  int algo_sr, N;
 };
+
+// exact float64 re-evaluation of the frames the fused kernel listed (spectral_exact.cu)
+int launch_spectral_exact(const StftArgs& a, cudaStream_t st);
 
 int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out);
 int launch_stft_features(const FpPlan& plan, StftArgs& a, bool spectrum_mode, cudaStream_t st);
@@ -117,6 +136,12 @@ struct FpShape {
   bool temporal = false;
   int64_t o_env = 0, o_att = 0, o_part = 0;
   int64_t o_wpart = 0, wpart_doubles = 0;  // scratch of the frame walk's loudness block parts (timedomain.cu)
+  // speech-specific group (only with SONAR_FP_ENABLE_SPEECH): the gate (4 doubles) and the tilt array behind the public
+  // layout, the gate's partial sums in the scratch
+  bool speech = false;
+  int64_t o_sgate = 0, o_tilt = 0, n_speech_frames = 0, o_spart = 0;
+  int64_t o_work = 0;   // scratch of the fused STFT kernel: its work counter (stream 0's copy is used)
+  int64_t o_xlist = 0;  // scratch of the fused STFT kernel: 1 + T ints (count, frames re-evaluated in float64; spectral_exact.cu)
   int64_t o_ylist = 0;  // scratch of the pitch detector: 1 + Tp ints (count, frames re-evaluated exactly; yin32.cu)
 };
 
@@ -154,7 +179,13 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
                const double* hann_dev, double* feat, int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
                int64_t o_voicing, int64_t o_hratio, int64_t o_inharm, int64_t o_tonal, double* scratch,
                int64_t scratch_stride, cudaStream_t st, cudaStream_t track_st = nullptr, cudaEvent_t fork = nullptr,
-               cudaEvent_t join = nullptr, bool* forked = nullptr, int* lists = nullptr, int64_t list_stride = 0);
+               cudaEvent_t join = nullptr, bool* forked = nullptr, int* lists = nullptr, int64_t list_stride = 0,
+               const double* speech_gate = nullptr, int64_t gate_stride = 0);
+// speech-specific group (speech.cu): IsSpeech gate (4 doubles at o_gate: flag, zcr, rms, periodicity) and spectral tilt
+size_t speech_gate_scratch_doubles();
+int launch_speech(const double* pcm, int64_t n, int64_t stride, int n_streams, double alpha, int sr, int64_t nf, double* feat,
+                  int64_t feat_stride, int64_t o_gate, int64_t o_tilt, double* scratch, int64_t scratch_stride,
+                  cudaStream_t st);
 // FP32 difference function on the packed pipe + exact float64 re-evaluation of the borderline frames (yin32.cu);
 // lists: per stream 1 + Tp ints, list_stride ints apart, counts zeroed by the caller
 int launch_yin32(const double* pcm, int64_t stride, int n_streams, double alpha, int sr, int64_t Tp, const double* hann_dev,
@@ -290,6 +321,20 @@ struct sonar_ctx {
   std::mutex prof_mu;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> prof_pool;
+  // where the most recent fingerprint batch keeps its lists of exactly re-evaluated frames (sonar_fp_exact_counts)
+  struct LastLists {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    const double* tmp = nullptr;
+    int64_t tstride = 0, o_xlist = 0, o_ylist = 0;
+    int ns = 0;
+  } last_lists;
+  // lag-sharded cross-correlation over the ranks of a job (nccl_shard.cu): an NCCL communicator created from a unique id
+  // the host distributes (sonar_nccl_init), and the resident workspace of the sharded call
+  void* nccl_comm = nullptr;
+  int nccl_world = 1, nccl_rank = 0;
+  void* shard_buf = nullptr;
+  size_t shard_bytes = 0;
 };
 
 namespace sonar {
@@ -299,6 +344,7 @@ namespace sonar {
 void prof_begin(const char* kernel, cudaStream_t st);
 void prof_end();
 void set_current_ctx(sonar_ctx* c);
+void nccl_release(sonar_ctx* ctx);  // nccl_shard.cu
 // speech.go:370-408 temporal block (temporal.cu)
 int fp_validate(const sonar_fp_params* p);
 int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s);

@@ -173,6 +173,11 @@ void sonar_destroy(sonar_ctx* ctx) {
   if (!ctx) return;
   int restore = 0;
   cudaGetDevice(&restore);
+  if (!ctx->devs.empty()) {
+    cudaSetDevice(ctx->devs[0].device);
+    cudaDeviceSynchronize();
+    sonar::nccl_release(ctx);
+  }
   for (auto& d : ctx->devs) {
     cudaSetDevice(d.device);
     cudaDeviceSynchronize();

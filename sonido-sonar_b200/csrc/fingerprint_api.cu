@@ -8,6 +8,7 @@
 //   ComputeSTFTBatch (batch form)  fingerprint/analyzers/spectral.go:234-285
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <thread>
@@ -52,8 +53,6 @@ int get_plan(sonar_ctx* ctx, int device, const sonar_fp_params* p, std::shared_p
 
 int fp_validate(const sonar_fp_params* p) {
   if (p->call_sample_rate <= 0) return set_error(SONAR_ERR_INVALID, "sample rate must be positive");  // speech.go:143
-  if (p->enable & SONAR_FP_ENABLE_SPEECH)
-    return set_error(SONAR_ERR_UNSUPPORTED, "speech feature group is outside this path's scope");
   if (!stft_supported(p->window_size))
     return set_error(SONAR_ERR_UNSUPPORTED, "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
   return SONAR_OK;
@@ -77,6 +76,19 @@ int fp_shape(const sonar_fp_params* p, int64_t n, FpShape* s) {
   s->tmp_doubles_per_stream += (size_t)s->wpart_doubles;
   s->o_ylist = (int64_t)s->tmp_doubles_per_stream;
   s->tmp_doubles_per_stream += (size_t)((s->sz.n_pitch_frames + 2) / 2 + 1);
+  s->o_work = (int64_t)s->tmp_doubles_per_stream;
+  s->tmp_doubles_per_stream += 2;
+  s->o_xlist = (int64_t)s->tmp_doubles_per_stream;  // 1 + T ints: frames re-evaluated in float64 (spectral_exact.cu)
+  s->tmp_doubles_per_stream += (size_t)((s->sz.n_frames + 2) / 2 + 1);
+  s->speech = (p->enable & SONAR_FP_ENABLE_SPEECH) != 0;
+  if (s->speech) {  // extractSpeechFeatures (speech.go:271-317): gate + tilt behind the public layout
+    s->n_speech_frames = s->sz.n_pitch_frames;  // (N-1024)/512+1, clamped at 0 (speech.go:530-532, 552-554)
+    s->o_sgate = s->L.total;
+    s->o_tilt = s->o_sgate + 4;
+    s->L.total = (s->o_tilt + s->n_speech_frames + 1) & ~(int64_t)1;
+    s->o_spart = (int64_t)s->tmp_doubles_per_stream;
+    s->tmp_doubles_per_stream += speech_gate_scratch_doubles();
+  }
   s->temporal = (p->enable & SONAR_FP_ENABLE_TEMPORAL) != 0;
   if (s->temporal) {
     s->o_env = s->L.total;
@@ -155,12 +167,38 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
   a.o_flux = L.spectral_flux;
   a.o_low = L.low_energy_ratio;
   a.o_high = L.high_energy_ratio;
-  rc = launch_stft_features(*plan, a, false, st);
-  if (rc) return rc;
-  if (!a.mfcc_on) {
-    rc = launch_fill_strided(feat_dev + L.mfcc, T * sh.sz.n_mfcc, L.total, ns, 0.0, st);
+  // The fused STFT kernel and the float64 re-evaluation of the frames it lists.  Enqueued AFTER the frame walk and the
+  // pitch detector: the alignment branch of the pair pipeline only waits for the walk's energies, so it starts ~7 ms
+  // earlier and runs beside the pitch kernel (whose CTAs leave room on an SM; the STFT kernel's fill the register file).
+  auto run_stft = [&]() -> int {
+    // only the third-generation kernel lists frames (the other geometries keep their stated FP32 bounds)
+    a.xlist = stft_v3_eligible(*plan, a) ? reinterpret_cast<int*>(tmp_dev + sh.o_xlist) : nullptr;
+    a.xlist_stride = 2 * tstride;
+    a.win64 = reinterpret_cast<const double*>(blob + plan->off_win64);
+    a.fac64 = reinterpret_cast<const double2*>(blob + plan->off_fac64);
+    a.melbins = reinterpret_cast<const int*>(blob + plan->off_melbins);
+    a.dct64 = reinterpret_cast<const double*>(blob + plan->off_dct64);
+    a.lift64 = reinterpret_cast<const double*>(blob + plan->off_lift64);
+    a.mel_invw = reinterpret_cast<const float*>(blob + plan->off_melinvw);
+    a.algo_sr = p->algo_sample_rate;
+    a.N = p->window_size;
+    a.work_counter = reinterpret_cast<unsigned*>(tmp_dev + sh.o_work);
+    rc = launch_fill_strided(tmp_dev + sh.o_work, 1, tstride, 1, 0.0, st);
     if (rc) return rc;
-  }
+    rc = launch_fill_strided(tmp_dev + sh.o_xlist, 1, tstride, ns, 0.0, st);  // empty lists
+    if (rc) return rc;
+    rc = launch_stft_features(*plan, a, false, st);
+    if (rc) return rc;
+    rc = launch_spectral_exact(a, st);  // the frames the fused kernel listed, in float64 and the reference's order
+    if (rc) return rc;
+    if (!a.mfcc_on) {
+      rc = launch_fill_strided(feat_dev + L.mfcc, T * sh.sz.n_mfcc, L.total, ns, 0.0, st);
+      if (rc) return rc;
+    }
+    return SONAR_OK;
+  };
+  static const bool stft_first = std::getenv("SONAR_STFT_FIRST") != nullptr;  // diagnostic: the r01 order
+  if (stft_first && (rc = run_stft())) return rc;
 
   // exact FP64 walks over the pre-emphasised PCM: short-time energy (+entropy) and ZCR
   const bool same_grid = !short_win && (Te == T) && p->energy_frame == p->window_size && p->energy_hop == p->hop_size;
@@ -198,6 +236,11 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
 
   // harmonic block (speech.go:464-509).  Enqueued before the variance / temporal kernels so that its tracker, a
   // sequential walk with one warp per stream, runs on the side stream beside them.
+  if (sh.speech) {  // before the pitch tracker: its first pass depends on the gate
+    rc = launch_speech(pcm_dev, n, stride, ns, p->pre_emph_alpha, p->algo_sample_rate, sh.n_speech_frames, feat_dev, L.total,
+                       sh.o_sgate, sh.o_tilt, tmp_dev + sh.o_spart, tstride, st);
+    if (rc) return rc;
+  }
   bool forked = false;
   {
     const double* hann = reinterpret_cast<const double*>(blob + plan->off_hann);
@@ -206,9 +249,11 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
     rc = launch_yin(pcm_dev, stride, ns, p->pre_emph_alpha, n < 1024 ? 0 : p->algo_sample_rate, Tp, hann, feat_dev, L.total,
                     L.pitch_estimate, L.pitch_confidence, L.voicing_strength, L.harmonic_ratio, L.inharmonicity_ratio,
                     L.tonal_centroid, tmp_dev, tstride, st, side ? side->st3 : nullptr, side ? side->fork : nullptr,
-                    side ? side->join : nullptr, &forked, reinterpret_cast<int*>(tmp_dev + sh.o_ylist), 2 * tstride);
+                    side ? side->join : nullptr, &forked, reinterpret_cast<int*>(tmp_dev + sh.o_ylist), 2 * tstride,
+                    sh.speech ? feat_dev + sh.o_sgate : nullptr, L.total);
     if (rc) return rc;
   }
+  if (!stft_first && (rc = run_stft())) return rc;
 
   if (Te >= 2) {
     rc = launch_variance(feat_dev + L.short_time_energy, Te, L.total, ns, feat_dev + L.scalars, L.total, st);
@@ -239,6 +284,13 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
   }
 
   if (side && forked) SONAR_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  ctx->last_lists.device = device;
+  ctx->last_lists.st = st;
+  ctx->last_lists.tmp = tmp_dev;
+  ctx->last_lists.tstride = tstride;
+  ctx->last_lists.o_xlist = sh.o_xlist;
+  ctx->last_lists.o_ylist = sh.o_ylist;
+  ctx->last_lists.ns = ns;
   return SONAR_OK;
 }
 
@@ -288,6 +340,62 @@ void scatter_block(const double* f, const FpShape& sh, sonar_fp_out* o) {
   }
 }
 
+// SpeechFeatures of one stream from its feature block (extractSpeechFeatures, speech.go:271-317): the voicing sweep is the
+// detector's voicing on the same frames as the harmonic block, the pauses and the speech rate are O(Te) scans of the
+// short-time energies (feature-sized, host side: speech.go:586-655,779-797).
+void scatter_speech(const double* f, const FpShape& sh, const sonar_fp_params* p, int64_t n, sonar_speech_out* o) {
+  const auto& L = sh.L;
+  o->is_speech = f[sh.o_sgate] != 0.0 ? 1 : 0;
+  o->reserved = 0;
+  o->n_frames = 0;
+  o->n_pause = 0;
+  o->speech_rate = 0.0;
+  if (!o->is_speech) return;  // speech.go:281-291: empty arrays, rate 0
+  const int64_t nf = sh.n_speech_frames, Te = sh.sz.n_energy_frames;
+  o->n_frames = nf;
+  if (o->voicing_probability && nf > 0) std::memcpy(o->voicing_probability, f + L.voicing_strength, sizeof(double) * (size_t)nf);
+  if (o->spectral_tilt && nf > 0) std::memcpy(o->spectral_tilt, f + sh.o_tilt, sizeof(double) * (size_t)nf);
+  const double* e = f + L.short_time_energy;
+  double silence = 0.0, thr = 0.0;
+  if (Te > 0) {  // sortedEnergies[len / 10] (the reference bubble-sorts a copy; the order statistic is the same value)
+    std::vector<double> srt(e, e + Te);
+    std::nth_element(srt.begin(), srt.begin() + Te / 10, srt.end());
+    thr = srt[(size_t)(Te / 10)];
+    int64_t silent = 0;
+    for (int64_t i = 0; i < Te; i++)
+      if (e[i] <= thr) silent++;
+    silence = (double)silent / (double)Te;
+  }
+  const double dur = (double)n / (double)p->algo_sample_rate;  // estimateSpeechRate :779-797
+  const double speech_time = dur * (1.0 - silence);
+  o->speech_rate = speech_time > 0 ? 4.0 * speech_time / dur : 3.0;
+  if (Te > 0) {  // extractPauseDurations :586-641
+    const double frame_time = (double)p->energy_hop / (double)p->algo_sample_rate;
+    bool in_pause = false;
+    int64_t start = 0, np = 0;
+    auto emit = [&](int64_t end) {
+      const double d = (double)(end - start) * frame_time;
+      if (d > 0.1) {
+        if (o->pause_duration && np < o->pause_cap) o->pause_duration[np] = d;
+        np++;
+      }
+    };
+    for (int64_t i = 0; i < Te; i++) {
+      if (e[i] <= thr) {
+        if (!in_pause) {
+          in_pause = true;
+          start = i;
+        }
+      } else if (in_pause) {
+        emit(i);
+        in_pause = false;
+      }
+    }
+    if (in_pause) emit(Te);
+    o->n_pause = np;
+  }
+}
+
 namespace {
 
 struct Chunk {  // consecutive streams of one device with identical length
@@ -305,7 +413,7 @@ struct DeviceJob {
 // the H2D copy of chunk k+1 and k+2 overlaps the kernels and the D2H of chunk k, and the host-side scatter of
 // a finished chunk into the caller's arrays overlaps the GPU work queued on the other slots.
 void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, const std::vector<Chunk>* chunks,
-                      const sonar_fp_params* p, int fmt, sonar_fp_out* outs, DeviceJob* job) {
+                      const sonar_fp_params* p, int fmt, sonar_fp_out* outs, DeviceJob* job, sonar_speech_out* speech) {
   set_current_ctx(ctx);
   auto fail = [&](int rc) {
     job->rc = rc;
@@ -321,7 +429,10 @@ void run_device_batch(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm, con
     Slot& s = dev->slot[si];
     SONAR_CUDA(cudaEventSynchronize(s.done));
     const double* h = static_cast<const double*>(s.h_out.p);
-    for (size_t i = 0; i < c->ids.size(); i++) scatter_block(h + (int64_t)i * c->sh.L.total, c->sh, &outs[c->ids[i]]);
+    for (size_t i = 0; i < c->ids.size(); i++) {
+      scatter_block(h + (int64_t)i * c->sh.L.total, c->sh, &outs[c->ids[i]]);
+      if (speech && c->sh.speech) scatter_speech(h + (int64_t)i * c->sh.L.total, c->sh, p, c->n, &speech[c->ids[i]]);
+    }
     pending[si] = nullptr;
     return SONAR_OK;
   };
@@ -383,7 +494,7 @@ using namespace sonar;
 extern "C" {
 
 static int fingerprint_batch(sonar_ctx* ctx, const double* const* pcm, int fmt, const int64_t* n, int n_streams,
-                             const sonar_fp_params* p, sonar_fp_out* outs);
+                             const sonar_fp_params* p, sonar_fp_out* outs, sonar_speech_out* speech = nullptr);
 
 int sonar_fingerprint_batch_f64(sonar_ctx* ctx, const double* const* pcm, const int64_t* n, int n_streams,
                                 const sonar_fp_params* p, sonar_fp_out* outs) {
@@ -398,7 +509,7 @@ int sonar_fingerprint_batch_pcm(sonar_ctx* ctx, const void* const* pcm, int samp
 }
 
 static int fingerprint_batch(sonar_ctx* ctx, const double* const* pcm, int fmt, const int64_t* n, int n_streams,
-                             const sonar_fp_params* p, sonar_fp_out* outs) {
+                             const sonar_fp_params* p, sonar_fp_out* outs, sonar_speech_out* speech) {
   if (!ctx || !p || (n_streams > 0 && (!pcm || !n || !outs)))
     return set_error(SONAR_ERR_INVALID, "audio data cannot be nil");  // fingerprint.go:139
   if (n_streams <= 0) return SONAR_OK;
@@ -424,11 +535,11 @@ static int fingerprint_batch(sonar_ctx* ctx, const double* const* pcm, int fmt, 
   }
   std::vector<DeviceJob> jobs(nd);
   if (nd == 1) {
-    run_device_batch(ctx, &ctx->devs[0], pcm, &per_dev[0], p, fmt, outs, &jobs[0]);
+    run_device_batch(ctx, &ctx->devs[0], pcm, &per_dev[0], p, fmt, outs, &jobs[0], speech);
   } else {
     std::vector<std::thread> th;
     for (int d = 0; d < nd; d++)
-      th.emplace_back(run_device_batch, ctx, &ctx->devs[d], pcm, &per_dev[d], p, fmt, outs, &jobs[d]);
+      th.emplace_back(run_device_batch, ctx, &ctx->devs[d], pcm, &per_dev[d], p, fmt, outs, &jobs[d], speech);
     for (auto& t : th) t.join();
     cudaSetDevice(ctx->devs[0].device);
   }
@@ -437,11 +548,41 @@ static int fingerprint_batch(sonar_ctx* ctx, const double* const* pcm, int fmt, 
   return SONAR_OK;
 }
 
+int sonar_fp_exact_counts(sonar_ctx* ctx, int64_t* spectral, int64_t* pitch) {
+  if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
+  std::lock_guard<std::mutex> call_lock(ctx->call_mu);
+  const auto& ll = ctx->last_lists;
+  if (spectral) *spectral = 0;
+  if (pitch) *pitch = 0;
+  if (ll.device < 0 || !ll.tmp || ll.ns <= 0) return SONAR_OK;
+  SONAR_CUDA(cudaSetDevice(ll.device));
+  SONAR_CUDA(cudaStreamSynchronize(ll.st));
+  std::vector<int> cx((size_t)ll.ns), cy((size_t)ll.ns);
+  SONAR_CUDA(cudaMemcpy2D(cx.data(), sizeof(int), ll.tmp + ll.o_xlist, sizeof(double) * (size_t)ll.tstride, sizeof(int),
+                          (size_t)ll.ns, cudaMemcpyDeviceToHost));
+  SONAR_CUDA(cudaMemcpy2D(cy.data(), sizeof(int), ll.tmp + ll.o_ylist, sizeof(double) * (size_t)ll.tstride, sizeof(int),
+                          (size_t)ll.ns, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < ll.ns; i++) {
+    if (spectral) *spectral += cx[i];
+    if (pitch) *pitch += cy[i];
+  }
+  return SONAR_OK;
+}
+
 int sonar_fingerprint_f64(sonar_ctx* ctx, const double* pcm, int64_t n, const sonar_fp_params* p,
                           sonar_fp_out* out) {
   if (!ctx || !pcm || !p || !out) return set_error(SONAR_ERR_INVALID, "audio data cannot be nil");
   const double* ptrs[1] = {pcm};
   return sonar_fingerprint_batch_f64(ctx, ptrs, &n, 1, p, out);
+}
+
+int sonar_fingerprint_speech_f64(sonar_ctx* ctx, const double* pcm, int64_t n, const sonar_fp_params* p, sonar_fp_out* out,
+                                 sonar_speech_out* speech) {
+  if (!ctx || !pcm || !p || !out || !speech) return set_error(SONAR_ERR_INVALID, "audio data cannot be nil");
+  sonar_fp_params q = *p;
+  q.enable |= SONAR_FP_ENABLE_SPEECH;
+  const double* ptrs[1] = {pcm};
+  return fingerprint_batch(ctx, ptrs, SONAR_PCM_F64, &n, 1, &q, out, speech);
 }
 
 int sonar_fingerprint_batch_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n, int64_t stride, int n_streams,
@@ -453,8 +594,8 @@ int sonar_fingerprint_batch_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n
   set_current_ctx(ctx);
   int rc = fp_validate(p);
   if (rc) return rc;
-  if (p->enable & SONAR_FP_ENABLE_TEMPORAL)
-    return set_error(SONAR_ERR_UNSUPPORTED, "temporal features are not part of the device layout");
+  if (p->enable & (SONAR_FP_ENABLE_TEMPORAL | SONAR_FP_ENABLE_SPEECH))
+    return set_error(SONAR_ERR_UNSUPPORTED, "temporal / speech features are not part of the device layout");
   FpShape sh;
   rc = fp_shape(p, n, &sh);
   if (rc) return rc;

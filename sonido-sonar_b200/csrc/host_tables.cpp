@@ -298,6 +298,12 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
   plan->off_chunk_region = take(sizeof(int) * R1);
   plan->off_hann = take(sizeof(double) * 1024);
   plan->off_zero = take(sizeof(double) * N);  // one frame of silence: the lone incomplete frame of an input shorter than the window
+  plan->off_win64 = take(sizeof(double) * N);
+  plan->off_fac64 = take(sizeof(double2) * N);
+  plan->off_melbins = take(sizeof(int) * (nm + 2));
+  plan->off_dct64 = take(sizeof(double) * (size_t)nc * nm);
+  plan->off_lift64 = take(sizeof(double) * nc);
+  plan->off_melinvw = take(sizeof(float) * kMaxMel);
   plan->blob_bytes = off;
   std::vector<unsigned char> host(off, 0);
   std::memcpy(host.data() + plan->off_win2, win2.data(), sizeof(float2) * M);
@@ -312,6 +318,42 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
   {  // un-normalised symmetric Hann(1024) of the pitch detector (tonal/pitch_detection.go:318-324)
     double* h = reinterpret_cast<double*>(host.data() + plan->off_hann);
     for (int i = 0; i < 1024; i++) h[i] = 0.5 * (1.0 - std::cos(2.0 * M_PI * (double)i / 1023.0));
+  }
+  {  // float64 tables of the exact re-evaluation, built the way the reference's constructors build them
+    std::memcpy(host.data() + plan->off_win64, w.data(), sizeof(double) * N);
+    // go-dsp fft/radix2.go getRadix2Factors: the table of size i takes its even entries from the table of size i / 2
+    // and evaluates the odd ones as sincos(-2 pi / i * k); the size-4 table is exact
+    std::vector<double2> prev = {make_double2(1, 0), make_double2(0, -1), make_double2(-1, 0), make_double2(0, 1)};
+    for (int i = 8; i <= N; i <<= 1) {
+      std::vector<double2> cur(i);
+      for (int k = 0; k < i; k += 2) cur[k] = prev[k / 2];
+      for (int k = 1; k < i; k += 2) {
+        const double ang = -2 * M_PI / (double)i * (double)k;
+        cur[k] = make_double2(std::cos(ang), std::sin(ang));
+      }
+      prev.swap(cur);
+    }
+    std::memcpy(host.data() + plan->off_fac64, prev.data(), sizeof(double2) * prev.size());
+    int* mb = reinterpret_cast<int*>(host.data() + plan->off_melbins);
+    for (int i = 0; i < nm + 2; i++) mb[i] = (int)bins[i];
+    double* d64 = reinterpret_cast<double*>(host.data() + plan->off_dct64);
+    for (int k = 0; k < nc; k++)  // mfcc.go:194-212
+      for (int n = 0; n < nm; n++) {
+        double v = std::cos(M_PI * (double)k * ((double)n + 0.5) / (double)nm);
+        if (k == 0)
+          v *= std::sqrt(1.0 / (double)nm);
+        else
+          v *= std::sqrt(2.0 / (double)nm);
+        d64[(size_t)k * nm + n] = v;
+      }
+    double* l64 = reinterpret_cast<double*>(host.data() + plan->off_lift64);
+    for (int i = 0; i < nc; i++)  // mfcc.go:230-245; multiplying by 1.0 is exact
+      l64[i] = (i == 0 || !p->use_liftering) ? 1.0 : 1.0 + (lifter / 2.0) * std::sin(M_PI * (double)i / lifter);
+    float* iw = reinterpret_cast<float*>(host.data() + plan->off_melinvw);
+    for (int f = 0; f < kMaxMel; f++) {  // a triangle's weights sum to (r - l) / 2
+      const double wsum = (f < nm && !empty_bank) ? 0.5 * (double)(bins[f + 2] - bins[f]) : 0.0;
+      iw[f] = wsum > 0.0 ? (float)(1.0 / wsum) : 0.f;
+    }
   }
   SONAR_CUDA(cudaMalloc(&plan->d_blob, off));
   SONAR_CUDA(cudaMemcpy(plan->d_blob, host.data(), off, cudaMemcpyHostToDevice));

@@ -41,8 +41,17 @@ constexpr int kRunOut3 = kSeg3 * kRun3 - 1;  // first of which only warms the fl
 constexpr unsigned kFull3 = 0xffffffffu;
 constexpr int kTileRow = 34;          // exchange tile row stride (float2): 16-byte rows, conflict-free LDS.128
 constexpr int kSlots3 = 24;           // lane-private mel slots (float2: both frames of a pack; alias the tile in the scan)
-constexpr int kRaw3 = 16;             // raw sums parked per frame
+constexpr int kRaw3 = 12;             // raw sums parked per frame
 constexpr int kMaxContrib3 = 12;      // lanes that may hold a part of one mel filter
+// ---- frames handed to the float64 re-evaluation (spectral_exact.cu) ---------------------------------------------
+// The FP32 transform leaves an absolute error of a few 1e-7 of the frame's RMS spectral level on every bin (random, white;
+// kEta bounds it generously: 2^-21 of the RMS level ~ 5 sigma, of the strongest bin where a bound must hold for sure).
+constexpr float kEta = 4.76837158e-7f;       // 2^-21
+constexpr int kExactBit = 0x40000000;        // set in the parked rolloff bin of a listed frame
+constexpr float kRollSum = 4e-6f;            // relative error of an FP32 cumulative sum of <= 1025 squares, with margin
+constexpr float kLogTau = 2e-5f;             // largest tolerated error bound of the mean of ln|X_k| (flatness; slope x 4)
+constexpr float kMelRatio = 9.2e-5f;         // (2 kEta / 1e-4)^2: a mel band this far below the mean level errs by > 1e-4 in ln E
+constexpr float kTinyMag = 1e-9f;            // magnitudes near the reference's 1e-10 validity threshold
 
 template <int LOGN, int HR_>
 struct V3G {
@@ -123,6 +132,11 @@ __device__ __forceinline__ float sqrt_fast3(float x) {  // MUFU; sqrt(0) = 0
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rsqrt_fast3(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float lg2_fast3(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -185,42 +199,15 @@ __device__ __forceinline__ void tw_apply(float2 (&v)[R], const float2* __restric
   }
 }
 
-// The frame's log-magnitude sums when some bin is <= 1e-10 (silence, digital zeros): bins below the threshold leave
-// the flatness mean and the slope regression (spectral_flatness.go:31-70, spectral_slope.go:42-51).  Rare and slow.
-template <class G>
-__device__ __noinline__ void slow_log_sums(const float* __restrict__ mrow2, const float* __restrict__ s_xtab, int lane,
-                                           float* __restrict__ out) {  // mrow2: the frame's component of the pair row
-  constexpr int BPL = G::BPL, M = G::M;
-  float sl = 0.f, sxy = 0.f, sxinv = 0.f, sxxinv = 0.f;
-  int ninv = 0;
-  for (int j = 0; j <= BPL; ++j) {
-    if (j == BPL && lane != 31) break;
-    const int k = BPL * lane + j;
-    const float m = mrow2[2 * ppos(k)], xv = s_xtab[spos(k)];
-    if (m > 1e-10f) {
-      const float l2 = lg2_fast3(m);
-      sl += l2;
-      sxy = fmaf(xv, l2, sxy);
-    } else if (k > 0) {
-      ++ninv;
-      sxinv += xv;
-      sxxinv = fmaf(xv, xv, sxxinv);
-    }
-  }
-  sl = warp_sum3(sl);
-  sxy = warp_sum3(sxy);
-  sxinv = warp_sum3(sxinv);
-  sxxinv = warp_sum3(sxxinv);
-  ninv = __reduce_add_sync(kFull3, ninv);
-  out[0] = sl, out[1] = sxy, out[2] = sxinv, out[3] = sxxinv, out[4] = __int_as_float(ninv);
-}
-
 // rolloff: first bin whose cumulative energy reaches 85 % (spectral_rolloff.go:19-55).  The lane whose range holds the
-// crossing is found from the prefix of the lanes' energies; its BPL (+1) bins are then scanned by the warp.
+// crossing is found from the prefix of the lanes' energies; its BPL (+1) bins are then scanned by the warp.  The choice is
+// safe when the threshold is further than `delta` (the bound on the FP32 error of cumulative sum minus threshold) from
+// the cumulative sums on both sides of the chosen bin; otherwise kExactBit is set and float64 decides.
 template <class G>
-__device__ __forceinline__ int rolloff_bin(const float* __restrict__ mrow2, float pre, float seg, float etot, int lane) {
+__device__ __forceinline__ int rolloff_bin(const float* __restrict__ mrow2, float pre, float seg, float etot, float delta,
+                                           int lane) {
   constexpr int BPL = G::BPL;
-  int rk = G::B - 1;
+  int rk = (G::B - 1) | kExactBit;
   const float target = 0.85f * etot;
   const float excl = pre - seg;
   const unsigned cb = __ballot_sync(kFull3, (pre >= target) && (excl < target || lane == 0));
@@ -235,8 +222,14 @@ __device__ __forceinline__ int rolloff_bin(const float* __restrict__ mrow2, floa
       const float up = __shfl_up_sync(kFull3, cum, o);
       if (lane >= o) cum += up;
     }
-    const unsigned hit = __ballot_sync(kFull3, lane < nbn && ex0 + cum >= target);
-    rk = BPL * cl + (hit ? __ffs(hit) - 1 : nbn - 1);
+    cum += ex0;
+    const unsigned hit = __ballot_sync(kFull3, lane < nbn && cum >= target);
+    const int h = hit ? __ffs(hit) - 1 : nbn - 1;
+    float below = __shfl_up_sync(kFull3, cum, 1);
+    if (lane == 0) below = ex0;
+    const float gap = fminf(cum - target, target - below);  // both positive at lane h when the search was clean
+    const float gh = __shfl_sync(kFull3, gap, h);
+    rk = (BPL * cl + h) | ((hit && gh > delta) ? 0 : kExactBit);
   }
   return rk;
 }
@@ -259,6 +252,7 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
   float* s_lift = reinterpret_cast<float*>(smem + L.lift);
   int* s_r0 = reinterpret_cast<int*>(smem + L.r0);
   __shared__ int s_ncontrib;
+  __shared__ float s_invw[kMaxMel];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* wb = smem + L.warp0 + (size_t)warp * L.per_warp;
@@ -287,6 +281,7 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
     s_whi[k] = 0.f;
   }
   if (threadIdx.x < 32) s_fmask[threadIdx.x] = 0u;
+  if (threadIdx.x < kMaxMel) s_invw[threadIdx.x] = a.mel_invw[threadIdx.x];
   if (threadIdx.x == 0) s_ncontrib = 0;
   if (lane == 0) macc[kZeroSlot] = make_float2(0.f, 0.f);
   __syncthreads();
@@ -350,7 +345,13 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
 #pragma unroll
   for (int v = 0; v < NV; ++v) woff[v] = ppos(k1 + KSTR * v) - KSTR * v;
 
-  for (int64_t run = (int64_t)blockIdx.x * kW3 + warp; run < a.total_runs; run += (int64_t)gridDim.x * kW3) {
+  // runs are handed out through a counter: a CTA that starts late (its SM was busy with another stream's kernel) simply
+  // takes fewer of them
+  for (;;) {
+    int64_t run = 0;
+    if (lane == 0) run = (int64_t)atomicAdd(a.work_counter, 1u);
+    run = __shfl_sync(kFull3, run, 0);
+    if (run >= a.total_runs) break;
     const int s = (int)(run / a.runs_per_stream);
     const int64_t t0 = (run % a.runs_per_stream) * (int64_t)kRunOut3;
     const int64_t tend = (t0 + kRunOut3 < T) ? t0 + kRunOut3 : T;
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
       __syncwarp();
       // ================= pass 2: radix-32 over the lanes of pass 1 ==========================================
       float fla = 0.f;  // this lane's part of the first frame's flux
+      float2 rinv = make_float2(0.f, 0.f);  // this lane's part of sum 1 / |X_k| of its pack's two frames
       {
         float2 z[32];
         const float4* rp = reinterpret_cast<const float4*>(tile + lane * kTileRow);
@@ -421,17 +423,26 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
           const float2 xb = __fadd2_rn(make_float2(zz.y, -zz.x), make_float2(pz.y, pz.x));
           const float2 qa = __fmul2_rn(xa, xa), qb = __fmul2_rn(xb, xb);
           const int e = woff[k2 % NV] + KSTR * k2;
-          const float ma = sqrt_fast3(qa.x + qa.y);
-          const float d = first_pack ? fmaxf(ma - oldb[2 * e], 0.f) : 0.f;
+          // |X| = q rsqrt(q): one MUFU gives the magnitude AND its reciprocal (the weak-bin test); the floor keeps
+          // q = 0 finite (|X| = 0, 1 / |X| = 1e18)
+          const float2 q = make_float2(qa.x + qa.y, qb.x + qb.y);
+          const float2 ri = make_float2(rsqrt_fast3(fmaxf(q.x, 1e-36f)), rsqrt_fast3(fmaxf(q.y, 1e-36f)));
+          const float2 m = __fmul2_rn(q, ri);
+          rinv = __fadd2_rn(rinv, ri);
+          const float d = first_pack ? fmaxf(m.x - oldb[2 * e], 0.f) : 0.f;
           fla = fmaf(d, d, fla);
-          row[e] = make_float2(ma, sqrt_fast3(qb.x + qb.y));
+          row[e] = m;
         }
         if (k1zero) {  // Z[M] pairs with itself
-          const float ma = fabsf(2.f * z[16].x);
-          const float d = first_pack ? fmaxf(ma - oldb[2 * nyq], 0.f) : 0.f;
+          const float2 m = make_float2(fabsf(2.f * z[16].x), fabsf(2.f * z[16].y));
+          rinv = __fadd2_rn(rinv, make_float2(__fdividef(1.f, fmaxf(m.x, 1e-18f)), __fdividef(1.f, fmaxf(m.y, 1e-18f))));
+          const float d = first_pack ? fmaxf(m.x - oldb[2 * nyq], 0.f) : 0.f;
           fla = fmaf(d, d, fla);
-          row[nyq] = make_float2(ma, fabsf(2.f * z[16].y));
+          row[nyq] = m;
         }
+#pragma unroll
+        for (int o = (PK == 1 ? 16 : 8); o >= 1; o >>= 1)  // over the lanes of the pack
+          rinv = __fadd2_rn(rinv, make_float2(__shfl_xor_sync(kFull3, rinv.x, o), __shfl_xor_sync(kFull3, rinv.y, o)));
       }
       // the next iteration's NEW rows start their trip from HBM now and join the ring at the end of the iteration
       double nx[NEW];
@@ -505,37 +516,33 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
         float2 sl = warp_sum3(ac.sl), sxy = warp_sum3(ac.sxy);
         const float2 fl = warp_sum3(ac.fl);
         const float mxa = warp_max3(ac.mxa), mxb = warp_max3(ac.mxb);
-        const float2 m00 = row[0];
-        float l2k0a = lg2_fast3(m00.x), l2k0b = lg2_fast3(m00.y), v0a = 1.f, v0b = 1.f;
-        float sxinva = 0.f, sxxinva = 0.f, sxinvb = 0.f, sxxinvb = 0.f;
-        int ninva = 0, ninvb = 0;
-        if (__any_sync(kFull3, !(ac.mn > 1e-10f))) {  // rare: redo the log sums of both frames with the threshold test
-          float* tmp = reinterpret_cast<float*>(macc);
-          __syncwarp();
-          slow_log_sums<G>(rowf, s_xtab, lane, tmp);
-          slow_log_sums<G>(rowf + 1, s_xtab, lane, tmp + 8);
-          sl = make_float2(tmp[0], tmp[8]);
-          sxy = make_float2(tmp[1], tmp[9]);
-          sxinva = tmp[2], sxxinva = tmp[3], ninva = __float_as_int(tmp[4]);
-          sxinvb = tmp[10], sxxinvb = tmp[11], ninvb = __float_as_int(tmp[12]);
-          v0a = m00.x > 1e-10f ? 1.f : 0.f;
-          v0b = m00.y > 1e-10f ? 1.f : 0.f;
-          l2k0a = v0a != 0.f ? l2k0a : 0.f;
-          l2k0b = v0b != 0.f ? l2k0b : 0.f;
-          __syncwarp();
-        }
-        const int rka = rolloff_bin<G>(rowf, pre.x, ac.seg.x, etot.x, lane);
-        const int rkb = rolloff_bin<G>(rowf + 1, pre.y, ac.seg.y, etot.y, lane);
+        const float mn = -warp_max3(-ac.mn);
+        const float2 ri = PK == 1 ? rinv : make_float2(__shfl_sync(kFull3, rinv.x, 16 * p), __shfl_sync(kFull3, rinv.y, 16 * p));
+        // float64 re-evaluation wanted (spectral_exact.cu): the mean of ln|X_k| cannot be trusted when
+        // kEta * RMS level * mean(1 / |X_k|) exceeds kLogTau, magnitudes near the 1e-10 validity threshold, silence, and
+        // anything not finite (the negated comparisons catch NaN)
+        const float clog = kLogTau * (float)B * sqrt_fast3((float)B) / kEta;
+        bool xa = !(ri.x * sqrt_fast3(etot.x) <= clog) || !(mn > kTinyMag) || !(etot.x > 0.f);
+        bool xb = !(ri.y * sqrt_fast3(etot.y) <= clog) || !(mn > kTinyMag) || !(etot.y > 0.f);
+        int rka = rolloff_bin<G>(rowf, pre.x, ac.seg.x, etot.x, 4.f * kEta * mxa * sm.x + kRollSum * etot.x, lane);
+        int rkb = rolloff_bin<G>(rowf + 1, pre.y, ac.seg.y, etot.y, 4.f * kEta * mxb * sm.y + kRollSum * etot.y, lane);
 
         __syncwarp();  // private mel slots visible
         // ---- ln + DCT-II + lifter (mfcc.go:136-157), both frames ----
         if (a.mfcc_on) {
+          float2 dens = make_float2(FLT_MAX, FLT_MAX);  // smallest mean energy density of a mel band
           for (int f = lane; f < a.n_mel; f += 32) {
             float2 v = make_float2(0.f, 0.f);
             for (int i = 0; i < ncontrib; ++i) v = pk::add(v, wbf2[s_moff[i * kMaxMel + f]]);
             macc[f] = make_float2(v.x > 0.f ? __logf(v.x) : -23.025850929940457f,
                                   v.y > 0.f ? __logf(v.y) : -23.025850929940457f);  // ln(1e-10)
+            const float iw = s_invw[f];
+            if (iw > 0.f) dens = make_float2(fminf(dens.x, v.x * iw), fminf(dens.y, v.y * iw));
           }
+          // a band whose level is below kMelRatio of the frame's mean level sits in the transform's noise: ln E errs by > 1e-4
+          const float lim = kMelRatio / (float)B;
+          xa = xa || __any_sync(kFull3, !(dens.x >= lim * etot.x));
+          xb = xb || __any_sync(kFull3, !(dens.y >= lim * etot.y));
           __syncwarp();
           // coefficient c by the lane pair (2c, 2c+1): each half sums every other filter
           const int nmp = a.n_mel | 1;
@@ -556,15 +563,15 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
         if (lane == 0) {
           const int slot = (int)(ta - first) & (kRun3 - 1);  // position inside the 32-frame segment
           float4* rs = reinterpret_cast<float4*>(rawsum + slot * kRaw3);
+          if (xa) rka |= kExactBit;
+          if (xb) rkb |= kExactBit;
           rs[0] = make_float4(sm.x, kc.x, etot.x, __int_as_float(rka));
-          rs[1] = make_float4(bw.x, sl.x, __int_as_float(ninva), mxa);
-          rs[2] = make_float4(sxy.x, l2k0a, sxinva, sxxinva);
-          rs[3] = make_float4(fl.x, plow.x, v0a, 0.f);
+          rs[1] = make_float4(bw.x, sl.x, sxy.x, mxa);
+          rs[2] = make_float4(fl.x, plow.x, 0.f, 0.f);
           if (slot + 1 < kRun3) {
-            rs[4] = make_float4(sm.y, kc.y, etot.y, __int_as_float(rkb));
-            rs[5] = make_float4(bw.y, sl.y, __int_as_float(ninvb), mxb);
-            rs[6] = make_float4(sxy.y, l2k0b, sxinvb, sxxinvb);
-            rs[7] = make_float4(fl.y, plow.y, v0b, 0.f);
+            rs[3] = make_float4(sm.y, kc.y, etot.y, __int_as_float(rkb));
+            rs[4] = make_float4(bw.y, sl.y, sxy.y, mxb);
+            rs[5] = make_float4(fl.y, plow.y, 0.f, 0.f);
           }
         }
         __syncwarp();  // private slots / macc reused by the next pack
@@ -584,19 +591,21 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
         const int64_t t = first + (int64_t)kRun3 * seg + lane;
         if (t >= t0 && t < tend) {
           const float4* rs4 = reinterpret_cast<const float4*>(rawsum + lane * kRaw3);
-          const float4 r0 = rs4[0], r1 = rs4[1], r2 = rs4[2], r3 = rs4[3];
-          const float sm = r0.x, kc = r0.y, etot = r0.z, bw = r1.x, sl = r1.y, mx = r1.w, sxy = r2.x, l2k0 = r2.y,
-                      sxinv = r2.z, sxxinv = r2.w, fl = r3.x, plow = r3.y, val0 = r3.z;
-          const int rk = __float_as_int(r0.w), ninv = __float_as_int(r1.z);
+          const float4 r0 = rs4[0], r1 = rs4[1], r2 = rs4[2];
+          const float sm = r0.x, kc = r0.y, etot = r0.z, bw = r1.x, sl = r1.y, sxy = r1.z, mx = r1.w, fl = r2.x, plow = r2.y;
+          const int rkx = __float_as_int(r0.w), rk = rkx & ~kExactBit;
+          if ((rkx & kExactBit) && a.xlist) {  // listed for spectral_exact.cu, which overwrites what is stored below
+            int* lst = a.xlist + (int64_t)s * a.xlist_stride;
+            lst[1 + atomicAdd(lst, 1)] = (int)t;
+          }
           const double fs = a.freq_scale;
           const double dsm = (double)sm;
           fo[a.o_centroid + t] = (double)kc * fs;
           fo[a.o_rolloff + t] = etot > 0.f ? (double)rk * fs : 0.0;
           fo[a.o_bandwidth + t] = sm > 0.f ? sqrt((double)bw / dsm) * fs : 0.0;
-          const float cnt = (float)(B - 1 - ninv) + val0;  // bins with m > 1e-10 (spectral_flatness.go:31-70)
           double flat = 0.0;
-          if (cnt > 0.f) {
-            const double gm = exp2((double)sl / (double)cnt);
+          {  // every bin counts: frames with a magnitude near 1e-10 are listed (spectral_flatness.go:31-70)
+            const double gm = exp2((double)sl / (double)B);
             const double am = dsm / (double)B;
             if (am > 1e-10) {
               flat = gm / am;
@@ -607,15 +616,10 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
           const double rms = sqrt((double)etot / (double)B);
           fo[a.o_crest + t] = rms > 0.0 ? (double)mx / rms : 0.0;
           double slope = 0.0;
-          if (a.slope_on) {
+          if (a.slope_on) {  // sum x = 0 for the centred abscissae (spectral_slope.go:42-64)
             const double LG = 0.30102999566398120;  // log10(2)
-            const double n = a.slope_ntot - (double)ninv;
-            if (n >= 2.0) {
-              const double sx = -(double)sxinv, sxx = a.slope_xxtot - (double)sxxinv;
-              const double sy = LG * ((double)sl - (double)l2k0), sxyd = LG * (double)sxy;
-              const double den = n * sxx - sx * sx;
-              if (den != 0.0) slope = (n * sxyd - sx * sy) / den;
-            }
+            const double n = a.slope_ntot;
+            if (n >= 2.0 && a.slope_xxtot != 0.0) slope = LG * (double)sxy / a.slope_xxtot;
           }
           fo[a.o_slope + t] = slope;
           if (t >= 1) fo[a.o_flux + t - 1] = sqrt((double)fl);

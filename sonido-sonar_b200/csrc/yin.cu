@@ -621,7 +621,8 @@ __global__ void __launch_bounds__(32) yin_track_kernel(const double* __restrict_
                                                        int n_streams, int64_t Tp, double* __restrict__ feat,
                                                        int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
                                                        int64_t o_voicing, int64_t o_hratio, int64_t o_inharm,
-                                                       int64_t o_tonal) {
+                                                       int64_t o_tonal, const double* __restrict__ speech_gate,
+                                                       int64_t gate_stride) {
   __shared__ double c_sm[5 + 32];  // corrected pitches: [0..4] = the five frames before this round
   __shared__ double raw_sm[32];
   const int s = blockIdx.x;
@@ -630,6 +631,13 @@ __global__ void __launch_bounds__(32) yin_track_kernel(const double* __restrict_
   double* fo = feat + (int64_t)s * feat_stride;
   if (lane < 5) c_sm[lane] = 0.0;
   __syncwarp();
+  // The speech-specific group (extractors/speech.go:194-205,529-549) sweeps the SAME detector over the same frames before
+  // the harmonic block when the signal is judged to be speech: its history (20 entries, pitch_detection.go:876-902) is
+  // what the harmonic block starts from.  Pass 0 of two replays that sweep without writing anything.
+  const int passes = (speech_gate && speech_gate[(int64_t)s * gate_stride] != 0.0) ? 2 : 1;
+  for (int pass = 0; pass < passes; ++pass) {
+  const bool write = pass == passes - 1;
+  const int64_t hist0 = pass == 0 ? 0 : (Tp < 20 ? Tp : 20);  // history entries before the pass's first frame
   for (int64_t base = 0; base < Tp; base += 32) {
     const int cnt = (int)((Tp - base < 32) ? (Tp - base) : 32);
     const int64_t i = base + lane;
@@ -647,7 +655,8 @@ __global__ void __launch_bounds__(32) yin_track_kernel(const double* __restrict_
       while (todo) {
         const int k = __ffs(todo) - 1;
         todo &= todo - 1;
-        const int64_t hlen = base + k;  // history entries before this frame
+        int64_t hlen = hist0 + base + k;  // history entries before this frame
+        if (hlen > 20) hlen = 20;
         double pitch = raw_sm[k];
         if (hlen >= 3) {  // applyOctaveCorrection :792-829 (needs >= 3 of the last five)
           const double h[5] = {c_sm[k], c_sm[k + 1], c_sm[k + 2], c_sm[k + 3], c_sm[k + 4]};
@@ -669,23 +678,27 @@ __global__ void __launch_bounds__(32) yin_track_kernel(const double* __restrict_
     if (lane < cnt) {
       const double c0 = c_sm[5 + lane], c1 = c_sm[4 + lane], c2 = c_sm[3 + lane];
       double pitch = c0;  // applyTemporalSmoothing :905-921 on the history that already includes this frame
-      if (i >= 2)
+      const int64_t hsize = hist0 + i + 1;  // history length including this frame (capped at 20: >= 3 either way)
+      if (hsize >= 3)
         pitch = median_nonzero3(c2, c1, c0);
-      else if (i == 1)
+      else if (hsize == 2)
         pitch = 0.3 * c0 + (1 - 0.3) * c1;  // history of two: blend with the previous (unsmoothed) output
       const double cf = conf < 0.5 ? 0.0 : conf;
-      fo[o_pitch + i] = pitch;
-      fo[o_conf + i] = cf;
-      fo[o_voicing + i] = cf;
-      fo[o_hratio + i] = cf * 10.0;               // speech.go:499
-      fo[o_inharm + i] = 1.0 - cf;                // speech.go:500
-      fo[o_tonal + i] = pitch > 0 ? pitch : 0.0;  // speech.go:503-505
+      if (write) {
+        fo[o_pitch + i] = pitch;
+        fo[o_conf + i] = cf;
+        fo[o_voicing + i] = cf;
+        fo[o_hratio + i] = cf * 10.0;               // speech.go:499
+        fo[o_inharm + i] = 1.0 - cf;                // speech.go:500
+        fo[o_tonal + i] = pitch > 0 ? pitch : 0.0;  // speech.go:503-505
+      }
     }
     __syncwarp();
-    const double carry = (lane < 5) ? c_sm[32 + lane] : 0.0;
+    const double carry = (lane < 5) ? c_sm[cnt + lane] : 0.0;  // the five entries that end with this round's last frame
     __syncwarp();
     if (lane < 5) c_sm[lane] = carry;
     __syncwarp();
+  }
   }
 }
 
@@ -711,7 +724,7 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
                const double* hann_dev, double* feat, int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
                int64_t o_voicing, int64_t o_hratio, int64_t o_inharm, int64_t o_tonal, double* scratch,
                int64_t scratch_stride, cudaStream_t st, cudaStream_t track_st, cudaEvent_t fork, cudaEvent_t join,
-               bool* forked, int* lists, int64_t list_stride) {
+               bool* forked, int* lists, int64_t list_stride, const double* speech_gate, int64_t gate_stride) {
   if (forked) *forked = false;
   if (Tp <= 0 || n_streams <= 0) return SONAR_OK;
   if (sr <= 0) {
@@ -768,7 +781,7 @@ int launch_yin(const double* pcm, int64_t stride, int n_streams, double alpha, i
   }
   prof_begin("yin_track_kernel", ts);
   yin_track_kernel<<<n_streams, 32, 0, ts>>>(scratch, scratch_stride, n_streams, Tp, feat, feat_stride, o_pitch, o_conf,
-                                             o_voicing, o_hratio, o_inharm, o_tonal);
+                                             o_voicing, o_hratio, o_inharm, o_tonal, speech_gate, gate_stride);
   prof_end();
   SONAR_CUDA(cudaGetLastError());
   if (ts != st) {

@@ -82,21 +82,28 @@ __device__ __forceinline__ void tw_apply_y(float2 (&v)[32], const float2* __rest
 // 1024-point forward transform of the warp: lane l holds x[l + 32 j] in v[j]; returns X[l + 32 k2] in v[k2].
 __device__ __forceinline__ void warp_fft1024(float2 (&v)[32], float2* __restrict__ tile, const float2* __restrict__ s_tw,
                                              int lane) {
-  pk::Fft<32>::run(v);
-  tw_apply_y<1>(v, s_tw + lane);
-  float2* tp = tile + lane;
+  // ONE instance of the radix-32 butterflies serves both passes (not unrolled): the kernel's straight-line code was
+  // 230 KB, far beyond the 32 KB instruction cache level, and instruction fetch was its largest stall
+  // (profiles/r02_yin32_ncu.md)
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    pk::Fft<32>::run(v);
+    if (h == 0) {
+      tw_apply_y<1>(v, s_tw + lane);
+      float2* tp = tile + lane;
 #pragma unroll
-  for (int q = 0; q < 32; ++q) tp[q * kTileRowY] = v[q];
-  __syncwarp();
-  const float4* rp = reinterpret_cast<const float4*>(tile + lane * kTileRowY);
+      for (int q = 0; q < 32; ++q) tp[q * kTileRowY] = v[q];
+      __syncwarp();
+      const float4* rp = reinterpret_cast<const float4*>(tile + lane * kTileRowY);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float4 f = rp[i];
-    v[2 * i] = make_float2(f.x, f.y);
-    v[2 * i + 1] = make_float2(f.z, f.w);
+      for (int i = 0; i < 16; ++i) {
+        const float4 f = rp[i];
+        v[2 * i] = make_float2(f.x, f.y);
+        v[2 * i + 1] = make_float2(f.z, f.w);
+      }
+      __syncwarp();
+    }
   }
-  __syncwarp();
-  pk::Fft<32>::run(v);
 }
 
 // Stages one frame: float64 pre-processing exactly as the reference, power-of-two scaling, FP32 copy in pbuf (padded
@@ -107,12 +114,19 @@ __device__ __forceinline__ void stage_frame(const double* __restrict__ x, int64_
                                             float* __restrict__ pbuf, float* __restrict__ ebuf, int lane, float* e0,
                                             float* etot, bool* finite) {
   // raw samples g0 - 2 .. g0 + 1023, coalesced, into the staging buffer (x[-1] = x[-2] = 0: pre_emphasis.go:135-155)
+  if (live && g0 >= 2 && g0 + kN <= limit) {  // the whole window lies inside the stream (all but the first and last frames)
+    const double* __restrict__ xs = x + (g0 - 2 + lane);
 #pragma unroll
-  for (int jj = 0; jj < 33; ++jj) {
-    const int e = lane + 32 * jj;
-    if (e < kN + 2) {
-      const int64_t g = g0 - 2 + e;
-      stage[pidx(e)] = (live && g >= 0 && g < limit) ? __ldg(x + g) : 0.0;
+    for (int jj = 0; jj < 32; ++jj) stage[pidx(lane + 32 * jj)] = __ldg(xs + 32 * jj);
+    if (lane < 2) stage[pidx(lane + kN)] = __ldg(xs + kN);
+  } else {
+#pragma unroll 1
+    for (int jj = 0; jj < 33; ++jj) {
+      const int e = lane + 32 * jj;
+      if (e < kN + 2) {
+        const int64_t g = g0 - 2 + e;
+        stage[pidx(e)] = (live && g >= 0 && g < limit) ? __ldg(x + g) : 0.0;
+      }
     }
   }
   __syncwarp();
@@ -228,6 +242,27 @@ __device__ __forceinline__ PickOut pick32(const float* __restrict__ rb, int comp
   }
   const float base = incl - run;
   const float bd = kKappa * (etot + e0);  // bound on |d32 - d|
+  // Screen without divisions: cm[tau] < 0.15 + eb[tau] (the only way a lag can be chosen OR make the choice unsure) needs
+  // d tau < 0.15 cum + bd tau (1 + cm) with cm < 0.15 + eb; 1.25 bd tau covers it for eb < 0.1, and eb >= 0.1 means
+  // bd tau >= 0.087 cum, which the second test catches.  Frames without any such lag (noise, silence with energy,
+  // most unvoiced audio) have no pitch for sure: the CMNDF itself is never formed for them.  Negated comparisons: NaN passes.
+  {
+    bool cand = false;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int tau = 16 * lane + k;
+      const float cum = base + loc[k], ft = (float)tau;
+      const bool in = tau >= 1 && tau + 1 < kHalf;
+      cand = cand || (in && (!(d[k] * ft >= fmaf(kThresh, cum, 1.25f * bd * ft)) || !(bd * ft < 0.08f * cum)));
+    }
+    if (!__any_sync(kFullY, cand)) {
+      PickOut none;
+      none.pitch = 0.f;
+      none.conf = 0.f;
+      none.flag = 0;
+      return none;
+    }
+  }
   float cm[17], eb[17];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
@@ -337,31 +372,32 @@ __global__ void __launch_bounds__(kYW * 32, 1)
     const int64_t fa = (pr % pairs_per_stream) * 2, fb = fa + 1;
     const double* __restrict__ x = pcm + (int64_t)s * stride;
     float2 qa[16], qb[16], nyqa, nyqb;
-    float e0[2], etot[2];
-    bool fin[2];
-    // ---- frame a, then frame b: stage, forward transform, conj(U) P -----------------------------------------
-    {
-      stage_frame(x, fa * kHop, limit, true, alpha, s_hann, stage, pbuf, ebuf, lane, &e0[0], &etot[0], &fin[0]);
+    float e0a = 0.f, e0b = 0.f, etota = 0.f, etotb = 0.f;
+    bool fina = true, finb = true;
+    // ---- frame a, then frame b: stage, forward transform, conj(U) P (one code instance, see warp_fft1024) -------
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      float* pb = pbuf + c * (kN + 32);
+      float e0c, etc;
+      bool fc;
+      stage_frame(x, (fa + c) * kHop, limit, c == 0 || fb < Tp, alpha, s_hann, stage, pb, ebuf + c * (kHalf + 4), lane, &e0c,
+                  &etc, &fc);
       float2 z[32];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) z[j] = make_float2(pbuf[pidx(lane + 32 * j)], pbuf[pidx(lane + 32 * j + kHalf)]);
-#pragma unroll
-      for (int j = 16; j < 32; ++j) z[j] = make_float2(0.f, 0.f);
-      __syncwarp();
-      warp_fft1024(z, tile, s_tw, lane);
-      spectrum_product(z, lane, qa, &nyqa);
-    }
-    {
-      float* pb2 = pbuf + (kN + 32);
-      stage_frame(x, fb * kHop, limit, fb < Tp, alpha, s_hann, stage, pb2, ebuf + kHalf + 4, lane, &e0[1], &etot[1], &fin[1]);
-      float2 z[32];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) z[j] = make_float2(pb2[pidx(lane + 32 * j)], pb2[pidx(lane + 32 * j + kHalf)]);
+      for (int j = 0; j < 16; ++j) z[j] = make_float2(pb[pidx(lane + 32 * j)], pb[pidx(lane + 32 * j + kHalf)]);
 #pragma unroll
       for (int j = 16; j < 32; ++j) z[j] = make_float2(0.f, 0.f);
       __syncwarp();
       warp_fft1024(z, tile, s_tw, lane);
       spectrum_product(z, lane, qb, &nyqb);
+      if (c == 0) {
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) qa[k2] = qb[k2];
+        nyqa = nyqb;
+        e0a = e0c, etota = etc, fina = fc;
+      } else {
+        e0b = e0c, etotb = etc, finb = fc;
+      }
     }
     // ---- Q = Q_a + i Q_b on all 1024 bins, conjugated for the inverse-by-forward transform --------------------
     {
@@ -391,18 +427,20 @@ __global__ void __launch_bounds__(kYW * 32, 1)
     }
     __syncwarp();
     // ---- CMNDF, first dip, refinement; borderline frames go to the exact list ---------------------------------
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const int64_t f = fa + c;
-      const PickOut o = pick32(rbuf, c, ebuf + c * (kHalf + 4), pbuf + c * (kN + 32), e0[c], etot[c], rscale, sr, lane);
+      const bool fin_c = c ? finb : fina;
+      const PickOut o = pick32(rbuf, c, ebuf + c * (kHalf + 4), pbuf + c * (kN + 32), c ? e0b : e0a, c ? etotb : etota, rscale,
+                               sr, lane);
       if (lane == 0 && f < Tp) {
         double* r = raw + (int64_t)s * raw_stride;
         r[f] = (double)o.pitch;
         r[Tp + f] = (double)o.conf;
-        if (o.flag || !fin[c]) {
+        if (o.flag || !fin_c) {
           int* lst = lists + (int64_t)s * list_stride;
           const int pos = atomicAdd(lst, 1);
-          lst[1 + pos] = (int)f | ((o.flag | (fin[c] ? 0 : 8)) << 27);  // frame (< 2^27) + reason bits (diagnostic)
+          lst[1 + pos] = (int)f | ((o.flag | (fin_c ? 0 : 8)) << 27);  // frame (< 2^27) + reason bits (diagnostic)
         }
       }
     }

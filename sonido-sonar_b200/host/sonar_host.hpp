@@ -252,8 +252,17 @@ struct TemporalFeatures {  // features.go:70-92
   std::vector<double> RMSEnergy, AttackTime, EnvelopeShape;
   double DynamicRange = 0, SilenceRatio = 0, PeakAmplitude = 0, AverageAmplitude = 0, OnsetDensity = 0;
 };
+struct SpeechFeatures {  // features.go:45-65
+  std::vector<std::vector<double>> FormantFrequencies;  // host-side LPC analysis in the reference: not produced here
+  std::vector<double> VoicingProbability, SpectralTilt, PauseDuration;
+  double SpeechRate = 0.0;
+  double VocalTractLength = 17.5;  // speech.go:288 default; the formant analyzer's estimate is not produced here
+  double Jitter = 0.0, Shimmer = 0.0;  // voice-quality analyzer: not produced here
+};
+
 struct ExtractedFeatures {  // features.go:5-27
   std::vector<std::vector<double>> MFCC, ChromaFeatures;
+  std::shared_ptr<sonido::extractors::SpeechFeatures> SpeechFeatures;
   std::shared_ptr<extractors::SpectralFeatures> SpectralFeatures;
   std::shared_ptr<extractors::EnergyFeatures> EnergyFeatures;
   std::shared_ptr<extractors::HarmonicFeatures> HarmonicFeatures;
@@ -298,9 +307,10 @@ class SpeechFeatureExtractor : public FeatureExtractor {
     p.enable = 0;
     if (config_.EnableMFCC) p.enable |= SONAR_FP_ENABLE_MFCC;
     if (config_.EnableTemporalFeatures) p.enable |= SONAR_FP_ENABLE_TEMPORAL;  // speech.go:201-211
-    // EnableSpeechFeatures (news, talk): LPC / formant / voice-quality analysis is host-side Go outside this
-    // path's scope; the group is non-fatal in the reference ("Continuing without speech features",
-    // speech.go:181-188), so the fingerprint is produced without it and the metadata says so.
+    // EnableSpeechFeatures (news, talk; speech.go:180-190): the frame-level group (IsSpeech gate, voicing sweep with
+    // the detector history it leaves behind, spectral tilt, pauses, speech rate) runs on the device; the LPC / formant /
+    // voice-quality scalars are host-side analyzers outside this path and keep their defaults.
+    if (config_.EnableSpeechFeatures) p.enable |= SONAR_FP_ENABLE_SPEECH;
     return p;
   }
   Result<ExtractedFeatures> ExtractFeatures(const analyzers::SpectrogramResult* spectrogram,
@@ -359,8 +369,27 @@ class SpeechFeatureExtractor : public FeatureExtractor {
     o.harmonic_ratio = hf->HarmonicRatio.data();
     o.inharmonicity_ratio = hf->InharmonicityRatio.data();
     o.tonal_centroid = hf->TonalCentroid.data();
-    if (sonar_fingerprint_f64(ctx, pcm.data(), (int64_t)pcm.size(), &p, &o) != SONAR_OK)
+    auto spf = std::make_shared<sonido::extractors::SpeechFeatures>();
+    if (config_.EnableSpeechFeatures) {
+      sonar_speech_out so;
+      std::memset(&so, 0, sizeof(so));
+      spf->VoicingProbability.assign(Tp, 0.0);
+      spf->SpectralTilt.assign(Tp, 0.0);
+      spf->PauseDuration.assign(Te / 2 + 1, 0.0);
+      so.voicing_probability = spf->VoicingProbability.data();
+      so.spectral_tilt = spf->SpectralTilt.data();
+      so.pause_duration = spf->PauseDuration.data();
+      so.pause_cap = (int64_t)spf->PauseDuration.size();
+      if (sonar_fingerprint_speech_f64(ctx, pcm.data(), (int64_t)pcm.size(), &p, &o, &so) != SONAR_OK)
+        return Err<ExtractedFeatures>(sonar_last_error());
+      spf->VoicingProbability.resize((size_t)so.n_frames);
+      spf->SpectralTilt.resize((size_t)so.n_frames);
+      spf->PauseDuration.resize((size_t)std::min<int64_t>(so.n_pause, so.pause_cap));
+      spf->SpeechRate = so.speech_rate;
+      f->SpeechFeatures = spf;
+    } else if (sonar_fingerprint_f64(ctx, pcm.data(), (int64_t)pcm.size(), &p, &o) != SONAR_OK) {
       return Err<ExtractedFeatures>(sonar_last_error());
+    }
     if (config_.EnableMFCC) {  // speech.go:168-178
       f->MFCC.assign(T, std::vector<double>((size_t)sz.n_mfcc));
       for (size_t t = 0; t < T; t++)
@@ -385,7 +414,8 @@ class SpeechFeatureExtractor : public FeatureExtractor {
                              {"spectrogram_frames", std::to_string(spectrogram->TimeFrames)},
                              {"optimization", "speech_optimized"},
                              {"backend", sonar_backend()}};
-    if (config_.EnableSpeechFeatures) f->ExtractionMetadata["speech_features"] = "skipped: outside the GPU path's scope";
+    if (config_.EnableSpeechFeatures)
+      f->ExtractionMetadata["speech_features"] = "frame-level group on the device; formants / jitter / shimmer: host analyzers, not run";
     return Result<ExtractedFeatures>{f, ""};
   }
   const config::FeatureConfig& Config() const { return config_; }

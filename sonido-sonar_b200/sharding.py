@@ -34,6 +34,22 @@ def actual_max_lag(max_lag: int, na: int, nb: int) -> int:
     return max(0, min(max_lag, na - 1, nb - 1))  # correlation.go:452-461
 
 
+def nccl_setup(lib: "capi.SonarLib", device=None, group=None):
+    """Gives the C library its own NCCL communicator over the ranks of `group`: rank 0 draws the unique id
+    (sonar_nccl_unique_id), torch.distributed only carries those 128 bytes, every rank calls sonar_nccl_init.  After this
+    `lib.xcorr_lag_sharded` runs the whole sharded correlation inside the library (one ncclAllGather, no host hops)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    uid = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(lib.nccl_unique_id()), dtype=torch.uint8).to(uid.device)
+    dist.broadcast(uid, src=0, group=group)
+    lib.nccl_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    return world, rank
+
+
 def xcorr_lag_sharded(lib: "capi.SonarLib", a, b, max_lag: int, device=None, group=None):
     """CrossCorrelation.Compute of ONE pair with the lags split over the ranks of `group`.
 

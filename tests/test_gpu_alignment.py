@@ -289,3 +289,29 @@ def test_xcorr_without_curve_is_screened_and_keeps_the_peak_exact(gpu, oracle):
     _, sb = oracle.xcorr_batch(As, Bs, 128, want_corr=False)
     for x, y in zip(sa, sb):
         check_summary(x, y)
+
+
+def test_library_side_lag_shard_with_its_own_nccl_communicator(gpu, oracle):
+    """sonar_xcorr_lag_sharded on a one-rank communicator (dlopen of libnccl, ncclCommInitRank, the in-place all-gather
+    path is skipped at world 1 but the shard geometry, the resident workspace and the summary are the N-rank ones):
+    identical to the unsharded evaluation and to the oracle, curve included.  The N > 1 form runs in bench.py --gpus N
+    (`lag_sharded.matches_unsharded`)."""
+    rng = np.random.default_rng(11)
+    base = np.convolve(rng.standard_normal(9000), np.ones(16) / 16, mode="same") + 1.0
+    a, b = base[500:8500].copy(), base[500 - 137:8500 - 137] + 0.01 * rng.standard_normal(8000)
+    try:
+        gpu.nccl_init(1, 0, gpu.nccl_unique_id())
+        s, corr = gpu.xcorr_lag_sharded(a, b, 700, want_corr=True)
+    finally:
+        gpu.nccl_shutdown()
+    corr0, s0 = gpu.xcorr(a, b, 700, want_corr=True)
+    corr1, s1 = oracle.xcorr(a, b, 700, want_corr=True)
+    assert np.array_equal(corr, corr0) and np.array_equal(corr, corr1)
+    for k in ("peak_lag", "peak_index", "peak_correlation", "second_peak", "snr", "sharpness", "peak_to_sidelobe"):
+        assert getattr(s, k) == getattr(s0, k), k
+    for k in ("peak_lag", "peak_index", "peak_correlation", "second_peak"):
+        assert getattr(s, k) == getattr(s1, k), k
+    for k in ("snr", "sharpness", "peak_to_sidelobe"):
+        assert getattr(s, k) == pytest.approx(getattr(s1, k), rel=1e-9), k
+    s2, _ = gpu.xcorr_lag_sharded(a, b, 700)  # no communicator: one shard
+    assert s2.peak_lag == s.peak_lag and s2.peak_correlation == s.peak_correlation

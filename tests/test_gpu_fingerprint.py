@@ -58,12 +58,25 @@ def feature_close(x, y, tol=1e-4, name=""):
     assert not bad.any(), f"{name}: {bad.sum()} of {y.size} outside tolerance; worst {np.max(np.abs(x - y) / np.maximum(bound, 1e-300)):.3g}x"
 
 
-def check_fp(a, b, bound=None):
+# Geometries the third-generation kernel serves (stft_v3.cu): it hands every frame whose FP32 result is not safe -- the
+# rolloff bin within the FP32 error of the 85 % threshold, bins or mel bands at the transform's noise floor, magnitudes
+# near the 1e-10 validity threshold, silence -- to the float64 re-evaluation in the reference's order
+# (spectral_exact.cu).  There the rolloff is BIT-EXACT and flatness / slope hold the plain 1e-4 on every input
+# (VERDICT r1 weak #4); the other geometries (first / second generation kernels) keep the stated per-input bound.
+STRICT_CASES = {"c1_music_fixed_sr", "c3_speech_512_160_40mel", "hamming", "voiced_yin", "voiced_yin_16k",
+                "run_boundaries", "single_frame", "silence"}
+
+
+def check_fp(a, b, bound=None, strict=False):
     for k in FP32_FEATURES:
-        if bound is not None and k in TOL:
+        if strict:
+            feature_close(a.arrays[k], b.arrays[k], tol=1e-4, name=k)
+        elif bound is not None and k in TOL:
             log_features_close(a.arrays[k], b.arrays[k], bound, k)
         else:
             feature_close(a.arrays[k], b.arrays[k], tol=TOL.get(k, 1e-4), name=k)
+    if strict:
+        assert np.array_equal(a.spectral_rolloff, b.spectral_rolloff), "rolloff bin (discrete) must be bit-exact"
     for k in EXACT:
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
     for k in FP64_CLOSE:
@@ -151,7 +164,34 @@ def test_fingerprint_matches_oracle(gpu, oracle, synth, name):
     pcm = make(synth)
     p = gpu.default_params(**kw)
     bound = log_feature_bound(oracle, pcm, p) if pcm.size >= p.window_size else None
-    check_fp(gpu.fingerprint(pcm, p), oracle.fingerprint(pcm, p), bound)
+    check_fp(gpu.fingerprint(pcm, p), oracle.fingerprint(pcm, p), bound, strict=name in STRICT_CASES)
+
+
+def test_weak_bins_take_the_float64_path(gpu, oracle):
+    """A tone 74 dB over its noise floor: every frame has bins at the FP32 transform's noise floor, so every frame is
+    listed and redone in float64 in the reference's order -- centroid / rolloff / bandwidth / crest / band ratios come
+    out BIT-EXACT, flatness / slope / MFCC to the last bits of log() (they held only 2e-3 in FP32).  Broadband input
+    (the BASELINE workloads) lists ~1 % of the frames: those whose rolloff threshold falls within the FP32 error."""
+    sr = 44100
+    t = np.arange(int(3.0 * sr)) / sr
+    x = 0.5 * np.sin(2 * np.pi * 440.0 * t) + 1e-4 * np.random.default_rng(5).standard_normal(t.size)
+    p = gpu.default_params(algo_sample_rate=sr, call_sample_rate=sr)
+    g = gpu.fingerprint(x, p)
+    listed, _ = gpu.exact_counts()
+    o = oracle.fingerprint(x, p)
+    T = g.mfcc.shape[0]
+    assert listed == T
+    for k in ("spectral_centroid", "spectral_rolloff", "spectral_bandwidth", "spectral_crest", "low_energy_ratio",
+              "high_energy_ratio"):
+        assert np.array_equal(g.arrays[k], o.arrays[k]), k
+    for k in ("mfcc", "spectral_flatness", "spectral_slope"):
+        np.testing.assert_allclose(g.arrays[k], o.arrays[k], rtol=1e-11, atol=1e-13, err_msg=k)
+    noise = np.random.default_rng(6).standard_normal(int(10.0 * sr)) * 0.2
+    gn = gpu.fingerprint(noise, p)
+    listed, _ = gpu.exact_counts()
+    on = oracle.fingerprint(noise, p)
+    assert 0 < listed < 0.03 * gn.mfcc.shape[0]
+    assert np.array_equal(gn.spectral_rolloff, on.spectral_rolloff)
 
 
 ALL_WINDOWS = ("hann", "hamming", "blackman", "blackman_harris", "kaiser", "tukey", "rectangular", "bartlett", "welch")
@@ -469,3 +509,52 @@ def test_yin_noise_sweep_decisions_match_the_oracle(gpu, oracle):
     assert np.array_equal(a.pitch_estimate > 0, b.pitch_estimate > 0)
     np.testing.assert_allclose(a.pitch_confidence, b.pitch_confidence, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(a.pitch_estimate, b.pitch_estimate, rtol=1e-4, atol=1e-6)
+
+
+def _speechy(seconds=6.0, sr=16000, seed=7):
+    n = int(seconds * sr)
+    t = np.arange(n) / sr
+    f0 = 140.0 * (1.0 + 0.05 * np.sin(2 * np.pi * 0.5 * t))
+    ph = 2 * np.pi * np.cumsum(f0) / sr
+    x = np.sin(ph) + 0.5 * np.sin(2 * ph) + 0.3 * np.sin(3 * ph)
+    gate = ((t % 1.5) < 1.0).astype(float)
+    return (0.3 * x + 2e-3 * np.random.default_rng(seed).standard_normal(n)) * gate
+
+
+@pytest.mark.parametrize("case", ["speech_16k", "speech_44k_1024", "noise_not_speech", "too_quiet", "short_600"])
+def test_speech_feature_group_matches_oracle(gpu, oracle, case):
+    """SURVEY §8 f1 / VERDICT r1 missing #3: EnableSpeechFeatures (extractors/speech.go:194-205,271-317) -- the IsSpeech
+    gate, the voicing sweep with the detector history it leaves to the harmonic block, the spectral tilt (bit-exact sums,
+    log10 to the last bits), pause durations and speech rate."""
+    sr = 44100 if case == "speech_44k_1024" else 16000
+    if case in ("speech_16k", "speech_44k_1024"):
+        x = _speechy(5.0, sr)
+    elif case == "noise_not_speech":
+        x = 0.2 * np.random.default_rng(3).standard_normal(2 * sr)
+    elif case == "too_quiet":
+        x = 1e-4 * _speechy(3.0, sr)
+    else:
+        x = _speechy(1.0, sr)[:600]
+    kw = dict(algo_sample_rate=sr, call_sample_rate=sr)
+    if sr == 16000:
+        kw.update(window_size=512, hop_size=160, energy_frame=512, energy_hop=160, n_mel=40)
+    p = gpu.default_params(**kw)
+    if case == "short_600":
+        p = gpu.default_params(window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=sr,
+                               call_sample_rate=sr)
+    g, gs = gpu.fingerprint_speech(x, p)
+    o, os_ = oracle.fingerprint_speech(x, p)
+    assert gs["is_speech"] == os_["is_speech"] == (case in ("speech_16k", "speech_44k_1024"))
+    assert gs["n_pause"] == os_["n_pause"] and gs["speech_rate"] == os_["speech_rate"]
+    assert np.array_equal(gs["pause_duration"], os_["pause_duration"])
+    assert gs["voicing_probability"].shape == os_["voicing_probability"].shape
+    np.testing.assert_allclose(gs["voicing_probability"], os_["voicing_probability"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(gs["spectral_tilt"], os_["spectral_tilt"], rtol=1e-13, atol=1e-13)
+    # the harmonic block saw the history the sweep left behind: same voiced pattern and values as the oracle's run
+    assert np.array_equal(g.pitch_estimate > 0, o.pitch_estimate > 0)
+    np.testing.assert_allclose(g.pitch_estimate, o.pitch_estimate, rtol=1e-4, atol=1e-6)
+    assert np.array_equal(g.short_time_energy, o.short_time_energy)
+    if gs["is_speech"]:
+        plain = gpu.fingerprint(x, p)
+        assert gs["n_pause"] >= 2
+        assert np.array_equal(g.pitch_estimate[3:], plain.pitch_estimate[3:])

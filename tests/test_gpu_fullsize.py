@@ -104,10 +104,10 @@ def _pair_bit_exact(gpu, oracle, q, r, sr, hop, max_lag_s, band, check_features)
         assert np.array_equal(g.short_time_energy, o.short_time_energy), side
         assert np.array_equal(g.zero_crossing_rate, o.zero_crossing_rate), side
         if check_features:
-            for k in FP32_KEYS:
+            for k in FP32_KEYS:  # flatness / slope included: frames with weak bins are redone in float64 (spectral_exact.cu)
                 y, x = o.arrays[k], g.arrays[k]
-                tol = 2e-3 if k in ("spectral_flatness", "spectral_slope") else 1e-4
-                assert np.all(np.abs(x - y) <= tol * np.maximum(np.abs(y), np.max(np.abs(y)))), (side, k)
+                assert np.all(np.abs(x - y) <= 1e-4 * np.maximum(np.abs(y), np.max(np.abs(y)))), (side, k)
+            assert np.array_equal(g.spectral_rolloff, o.spectral_rolloff), (side, "rolloff bin is a discrete choice")
             assert np.allclose(g.pitch_estimate, o.pitch_estimate, rtol=1e-4, atol=1e-6), side
             assert np.allclose(g.pitch_confidence, o.pitch_confidence, rtol=1e-4, atol=1e-6), side
     ea, eb = oq.short_time_energy, orf.short_time_energy
@@ -151,15 +151,11 @@ def test_c1_thirty_seconds_both_sample_rate_modes(gpu, oracle, synth, algo_sr):
     g, o = gpu.fingerprint(pcm, p), oracle.fingerprint(pcm, p)
     assert g.mfcc.shape == (5164, 13) and g.sizes == o.sizes
     assert np.array_equal(g.short_time_energy, o.short_time_energy) and np.array_equal(g.zero_crossing_rate, o.zero_crossing_rate)
-    from test_gpu_fingerprint import log_feature_bound, log_features_close
-    bound = log_feature_bound(oracle, pcm, p)  # flatness / slope: 1e-4 + the stated per-input bound
     for k in FP32_KEYS:
         y, x = o.arrays[k], g.arrays[k]
-        if k in ("spectral_flatness", "spectral_slope"):
-            log_features_close(x, y, bound, k)
-            continue
         scale = np.max(np.abs(y))
         assert np.all(np.abs(x - y) <= 1e-4 * np.maximum(np.abs(y), scale)), k
+    assert np.array_equal(g.spectral_rolloff, o.spectral_rolloff)
     for k in ("pitch_estimate", "pitch_confidence", "voicing_strength", "harmonic_ratio", "inharmonicity_ratio", "tonal_centroid"):
         assert np.allclose(g.arrays[k], o.arrays[k], rtol=1e-4, atol=1e-6), k
     assert g.energy_variance == pytest.approx(o.energy_variance, rel=1e-10)

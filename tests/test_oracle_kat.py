@@ -548,3 +548,83 @@ def test_too_short_still_errors(oracle, capi):
     with pytest.raises(capi.SonarError) as e:
         oracle.stft(np.zeros(768), 1024, 256)  # (768 - 1024)/256 + 1 = 0
     assert "signal too short" in e.value.msg
+
+
+# ---- speech-specific group: independent numpy restatement of the Go -------------------------------
+
+def _speechy(seconds=6.0, sr=16000, seed=7):
+    """Voiced bursts (140 Hz harmonic stack with a little noise) separated by digitally silent gaps (their energies tie
+    at the 10th-percentile threshold, so they count as pauses): passes detectSpeech, has pauses longer than 100 ms and a
+    pitch the detector tracks."""
+    n = int(seconds * sr)
+    t = np.arange(n) / sr
+    f0 = 140.0 * (1.0 + 0.05 * np.sin(2 * np.pi * 0.5 * t))
+    ph = 2 * np.pi * np.cumsum(f0) / sr
+    x = np.sin(ph) + 0.5 * np.sin(2 * ph) + 0.3 * np.sin(3 * ph)
+    gate = ((t % 1.5) < 1.0).astype(float)
+    rng = np.random.default_rng(seed)
+    return (0.3 * x + 2e-3 * rng.standard_normal(n)) * gate
+
+
+def _speech_params(lib, sr=16000):
+    return lib.default_params(window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=sr,
+                              call_sample_rate=sr, n_mel=40)
+
+
+def test_speech_group_against_numpy(oracle):
+    sr = 16000
+    x = _speechy(sr=sr)
+    p = _speech_params(oracle, sr)
+    fp, sp = oracle.fingerprint_speech(x, p)
+    plain = oracle.fingerprint(x, p)
+    y = x - 0.97 * np.concatenate(([0.0], x[:-1]))  # pre_emphasis.go:184-190
+    # detectSpeech (speech_analysis.go:113-207)
+    zc = np.count_nonzero((y[:-1] >= 0) != (y[1:] >= 0)) / (y.size - 1)
+    f = y[:1024]
+    mc = max(max(np.dot(f[: 1024 - lag], f[lag:]) / (1024 - lag) for lag in range(20, 400)), 0.0) / np.mean(f * f)
+    assert 0.01 <= zc <= 0.3 and np.sqrt(np.mean(y * y)) >= 1e-3 and mc > 0.1 and sp["is_speech"]
+    nf = (x.size - 1024) // 512 + 1
+    assert sp["voicing_probability"].size == nf == sp["spectral_tilt"].size
+    # the voicing sweep is the detector's voicing on the same frames as the harmonic block (speech.go:529-549)
+    assert np.array_equal(sp["voicing_probability"], fp.voicing_strength)
+    assert np.array_equal(fp.voicing_strength, plain.voicing_strength)
+    # ... and leaves its 20-frame history behind: only the first frames of the pitch track can differ (median of three)
+    assert np.array_equal(fp.pitch_estimate[3:], plain.pitch_estimate[3:])
+    # extractSpectralTilt (speech.go:551-584)
+    tilt = np.zeros(nf)
+    for i in range(nf):
+        fr = y[i * 512: i * 512 + 1024]
+        hi, lo = 0.0, 0.0
+        for j in range(1, fr.size):
+            d = fr[j] - fr[j - 1]
+            hi += d * d
+            lo += fr[j] * fr[j]
+        tilt[i] = -10 * np.log10(hi / lo) if lo > 0 else 0.0
+    np.testing.assert_allclose(sp["spectral_tilt"], tilt, rtol=1e-13, atol=1e-13)
+    # extractPauseDurations / estimateSpeechRate (speech.go:586-655,779-797)
+    e = fp.short_time_energy
+    thr = np.sort(e)[e.size // 10]
+    low = np.concatenate((e <= thr, [False]))
+    pauses, start = [], None
+    for i, v in enumerate(low):
+        if v and start is None:
+            start = i
+        elif not v and start is not None:
+            d = (i - start) * (160 / sr)
+            if d > 0.1:
+                pauses.append(d)
+            start = None
+    assert sp["n_pause"] == len(pauses) >= 2
+    np.testing.assert_allclose(sp["pause_duration"], pauses, rtol=1e-15)
+    assert sp["speech_rate"] == pytest.approx(4.0 * (1.0 - np.count_nonzero(e <= thr) / e.size), rel=1e-14)
+
+
+def test_speech_group_not_speech_returns_empty(oracle, synth):
+    """White noise: the zero-crossing rate is ~0.5 (> 0.3), detectSpeech says no -> empty arrays, rate 0 (speech.go:281-291)
+    and the fingerprint is the one computed without the group."""
+    x = 0.2 * np.random.default_rng(3).standard_normal(16000 * 2)
+    p = _speech_params(oracle)
+    fp, sp = oracle.fingerprint_speech(x, p)
+    assert not sp["is_speech"] and sp["voicing_probability"].size == 0 and sp["n_pause"] == 0 and sp["speech_rate"] == 0.0
+    plain = oracle.fingerprint(x, p)
+    assert np.array_equal(fp.pitch_estimate, plain.pitch_estimate) and np.array_equal(fp.mfcc, plain.mfcc)
