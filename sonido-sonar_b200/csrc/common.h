@@ -65,7 +65,10 @@ struct FpPlan {  // immutable once built; cached per context keyed by the parame
          off_chunk_region = 0, off_hann = 0, off_zero = 0;
   // float64 tables of the exact re-evaluation (spectral_exact.cu): window, go-dsp radix-2 factors, mel bin points,
   // DCT-II, lifter; float32 1 / (sum of a filter's weights) for the fused kernel's weak-band test
-  size_t off_win64 = 0, off_fac64 = 0, off_melbins = 0, off_dct64 = 0, off_lift64 = 0, off_melinvw = 0;
+  size_t off_win64 = 0, off_fac64 = 0, off_melbins = 0, off_dct64 = 0, off_lift64 = 0, off_melinvw = 0, off_chirp = 0,
+         off_bluefb = 0;
+  bool exact_only = false;  // no fused FP32 kernel for this length: every frame takes the float64 route (spectral_exact.cu)
+  int fft_len = 0;          // its radix-2 transform length: N, or NextPowerOf2(2 N - 1) on the Bluestein route
   std::vector<MelRegion> h_regions;  // host copy of the mel region table (kernel eligibility checks)
   ~FpPlan();
 };
@@ -110,6 +113,11 @@ struct StftArgs {
   const double* lift64;
   const float* mel_invw;
   int algo_sr, N;
+  // float64 route for every frame (lengths without a fused kernel): no lists, frames 0 .. T-1, flux included;
+  // fft_len > N: go-dsp's Bluestein (chirp_inv = conj w_i, blue_fb = FFT of the chirp sequence b)
+  int exact_all, fft_len;
+  const double2* chirp_inv;
+  const double2* blue_fb;
 };
 
 // exact float64 re-evaluation of the frames the fused kernel listed (spectral_exact.cu)
@@ -118,6 +126,7 @@ int launch_spectral_exact(const StftArgs& a, cudaStream_t st);
 int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out);
 int launch_stft_features(const FpPlan& plan, StftArgs& a, bool spectrum_mode, cudaStream_t st);
 bool stft_supported(int window_size);
+bool stft_exact_only(int window_size);
 // second-generation kernel (stft_v2.cu): N = 1024, aligned PCM, features mode
 bool stft_v2_eligible(const FpPlan& plan, const StftArgs& a);
 int launch_stft_v2(const FpPlan& plan, StftArgs& a, cudaStream_t st);

@@ -53,8 +53,9 @@ int get_plan(sonar_ctx* ctx, int device, const sonar_fp_params* p, std::shared_p
 
 int fp_validate(const sonar_fp_params* p) {
   if (p->call_sample_rate <= 0) return set_error(SONAR_ERR_INVALID, "sample rate must be positive");  // speech.go:143
-  if (!stft_supported(p->window_size))
-    return set_error(SONAR_ERR_UNSUPPORTED, "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
+  if (!stft_supported(p->window_size) && !stft_exact_only(p->window_size))
+    return set_error(SONAR_ERR_UNSUPPORTED,
+                     "window size must be 256, 512, 1024, 2048 (fused kernels) or any length in [8, 2048] (float64 route)");
   return SONAR_OK;
 }
 
@@ -182,6 +183,20 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
     a.mel_invw = reinterpret_cast<const float*>(blob + plan->off_melinvw);
     a.algo_sr = p->algo_sample_rate;
     a.N = p->window_size;
+    a.fft_len = plan->fft_len;
+    a.chirp_inv = reinterpret_cast<const double2*>(blob + plan->off_chirp);
+    a.blue_fb = reinterpret_cast<const double2*>(blob + plan->off_bluefb);
+    if (plan->exact_only) {  // no fused kernel for this window length: every frame in float64 (Bluestein if not 2^k)
+      a.exact_all = 1;
+      a.xlist = nullptr;
+      rc = launch_spectral_exact(a, st);
+      if (rc) return rc;
+      if (!a.mfcc_on) {
+        rc = launch_fill_strided(feat_dev + L.mfcc, T * sh.sz.n_mfcc, L.total, ns, 0.0, st);
+        if (rc) return rc;
+      }
+      return SONAR_OK;
+    }
     a.work_counter = reinterpret_cast<unsigned*>(tmp_dev + sh.o_work);
     rc = launch_fill_strided(tmp_dev + sh.o_work, 1, tstride, 1, 0.0, st);
     if (rc) return rc;
@@ -617,8 +632,9 @@ int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int ho
   const int64_t T = (n - win) / hop + 1;
   if (T <= 0) return set_error(SONAR_ERR_TOO_SHORT, "signal too short for given window size and hop size");
   if (!mag) return set_error(SONAR_ERR_INVALID, "nil argument");
-  if (!stft_supported(win))
-    return set_error(SONAR_ERR_UNSUPPORTED, "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
+  if (!stft_supported(win) && !stft_exact_only(win))
+    return set_error(SONAR_ERR_UNSUPPORTED,
+                     "window size must be 256, 512, 1024, 2048 (fused kernels) or any length in [8, 2048] (float64 route)");
   std::lock_guard<std::mutex> call_lock(ctx->call_mu);
   set_current_ctx(ctx);
   sonar_fp_params p;
@@ -665,7 +681,18 @@ int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int ho
     d += (size_t)T * B;
   }
   if (cplx) a.cplx = d;
-  rc = launch_stft_features(*plan, a, true, s.st);
+  if (plan->exact_only) {  // go-dsp's route for this length (Bluestein when it is not a power of two), float64
+    a.exact_all = 1;
+    a.N = win;
+    a.fft_len = plan->fft_len;
+    a.win64 = reinterpret_cast<const double*>(blob + plan->off_win64);
+    a.fac64 = reinterpret_cast<const double2*>(blob + plan->off_fac64);
+    a.chirp_inv = reinterpret_cast<const double2*>(blob + plan->off_chirp);
+    a.blue_fb = reinterpret_cast<const double2*>(blob + plan->off_bluefb);
+    rc = launch_spectral_exact(a, s.st);
+  } else {
+    rc = launch_stft_features(*plan, a, true, s.st);
+  }
   if (rc) return rc;
   SONAR_CUDA(cudaMemcpyAsync(mag, a.mag, per, cudaMemcpyDeviceToHost, s.st));
   if (phase) SONAR_CUDA(cudaMemcpyAsync(phase, a.phase, per, cudaMemcpyDeviceToHost, s.st));

@@ -186,8 +186,14 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
     case 1024: plan->R1 = 16, plan->R2 = 32; break;
     case 2048: plan->R1 = 32, plan->R2 = 32; break;
     default:
-      return set_error(SONAR_ERR_UNSUPPORTED,
-                       "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
+      // any other length goes the way go-dsp sends it (fft.FFT: Bluestein for lengths that are not a power of two;
+      // the remaining powers of two take the same float64 kernel with its radix-2 transform): spectral_exact.cu
+      if (N < 8 || N > 2048)
+        return set_error(SONAR_ERR_UNSUPPORTED,
+                         "window size must be 256, 512, 1024, 2048 (fused kernels) or any length in [8, 2048] (float64 route)");
+      plan->R1 = 1, plan->R2 = 1;
+      plan->exact_only = true;
+      break;
   }
   const int R1 = plan->R1, R2 = plan->R2, M = N / 2, B = M + 1;
   plan->N = N;
@@ -255,7 +261,7 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
   // mel regions
   std::vector<MelRegion> reg(nm + 3);
   std::vector<int64_t> bins;
-  const bool ok = host_mel_bins(nm, N, p->algo_sample_rate, p->low_hz, high, bins);
+  const bool ok = host_mel_bins(nm, (B - 1) * 2 /* mfcc.go:173-175 */, p->algo_sample_rate, p->low_hz, high, bins);
   if (!ok) return set_error(SONAR_ERR_UNSUPPORTED, "mel bin points are not representable (negative bins)");
   const bool empty_bank = bins[nm + 1] <= 0 || bins[nm + 1] == bins[0];
   for (auto& r : reg) r = MelRegion{INT_MAX, 0.f, 0.f, 0.f, 0.f};
@@ -299,7 +305,16 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
   plan->off_hann = take(sizeof(double) * 1024);
   plan->off_zero = take(sizeof(double) * N);  // one frame of silence: the lone incomplete frame of an input shorter than the window
   plan->off_win64 = take(sizeof(double) * N);
-  plan->off_fac64 = take(sizeof(double2) * N);
+  const bool pow2 = (N & (N - 1)) == 0;
+  int MF = N;  // length of the radix-2 transforms of the float64 route
+  if (!pow2) {
+    MF = 1;
+    while (MF < 2 * N - 1) MF <<= 1;
+  }
+  plan->fft_len = MF;
+  plan->off_fac64 = take(sizeof(double2) * MF);
+  plan->off_chirp = take(sizeof(double2) * N);
+  plan->off_bluefb = take(sizeof(double2) * MF);
   plan->off_melbins = take(sizeof(int) * (nm + 2));
   plan->off_dct64 = take(sizeof(double) * (size_t)nc * nm);
   plan->off_lift64 = take(sizeof(double) * nc);
@@ -324,7 +339,7 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
     // go-dsp fft/radix2.go getRadix2Factors: the table of size i takes its even entries from the table of size i / 2
     // and evaluates the odd ones as sincos(-2 pi / i * k); the size-4 table is exact
     std::vector<double2> prev = {make_double2(1, 0), make_double2(0, -1), make_double2(-1, 0), make_double2(0, 1)};
-    for (int i = 8; i <= N; i <<= 1) {
+    for (int i = 8; i <= MF; i <<= 1) {
       std::vector<double2> cur(i);
       for (int k = 0; k < i; k += 2) cur[k] = prev[k / 2];
       for (int k = 1; k < i; k += 2) {
@@ -333,7 +348,50 @@ int build_fp_plan(const sonar_fp_params* p, std::shared_ptr<FpPlan>* out) {
       }
       prev.swap(cur);
     }
-    std::memcpy(host.data() + plan->off_fac64, prev.data(), sizeof(double2) * prev.size());
+    std::memcpy(host.data() + plan->off_fac64, prev.data(), sizeof(double2) * std::min<size_t>(prev.size(), (size_t)MF));
+    if (!pow2) {
+      // go-dsp fft/bluestein.go: w_i = exp(i pi i^2 / n) (math.Sincos; w_0 = 1 exactly), b[i] = b[MF - i] = w_i, and the
+      // spectrum of b by the same radix-2 transform the kernel runs (bit reversal, then log2 MF butterfly stages)
+      std::vector<double2> chirp(N), b(MF, make_double2(0, 0));
+      double2* cinv = reinterpret_cast<double2*>(host.data() + plan->off_chirp);
+      for (int i = 0; i < N; i++) {
+        double sn = 0.0, cs = 1.0;
+        if (i != 0) {
+          const double ang = M_PI / (double)N * (double)((int64_t)i * i);
+          sn = std::sin(ang);
+          cs = std::cos(ang);
+        }
+        chirp[i] = make_double2(cs, sn);
+        cinv[i] = make_double2(cs, -sn);
+        b[i] = chirp[i];
+        if (i != 0) b[MF - i] = chirp[i];
+      }
+      int bits = 0;
+      while ((1 << bits) < MF) bits++;
+      std::vector<double2> r(MF);
+      for (int i = 0; i < MF; i++) {
+        int rv = 0;
+        for (int q = 0; q < bits; q++)
+          if (i & (1 << q)) rv |= 1 << (bits - 1 - q);
+        r[i] = b[rv];
+      }
+      for (int stage = 2; stage <= MF; stage <<= 1) {
+        const int blocks = MF / stage, s2 = stage / 2;
+        for (int nb = 0; nb < MF; nb += stage)
+          for (int j = 0; j < s2; j++) {
+            const int i1 = nb + j, i2 = i1 + s2;
+            double2 t = r[i2];
+            if (stage != 2) {
+              const double2 f = prev[(size_t)blocks * j];
+              t = make_double2(r[i2].x * f.x - r[i2].y * f.y, r[i2].x * f.y + r[i2].y * f.x);
+            }
+            const double2 a1 = r[i1];
+            r[i1] = make_double2(a1.x + t.x, a1.y + t.y);
+            r[i2] = make_double2(a1.x - t.x, a1.y - t.y);
+          }
+      }
+      std::memcpy(host.data() + plan->off_bluefb, r.data(), sizeof(double2) * MF);
+    }
     int* mb = reinterpret_cast<int*>(host.data() + plan->off_melbins);
     for (int i = 0; i < nm + 2; i++) mb[i] = (int)bins[i];
     double* d64 = reinterpret_cast<double*>(host.data() + plan->off_dct64);

@@ -530,6 +530,8 @@ int launch_geom(const FpPlan& plan, StftArgs& a, bool spectrum, cudaStream_t st)
 }  // namespace
 
 bool stft_supported(int w) { return w == 256 || w == 512 || w == 1024 || w == 2048; }
+// lengths served by the float64 route only (spectral_exact.cu; go-dsp's Bluestein for lengths that are not powers of two)
+bool stft_exact_only(int w) { return w >= 8 && w <= 2048 && !stft_supported(w); }
 
 int launch_stft_features(const FpPlan& plan, StftArgs& a, bool spectrum, cudaStream_t st) {
   if (!spectrum && stft_v3_eligible(plan, a)) return launch_stft_v3(plan, a, st);

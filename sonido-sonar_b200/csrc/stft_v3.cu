@@ -199,16 +199,70 @@ __device__ __forceinline__ void tw_apply(float2 (&v)[R], const float2* __restric
   }
 }
 
+// Second look at a frame whose rolloff threshold sits within the FP32 SUMMATION error of a cumulative sum: the same
+// magnitudes summed in float64 (their squares and partial sums are exact to ~1e-16), which leaves only the transform's
+// own error `dfft` (relative to the total energy) as the margin.  Rare (~1 % of broadband frames), hence not inlined.
+template <class G>
+__device__ __noinline__ int rolloff_refine(const float* __restrict__ mrow2, float dfft, int lane) {
+  constexpr int BPL = G::BPL;
+  double e[BPL + 1], seg = 0.0;
+#pragma unroll
+  for (int j = 0; j < BPL; ++j) {
+    const double m = (double)mrow2[2 * ppos(BPL * lane + j)];
+    e[j] = m * m;
+    seg += e[j];
+  }
+  e[BPL] = 0.0;
+  if (lane == 31) {
+    const double m = (double)mrow2[2 * ppos(G::M)];
+    e[BPL] = m * m;
+    seg += e[BPL];
+  }
+  double pre = seg;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(kFull3, pre, o);
+    if (lane >= o) pre += up;
+  }
+  const double tot = __shfl_sync(kFull3, pre, 31), target = 0.85 * tot, excl = pre - seg;
+  const unsigned cb = __ballot_sync(kFull3, (pre >= target) && (excl < target || lane == 0));
+  if (!cb) return (G::B - 1) | kExactBit;  // not a number
+  const int cl = __ffs(cb) - 1;
+  int k = 0;
+  double gap = 0.0;
+  if (lane == cl) {
+    double cum = excl, below = excl;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j <= BPL; ++j) {
+      if (j == BPL && lane != 31) break;
+      const double nxt = cum + e[j];
+      if (!found && nxt >= target) {
+        found = true;
+        k = j;
+        below = cum;
+        gap = fmin(nxt - target, target - cum);
+      }
+      cum = nxt;
+    }
+    (void)below;
+  }
+  k = __shfl_sync(kFull3, k, cl);
+  gap = __shfl_sync(kFull3, gap, cl);
+  return (BPL * cl + k) | ((gap > (double)dfft * tot) ? 0 : kExactBit);
+}
+
 // rolloff: first bin whose cumulative energy reaches 85 % (spectral_rolloff.go:19-55).  The lane whose range holds the
 // crossing is found from the prefix of the lanes' energies; its BPL (+1) bins are then scanned by the warp.  The choice is
-// safe when the threshold is further than `delta` (the bound on the FP32 error of cumulative sum minus threshold) from
-// the cumulative sums on both sides of the chosen bin; otherwise kExactBit is set and float64 decides.
+// safe when the threshold is further than `delta` (transform error + FP32 summation error, both relative to the total)
+// from the cumulative sums on both sides of the chosen bin; otherwise rolloff_refine removes the summation error, and
+// only a threshold within the transform's error `dfft` of a cumulative sum sets kExactBit (float64 from the PCM decides).
 template <class G>
-__device__ __forceinline__ int rolloff_bin(const float* __restrict__ mrow2, float pre, float seg, float etot, float delta,
+__device__ __forceinline__ int rolloff_bin(const float* __restrict__ mrow2, float pre, float seg, float etot, float dfft,
                                            int lane) {
   constexpr int BPL = G::BPL;
   int rk = (G::B - 1) | kExactBit;
-  const float target = 0.85f * etot;
+  const float target = 0.85f * etot, delta = (dfft + kRollSum) * etot;
   const float excl = pre - seg;
   const unsigned cb = __ballot_sync(kFull3, (pre >= target) && (excl < target || lane == 0));
   if (cb) {
@@ -229,9 +283,9 @@ __device__ __forceinline__ int rolloff_bin(const float* __restrict__ mrow2, floa
     if (lane == 0) below = ex0;
     const float gap = fminf(cum - target, target - below);  // both positive at lane h when the search was clean
     const float gh = __shfl_sync(kFull3, gap, h);
-    rk = (BPL * cl + h) | ((hit && gh > delta) ? 0 : kExactBit);
+    if (hit && gh > delta) return BPL * cl + h;
   }
-  return rk;
+  return rolloff_refine<G>(mrow2, dfft, lane);
 }
 
 template <int LOGN, int HR>
@@ -524,8 +578,11 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
         const float clog = kLogTau * (float)B * sqrt_fast3((float)B) / kEta;
         bool xa = !(ri.x * sqrt_fast3(etot.x) <= clog) || !(mn > kTinyMag) || !(etot.x > 0.f);
         bool xb = !(ri.y * sqrt_fast3(etot.y) <= clog) || !(mn > kTinyMag) || !(etot.y > 0.f);
-        int rka = rolloff_bin<G>(rowf, pre.x, ac.seg.x, etot.x, 4.f * kEta * mxa * sm.x + kRollSum * etot.x, lane);
-        int rkb = rolloff_bin<G>(rowf + 1, pre.y, ac.seg.y, etot.y, 4.f * kEta * mxb * sm.y + kRollSum * etot.y, lane);
+        // transform error of a cumulative sum of squares: sum 2 m_k e_k with |e_k| <= kEta * RMS level, all aligned
+        // (~50 standard deviations of the actual, random, sum) + 1e-7 for the rounding of the window / twiddle tables
+        const float irb = 2.f * kEta * rsqrt_fast3((float)B);
+        int rka = rolloff_bin<G>(rowf, pre.x, ac.seg.x, etot.x, irb * sm.x * rsqrt_fast3(fmaxf(etot.x, 1e-36f)) + 1e-7f, lane);
+        int rkb = rolloff_bin<G>(rowf + 1, pre.y, ac.seg.y, etot.y, irb * sm.y * rsqrt_fast3(fmaxf(etot.y, 1e-36f)) + 1e-7f, lane);
 
         __syncwarp();  // private mel slots visible
         // ---- ln + DCT-II + lifter (mfcc.go:136-157), both frames ----
