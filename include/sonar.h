@@ -569,6 +569,15 @@ typedef struct sonar_cmp_features {
   double dynamic_range, silence_ratio, onset_density;
 } sonar_cmp_features;
 
+/* AlignmentExtractor.TruncateToAlignmentPCM (fingerprint/extractors/alignment.go:223-297): where the aligned,
+ * 0.5 s-padded segments of the two streams start and how long they are, from AlignmentFeatures.TemporalOffset
+ * (seconds; > 0: stream 2 is ahead).  Pure index arithmetic -- the segments are pcm1[start1 : start1+len] and
+ * pcm2[start2 : start2+len]; the shim slices, re-fingerprints both (sonar_fingerprint_batch_*) and compares
+ * (sonar_compare_f64): the rest of the CDN-latency loop.  Errors as the reference's: "offset too large: ...",
+ * "no overlapping audio after alignment". */
+int sonar_truncate_to_alignment(int64_t n1, int64_t n2, int sample_rate, double offset_seconds, int64_t* start1,
+                                int64_t* start2, int64_t* length);
+
 /* feature weights in the order mfcc, spectral, chroma, temporal, speech,
  * harmonic, energy (comparison.go:1055-1104; fp1.Metadata["feature_weights"]) */
 typedef struct sonar_cmp_weights { double w[7]; } sonar_cmp_weights;

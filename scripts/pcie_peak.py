@@ -1,15 +1,15 @@
 """Host <-> device copy ceiling of the box, alone and with every rank copying at once (the e2e leg stops
 scaling at ~130 GB/s aggregate on 8 ranks -- is that the hardware?).
 usage: python scripts/pcie_peak.py                               one GPU
-       python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/pcie_peak.py [--numa]
---numa binds each rank to the CPUs of its GPU's NUMA node before the pinned buffer is allocated (first touch)."""
+       python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/pcie_peak.py [--bind-numa]
+--bind-numa binds each rank to the CPUs of its GPU's NUMA node before the pinned buffer is allocated (first touch)."""
 import json, os, sys, time
 import torch
 
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 numa = None
-if "--numa" in sys.argv:
+if "--bind-numa" in sys.argv:
     from bench import bind_to_gpu_numa
     numa = bind_to_gpu_numa(lr)
 torch.cuda.set_device(lr)

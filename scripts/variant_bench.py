@@ -4,9 +4,11 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("sonido-sonar_b200")
-S, SEC = 16, 300.0
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+SEC = 300.0
 n = int(SEC * 44100); stride = (n + 1) & ~1
-x = torch.from_numpy(pkg.synth.sweep_noise(SEC, seed=9)).cuda()
+sig = sys.argv[2] if len(sys.argv) > 2 else "sweep"
+x = torch.from_numpy(pkg.synth.sweep_noise(SEC, seed=9) if sig == "sweep" else pkg.synth.envelope_noise(n, seed=2)).cuda()
 pcm = torch.zeros((S, stride), dtype=torch.float64, device="cuda"); pcm[:, :n] = x
 libs = sorted(glob.glob(os.path.join(ROOT, "build", "variants", "libsonar_*.so"))) + [None]
 ref = None

@@ -187,6 +187,7 @@ EXPORTS = (
     "sonar_xcorr_shard_open", "sonar_xcorr_shard_metrics_f64", "sonar_xcorr_shard_corr",
     "sonar_xcorr_shard_close", "sonar_xcorr_merge_peaks", "sonar_xcorr_merge_metrics",
     "sonar_nccl_unique_id", "sonar_nccl_init", "sonar_nccl_shutdown", "sonar_xcorr_lag_sharded",
+    "sonar_truncate_to_alignment",
     "sonar_align_xcorr_f64", "sonar_dtw_f64", "sonar_dtw_batch_f64", "sonar_align_dtw_scalars",
     "sonar_colstats_cosine_f64", "sonar_colstats_f64", "sonar_compare_f64",
     "sonar_music_spectral_f64", "sonar_compare_batch_f64", "sonar_align_pairs_sizes", "sonar_align_pairs_f64", "sonar_align_pairs_pcm", "sonar_align_pairs_dev",
@@ -822,6 +823,15 @@ class SonarLib:
             f.silence_ratio = fp.scalars["silence_ratio"]
             f.onset_density = fp.scalars["onset_density"]
         return f, keep
+
+    def truncate_to_alignment(self, n1: int, n2: int, sample_rate: int, offset_seconds: float):
+        """sonar_truncate_to_alignment: (start1, start2, length) of TruncateToAlignmentPCM's segments."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.lib.sonar_truncate_to_alignment.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_double, c_int64_p, c_int64_p,
+                                                         c_int64_p]
+        self._chk(self.lib.sonar_truncate_to_alignment(n1, n2, sample_rate, offset_seconds, C.byref(a), C.byref(b),
+                                                       C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
 
     def compare_batch(self, query: CmpFeatures, candidates, weights, content_filter=False):
         """sonar_compare_batch_f64: FingerprintComparator.BatchCompare (None candidates are skipped)."""

@@ -419,6 +419,41 @@ struct sonar_xcorr_shard {
 
 extern "C" {
 
+int sonar_truncate_to_alignment(int64_t n1, int64_t n2, int sample_rate, double offset_seconds, int64_t* start1,
+                                int64_t* start2, int64_t* length) {
+  if (!start1 || !start2 || !length) return set_error(SONAR_ERR_INVALID, "nil argument");
+  const double srf = (double)sample_rate;
+  /* int(math.Round(math.Abs(offsetSeconds) * sampleRateFloat)): math.Round rounds half away from zero = std::round */
+  const int64_t off = (int64_t)std::round(std::fabs(offset_seconds) * srf);
+  int64_t s1 = 0, s2 = 0, common = 0;
+  if (offset_seconds > 0) { /* :241-253 */
+    s2 = off;
+    if (s2 >= n2)
+      return set_error(SONAR_ERR_INVALID, "offset too large: need to skip " + std::to_string(s2) + " samples but pcm2 only has " +
+                                         std::to_string(n2));
+    common = std::min(n1 - s1, n2 - s2);
+  } else if (offset_seconds < 0) { /* :255-267 */
+    s1 = off;
+    if (s1 >= n1)
+      return set_error(SONAR_ERR_INVALID, "offset too large: need to skip " + std::to_string(s1) + " samples but pcm1 only has " +
+                                         std::to_string(n1));
+    common = std::min(n1 - s1, n2 - s2);
+  } else {
+    common = std::min(n1, n2); /* :269-272 */
+  }
+  if (common <= 0) return set_error(SONAR_ERR_INVALID, "no overlapping audio after alignment"); /* :275-277 */
+  const int64_t pad = (int64_t)(0.5 * srf); /* :281-286 */
+  if (common > 2 * pad) {
+    s1 += pad;
+    s2 += pad;
+    common -= 2 * pad;
+  }
+  *start1 = s1;
+  *start2 = s2;
+  *length = common;
+  return SONAR_OK;
+}
+
 int sonar_xcorr_ncc_f64(sonar_ctx* ctx, const double* a, int64_t na, const double* b, int64_t nb, int max_lag,
                         double* corr, sonar_xcorr_summary* out) {
   if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");

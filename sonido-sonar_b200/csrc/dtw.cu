@@ -80,6 +80,12 @@ constexpr int kStageBytes = 48 * 1024;  // cost cells staged in shared memory be
 //    indices that advances by one every two diagonals, so they are staged in two shared-memory rings
 //    (refilled every 256 diagonals) and the local distance of the NEXT diagonal is computed before the
 //    barrier, off the dependent min/add chain.
+// math.Min (Go): NaN when either argument is NaN; the costs are sums of non-negative distances, so -0 never occurs
+__device__ __forceinline__ double go_min(double a, double b) {
+  if (a != a || b != b) return a + b;  // NaN
+  return a < b ? a : b;
+}
+
 template <bool STAGED, bool ONECELL>
 __global__ void __launch_bounds__(1024) dtw_fill_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
                                                         DtwGeom g, int dim, int step, double* __restrict__ cells_all,
@@ -158,13 +164,13 @@ __global__ void __launch_bounds__(1024) dtw_fill_kernel(const double* __restrict
       else
         ld = local_dist(q + (int64_t)(i - 1) * dim, r + (int64_t)(j - 1) * dim, dim);
       const double v = line[o - 1], h = line[o + 1], dg = line[o];
-      double mc;
+      double mc;  // Go's math.Min: NaN if either argument is NaN (fmin would drop it)
       if (step == SONAR_STEP_SYMMETRIC2)
-        mc = fmin(fmin(v, h), dg);
+        mc = go_min(go_min(v, h), dg);
       else if (step == SONAR_STEP_ASYMMETRIC)
-        mc = fmin(v, h);
+        mc = go_min(v, h);
       else
-        mc = fmin(v + 1.0, fmin(h + 1.0, dg));
+        mc = go_min(v + 1.0, go_min(h + 1.0, dg));
       const double c = ld + mc;
       line[o] = c;
       if constexpr (ONECELL) {
@@ -216,9 +222,34 @@ __device__ __forceinline__ double dist1(double a, double b) {
 //   * |q - r| needs no per-cell range test when the sequences were pre-screened (FAST, see dtw_safe_range);
 // The backtrack's choice at every cell (findPreviousStep's strict-'<' scan: vertical, horizontal, diagonal)
 // is a function of the finished cost store; dtw_dirs_kernel derives it for all cells in parallel afterwards.
-template <int STEP>
+// min of two NON-NEGATIVE doubles (finite, +0 or +Inf) through their bit patterns: IEEE-754 orders them like unsigned
+// integers, and an integer compare + select has a third of the latency of DSETP + select on this chip (the FP64 pipe's
+// dependent-issue latency is what the fill's chain of (min, min, add) per diagonal consists of).
+__device__ __forceinline__ double umin_nonneg(double a, double b) {
+  return (unsigned long long)__double_as_longlong(a) < (unsigned long long)__double_as_longlong(b) ? a : b;
+}
+
+template <int STEP, bool NANSAFE = false, bool INTMIN = false>
 __device__ __forceinline__ double dtw_relax(double v, double hh, double dg, double ld) {
   double mc;
+  if (INTMIN) {  // screened input: every cost is a sum of |q - r| >= +0 or the +Inf of a cell outside the band
+    if (STEP == SONAR_STEP_SYMMETRIC2)
+      mc = umin_nonneg(umin_nonneg(v, hh), dg);
+    else if (STEP == SONAR_STEP_ASYMMETRIC)
+      mc = umin_nonneg(v, hh);
+    else
+      mc = umin_nonneg(v + 1.0, umin_nonneg(hh + 1.0, dg));
+    return ld + mc;
+  }
+  if (NANSAFE) {  // inputs that failed the screen may be NaN / Inf: math.Min propagates NaN
+    if (STEP == SONAR_STEP_SYMMETRIC2)
+      mc = go_min(go_min(v, hh), dg);
+    else if (STEP == SONAR_STEP_ASYMMETRIC)
+      mc = go_min(v, hh);
+    else
+      mc = go_min(v + 1.0, go_min(hh + 1.0, dg));
+    return ld + mc;
+  }
   if (STEP == SONAR_STEP_SYMMETRIC2) {  // min(a, b) as (a < b ? a : b) equals math.Min for non-NaN values
     const double t = v < hh ? v : hh;
     mc = t < dg ? t : dg;
@@ -316,7 +347,7 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
     for (int h = 0; h < H; ++h) {
       const int x = 2 * h + 1;
       const double hh = (h == H - 1) ? edge : L[x + 1 < NPL ? x + 1 : x];
-      c[h] = dtw_relax<STEP>(L[x - 1], hh, L[x], local(Q[h], R[h + 1], ok[h]));  // cell (ib+h, jb-h): q[ib+h-1], r[jb-h-1]
+      c[h] = dtw_relax<STEP, !FAST, FAST>(L[x - 1], hh, L[x], local(Q[h], R[h + 1], ok[h]));  // cell (ib+h, jb-h): q[ib+h-1], r[jb-h-1]
     }
 #pragma unroll
     for (int h = 0; h < H; ++h) {
@@ -332,7 +363,7 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
     for (int h = 0; h < H; ++h) {
       const int x = 2 * h;
       const double v = (h == 0) ? edge : L[x > 0 ? x - 1 : 0];
-      c[h] = dtw_relax<STEP>(v, L[x + 1], L[x], local(Q[h], R[h], ok[h]));  // cell (ib+h, jb-h+1): q[ib+h-1], r[jb-h]
+      c[h] = dtw_relax<STEP, !FAST, FAST>(v, L[x + 1], L[x], local(Q[h], R[h], ok[h]));  // cell (ib+h, jb-h+1): q[ib+h-1], r[jb-h]
     }
 #pragma unroll
     for (int h = 0; h < H; ++h) {

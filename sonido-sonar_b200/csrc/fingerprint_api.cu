@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <sstream>
 #include <thread>
 
@@ -168,9 +169,11 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
   a.o_flux = L.spectral_flux;
   a.o_low = L.low_energy_ratio;
   a.o_high = L.high_energy_ratio;
-  // The fused STFT kernel and the float64 re-evaluation of the frames it lists.  Enqueued AFTER the frame walk and the
-  // pitch detector: the alignment branch of the pair pipeline only waits for the walk's energies, so it starts ~7 ms
-  // earlier and runs beside the pitch kernel (whose CTAs leave room on an SM; the STFT kernel's fill the register file).
+  // The fused STFT kernel and the float64 re-evaluation of the frames it lists.  Enqueued AFTER the frame walk: the
+  // alignment branch of the pair pipeline only waits for the walk's energies.  The STFT kernel's CTAs fill the register
+  // file of an SM, so the branch's kernels mostly queue behind it and then run beside the pitch kernel, whose CTAs leave
+  // room.  (Measured, 32 pairs: STFT before the walk 30.2 ms, after the pitch kernel 27.6 ms -- but then the pitch
+  // tracker and the branch share the SMs with the STFT kernel and stretch it from 6.8 to 7.8 .. 10 ms.)
   auto run_stft = [&]() -> int {
     // only the third-generation kernel lists frames (the other geometries keep their stated FP32 bounds)
     a.xlist = stft_v3_eligible(*plan, a) ? reinterpret_cast<int*>(tmp_dev + sh.o_xlist) : nullptr;
@@ -212,8 +215,11 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
     }
     return SONAR_OK;
   };
-  static const bool stft_first = std::getenv("SONAR_STFT_FIRST") != nullptr;  // diagnostic: the r01 order
-  if (stft_first && (rc = run_stft())) return rc;
+  // order on `st`: frame walk -> [energies ready: the alignment branch may start] -> STFT (+ float64 re-evaluation) ->
+  // pitch detector -> small kernels.  SONAR_FP_ORDER=stft_first / yin_first select the other two orders (diagnostic).
+  static const char* order_env = std::getenv("SONAR_FP_ORDER");
+  static const int order = !order_env ? 0 : (std::string(order_env) == "stft_first" ? 1 : (std::string(order_env) == "yin_first" ? 2 : 0));
+  if (order == 1 && (rc = run_stft())) return rc;
 
   // exact FP64 walks over the pre-emphasised PCM: short-time energy (+entropy) and ZCR
   const bool same_grid = !short_win && (Te == T) && p->energy_frame == p->window_size && p->energy_hop == p->hop_size;
@@ -241,7 +247,13 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
   }
   // the alignment branch of the pair pipeline only needs the short-time energies: it may start on its own stream
   // here, next to the rest of the fingerprint (loudness range, YIN)
-  if (energy_ready) SONAR_CUDA(cudaEventRecord(energy_ready, st));
+  // The alignment branch starts right behind the walk; its first kernels (z-score, FFT screen) then share the SMs with
+  // the STFT kernel, which costs that kernel ~10 % (7.3 -> 8.2 ms) but the step 2.8 ms less (24.8 vs 27.6 ms, 32 pairs)
+  // than starting the branch behind the STFT kernel (SONAR_ALIGN_LATE, diagnostic)
+  static const bool align_early = std::getenv("SONAR_ALIGN_LATE") == nullptr;
+  if (energy_ready && (align_early || order != 0)) SONAR_CUDA(cudaEventRecord(energy_ready, st));
+  if (order == 0 && (rc = run_stft())) return rc;
+  if (energy_ready && !align_early && order == 0) SONAR_CUDA(cudaEventRecord(energy_ready, st));
   if (Te > T) {  // band ratios only exist where a magnitude frame does (speech.go:436-456)
     rc = launch_fill_strided(feat_dev + L.low_energy_ratio + T, Te - T, L.total, ns, 0.0, st);
     if (rc) return rc;
@@ -268,7 +280,7 @@ int enqueue_fingerprint(sonar_ctx* ctx, int device, const sonar_fp_params* p, co
                     sh.speech ? feat_dev + sh.o_sgate : nullptr, L.total);
     if (rc) return rc;
   }
-  if (!stft_first && (rc = run_stft())) return rc;
+  if (order == 2 && (rc = run_stft())) return rc;
 
   if (Te >= 2) {
     rc = launch_variance(feat_dev + L.short_time_energy, Te, L.total, ns, feat_dev + L.scalars, L.total, st);

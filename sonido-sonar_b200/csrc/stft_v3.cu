@@ -34,14 +34,21 @@
 namespace sonar {
 namespace {
 
-constexpr int kW3 = 12;               // warps per CTA (one CTA per SM)
+#ifndef V3_WARPS
+#define V3_WARPS 12
+#endif
+constexpr int kW3 = V3_WARPS;         // warps per CTA (one CTA per SM)
 constexpr int kRun3 = 32;             // frames per segment: finished in FP64 one frame per lane
 constexpr int kSeg3 = 4;              // segments per run: a warp walks kSeg3 * 32 consecutive frames of one stream, the
 constexpr int kRunOut3 = kSeg3 * kRun3 - 1;  // first of which only warms the flux up (it has no predecessor at hand)
 constexpr unsigned kFull3 = 0xffffffffu;
 constexpr int kTileRow = 34;          // exchange tile row stride (float2): 16-byte rows, conflict-free LDS.128
 constexpr int kSlots3 = 24;           // lane-private mel slots (float2: both frames of a pack; alias the tile in the scan)
+#ifdef V3_RAW16
+constexpr int kRaw3 = 16;
+#else
 constexpr int kRaw3 = 12;             // raw sums parked per frame
+#endif
 constexpr int kMaxContrib3 = 12;      // lanes that may hold a part of one mel filter
 // ---- frames handed to the float64 re-evaluation (spectral_exact.cu) ---------------------------------------------
 // The FP32 transform leaves an absolute error of a few 1e-7 of the frame's RMS spectral level on every bin (random, white;
@@ -284,8 +291,15 @@ __device__ __forceinline__ int rolloff_bin(const float* __restrict__ mrow2, floa
     const float gap = fminf(cum - target, target - below);  // both positive at lane h when the search was clean
     const float gh = __shfl_sync(kFull3, gap, h);
     if (hit && gh > delta) return BPL * cl + h;
+#ifdef V3_NO_REFINE
+    return (BPL * cl + h) | kExactBit;
+#endif
   }
+#ifdef V3_NO_REFINE
+  return rk;
+#else
   return rolloff_refine<G>(mrow2, dfft, lane);
+#endif
 }
 
 template <int LOGN, int HR>
@@ -399,13 +413,18 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
 #pragma unroll
   for (int v = 0; v < NV; ++v) woff[v] = ppos(k1 + KSTR * v) - KSTR * v;
 
-  // runs are handed out through a counter: a CTA that starts late (its SM was busy with another stream's kernel) simply
-  // takes fewer of them
+  // (V3_DYNAMIC_RUNS: runs handed out through a counter, so that a CTA that starts late -- its SM busy with another
+  // stream's kernel -- simply takes fewer of them)
+#ifndef V3_DYNAMIC_RUNS  // static striding measured 2.5 % faster at 64 streams (7.36 vs 7.57 ms); the counter only pays
+                         // off when CTAs start late, which the walk -> STFT order avoids
+  for (int64_t run = (int64_t)blockIdx.x * kW3 + warp; run < a.total_runs; run += (int64_t)gridDim.x * kW3) {
+#else
   for (;;) {
     int64_t run = 0;
     if (lane == 0) run = (int64_t)atomicAdd(a.work_counter, 1u);
     run = __shfl_sync(kFull3, run, 0);
     if (run >= a.total_runs) break;
+#endif
     const int s = (int)(run / a.runs_per_stream);
     const int64_t t0 = (run % a.runs_per_stream) * (int64_t)kRunOut3;
     const int64_t tend = (t0 + kRunOut3 < T) ? t0 + kRunOut3 : T;
@@ -482,7 +501,9 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
           const float2 q = make_float2(qa.x + qa.y, qb.x + qb.y);
           const float2 ri = make_float2(rsqrt_fast3(fmaxf(q.x, 1e-36f)), rsqrt_fast3(fmaxf(q.y, 1e-36f)));
           const float2 m = __fmul2_rn(q, ri);
+#ifndef V3_NO_WEAK
           rinv = __fadd2_rn(rinv, ri);
+#endif
           const float d = first_pack ? fmaxf(m.x - oldb[2 * e], 0.f) : 0.f;
           fla = fmaf(d, d, fla);
           row[e] = m;
@@ -593,8 +614,10 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
             for (int i = 0; i < ncontrib; ++i) v = pk::add(v, wbf2[s_moff[i * kMaxMel + f]]);
             macc[f] = make_float2(v.x > 0.f ? __logf(v.x) : -23.025850929940457f,
                                   v.y > 0.f ? __logf(v.y) : -23.025850929940457f);  // ln(1e-10)
+#ifndef V3_NO_WEAK
             const float iw = s_invw[f];
             if (iw > 0.f) dens = make_float2(fminf(dens.x, v.x * iw), fminf(dens.y, v.y * iw));
+#endif
           }
           // a band whose level is below kMelRatio of the frame's mean level sits in the transform's noise: ln E errs by > 1e-4
           const float lim = kMelRatio / (float)B;
@@ -651,10 +674,12 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
           const float4 r0 = rs4[0], r1 = rs4[1], r2 = rs4[2];
           const float sm = r0.x, kc = r0.y, etot = r0.z, bw = r1.x, sl = r1.y, sxy = r1.z, mx = r1.w, fl = r2.x, plow = r2.y;
           const int rkx = __float_as_int(r0.w), rk = rkx & ~kExactBit;
+#ifndef V3_NO_LIST
           if ((rkx & kExactBit) && a.xlist) {  // listed for spectral_exact.cu, which overwrites what is stored below
             int* lst = a.xlist + (int64_t)s * a.xlist_stride;
             lst[1 + atomicAdd(lst, 1)] = (int)t;
           }
+#endif
           const double fs = a.freq_scale;
           const double dsm = (double)sm;
           fo[a.o_centroid + t] = (double)kc * fs;

@@ -315,3 +315,34 @@ def test_library_side_lag_shard_with_its_own_nccl_communicator(gpu, oracle):
         assert getattr(s, k) == pytest.approx(getattr(s1, k), rel=1e-9), k
     s2, _ = gpu.xcorr_lag_sharded(a, b, 700)  # no communicator: one shard
     assert s2.peak_lag == s.peak_lag and s2.peak_correlation == s.peak_correlation
+
+
+def test_cdn_latency_loop_align_truncate_refingerprint_compare(gpu, oracle, synth):
+    """SURVEY §8 f3 / VERDICT r1 missing #6: the whole loop around the hot path -- ExtractAlignmentFeatures on both
+    streams, TruncateToAlignmentPCM by the detected offset (extractors/alignment.go:223-297), GenerateFingerprint of
+    the two aligned segments, FingerprintComparator.Compare -- through the C ABI, against the same chain on the oracle."""
+    sr, hop = 44100, 256
+    q, r = synth.aligned_pair(20.0, offset_seconds=2.37, sr=sr, seed=77)
+    p = gpu.default_params(algo_sample_rate=sr, call_sample_rate=sr)
+    w = [0.5, 0.2, 0.0, 0.1, 0.0, 0.2, 0.0]
+
+    def chain(lib):
+        res = lib.align_pairs([q], [r], p, 5.0, 50)[0]
+        off_s = res["corr_alignment"].offset_seconds
+        s1, s2, n = lib.truncate_to_alignment(q.size, r.size, sr, off_s)
+        f1, f2 = lib.fingerprint_batch([q[s1:s1 + n], r[s2:s2 + n]], p)
+        c1, k1 = lib.cmp_features(f1)
+        c2, k2 = lib.cmp_features(f2)
+        return res, (s1, s2, n), f1, f2, lib.compare(c1, c2, w).as_dict()
+
+    rg, tg, g1, g2, cg = chain(gpu)
+    ro, to, o1, o2, co = chain(oracle)
+    assert rg["xcorr"].peak_lag == ro["xcorr"].peak_lag and rg["corr_alignment"].offset == ro["corr_alignment"].offset
+    assert tg == to
+    for a, b in ((g1, o1), (g2, o2)):
+        assert np.array_equal(a.short_time_energy, b.short_time_energy)
+        assert np.array_equal(a.spectral_rolloff, b.spectral_rolloff)
+        np.testing.assert_allclose(a.mfcc, b.mfcc, rtol=1e-4, atol=1e-4 * np.max(np.abs(b.mfcc)))
+    for k in cg:
+        assert cg[k] == pytest.approx(co[k], rel=1e-6, abs=1e-9, nan_ok=True), k
+    assert cg["dist_mfcc"] < 1e-3 and cg["overall_similarity"] > 0.7  # the aligned segments are the same programme

@@ -74,3 +74,23 @@ def test_dtw_errors(gpu, capi):
     with pytest.raises(capi.SonarError) as e:
         gpu.dtw(np.zeros((0, 1)), np.zeros((4, 1)))
     assert e.value.code == capi.ERR_EMPTY and "empty sequences provided" in e.value.msg
+
+
+@pytest.mark.parametrize("n,m,dim,band,step", [(300, 300, 1, 50, 0), (120, 140, 1, -1, 0), (200, 200, 3, 30, 2),
+                                               (90, 90, 1, 10, 1)])
+def test_dtw_nan_inputs_propagate_like_math_min(gpu, oracle, n, m, dim, band, step):
+    """Go's math.Min returns NaN when either argument is NaN (dtw.go:137-164), fmin would drop it.  With a
+    NaN (and an Inf) inside the sequences the cost matrix turns NaN behind it and the backtrack's strict '<' scan
+    (dtw.go:191-217) walks differently: path, costs and matrix must still equal the oracle's."""
+    rng = np.random.default_rng(n + m + dim + band)
+    q = np.cumsum(rng.standard_normal((n, dim)), axis=0)
+    r = np.cumsum(rng.standard_normal((m, dim)), axis=0)
+    q[n // 3, 0] = np.nan
+    r[2 * m // 3, dim - 1] = np.inf
+    small = n * m <= 100000
+    a = gpu.dtw(q, r, band=band, step=step, want_matrix=small)
+    b = oracle.dtw(q, r, band=band, step=step, want_matrix=small)
+    assert np.array_equal(a["path_query"], b["path_query"]) and np.array_equal(a["path_ref"], b["path_ref"])
+    assert np.array_equal(a["path_cost"], b["path_cost"], equal_nan=True)
+    if small:
+        assert np.array_equal(a["cost_matrix"], b["cost_matrix"], equal_nan=True)

@@ -628,3 +628,23 @@ def test_speech_group_not_speech_returns_empty(oracle, synth):
     assert not sp["is_speech"] and sp["voicing_probability"].size == 0 and sp["n_pause"] == 0 and sp["speech_rate"] == 0.0
     plain = oracle.fingerprint(x, p)
     assert np.array_equal(fp.pitch_estimate, plain.pitch_estimate) and np.array_equal(fp.mfcc, plain.mfcc)
+
+
+@pytest.mark.parametrize("n1,n2,sr,off", [(441000, 441000, 44100, 7.3), (441000, 400000, 44100, -3.21), (20000, 50000, 16000, 0.0),
+                                          (30000, 30000, 44100, 0.1), (50000, 50000, 44100, 0.99999)])
+def test_truncate_to_alignment_against_the_go_arithmetic(oracle, n1, n2, sr, off):
+    """TruncateToAlignmentPCM (extractors/alignment.go:223-297) restated in Python."""
+    o = int(np.floor(abs(off) * sr + 0.5))  # math.Round: half away from zero (the argument is non-negative)
+    s1, s2 = (0, o) if off > 0 else ((o, 0) if off < 0 else (0, 0))
+    common = min(n1 - s1, n2 - s2)
+    pad = int(0.5 * sr)
+    if common > 2 * pad:
+        s1, s2, common = s1 + pad, s2 + pad, common - 2 * pad
+    assert oracle.truncate_to_alignment(n1, n2, sr, off) == (s1, s2, common)
+
+
+def test_truncate_to_alignment_errors(oracle, capi):
+    with pytest.raises(capi.SonarError, match="offset too large: need to skip 88200 samples but pcm2 only has 1000"):
+        oracle.truncate_to_alignment(50000, 1000, 44100, 2.0)
+    with pytest.raises(capi.SonarError, match="offset too large: need to skip 44100 samples but pcm1 only has 44100"):
+        oracle.truncate_to_alignment(44100, 90000, 44100, -1.0)
