@@ -153,14 +153,13 @@ __device__ __forceinline__ float lg2_fast3(float x) {
 // Per-lane accumulators of the scan; every float2 is (frame a, frame b) of a pack.
 struct BinAcc3 {
   float2 seg, sl, sxy, fl, s0, s1, s2, mlo, mhi, pend;
-  float mxa, mxb, mn;
+  float mxa, mxb;
   float2* pp;  // next lane-private mel slot
 };
 __device__ __forceinline__ void acc_init(BinAcc3& s, float2* pp) {
   const float2 z = make_float2(0.f, 0.f);
   s.seg = s.sl = s.sxy = s.fl = s.s0 = s.s1 = s.s2 = s.mlo = s.mhi = s.pend = z;
   s.mxa = s.mxb = 0.f;
-  s.mn = FLT_MAX;
   s.pp = pp;
 }
 // One bin of the scan for both frames of a pack: m = (|X_a[k]|, |X_b[k]|), pv = |X[k]| of the frame before a.
@@ -188,7 +187,6 @@ __device__ __forceinline__ void bin_step3(BinAcc3& s, bool flux_a, int jj, bool 
   }
   s.mxa = fmaxf(s.mxa, m.x);
   s.mxb = fmaxf(s.mxb, m.y);
-  s.mn = fminf(s.mn, fminf(m.x, m.y));
   const float2 l2 = make_float2(lg2_fast3(m.x), lg2_fast3(m.y));
   s.sl = pk::add(s.sl, l2);
   s.sxy = pk::fma(l2, xv, s.sxy);  // xtab[0] == 0: bin 0 never enters the regression
@@ -496,10 +494,11 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
           const float2 xb = __fadd2_rn(make_float2(zz.y, -zz.x), make_float2(pz.y, pz.x));
           const float2 qa = __fmul2_rn(xa, xa), qb = __fmul2_rn(xb, xb);
           const int e = woff[k2 % NV] + KSTR * k2;
-          // |X| = q rsqrt(q): one MUFU gives the magnitude AND its reciprocal (the weak-bin test); the floor keeps
-          // q = 0 finite (|X| = 0, 1 / |X| = 1e18)
+          // |X| = q rsqrt(q): one MUFU gives the magnitude AND its reciprocal (the weak-bin test)
           const float2 q = make_float2(qa.x + qa.y, qb.x + qb.y);
-          const float2 ri = make_float2(rsqrt_fast3(fmaxf(q.x, 1e-36f)), rsqrt_fast3(fmaxf(q.y, 1e-36f)));
+          // (the 1e-36 keeps q = 0 finite: |X| = 0, 1 / |X| = 1e18; one packed add for both frames)
+          const float2 qt = __fadd2_rn(q, make_float2(1e-36f, 1e-36f));
+          const float2 ri = make_float2(rsqrt_fast3(qt.x), rsqrt_fast3(qt.y));
           const float2 m = __fmul2_rn(q, ri);
 #ifndef V3_NO_WEAK
           rinv = __fadd2_rn(rinv, ri);
@@ -591,14 +590,18 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
         float2 sl = warp_sum3(ac.sl), sxy = warp_sum3(ac.sxy);
         const float2 fl = warp_sum3(ac.fl);
         const float mxa = warp_max3(ac.mxa), mxb = warp_max3(ac.mxb);
-        const float mn = -warp_max3(-ac.mn);
         const float2 ri = PK == 1 ? rinv : make_float2(__shfl_sync(kFull3, rinv.x, 16 * p), __shfl_sync(kFull3, rinv.y, 16 * p));
         // float64 re-evaluation wanted (spectral_exact.cu): the mean of ln|X_k| cannot be trusted when
-        // kEta * RMS level * mean(1 / |X_k|) exceeds kLogTau, magnitudes near the 1e-10 validity threshold, silence, and
-        // anything not finite (the negated comparisons catch NaN)
+        // kEta * RMS level * mean(1 / |X_k|) exceeds kLogTau; a magnitude near the reference's 1e-10 validity threshold
+        // shows as sum 1 / |X_k| >= 1 / kTinyMag; silence; anything not finite (the negated comparisons catch NaN)
         const float clog = kLogTau * (float)B * sqrt_fast3((float)B) / kEta;
-        bool xa = !(ri.x * sqrt_fast3(etot.x) <= clog) || !(mn > kTinyMag) || !(etot.x > 0.f);
-        bool xb = !(ri.y * sqrt_fast3(etot.y) <= clog) || !(mn > kTinyMag) || !(etot.y > 0.f);
+#ifdef V3_NO_XFLAGS
+        bool xa = false, xb = false;
+        (void)clog, (void)ri;
+#else
+        bool xa = !(ri.x * sqrt_fast3(etot.x) <= clog) || !(ri.x < 1.f / kTinyMag) || !(etot.x > 0.f);
+        bool xb = !(ri.y * sqrt_fast3(etot.y) <= clog) || !(ri.y < 1.f / kTinyMag) || !(etot.y > 0.f);
+#endif
         // transform error of a cumulative sum of squares: sum 2 m_k e_k with |e_k| <= kEta * RMS level, all aligned
         // (~50 standard deviations of the actual, random, sum) + 1e-7 for the rounding of the window / twiddle tables
         const float irb = 2.f * kEta * rsqrt_fast3((float)B);

@@ -84,7 +84,7 @@ __device__ __forceinline__ void warp_fft1024(float2 (&v)[32], float2* __restrict
                                              int lane) {
   // ONE instance of the radix-32 butterflies serves both passes (not unrolled): the kernel's straight-line code was
   // 230 KB, far beyond the 32 KB instruction cache level, and instruction fetch was its largest stall
-  // (profiles/r02_yin32_ncu.md)
+  // (profiles/r02_kernels_ncu_full.md)
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     pk::Fft<32>::run(v);
