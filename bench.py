@@ -389,13 +389,20 @@ def extra_legs(lib, capi, synth, torch, ext, barrier, reduce_max, rank, world, p
     pairs_rank = 1024 // world
     d5 = torch.empty((2 * P5, st5), dtype=torch.float64, device="cuda")
     true_lags = []
+    # the 32 resident pairs are windows of ONE long realisation of the C2 process per rank (envelope x noise): the CDN
+    # copy starts at a_i, the source at a_i + offset_i, each CDN copy gets its own additive noise (built on the device:
+    # generating 32 independent 10-min pairs with numpy took a minute of host time per rank)
+    span = n5 + int(180 * sr)
+    base5 = torch.from_numpy(synth.envelope_noise(span, sr, seed=300 + rank)).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(500 + rank)
     for i in range(P5):
         rng = np.random.default_rng(200 + rank * P5 + i)
-        off = float(rng.uniform(-55.0, 55.0))
-        q, r = synth.aligned_pair(600.0, offset_seconds=off, sr=sr, seed=300 + 2 * (rank * P5 + i))
-        d5[2 * i, :n5] = torch.from_numpy(q).cuda()
-        d5[2 * i + 1, :n5] = torch.from_numpy(r).cuda()
-        true_lags.append(off * sr / HOP)
+        off = int(round(float(rng.uniform(-55.0, 55.0)) * sr))
+        a_i = int(60 * sr) + int(rng.integers(0, 60 * sr))
+        d5[2 * i, :n5] = base5[a_i + off: a_i + off + n5]
+        d5[2 * i + 1, :n5] = base5[a_i: a_i + n5] + 0.02 * torch.randn(n5, dtype=torch.float64, device="cuda", generator=gen)
+        true_lags.append(off / HOP)
+    del base5
     bufs5 = lib.alloc_pair_outputs(P5, n5, p1, MAX_LAG_S, features=False, corr=False)
     res5 = [None]
 

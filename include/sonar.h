@@ -38,7 +38,8 @@
 extern "C" {
 #endif
 
-#define SONAR_ABI_VERSION 1
+#define SONAR_ABI_VERSION 2   /* 2: sonar_speech_out, sonar_fingerprint_speech_f64, sonar_fp_exact_counts, sonar_nccl_*,
+                                 sonar_xcorr_lag_sharded, sonar_truncate_to_alignment (additions only) */
 
 typedef struct sonar_ctx sonar_ctx;
 
@@ -146,6 +147,8 @@ int sonar_window_f64(int window_type, int size, int symmetric, int normalize,
  * (SURVEY §0 F2-F4). Zero-initialise, then sonar_fp_params_default(). */
 typedef struct sonar_fp_params {
   int32_t window_size;       /* FingerprintConfig.WindowSize  (fingerprint.go:177)            */
+                             /* 256 / 512 / 1024 / 2048: fused FP32 kernels (1024/256 and 512/160 with float64 re-evaluation of
+                                unsafe frames); any other length in [8, 2048]: float64 route, go-dsp's transform (Bluestein) */
   int32_t hop_size;          /* FingerprintConfig.HopSize     (fingerprint.go:180)            */
   int32_t window_type;       /* FeatureConfig.WindowType      (fingerprint.go:182)            */
   int32_t algo_sample_rate;  /* extractor's config.SampleRate (speech.go:70-96). Stock

@@ -36,6 +36,8 @@ struct PairGeom {
   int band = 0;
   DtwGeom g{};
   int64_t path_cap = 0;
+  int64_t path_tail = 0;  // entries of a path array that travel with the result copy: the path is emitted at the END of its
+                          // capacity and is rarely longer than the sequences plus a few percent (rest fetched on demand)
   size_t z_pair = 0, corr_pair = 0;  // doubles per pair (even)
 };
 
@@ -91,6 +93,7 @@ int pair_geometry(const sonar_fp_params* p, int64_t n, double max_lag_seconds, i
   G->band = band;
   dtw_geometry(G->dtw_len, G->dtw_len, band, &G->g);
   G->path_cap = 2 * (int64_t)G->dtw_len;
+  G->path_tail = std::min<int64_t>(G->path_cap, (int64_t)G->dtw_len + G->dtw_len / 8 + 64);
   if (sizeof(double) * (size_t)(G->g.n_off + 2) > 140 * 1024)
     return set_error(SONAR_ERR_UNSUPPORTED, "sonar_align_pairs needs a Sakoe-Chiba band (dtw_band > 0) for long streams");
   G->z_pair = 2 * (size_t)((G->Te + 1) & ~(int64_t)1);
@@ -211,7 +214,7 @@ int enqueue_chunk(sonar_ctx* ctx, int device, const sonar_fp_params* p, const Pa
 
 // host side of pair i of a finished chunk: h = pinned copy of the chunk's result block
 int finish_pair(const sonar_fp_params* p, const PairGeom& G, const ChunkLayout& L, const void* h, int i, bool feat,
-                sonar_pair_out* o) {
+                sonar_pair_out* o, const void* d_out) {
   if (feat) {
     const double* f = at<double>(h, L.o_feat) + (size_t)(2 * i) * G.sh.L.total;
     std::thread ref_side([&] { scatter_block(f + G.sh.L.total, G.sh, &o->reference); });
@@ -230,6 +233,17 @@ int finish_pair(const sonar_fp_params* p, const PairGeom& G, const ChunkLayout& 
   o->dtw_length = G.dtw_len;
   sonar_dtw_out& w = o->dtw;
   const int64_t len = dout.path_len;
+  if (len > G.path_tail && len <= G.path_cap && (w.path_query || w.path_ref || w.path_cost)) {
+    // a path longer than the tail that travelled (a walk that wanders inside the band): fetch its head now
+    const size_t lo = (size_t)(G.path_cap - len), cnt = (size_t)(len - G.path_tail);
+    void* hm = const_cast<void*>(h);
+    SONAR_CUDA(cudaMemcpy(at<double>(hm, L.o_pc) + (size_t)i * G.path_cap + lo,
+                          at<double>(d_out, L.o_pc) + (size_t)i * G.path_cap + lo, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+    SONAR_CUDA(cudaMemcpy(at<int32_t>(hm, L.o_pq) + (size_t)i * G.path_cap + lo,
+                          at<int32_t>(d_out, L.o_pq) + (size_t)i * G.path_cap + lo, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost));
+    SONAR_CUDA(cudaMemcpy(at<int32_t>(hm, L.o_pr) + (size_t)i * G.path_cap + lo,
+                          at<int32_t>(d_out, L.o_pr) + (size_t)i * G.path_cap + lo, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost));
+  }
   w.path_len = len;
   w.total_cost = dout.total_cost;
   w.distance = dout.total_cost / (double)len;
@@ -317,7 +331,7 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
     std::vector<int> rcs(pd.count, SONAR_OK);
     std::vector<std::string> errs(pd.count);
     auto one = [&](int i) {
-      rcs[i] = finish_pair(p, G, L, s.h_out.p, i, pd.feat, &outs[(*ids)[pd.first + i]]);
+      rcs[i] = finish_pair(p, G, L, s.h_out.p, i, pd.feat, &outs[(*ids)[pd.first + i]], s.d_out.p);
       if (rcs[i]) errs[i] = sonar_last_error();
     };
     if (pd.feat && pd.count > 1) {
@@ -390,10 +404,24 @@ void run_pairs_device(sonar_ctx* ctx, DevCtx* dev, const double* const* pcm_q, c
     rc = enqueue_chunk(ctx, dev->device, p, G, L, c, pcm_dev, lane.d_tmp.p, lane.d_out.p, stage.st, lane.st2, lane.mid,
                        lane.fpdone, curve, feat);
     if (rc) return fail(rc);
+    // Result copy: [features] [curve] | the TAILS of the three path arrays (42 MB of capacity per 32 pairs, half of it
+    // unused: at 8 ranks the host's D2H ceiling of 92 GB/s made the full copy 3.6 ms of a 25 ms step) | descriptors
     const size_t from = feat ? 0 : (curve ? L.o_corr : L.o_pc);
-    if ((e = cudaMemcpyAsync(static_cast<unsigned char*>(lane.h_out.p) + from,
-                             static_cast<unsigned char*>(lane.d_out.p) + from, L.out_bytes - from,
-                             cudaMemcpyDeviceToHost, lane.st2)) != cudaSuccess)
+    unsigned char* hb = static_cast<unsigned char*>(lane.h_out.p);
+    unsigned char* db = static_cast<unsigned char*>(lane.d_out.p);
+    if (from < L.o_pc && (e = cudaMemcpyAsync(hb + from, db + from, L.o_pc - from, cudaMemcpyDeviceToHost, lane.st2)) != cudaSuccess)
+      return fail(cuda_error(e, "cudaMemcpyAsync(D2H results)"));
+    {
+      const size_t skip = (size_t)(G.path_cap - G.path_tail);
+      const struct { size_t off, elem; } arr[3] = {{L.o_pc, sizeof(double)}, {L.o_pq, sizeof(int32_t)}, {L.o_pr, sizeof(int32_t)}};
+      for (const auto& a : arr) {
+        const size_t pitch = a.elem * (size_t)G.path_cap, o0 = a.off + a.elem * skip;
+        if ((e = cudaMemcpy2DAsync(hb + o0, pitch, db + o0, pitch, a.elem * (size_t)G.path_tail, (size_t)c,
+                                   cudaMemcpyDeviceToHost, lane.st2)) != cudaSuccess)
+          return fail(cuda_error(e, "cudaMemcpy2DAsync(D2H paths)"));
+      }
+    }
+    if ((e = cudaMemcpyAsync(hb + L.o_seqs, db + L.o_seqs, L.out_bytes - L.o_seqs, cudaMemcpyDeviceToHost, lane.st2)) != cudaSuccess)
       return fail(cuda_error(e, "cudaMemcpyAsync(D2H results)"));
     if ((e = cudaEventRecord(lane.done, lane.st2)) != cudaSuccess) return fail(cuda_error(e, "cudaEventRecord"));
     pending[li].first = first;

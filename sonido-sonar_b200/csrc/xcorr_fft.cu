@@ -96,7 +96,10 @@ __global__ void __launch_bounds__(kXsThreads) xs_curve_kernel(const XcorrPair* _
     const double den = sqrt(q1 * q2);
     const double num = inv[(int64_t)blockIdx.y * w.N + (lag & (w.N - 1))].x / (double)w.N;
     c = den < 1e-10 ? 0.0 : num / den;
-    if (!(r1 > kSmallQ * PA[p.na]) || !(r2 > kSmallQ * PB[p.nb]))
+    // exact evaluation wanted: overlap energy too small for the error bound, or a denominator near the reference's
+    // `den < 1e-10 -> 0` rule (correlation.go:401-405), which the prefix-sum denominator could take differently from the
+    // per-lag sequential sums (sequences that took the non-normalised branch of z-scoring: ADVICE r1)
+    if (!(r1 > kSmallQ * PA[p.na]) || !(r2 > kSmallQ * PB[p.nb]) || !(den > 1e-9))
       w.need[(int64_t)blockIdx.y * w.need_stride + xs_block_of(p, j, w.bps)] = 1;
   }
   p.corr[j - p.idx_lo] = c;
@@ -129,7 +132,11 @@ __global__ void __launch_bounds__(kXsThreads) xs_select_kernel(const XcorrPair* 
     }
     __syncthreads();
   }
-  const double thr = s2[0] - kDelta, thr_peak = s1[0] - kDelta;
+  // candidate band: kDelta, widened for long sequences to the worst-case cancellation error of a prefix-sum difference
+  // relative to the smallest overlap energy the screen accepts (n eps / kSmallQ; 9e-8 at 10 minutes)
+  const double nmax = (double)(p.na > p.nb ? p.na : p.nb);
+  const double delta = fmax(kDelta, 4.0 * nmax * 2.220446049250313e-16 / kSmallQ);
+  const double thr = s2[0] - delta, thr_peak = s1[0] - delta;
   unsigned char* need = w.need + (int64_t)blockIdx.x * w.need_stride;
   for (int64_t i = t; i < cnt; i += kXsThreads) {
     const double v = fabs(c[i]);

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(path):
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     lib.sonar_abi_version.restype = C.c_int
-    assert lib.sonar_abi_version() == 1
+    assert lib.sonar_abi_version() == 2
     lib.sonar_backend.restype = C.c_char_p
     assert lib.sonar_backend() == (b"cuda-sm100a" if path == PRODUCT else b"cpu-oracle")
 

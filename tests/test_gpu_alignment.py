@@ -346,3 +346,40 @@ def test_cdn_latency_loop_align_truncate_refingerprint_compare(gpu, oracle, synt
     for k in cg:
         assert cg[k] == pytest.approx(co[k], rel=1e-6, abs=1e-9, nan_ok=True), k
     assert cg["dist_mfcc"] < 1e-3 and cg["overall_similarity"] > 0.7  # the aligned segments are the same programme
+
+
+@pytest.mark.parametrize("scale", [1.6e-14, 2.0e-14, 2.6e-14])
+def test_screened_ncc_denominators_at_the_1e_10_rule(gpu, oracle, scale):
+    """one sequence takes z-scoring's non-normalised branch (sigma < 1e-10, correlation.go:464-501), so the
+    per-lag denominators sit around the reference's `den < 1e-10 -> 0` rule (correlation.go:401-405) and change side
+    with the overlap length.  The screened form (no curve requested) must land on the reference's peak, second peak and
+    lag all the same: lags whose prefix-sum denominator is near the rule are evaluated in the reference's order."""
+    rng = np.random.default_rng(int(scale * 1e16))
+    n = 5000
+    a = rng.standard_normal(n)
+    b = 3.0 + scale * np.roll(a, 17) + 0.3 * scale * rng.standard_normal(n)
+    assert np.std(b) < 1e-10
+    _, s = gpu.xcorr(a, b, 400, want_corr=False)
+    corr, so = oracle.xcorr(a, b, 400, want_corr=True)
+    if scale == 2.0e-14:  # both sides of the rule occur on one curve (1.6e-14: every lag below it, 2.6e-14: none)
+        assert np.count_nonzero(corr == 0.0) > 0 and np.count_nonzero(corr) > 0
+    assert (s.peak_lag, s.peak_index) == (so.peak_lag, so.peak_index)
+    assert s.peak_correlation == so.peak_correlation and s.second_peak == so.second_peak
+    cg, _ = gpu.xcorr(a, b, 400, want_corr=True)
+    assert np.array_equal(cg, corr)
+
+
+def test_pair_pipeline_long_wandering_path_is_fetched_completely(gpu, oracle, synth):
+    """The pair pipeline's result copy carries the tail of each path array (sequence length + 12.5 %); two unrelated
+    streams make the DTW wander inside its band, so the path is longer than that and its head is fetched on demand:
+    path and costs must still be the oracle's, bit for bit."""
+    sr = 44100
+    q = synth.envelope_noise(int(12 * sr), sr, seed=91)
+    r = synth.envelope_noise(int(12 * sr), sr, seed=92)
+    p = gpu.default_params(algo_sample_rate=sr, call_sample_rate=sr)
+    g = gpu.align_pairs([q], [r], p, 2.0, 50)[0]
+    o = oracle.align_pairs([q], [r], p, 2.0, 50)[0]
+    assert g["path_query"].size == o["path_query"].size
+    assert g["path_query"].size > 1.125 * (o["path_query"].max() + 1) + 64, "the case must exceed the travelling tail"
+    assert np.array_equal(g["path_query"], o["path_query"]) and np.array_equal(g["path_ref"], o["path_ref"])
+    assert np.array_equal(g["path_cost"], o["path_cost"], equal_nan=True)
