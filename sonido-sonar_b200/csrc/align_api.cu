@@ -350,7 +350,78 @@ void run_dtw_device(sonar_ctx* ctx, DevCtx* dev, const double* const* q, const d
 
 // ---- comparison --------------------------------------------------------------
 
+// Statistics of a Compare / BatchCompare call are gathered first and computed together: the comparison logic runs twice
+// over the same code -- a COLLECT pass that only registers the (array, frames, dim) triples it would ask for, then ONE
+// upload of the distinct arrays, ONE colstats_batch_kernel launch, ONE copy back -- and a LOOKUP pass that reads the
+// table.  The query's arrays are uploaded and reduced once however many candidates follow (round 1 / 2: fourteen
+// blocking upload-launch-download round trips per candidate, the query's statistics recomputed for each).
+struct StatsBatch {
+  enum Mode { COLLECT, LOOKUP } mode = COLLECT;
+  struct Key {
+    const double* x;
+    int64_t t;
+    int dim;
+    bool operator<(const Key& o) const {
+      return x != o.x ? x < o.x : (t != o.t ? t < o.t : dim < o.dim);
+    }
+  };
+  std::map<Key, size_t> index;  // -> offset of the 2 * dim statistics in `stats`
+  std::vector<Key> order;
+  std::vector<double> stats;
+  size_t n_stats = 0;
+};
+static thread_local StatsBatch* g_stats_batch = nullptr;
+
+static int stats_batch_run(sonar_ctx* ctx, StatsBatch& b) {
+  b.stats.assign(b.n_stats, 0.0);
+  if (b.order.empty()) return SONAR_OK;
+  DevCtx& dev = ctx->devs[0];
+  Slot& s = dev.slot[0];
+  size_t n_in = 0, n_cols = 0;
+  for (const auto& k : b.order) {
+    n_in += (size_t)k.t * k.dim;
+    n_cols += (size_t)k.dim;
+  }
+  int rc;
+  if ((rc = dev.ensure_dev(s.d_in, sizeof(double) * n_in)) || (rc = dev.ensure_dev(s.d_out, sizeof(double) * b.n_stats)) ||
+      (rc = dev.ensure_dev(s.d_tmp, sizeof(ColJob) * n_cols)))
+    return rc;
+  std::vector<ColJob> jobs;
+  jobs.reserve(n_cols);
+  size_t off = 0;
+  for (const auto& k : b.order) {
+    const size_t so = b.index[k];
+    SONAR_CUDA(cudaMemcpyAsync(static_cast<double*>(s.d_in.p) + off, k.x, sizeof(double) * (size_t)k.t * k.dim,
+                               cudaMemcpyHostToDevice, s.st));
+    for (int c = 0; c < k.dim; c++)
+      jobs.push_back(ColJob{(int64_t)(off + c), k.t, k.dim, (int64_t)(so + c), (int64_t)(so + k.dim + c)});
+    off += (size_t)k.t * k.dim;
+  }
+  SONAR_CUDA(cudaMemcpyAsync(s.d_tmp.p, jobs.data(), sizeof(ColJob) * jobs.size(), cudaMemcpyHostToDevice, s.st));
+  if ((rc = launch_colstats_batch(static_cast<const double*>(s.d_in.p), static_cast<const ColJob*>(s.d_tmp.p),
+                                  (int)jobs.size(), static_cast<double*>(s.d_out.p), s.st)))
+    return rc;
+  SONAR_CUDA(cudaMemcpyAsync(b.stats.data(), s.d_out.p, sizeof(double) * b.n_stats, cudaMemcpyDeviceToHost, s.st));
+  SONAR_CUDA(cudaStreamSynchronize(s.st));  // also keeps `jobs` alive until its copy has been read
+  return SONAR_OK;
+}
+
 int gpu_colstats(sonar_ctx* ctx, const double* x, int64_t t, int dim, double* st) {
+  if (StatsBatch* b = g_stats_batch) {
+    const StatsBatch::Key k{x, t, dim};
+    if (b->mode == StatsBatch::COLLECT) {
+      if (!b->index.count(k)) {
+        b->index[k] = b->n_stats;
+        b->order.push_back(k);
+        b->n_stats += 2 * (size_t)dim;
+      }
+      for (int i = 0; i < 2 * dim; i++) st[i] = 0.0;
+    } else {
+      const size_t so = b->index.at(k);
+      for (int i = 0; i < 2 * dim; i++) st[i] = b->stats[so + i];
+    }
+    return SONAR_OK;
+  }
   DevCtx& dev = ctx->devs[0];
   Slot& s = dev.slot[0];
   const size_t nd = (size_t)t * dim;
@@ -724,6 +795,8 @@ int sonar_colstats_cosine_f64(sonar_ctx* ctx, const double* x, int64_t tx, const
 
 static int compare_locked(sonar_ctx* ctx, const sonar_cmp_features* f1, const sonar_cmp_features* f2,
                           const sonar_cmp_weights* w, int content_filter, sonar_cmp_result* o);
+static int compare_many(sonar_ctx* ctx, const sonar_cmp_features* query, const sonar_cmp_features* const* cands, int n,
+                        const sonar_cmp_weights* w, int content_filter, sonar_cmp_result* results);
 
 int sonar_compare_f64(sonar_ctx* ctx, const sonar_cmp_features* f1, const sonar_cmp_features* f2,
                       const sonar_cmp_weights* w, int content_filter, sonar_cmp_result* o) {
@@ -731,7 +804,8 @@ int sonar_compare_f64(sonar_ctx* ctx, const sonar_cmp_features* f1, const sonar_
   std::lock_guard<std::mutex> call_lock(ctx->call_mu);
   set_current_ctx(ctx);
   SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
-  return compare_locked(ctx, f1, f2, w, content_filter, o);
+  const sonar_cmp_features* cands[1] = {f2};
+  return compare_many(ctx, f1, cands, 1, w, content_filter, o);
 }
 
 int sonar_compare_batch_f64(sonar_ctx* ctx, const sonar_cmp_features* query, const sonar_cmp_features* const* cands,
@@ -741,14 +815,34 @@ int sonar_compare_batch_f64(sonar_ctx* ctx, const sonar_cmp_features* query, con
   std::lock_guard<std::mutex> call_lock(ctx->call_mu);
   set_current_ctx(ctx);
   SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
-  for (int i = 0; i < n; i++) {
-    if (!cands[i]) {  // comparison.go:1123-1125: nil candidates are skipped
-      std::memset(&results[i], 0, sizeof(results[i]));
-      results[i].n_features = -1;
-      continue;
+  return compare_many(ctx, query, cands, n, w, content_filter, results);
+}
+
+// COLLECT pass -> one batched statistics launch -> LOOKUP pass (see StatsBatch)
+static int compare_many(sonar_ctx* ctx, const sonar_cmp_features* query, const sonar_cmp_features* const* cands, int n,
+                        const sonar_cmp_weights* w, int content_filter, sonar_cmp_result* results) {
+  StatsBatch batch;
+  struct Guard {
+    ~Guard() { g_stats_batch = nullptr; }
+  } guard;
+  g_stats_batch = &batch;
+  for (int pass = 0; pass < 2; pass++) {
+    batch.mode = pass == 0 ? StatsBatch::COLLECT : StatsBatch::LOOKUP;
+    for (int i = 0; i < n; i++) {
+      if (!cands[i]) {  // comparison.go:1123-1125: nil candidates are skipped
+        std::memset(&results[i], 0, sizeof(results[i]));
+        results[i].n_features = -1;
+        continue;
+      }
+      int rc = compare_locked(ctx, query, cands[i], w, content_filter, &results[i]);
+      if (rc) return rc;
     }
-    int rc = compare_locked(ctx, query, cands[i], w, content_filter, &results[i]);
-    if (rc) return rc;
+    if (pass == 0) {
+      g_stats_batch = nullptr;  // the real launch
+      int rc = stats_batch_run(ctx, batch);
+      if (rc) return rc;
+      g_stats_batch = &batch;
+    }
   }
   return SONAR_OK;
 }

@@ -118,6 +118,7 @@ struct StftArgs {
   int exact_all, fft_len;
   const double2* chirp_inv;
   const double2* blue_fb;
+  int v4_lockstep;  // stft_v4_kernel: warps of one role on one scheduler meet at a named barrier every iteration
 };
 
 // exact float64 re-evaluation of the frames the fused kernel listed (spectral_exact.cu)
@@ -287,6 +288,12 @@ std::vector<double> host_bark_bank(int n_filters, int fft_size, int sample_rate,
 
 // ---- column statistics (colstats.cu) ----------------------------------------
 int launch_colstats(const double* x, int64_t t, int dim, double* stats, cudaStream_t st);
+struct ColJob {  // one column of one array: x[off + i * dim], i < t; results at out[out_mean], out[out_std]
+  int64_t off, t;
+  int dim;
+  int64_t out_mean, out_std;
+};
+int launch_colstats_batch(const double* base, const ColJob* jobs, int n_jobs, double* out, cudaStream_t st);
 
 // ---- context ------------------------------------------------------------------
 struct Buf {  // growable allocation (device or pinned host)

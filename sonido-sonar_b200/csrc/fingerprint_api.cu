@@ -635,8 +635,12 @@ int sonar_fingerprint_batch_dev(sonar_ctx* ctx, const double* pcm_dev, int64_t n
                              static_cast<double*>(s.d_tmp.p), s.st);
 }
 
-int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int hop, int window_type, double* mag,
-                   double* phase, double* cplx) {
+// Materialising STFT of the signal [carry | pcm]: `carry_n` samples already resident on the device (the streamer's
+// buffer, `d_carry`) followed by n host samples.  On success the last `keep` samples of the signal are left in `d_carry`
+// (device to device): the streaming form never uploads a sample twice.
+static int stft_core(sonar_ctx* ctx, const double* pcm, int64_t n_host, double* d_carry, int64_t carry_n, int64_t keep,
+                     int win, int hop, int window_type, double* mag, double* phase, double* cplx) {
+  const int64_t n = n_host + carry_n;
   if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
   if (!pcm || n <= 0) return set_error(SONAR_ERR_EMPTY, "empty signal");  // analyzers/spectral.go:387
   if (win <= 0) return set_error(SONAR_ERR_INVALID, "window size must be positive");
@@ -672,7 +676,10 @@ int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int ho
   const int64_t stride = (n + 1) & ~(int64_t)1;
   if ((rc = dev.ensure_dev(s.d_in, sizeof(double) * (size_t)stride)) || (rc = dev.ensure_dev(s.d_out, out_bytes)))
     return rc;
-  SONAR_CUDA(cudaMemcpyAsync(s.d_in.p, pcm, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s.st));
+  if (carry_n > 0)
+    SONAR_CUDA(cudaMemcpyAsync(s.d_in.p, d_carry, sizeof(double) * (size_t)carry_n, cudaMemcpyDeviceToDevice, s.st));
+  SONAR_CUDA(cudaMemcpyAsync(static_cast<double*>(s.d_in.p) + carry_n, pcm, sizeof(double) * (size_t)n_host,
+                             cudaMemcpyHostToDevice, s.st));
   const unsigned char* blob = static_cast<const unsigned char*>(plan->d_blob);
   StftArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -706,11 +713,19 @@ int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int ho
     rc = launch_stft_features(*plan, a, true, s.st);
   }
   if (rc) return rc;
+  if (d_carry && keep > 0)  // the streamer's next buffer: the tail of this signal (stream order: after the kernel)
+    SONAR_CUDA(cudaMemcpyAsync(d_carry, static_cast<const double*>(s.d_in.p) + (n - keep), sizeof(double) * (size_t)keep,
+                               cudaMemcpyDeviceToDevice, s.st));
   SONAR_CUDA(cudaMemcpyAsync(mag, a.mag, per, cudaMemcpyDeviceToHost, s.st));
   if (phase) SONAR_CUDA(cudaMemcpyAsync(phase, a.phase, per, cudaMemcpyDeviceToHost, s.st));
   if (cplx) SONAR_CUDA(cudaMemcpyAsync(cplx, a.cplx, 2 * per, cudaMemcpyDeviceToHost, s.st));
   SONAR_CUDA(cudaStreamSynchronize(s.st));
   return SONAR_OK;
+}
+
+int sonar_stft_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int hop, int window_type, double* mag,
+                   double* phase, double* cplx) {
+  return stft_core(ctx, pcm, n, nullptr, 0, 0, win, hop, window_type, mag, phase, cplx);
 }
 
 int sonar_music_spectral_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int win, int hop, int window_type,
@@ -824,7 +839,8 @@ int sonar_music_spectral_f64(sonar_ctx* ctx, const double* pcm, int64_t n, int w
 struct sonar_stft_stream {
   sonar_ctx* ctx;
   int win, hop, wtype;
-  std::vector<double> buffer;
+  double* d_carry;   // device: the samples the reference's streamer keeps between chunks (always fewer than `win`)
+  int64_t n_carry;
 };
 
 namespace {
@@ -839,17 +855,21 @@ int sonar_stft_stream_open(sonar_ctx* ctx, int win, int hop, int window_type, so
   if (!ctx) return set_error(SONAR_ERR_INVALID, "nil argument");
   if (!stft_supported(win))
     return set_error(SONAR_ERR_UNSUPPORTED, "window size must be 256, 512, 1024 or 2048 on the fused GPU path");
-  *out = new sonar_stft_stream{ctx, win, hop, window_type, {}};
-  (*out)->buffer.reserve((size_t)win * 2);
+  std::lock_guard<std::mutex> call_lock(ctx->call_mu);
+  set_current_ctx(ctx);
+  SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
+  double* d = nullptr;
+  SONAR_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)win));
+  *out = new sonar_stft_stream{ctx, win, hop, window_type, d, 0};
   return SONAR_OK;
 }
 
 int64_t sonar_stft_stream_frames(const sonar_stft_stream* s, int64_t chunk_len) {
   if (!s || chunk_len <= 0) return 0;
-  return stream_frames_for((int64_t)s->buffer.size() + chunk_len, s->win, s->hop);
+  return stream_frames_for(s->n_carry + chunk_len, s->win, s->hop);
 }
 
-int64_t sonar_stft_stream_buffered(const sonar_stft_stream* s) { return s ? (int64_t)s->buffer.size() : 0; }
+int64_t sonar_stft_stream_buffered(const sonar_stft_stream* s) { return s ? s->n_carry : 0; }
 
 int sonar_stft_stream_process(sonar_stft_stream* s, const double* chunk, int64_t n, double* mag, double* phase,
                               double* cplx, int64_t cap_frames, int64_t* n_frames) {
@@ -857,23 +877,33 @@ int sonar_stft_stream_process(sonar_stft_stream* s, const double* chunk, int64_t
   *n_frames = 0;
   if (n <= 0) return SONAR_OK;  // spectral.go:324-326
   if (!chunk) return set_error(SONAR_ERR_INVALID, "nil argument");
-  const int64_t len = (int64_t)s->buffer.size() + n;
+  const int64_t len = s->n_carry + n;
   const int64_t T = stream_frames_for(len, s->win, s->hop);
   if (T > 0 && (!mag || cap_frames < T)) return set_error(SONAR_ERR_INVALID, "frame capacity too small");
-  s->buffer.insert(s->buffer.end(), chunk, chunk + n);
-  if (T == 0) return SONAR_OK;
-  // the frames the reference's loop extracts are those of the batch transform over the buffer: frame k starts k hops in
-  const int rc = sonar_stft_f64(s->ctx, s->buffer.data(), len, s->win, s->hop, s->wtype, mag, phase, cplx);
-  if (rc) {
-    s->buffer.resize((size_t)(len - n));  // nothing consumed
-    return rc;
+  if (T == 0) {  // not a window yet (len < win): the chunk joins the device-resident buffer
+    sonar_ctx* ctx = s->ctx;
+    std::lock_guard<std::mutex> call_lock(ctx->call_mu);
+    set_current_ctx(ctx);
+    SONAR_CUDA(cudaSetDevice(ctx->devs[0].device));
+    cudaStream_t st = ctx->devs[0].slot[0].st;
+    SONAR_CUDA(cudaMemcpyAsync(s->d_carry + s->n_carry, chunk, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SONAR_CUDA(cudaStreamSynchronize(st));
+    s->n_carry = len;
+    return SONAR_OK;
   }
-  // spectral.go:364-369: T - 1 plain advances, then the last one empties the buffer if a hop does not fit any more
+  // the frames the reference's loop extracts are those of the batch transform over [buffer | chunk]: frame k starts k
+  // hops in.  spectral.go:364-369: T - 1 plain advances, then the last one empties the buffer if a hop does not fit any more
   const int64_t rem = len - (T - 1) * (int64_t)s->hop;
   const int64_t keep = (int64_t)s->hop >= rem ? 0 : rem - s->hop;
-  s->buffer.erase(s->buffer.begin(), s->buffer.end() - keep);
+  const int rc = stft_core(s->ctx, chunk, n, s->d_carry, s->n_carry, keep, s->win, s->hop, s->wtype, mag, phase, cplx);
+  if (rc) return rc;  // nothing consumed: the buffer is only rewritten behind a successful transform
+  s->n_carry = keep;
   *n_frames = T;
   return SONAR_OK;
 }
 
-void sonar_stft_stream_close(sonar_stft_stream* s) { delete s; }
+void sonar_stft_stream_close(sonar_stft_stream* s) {
+  if (!s) return;
+  if (s->d_carry) cudaFree(s->d_carry);
+  delete s;
+}

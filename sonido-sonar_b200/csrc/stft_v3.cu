@@ -719,6 +719,600 @@ __global__ void __launch_bounds__(kW3 * 32, 1) stft_v3_kernel(const StftArgs a) 
   }
 }
 
+
+// =====================================================================================================================
+// Fourth generation: the same arithmetic, WARP SPECIALISED.  The third-generation kernel is bound by the dependent-issue
+// latency of one warp's instruction stream: 12 warps x 168 registers fill the register file, its time is inversely
+// proportional to the resident warps (profiles/r02_stft_v3_ncu.md), and the 168 registers are needed by the transform
+// (64 for the radix-32 points + 40 for the sample ring), not by the per-bin scan.  Here a frame pair's work is split
+// between TWO warps that run concurrently:
+//   * a TRANSFORM warp (sample ring, window, pass 1, transposition, pass 2, Hermitian split, magnitudes) and
+//   * a SCAN warp (per-bin scan, reductions, rolloff, mel combine, ln + DCT, float64 finishing),
+// handing the magnitude rows over through a double-buffered shared-memory row and two mbarriers per buffer (full /
+// empty; one arrival each, by lane 0 after a __syncwarp).  `setmaxnreg` moves registers from the scan warpgroups (96) to
+// the transform warpgroups (160): 8 x 32 x (160 + 96) = 65,536, i.e. SIXTEEN resident warps per SM instead of twelve,
+// each with half the instruction stream per frame.  The double buffer also removes the flux work-around of the third
+// generation (the first frame's flux taken in pass 2 from the row about to be overwritten): the scan warp keeps the
+// previous frame's magnitudes of its own bins in registers.
+constexpr int kPairs4 = 8;                  // transform / scan warp pairs per CTA (one CTA per SM)
+constexpr int kThreads4 = kPairs4 * 64;     // warps 0..7 transform, 8..15 scan (two warpgroups each)
+constexpr int kRegsFft4 = 160, kRegsScan4 = 96;
+
+struct V4Smem {
+  size_t tw, win, xtab, wlo, whi, fmask, moff, dct, lift, r0, pair0, per_pair, total;
+  size_t p_tile, p_mag, p_priv, p_raw, p_macc, mag_bytes;
+};
+template <class G>
+__host__ __device__ inline V4Smem v4_layout(int n_mel, int n_mfcc) {
+  V4Smem L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += (bytes + 15) & ~(size_t)15;
+    return r;
+  };
+  L.tw = take(sizeof(float2) * G::J * 32);
+  L.win = take(sizeof(float) * G::N);
+  L.xtab = take(sizeof(float) * G::ROW);
+  L.wlo = take(sizeof(float) * G::ROW);
+  L.whi = take(sizeof(float) * G::ROW);
+  L.fmask = take(sizeof(unsigned) * 32);
+  L.moff = take(sizeof(unsigned short) * kMaxContrib3 * kMaxMel);
+  L.dct = take(sizeof(float) * (size_t)n_mfcc * (n_mel | 1));
+  L.lift = take(sizeof(float) * n_mfcc);
+  L.r0 = take(sizeof(int) * 33);
+  o = (o + 127) & ~(size_t)127;
+  L.pair0 = o;
+  size_t w = 0;
+  auto wtake = [&](size_t bytes) {
+    size_t r = w;
+    w += (bytes + 127) & ~(size_t)127;
+    return r;
+  };
+  L.mag_bytes = (sizeof(float2) * G::PK * G::PROW + 127) & ~(size_t)127;
+  L.p_tile = wtake(sizeof(float2) * 32 * kTileRow);
+  L.p_mag = wtake(2 * L.mag_bytes);
+  L.p_priv = wtake(sizeof(float2) * kSlots3 * 32);
+  L.p_raw = wtake(sizeof(float) * kRaw3 * kRun3);
+  L.p_macc = wtake(sizeof(float2) * (kMaxMel + 4));
+  L.per_pair = w;
+  L.total = o + w * kPairs4;
+  return L;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit (cp.async.bulk), completion counted in bytes on an mbarrier:
+// no registers are tied up while the rows travel from HBM
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("fence.proxy.async.shared::cta;\n"
+               "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+
+// Named barrier of two warps (the two warps of one role that share a scheduler): keeps them within a few instructions
+// of each other, so the second one finds the code the first one fetched in the instruction caches -- the two loops
+// together are 50 KB of straight-line code, more than the 32 KB L1.5 holds, and four independent streams per scheduler
+// were fetch-bound (ncu: no_instruction 1.2 cycles per issue).
+__device__ __forceinline__ void mate_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// ---- transform warp ---------------------------------------------------------------------------------------------------
+template <class G>
+__device__ __forceinline__ void v4_transform(const StftArgs& a, int pr, int lane, const float2* s_tw,
+                                             const float* s_win, float2* tile,
+                                             unsigned char* magbuf, size_t mag_bytes,
+                                             unsigned long long* bar, unsigned long long* tbar) {
+  constexpr int N = G::N, M = G::M, J = G::J, FR = G::FR, PK = G::PK, RR = G::RR, NEW = G::NEW, KSTR = G::KSTR,
+                PROW = G::PROW, H = G::H;
+  (void)N;
+  const int k1 = PK == 1 ? lane : (lane & 15);
+  const int src = PK == 1 ? ((32 - lane) & 31) : ((lane & 16) | ((16 - k1) & 15));
+  const bool k1zero = k1 == 0;
+  const int64_t T = a.T;
+  const int nyq = ppos(M);
+  constexpr int NV = PK == 1 ? 4 : 8;
+  int woff[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) woff[v] = ppos(k1 + KSTR * v) - KSTR * v;
+  unsigned gi = 0;  // iterations handed over so far (the scan warp counts the same way)
+  unsigned tphase = 0;  // parity of the staging barrier's next completion
+  const double* stage = reinterpret_cast<const double*>(tile);  // the tile is idle between pass 2's loads and pass 1
+
+  // lockstep: every warp runs the same number of rounds and of iterations per round (a run past the end of the work, or
+  // the frames past the end of a stream's last run, only keep the barrier counts equal: loads read silence, stores are
+  // masked by the scan warp)
+  const int lock = a.v4_lockstep;
+  const int bid = 1 + (pr & 3);
+  const int64_t stride_runs = (int64_t)gridDim.x * kPairs4;
+  const int64_t run_end = lock ? ((a.total_runs + stride_runs - 1) / stride_runs) * stride_runs : a.total_runs;
+  constexpr int kNitFull = (kRunOut3 + 1 + FR - 1) / FR;
+  for (int64_t run = (int64_t)blockIdx.x * kPairs4 + pr; run < run_end; run += stride_runs) {
+    if (run >= a.total_runs) {  // barrier counts only
+      for (int it = 0; it < kNitFull * (lock > 1 ? 2 : 1); ++it) mate_sync(bid);
+      continue;
+    }
+    const int s = (int)(run / a.runs_per_stream);
+    const int64_t t0 = (run % a.runs_per_stream) * (int64_t)kRunOut3;
+    const int64_t tend = (t0 + kRunOut3 < T) ? t0 + kRunOut3 : T;
+    const double* __restrict__ x = a.pcm + (int64_t)s * a.stride;
+    const int64_t first = t0 - 1;
+    const int nfr = (int)(tend - first);
+    const int nit = lock ? kNitFull : (nfr + FR - 1) / FR;
+
+    float ring[RR];
+    const double* __restrict__ xl = x + (first * H + lane);
+    int64_t rows_left;
+    {
+      const int64_t g0 = first * H + lane;
+      rows_left = (a.n - g0 + 31) >> 5;
+      const int jlo = g0 < 0 ? (int)((-g0 + 31) >> 5) : 0;
+      const int jhi = rows_left < RR ? (int)(rows_left < 0 ? 0 : rows_left) : RR;
+#pragma unroll
+      for (int j = 0; j < RR; ++j) ring[j] = (j >= jlo && j < jhi) ? (float)__ldg(xl + 32 * j) : 0.f;
+    }
+
+    for (int it = 0; it < nit; ++it, ++gi) {
+      if (lock) mate_sync(bid);
+      // ---- pass 1 ----
+#pragma unroll
+      for (int p = 0; p < PK; ++p) {
+        float2 c[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const float w = s_win[lane + 32 * j];
+          c[j] = make_float2(ring[j + 2 * p * G::HR] * w, ring[j + (2 * p + 1) * G::HR] * w);
+        }
+        pk::Fft<J>::run(c);
+        tw_apply<J, 1>(c, s_tw + lane);
+        float2* tp = tile + (p * J) * kTileRow + lane;
+#pragma unroll
+        for (int q = 0; q < J; ++q) tp[q * kTileRow] = c[q];
+      }
+      __syncwarp();
+      if (lock > 1) mate_sync(bid);
+      // ---- pass 2 + Hermitian split + magnitudes into the buffer the scan warp has released ----
+      const unsigned b = gi & 1u, use = gi >> 1;
+      const bool more = it + 1 < nit;
+      bool staged = false;
+      {
+        float2 z[32];
+        const float4* rp = reinterpret_cast<const float4*>(tile + lane * kTileRow);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 f = rp[i];
+          z[2 * i] = make_float2(f.x, f.y);
+          z[2 * i + 1] = make_float2(f.z, f.w);
+        }
+        // The tile is idle from here to the next pass 1: the NEW sample rows of the next iteration (one contiguous block
+        // of the stream) are staged in it by ONE bulk copy, in flight behind pass 2 and the split.  Rows that leave the
+        // stream (its first and last iterations) take the register path below.
+        __syncwarp();
+        if (more) {
+          const int r0 = FR * G::HR * (it + 1) + (RR - NEW);
+          const int64_t gs = first * H + 32 * (int64_t)r0;  // first sample of the block
+          staged = gs >= 0 && gs + 32 * NEW <= a.n && ((reinterpret_cast<uintptr_t>(x + gs) & 15) == 0);
+          if (staged && lane == 0) {
+            mbar_expect_tx(tbar, 32 * NEW * sizeof(double));
+            tma_load_1d(tile, x + gs, 32 * NEW * sizeof(double), tbar);
+          }
+        }
+        pk::Fft<32>::run(z);
+        if (use > 0) mbar_wait(bar + 2 + b, (use - 1) & 1u);
+        float2* row = reinterpret_cast<float2*>(magbuf + b * mag_bytes) + (PK == 1 ? 0 : (lane >> 4)) * PROW;
+        float2 rinv = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const float2 mine = k1zero ? z[(32 - k2) & 31] : z[31 - k2];
+          const float2 pz = make_float2(__shfl_sync(kFull3, mine.x, src), __shfl_sync(kFull3, mine.y, src));
+          const float2 zz = z[k2];
+          const float2 xa = __fadd2_rn(zz, make_float2(pz.x, -pz.y));
+          const float2 xb = __fadd2_rn(make_float2(zz.y, -zz.x), make_float2(pz.y, pz.x));
+          const float2 qa = __fmul2_rn(xa, xa), qb = __fmul2_rn(xb, xb);
+          const int e = woff[k2 % NV] + KSTR * k2;
+          const float2 q = make_float2(qa.x + qa.y, qb.x + qb.y);
+          const float2 qt = __fadd2_rn(q, make_float2(1e-36f, 1e-36f));
+          const float2 ri = make_float2(rsqrt_fast3(qt.x), rsqrt_fast3(qt.y));
+          const float2 m = __fmul2_rn(q, ri);
+          rinv = __fadd2_rn(rinv, ri);
+          row[e] = m;
+        }
+        if (k1zero) {  // Z[M] pairs with itself
+          const float2 m = make_float2(fabsf(2.f * z[16].x), fabsf(2.f * z[16].y));
+          rinv = __fadd2_rn(rinv, make_float2(__fdividef(1.f, fmaxf(m.x, 1e-18f)), __fdividef(1.f, fmaxf(m.y, 1e-18f))));
+          row[nyq] = m;
+        }
+#pragma unroll
+        for (int o = (PK == 1 ? 16 : 8); o >= 1; o >>= 1)
+          rinv = __fadd2_rn(rinv, make_float2(__shfl_xor_sync(kFull3, rinv.x, o), __shfl_xor_sync(kFull3, rinv.y, o)));
+        if (k1zero) row[M + 2] = rinv;  // sum 1 / |X_k| of the pack's two frames (a free slot behind the Nyquist bin)
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar + b);
+      // ---- the next iteration's new rows ----
+      if (staged) {
+        mbar_wait(tbar, tphase);
+        tphase ^= 1u;
+#pragma unroll
+        for (int j = 0; j < RR - NEW; ++j) ring[j] = ring[j + NEW];
+#pragma unroll
+        for (int j = 0; j < NEW; ++j) ring[RR - NEW + j] = (float)stage[lane + 32 * j];
+        __syncwarp();  // every lane has its samples: pass 1 may overwrite the tile
+      } else if (more) {
+        double nx[NEW];
+        const int r0 = FR * G::HR * (it + 1) + (RR - NEW);
+        const double* __restrict__ src_p = xl + 32 * (int64_t)r0;
+        const int64_t left = rows_left - r0;
+        const int jhi = left < NEW ? (int)(left < 0 ? 0 : left) : NEW;
+        const int jlo = (t0 == 0 && it == 0) ? ((H - lane + 31) >> 5) - r0 : 0;
+#pragma unroll
+        for (int j = 0; j < NEW; ++j) nx[j] = (j >= jlo && j < jhi) ? __ldg(src_p + 32 * j) : 0.0;
+#pragma unroll
+        for (int j = 0; j < RR - NEW; ++j) ring[j] = ring[j + NEW];
+#pragma unroll
+        for (int j = 0; j < NEW; ++j) ring[RR - NEW + j] = (float)nx[j];
+      }
+    }
+  }
+}
+
+// ---- scan warp --------------------------------------------------------------------------------------------------------
+template <class G>
+__device__ __forceinline__ void v4_scan(const StftArgs& a, int pr, int lane, const float* s_xtab,
+                                        const float* s_wlo, const float* s_whi,
+                                        unsigned fmask, const unsigned short* s_moff,
+                                        const float* s_dct, const float* s_lift,
+                                        const float* s_invw, int ncontrib, float2* wbf2,
+                                        const unsigned char* magbuf, size_t mag_bytes,
+                                        float2* priv, float* rawsum,
+                                        float2* macc, unsigned long long* bar) {
+  constexpr int M = G::M, B = G::B, FR = G::FR, PK = G::PK, BPL = G::BPL, PROW = G::PROW;
+  const int64_t T = a.T;
+  const int nyq = ppos(M);
+  const float k0f = (float)(BPL * lane);
+  unsigned gi = 0;
+
+  const int lock = a.v4_lockstep;
+  const int bid = 5 + (pr & 3);
+  const int64_t stride_runs = (int64_t)gridDim.x * kPairs4;
+  const int64_t run_end = lock ? ((a.total_runs + stride_runs - 1) / stride_runs) * stride_runs : a.total_runs;
+  constexpr int kNitFull = (kRunOut3 + 1 + FR - 1) / FR;
+  for (int64_t run = (int64_t)blockIdx.x * kPairs4 + pr; run < run_end; run += stride_runs) {
+    if (run >= a.total_runs) {  // barrier counts only
+      for (int it = 0; it < kNitFull * (lock > 1 ? 1 + PK : 1); ++it) mate_sync(bid);
+      continue;
+    }
+    const int s = (int)(run / a.runs_per_stream);
+    const int64_t t0 = (run % a.runs_per_stream) * (int64_t)kRunOut3;
+    const int64_t tend = (t0 + kRunOut3 < T) ? t0 + kRunOut3 : T;
+    double* __restrict__ fo = a.feat + (int64_t)s * a.feat_stride;
+    const int64_t first = t0 - 1;
+    const int nfr = (int)(tend - first);
+    const int nit = lock ? kNitFull : (nfr + FR - 1) / FR;
+    // |X| of the frame before the iteration's first one, this lane's own bins (the run's first frame only warms the
+    // flux up: its predecessor does not matter)
+    float prevb[BPL], prevny = 0.f;
+#pragma unroll
+    for (int j = 0; j < BPL; ++j) prevb[j] = 0.f;
+
+    for (int it = 0; it < nit; ++it, ++gi) {
+      const int64_t tf = first + (int64_t)FR * it;
+      const bool more = it + 1 < nit;
+      const unsigned b = gi & 1u, use = gi >> 1;
+      if (lock) mate_sync(bid);
+      mbar_wait(bar + b, use & 1u);
+      const float2* buf = reinterpret_cast<const float2*>(magbuf + b * mag_bytes);
+#pragma unroll
+      for (int p = 0; p < PK; ++p) {
+        const float2* row = buf + p * PROW;
+        const float* rowf = reinterpret_cast<const float*>(row);
+        BinAcc3 ac;
+        acc_init(ac, priv + lane);
+#pragma unroll
+        for (int q = 0; q < BPL / 4; ++q) {
+          const int tc = spos(BPL * lane + 4 * q);
+          const float4 xv = *reinterpret_cast<const float4*>(s_xtab + tc);
+          const float4 lv = *reinterpret_cast<const float4*>(s_wlo + tc);
+          const float4 hv = *reinterpret_cast<const float4*>(s_whi + tc);
+          const float4 m01 = *reinterpret_cast<const float4*>(row + ppos(BPL * lane + 4 * q));
+          const float4 m23 = *reinterpret_cast<const float4*>(row + ppos(BPL * lane + 4 * q + 2));
+          float pv[4];
+          if (p > 0) {
+            const float4 r01 = *reinterpret_cast<const float4*>(row - PROW + ppos(BPL * lane + 4 * q));
+            const float4 r23 = *reinterpret_cast<const float4*>(row - PROW + ppos(BPL * lane + 4 * q + 2));
+            pv[0] = r01.y, pv[1] = r01.w, pv[2] = r23.y, pv[3] = r23.w;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pv[u] = prevb[4 * q + u];
+          }
+          const float2 mm[4] = {make_float2(m01.x, m01.y), make_float2(m01.z, m01.w), make_float2(m23.x, m23.y),
+                                make_float2(m23.z, m23.w)};
+          const float xx[4] = {xv.x, xv.y, xv.z, xv.w}, ll[4] = {lv.x, lv.y, lv.z, lv.w}, hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            bin_step3(ac, true, 4 * q + u, (fmask >> (4 * q + u)) & 1u, mm[u], pv[u], xx[u], ll[u], hh[u]);
+            if (p == PK - 1) prevb[4 * q + u] = mm[u].y;
+          }
+        }
+        if (lane == 31) {  // Nyquist bin
+          const float2 mq = row[nyq];
+          const float pv = p == 0 ? prevny : row[nyq - PROW].y;
+          bin_step3(ac, true, BPL, (fmask >> BPL) & 1u, mq, pv, s_xtab[spos(M)], s_wlo[spos(M)], s_whi[spos(M)]);
+          if (p == PK - 1) prevny = mq.y;
+        }
+        ac.pp[0] = pk::add(ac.pend, ac.mlo);
+        ac.pp[32] = ac.mhi;
+        if (lock > 1) mate_sync(bid);
+
+        const int64_t ta = tf + 2 * p, tb = ta + 1;
+        const bool oka = ta >= t0 && ta < tend, okb = tb >= t0 && tb < tend;
+        float2 pre = ac.seg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float2 up = make_float2(__shfl_up_sync(kFull3, pre.x, o), __shfl_up_sync(kFull3, pre.y, o));
+          if (lane >= o) pre = pk::add(pre, up);
+        }
+        const float2 etot = make_float2(__shfl_sync(kFull3, pre.x, 31), __shfl_sync(kFull3, pre.y, 31));
+        const float2 plow = make_float2(__shfl_sync(kFull3, pre.x, 7), __shfl_sync(kFull3, pre.y, 7));
+        const float2 sm = warp_sum3(ac.s0);
+        const float2 skm = warp_sum3(pk::fma(ac.s0, k0f, ac.s1));
+        const float2 kc = make_float2(sm.x > 0.f ? __fdividef(skm.x, sm.x) : 0.f, sm.y > 0.f ? __fdividef(skm.y, sm.y) : 0.f);
+        const float2 dk = make_float2(k0f - kc.x, k0f - kc.y);
+        const float2 bw = warp_sum3(__ffma2_rn(__fmul2_rn(dk, dk), ac.s0, __ffma2_rn(pk::scale(dk, 2.f), ac.s1, ac.s2)));
+        float2 sl = warp_sum3(ac.sl), sxy = warp_sum3(ac.sxy);
+        const float2 fl = warp_sum3(ac.fl);
+        const float mxa = warp_max3(ac.mxa), mxb = warp_max3(ac.mxb);
+        const float2 ri = row[M + 2];
+        const float clog = kLogTau * (float)B * sqrt_fast3((float)B) / kEta;
+        bool xa = !(ri.x * sqrt_fast3(etot.x) <= clog) || !(ri.x < 1.f / kTinyMag) || !(etot.x > 0.f);
+        bool xb = !(ri.y * sqrt_fast3(etot.y) <= clog) || !(ri.y < 1.f / kTinyMag) || !(etot.y > 0.f);
+        const float irb = 2.f * kEta * rsqrt_fast3((float)B);
+        int rka = rolloff_bin<G>(rowf, pre.x, ac.seg.x, etot.x, irb * sm.x * rsqrt_fast3(fmaxf(etot.x, 1e-36f)) + 1e-7f, lane);
+        int rkb = rolloff_bin<G>(rowf + 1, pre.y, ac.seg.y, etot.y, irb * sm.y * rsqrt_fast3(fmaxf(etot.y, 1e-36f)) + 1e-7f, lane);
+
+        __syncwarp();  // private mel slots visible; the last read of this pack's row is behind every lane
+        if (p == PK - 1 && lane == 0) mbar_arrive(bar + 2 + b);  // the transform warp may overwrite the buffer
+        if (a.mfcc_on) {
+          float2 dens = make_float2(FLT_MAX, FLT_MAX);
+          for (int f = lane; f < a.n_mel; f += 32) {
+            float2 v = make_float2(0.f, 0.f);
+            for (int i = 0; i < ncontrib; ++i) v = pk::add(v, wbf2[s_moff[i * kMaxMel + f]]);
+            macc[f] = make_float2(v.x > 0.f ? __logf(v.x) : -23.025850929940457f,
+                                  v.y > 0.f ? __logf(v.y) : -23.025850929940457f);  // ln(1e-10)
+            const float iw = s_invw[f];
+            if (iw > 0.f) dens = make_float2(fminf(dens.x, v.x * iw), fminf(dens.y, v.y * iw));
+          }
+          const float lim = kMelRatio / (float)B;
+          xa = xa || __any_sync(kFull3, !(dens.x >= lim * etot.x));
+          xb = xb || __any_sync(kFull3, !(dens.y >= lim * etot.y));
+          __syncwarp();
+          const int nmp = a.n_mel | 1;
+          for (int c0 = 0; c0 < a.n_mfcc; c0 += 16) {
+            const int c = c0 + (lane >> 1);
+            float2 acc = make_float2(0.f, 0.f);
+            if (c < a.n_mfcc)
+              for (int f = lane & 1; f < a.n_mel; f += 2) acc = pk::fma(macc[f], s_dct[c * nmp + f], acc);
+            acc = pk::add(acc, make_float2(__shfl_xor_sync(kFull3, acc.x, 1), __shfl_xor_sync(kFull3, acc.y, 1)));
+            if (c < a.n_mfcc && !(lane & 1)) {
+              const float lf = s_lift[c];
+              if (oka) fo[a.o_mfcc + ta * a.n_mfcc + c] = (double)(acc.x * lf);
+              if (okb) fo[a.o_mfcc + tb * a.n_mfcc + c] = (double)(acc.y * lf);
+            }
+          }
+        }
+        if (lane == 0) {
+          const int slot = (int)(ta - first) & (kRun3 - 1);
+          float4* rs = reinterpret_cast<float4*>(rawsum + slot * kRaw3);
+          if (xa) rka |= kExactBit;
+          if (xb) rkb |= kExactBit;
+          rs[0] = make_float4(sm.x, kc.x, etot.x, __int_as_float(rka));
+          rs[1] = make_float4(bw.x, sl.x, sxy.x, mxa);
+          rs[2] = make_float4(fl.x, plow.x, 0.f, 0.f);
+          if (slot + 1 < kRun3) {
+            rs[3] = make_float4(sm.y, kc.y, etot.y, __int_as_float(rkb));
+            rs[4] = make_float4(bw.y, sl.y, sxy.y, mxb);
+            rs[5] = make_float4(fl.y, plow.y, 0.f, 0.f);
+          }
+        }
+        __syncwarp();  // private slots / macc / parked sums: reused by the next pack, read by the finishing below
+      }
+
+      if (((FR * (it + 1)) & (kRun3 - 1)) == 0 || !more) {
+        const int seg = (FR * it) / kRun3;
+        const int64_t t = first + (int64_t)kRun3 * seg + lane;
+        if (t >= t0 && t < tend) {
+          const float4* rs4 = reinterpret_cast<const float4*>(rawsum + lane * kRaw3);
+          const float4 r0 = rs4[0], r1 = rs4[1], r2 = rs4[2];
+          const float sm = r0.x, kc = r0.y, etot = r0.z, bw = r1.x, sl = r1.y, sxy = r1.z, mx = r1.w, fl = r2.x, plow = r2.y;
+          const int rkx = __float_as_int(r0.w), rk = rkx & ~kExactBit;
+          if ((rkx & kExactBit) && a.xlist) {
+            int* lst = a.xlist + (int64_t)s * a.xlist_stride;
+            lst[1 + atomicAdd(lst, 1)] = (int)t;
+          }
+          const double fs = a.freq_scale;
+          const double dsm = (double)sm;
+          fo[a.o_centroid + t] = (double)kc * fs;
+          fo[a.o_rolloff + t] = etot > 0.f ? (double)rk * fs : 0.0;
+          fo[a.o_bandwidth + t] = sm > 0.f ? sqrt((double)bw / dsm) * fs : 0.0;
+          double flat = 0.0;
+          {
+            const double gm = exp2((double)sl / (double)B);
+            const double am = dsm / (double)B;
+            if (am > 1e-10) {
+              flat = gm / am;
+              if (flat > 1.0) flat = 1.0;
+            }
+          }
+          fo[a.o_flatness + t] = flat;
+          const double rms = sqrt((double)etot / (double)B);
+          fo[a.o_crest + t] = rms > 0.0 ? (double)mx / rms : 0.0;
+          double slope = 0.0;
+          if (a.slope_on) {
+            const double LG = 0.30102999566398120;  // log10(2)
+            const double n = a.slope_ntot;
+            if (n >= 2.0 && a.slope_xxtot != 0.0) slope = LG * (double)sxy / a.slope_xxtot;
+          }
+          fo[a.o_slope + t] = slope;
+          if (t >= 1) fo[a.o_flux + t - 1] = sqrt((double)fl);
+          if (t < a.Te) {
+            fo[a.o_low + t] = etot > 0.f ? (double)plow / (double)etot : 0.0;
+            fo[a.o_high + t] = etot > 0.f ? ((double)etot - (double)plow) / (double)etot : 0.0;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+template <int LOGN, int HR>
+__global__ void __launch_bounds__(kThreads4, 1) stft_v4_kernel(const StftArgs a) {
+  using G = V3G<LOGN, HR>;
+  constexpr int N = G::N, M = G::M, B = G::B, J = G::J, BPL = G::BPL, ROW = G::ROW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const V4Smem L = v4_layout<G>(a.n_mel, a.n_mfcc);
+  float2* s_tw = reinterpret_cast<float2*>(smem + L.tw);
+  float* s_win = reinterpret_cast<float*>(smem + L.win);
+  float* s_xtab = reinterpret_cast<float*>(smem + L.xtab);
+  float* s_wlo = reinterpret_cast<float*>(smem + L.wlo);
+  float* s_whi = reinterpret_cast<float*>(smem + L.whi);
+  unsigned* s_fmask = reinterpret_cast<unsigned*>(smem + L.fmask);
+  unsigned short* s_moff = reinterpret_cast<unsigned short*>(smem + L.moff);
+  float* s_dct = reinterpret_cast<float*>(smem + L.dct);
+  float* s_lift = reinterpret_cast<float*>(smem + L.lift);
+  int* s_r0 = reinterpret_cast<int*>(smem + L.r0);
+  __shared__ int s_ncontrib;
+  __shared__ float s_invw[kMaxMel];
+  __shared__ __align__(8) unsigned long long s_bar[kPairs4][4];  // full[0], full[1], empty[0], empty[1]
+  __shared__ __align__(8) unsigned long long s_tbar[kPairs4];    // staging copies of the transform warps
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pr = warp & (kPairs4 - 1);
+  unsigned char* pb = smem + L.pair0 + (size_t)pr * L.per_pair;
+  float2* wbf2 = reinterpret_cast<float2*>(pb);
+  float2* tile = reinterpret_cast<float2*>(pb + L.p_tile);
+  unsigned char* magbuf = pb + L.p_mag;
+  float2* priv = reinterpret_cast<float2*>(pb + L.p_priv);
+  float* rawsum = reinterpret_cast<float*>(pb + L.p_raw);
+  float2* macc = reinterpret_cast<float2*>(pb + L.p_macc);
+  constexpr int kZeroSlot = kMaxMel + 2;
+
+  // ---- tables, once per CTA (as in stft_v3_kernel) ----
+  for (int i = threadIdx.x; i < J * 32; i += blockDim.x) {
+    const int k1 = i / 32, l = i % 32;
+    double dsn, dcs;
+    sincospi(-2.0 * (double)((k1 * l) % N) / (double)N, &dsn, &dcs);
+    s_tw[i] = make_float2((float)dcs, (float)dsn);
+  }
+  {
+    const float* wsrc = reinterpret_cast<const float*>(a.win2);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_win[i] = __ldg(wsrc + i);
+  }
+  for (int k = threadIdx.x; k < ROW; k += blockDim.x) {
+    s_xtab[k] = 0.f;
+    s_wlo[k] = 0.f;
+    s_whi[k] = 0.f;
+  }
+  if (threadIdx.x < 32) s_fmask[threadIdx.x] = 0u;
+  if (threadIdx.x < kMaxMel) s_invw[threadIdx.x] = a.mel_invw[threadIdx.x];
+  if (threadIdx.x == 0) s_ncontrib = 0;
+  if (warp >= kPairs4 && lane == 0) macc[kZeroSlot] = make_float2(0.f, 0.f);
+  if (threadIdx.x < kPairs4 * 4) mbar_init(&s_bar[0][0] + threadIdx.x, 1u);
+  if (threadIdx.x < kPairs4) mbar_init(&s_tbar[threadIdx.x], 1u);
+  __syncthreads();
+  for (int k = threadIdx.x; k < B; k += blockDim.x) {
+    s_xtab[spos(k)] = a.xtab[k];
+    int r = 0;
+    while (k >= a.regions[r].next_b) ++r;
+    const MelRegion reg = a.regions[r];
+    const float kf = (float)k;
+    s_wlo[spos(k)] = (reg.bhi - kf) * reg.inv_f;
+    s_whi[spos(k)] = (kf - reg.blo) * reg.inv_r;
+    int rp = 0;
+    if (k > 0)
+      while (k - 1 >= a.regions[rp].next_b) ++rp;
+    if (r != rp && ((k % BPL) || k == M)) atomicOr(&s_fmask[k == M ? 31 : (k / BPL)], 1u << (k == M ? BPL : (k % BPL)));
+    if ((k % BPL) == 0 && k < M) s_r0[k / BPL] = r;
+  }
+  {
+    const int nmp = a.n_mel | 1;
+    for (int i = threadIdx.x; i < a.n_mfcc * a.n_mel; i += blockDim.x)
+      s_dct[(i / a.n_mel) * nmp + (i % a.n_mel)] = a.dct[i];
+    for (int i = threadIdx.x; i < a.n_mfcc; i += blockDim.x) s_lift[i] = a.lift[i];
+  }
+  __syncthreads();
+  const unsigned short zero_off = (unsigned short)((macc + kZeroSlot) - wbf2);  // the same for every pair
+  const unsigned short priv_off = (unsigned short)(priv - wbf2);
+  for (int f = threadIdx.x; f < kMaxMel; f += blockDim.x) {
+    int cnt = 0;
+    if (f < a.n_mel) {
+      for (int j = 0; j < 32; ++j) {
+        int rl = 0;
+        const int kl = (j == 31) ? B - 1 : BPL * j + BPL - 1;
+        while (kl >= a.regions[rl].next_b) ++rl;
+        const int first = s_r0[j] - 1, last = rl;
+        if (f + 1 >= first && f + 1 <= last && cnt < kMaxContrib3)
+          s_moff[(cnt++) * kMaxMel + f] = (unsigned short)(priv_off + (f + 1 - first) * 32 + j);
+      }
+      atomicMax(&s_ncontrib, cnt);
+    }
+    for (int i = cnt; i < kMaxContrib3; ++i) s_moff[i * kMaxMel + f] = zero_off;
+  }
+  __syncthreads();
+
+  if (warp < kPairs4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kRegsFft4));
+    v4_transform<G>(a, pr, lane, s_tw, s_win, tile, magbuf, L.mag_bytes, &s_bar[pr][0], &s_tbar[pr]);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kRegsScan4));
+    v4_scan<G>(a, pr, lane, s_xtab, s_wlo, s_whi, s_fmask[lane], s_moff, s_dct, s_lift, s_invw, s_ncontrib, wbf2, magbuf,
+               L.mag_bytes, priv, rawsum, macc, &s_bar[pr][0]);
+  }
+}
+
+template <int LOGN, int HR>
+int v4_launch(StftArgs& a, cudaStream_t st) {
+  using G = V3G<LOGN, HR>;
+  a.runs_per_stream = (int)((a.T + kRunOut3 - 1) / kRunOut3);
+  a.total_runs = (int64_t)a.runs_per_stream * a.n_streams;
+  const V4Smem L = v4_layout<G>(a.n_mel, a.n_mfcc);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t ctas = (a.total_runs + kPairs4 - 1) / kPairs4;
+  if (ctas > sms) ctas = sms;  // persistent: one CTA per SM, pairs stride over the runs
+  if (ctas < 1) ctas = 1;
+  static const int lockstep = std::getenv("SONAR_V4_LOCKSTEP") ? std::atoi(std::getenv("SONAR_V4_LOCKSTEP")) : 0;
+  a.v4_lockstep = lockstep;
+  prof_begin("stft_features_kernel", st);
+  SONAR_CUDA(cudaFuncSetAttribute(stft_v4_kernel<LOGN, HR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  stft_v4_kernel<LOGN, HR><<<(unsigned)ctas, kThreads4, L.total, st>>>(a);
+  prof_end();
+  SONAR_CUDA(cudaGetLastError());
+  return SONAR_OK;
+}
+
 template <class G>
 bool v3_mel_eligible(const FpPlan& plan, const StftArgs& a) {
   constexpr int BPL = G::BPL, B = G::B;
@@ -777,6 +1371,19 @@ bool stft_v3_eligible(const FpPlan& plan, const StftArgs& a) {
 }
 
 int launch_stft_v3(const FpPlan& plan, StftArgs& a, cudaStream_t st) {
+  // The warp-specialised form (stft_v4_kernel: transform / scan warp pairs, TMA-staged sample rows, mbarrier hand-over,
+  // setmaxnreg) is bit-identical in its results but measures 7.85 ms against 7.16 ms per 64 x 300 s: sixteen warps issue
+  // no more than twelve (0.52 against 0.56 slots per scheduler-cycle) because the two roles' loops together are 50 KB of
+  // straight-line code and the SM delivers instructions at full rate only out of its 32 KB L1.5 instruction cache
+  // (scripts/microbench/icache_bw.cu).  It stays selectable for measurements: SONAR_STFT_V4=1.
+  static const bool v4 = std::getenv("SONAR_STFT_V4") != nullptr;
+  constexpr size_t kSmemMax = 227 * 1024;
+  const bool fits = plan.N == 1024 ? v4_layout<V3G<10, 8>>(a.n_mel, a.n_mfcc).total <= kSmemMax
+                                   : v4_layout<V3G<9, 5>>(a.n_mel, a.n_mfcc).total <= kSmemMax;
+  if (v4 && fits) {
+    if (plan.N == 1024) return v4_launch<10, 8>(a, st);
+    return v4_launch<9, 5>(a, st);
+  }
   if (plan.N == 1024) return v3_launch<10, 8>(a, st);
   return v3_launch<9, 5>(a, st);
 }

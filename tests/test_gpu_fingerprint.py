@@ -592,3 +592,17 @@ def test_unsupported_window_lengths_say_so(gpu, capi, synth):
                                algo_sample_rate=44100)
         with pytest.raises(capi.SonarError, match="window size"):
             gpu.fingerprint(x, p)
+
+
+def test_warp_specialised_stft_variant_matches_oracle():
+    """stft_v4_kernel (SONAR_STFT_V4=1: transform / scan warp pairs, TMA-staged sample rows, mbarrier hand-over,
+    setmaxnreg) is an opt-in measurement variant of the fused STFT kernel: the same parity cases, the
+    seam test and the ragged batch must hold with it.  The switch is read once per process, hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SONAR_STFT_V4="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_fingerprint.py"), "-m", "gpu",
+                        "-x", "-q", "-k", "test_fingerprint_matches_oracle or test_seams_between_runs or "
+                        "test_batch_ragged or test_every_window_type or test_weak_bins"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
