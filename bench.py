@@ -735,7 +735,8 @@ def run_ours(args, rank, world, local_rank):
             avg_ms = k_ms / k_n
             achieved = frames_per_launch * ALGO_BYTES_PER_FRAME / (avg_ms / 1e3) / 1e9
             tr = ncu_traffic()
-            roof = {"kernel": "stft_features_kernel (fused framed STFT + MFCC + spectral descriptors)", "bound": "hbm",
+            roof = {"kernel": "stft_features_kernel (fused framed STFT + MFCC + spectral descriptors: transform + scan kernel "
+                              "pair, one timing pair around both)", "bound": "hbm",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     # ncu capture of the same kernel, scaled from its frames per launch to this run's
                     "traffic": (tr["dram_bytes_per_launch"] / tr["frames_per_launch"] * frames_per_launch) if tr else None,

@@ -10,7 +10,7 @@
               "fma.rn.f32 %4, %4, %8, %9;\n\tfma.rn.f32 %5, %5, %8, %9;\n\tfma.rn.f32 %6, %6, %8, %9;\n\tfma.rn.f32 %7, %7, %8, %9;\n\t"
 #define ASM8() asm volatile(BODY8 : "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3), "+f"(a4), "+f"(a5), "+f"(a6), "+f"(a7) : "f"(m), "f"(c));
 #define ASM64() R8(ASM8())
-#define ASM512() R8(ASM64())
+#define ASM256() ASM64() ASM64() ASM64() ASM64()  // 4 KB
 
 template <int KB>  // loop body of KB kilobytes = KB * 64 instructions
 __global__ void __launch_bounds__(512, 1) k(float* out, int iters, int stagger, unsigned long long* cyc) {
@@ -21,9 +21,10 @@ __global__ void __launch_bounds__(512, 1) k(float* out, int iters, int stagger, 
   const long long t0 = clock64();
   while (clock64() - t0 < (long long)warp * stagger) {}
   const long long t1 = clock64();
+#pragma unroll 1  // the loop body stays KB kilobytes (unrolled, it would be 4 x that)
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int r = 0; r < KB / 8; ++r) { ASM512() }
+    for (int r = 0; r < KB / 4; ++r) { ASM256() }
   }
   const long long t2 = clock64();
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
@@ -60,11 +61,14 @@ int main() {
       run<8>(warps, stagger);
       run<16>(warps, stagger);
       run<24>(warps, stagger);
+      run<28>(warps, stagger);
       run<32>(warps, stagger);
+      run<36>(warps, stagger);
       run<40>(warps, stagger);
       run<48>(warps, stagger);
       run<64>(warps, stagger);
       run<96>(warps, stagger);
+      run<160>(warps, stagger);
     }
   }
   return 0;

@@ -134,6 +134,9 @@ int launch_stft_v2(const FpPlan& plan, StftArgs& a, cudaStream_t st);
 // third generation (stft_v3.cu): 1024 / 256 and 512 / 160, two frames per complex FFT, register-resident sample ring
 bool stft_v3_eligible(const FpPlan& plan, const StftArgs& a);
 int launch_stft_v3(const FpPlan& plan, StftArgs& a, cudaStream_t st);
+// fifth generation (stft_v5.cu): the same work as a transform kernel + a scan kernel, each within the 32 KB instruction cache
+int launch_stft_v5(const FpPlan& plan, StftArgs& a, cudaStream_t st);
+void stft_workspace_release(int device, cudaStream_t st);  // frees the pair's workspace of a stream about to be destroyed
 
 // ---- fingerprint sequencing shared by the host-pointer, device-resident and pipeline entry points ----------
 struct FpShape {
@@ -359,6 +362,7 @@ namespace sonar {
 // (sonar_profile_enable), records a CUDA event before and after the kernel on its own stream.
 void prof_begin(const char* kernel, cudaStream_t st);
 void prof_end();
+void prof_count_launch();  // a second kernel launched inside one prof_begin / prof_end pair
 void set_current_ctx(sonar_ctx* c);
 void nccl_release(sonar_ctx* ctx);  // nccl_shard.cu
 // speech.go:370-408 temporal block (temporal.cu)

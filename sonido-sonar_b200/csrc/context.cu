@@ -61,6 +61,9 @@ void prof_end() {
   g_cur->prof.push_back(g_open);
   g_open = sonar_ctx::ProfRec{nullptr, nullptr, nullptr};
 }
+void prof_count_launch() {
+  if (g_cur) g_cur->launches.fetch_add(1, std::memory_order_relaxed);
+}
 void set_current_ctx(sonar_ctx* c) { g_cur = c; }
 
 int DevCtx::ensure_dev(Buf& b, size_t bytes) {
@@ -191,6 +194,8 @@ void sonar_destroy(sonar_ctx* ctx) {
       if (s.done) cudaEventDestroy(s.done);
       if (s.mid) cudaEventDestroy(s.mid);
       if (s.fpdone) cudaEventDestroy(s.fpdone);
+      sonar::stft_workspace_release(d.device, s.st);  // the STFT kernel pair's row workspace of this stream
+      sonar::stft_workspace_release(d.device, s.st2);
       if (s.st) cudaStreamDestroy(s.st);
       if (s.st2) cudaStreamDestroy(s.st2);
       if (s.fork) cudaEventDestroy(s.fork);

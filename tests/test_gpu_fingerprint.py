@@ -594,15 +594,30 @@ def test_unsupported_window_lengths_say_so(gpu, capi, synth):
             gpu.fingerprint(x, p)
 
 
-def test_warp_specialised_stft_variant_matches_oracle():
-    """stft_v4_kernel (SONAR_STFT_V4=1: transform / scan warp pairs, TMA-staged sample rows, mbarrier hand-over,
-    setmaxnreg) is an opt-in measurement variant of the fused STFT kernel: the same parity cases, the
-    seam test and the ragged batch must hold with it.  The switch is read once per process, hence the subprocess."""
+@pytest.mark.parametrize("switch", ["SONAR_STFT_V3", "SONAR_STFT_V4"])
+def test_other_generations_of_the_fused_stft_kernel_match_oracle(switch):
+    """The default fused STFT is the transform / scan kernel pair (stft_v5.cu).  The single-role kernel (stft_v3_kernel,
+    SONAR_STFT_V3=1: also the fallback when the pair's workspace or a mel bank's slots do not fit) and its warp-specialised
+    form (stft_v4_kernel, SONAR_STFT_V4=1: a measurement variant) must hold the same parity cases, the
+    seam test and the ragged batch.  The switch is read once per process, hence the subprocess."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SONAR_STFT_V4="1")
+    env = dict(os.environ)
+    env[switch] = "1"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_fingerprint.py"), "-m", "gpu",
                         "-x", "-q", "-k", "test_fingerprint_matches_oracle or test_seams_between_runs or "
                         "test_batch_ragged or test_every_window_type or test_weak_bins"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_stft_kernel_pair_in_small_workspace_groups(synth):
+    """stft_v5.cu processes the streams of a batch in groups that fit its row workspace (SONAR_STFT_WS_MB): with a 1 MB
+    cap every stream is its own group (one transform + scan launch each); the batch must equal the single calls."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SONAR_STFT_WS_MB="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_fingerprint.py"), "-m", "gpu",
+                        "-x", "-q", "-k", "test_batch_ragged or test_seams_between_runs or test_short_input_batch"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
