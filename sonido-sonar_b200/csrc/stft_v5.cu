@@ -25,7 +25,19 @@
 namespace sonar {
 namespace {
 
-constexpr int kTW5 = 12;           // transform warps per CTA
+#ifndef V5_TW
+#define V5_TW 12
+#endif
+// (The register file is partitioned per scheduler, 16,384 registers each: 12 warps = 3 per scheduler x 168 registers and
+// 16 warps = 4 x 128 are the two shapes that fill it; 13-15 warps put four warps on one scheduler and are capped at 128
+// registers as well -- `too many resources requested` at 14 x 144 -- and at 128 the transform spills ~60 words per
+// thread, which 217 KB of configured shared memory leave no L1 for.)
+#ifdef V5_TREGS  // variant builds: an explicit register cap
+#define V5_TATTR __maxnreg__(V5_TREGS)
+#else
+#define V5_TATTR __launch_bounds__(V5_TW * 32, 1)
+#endif
+constexpr int kTW5 = V5_TW;        // transform warps per CTA
 constexpr int kSW5 = 16;           // scan warps per CTA (fewer when the mel bank's private slots do not fit)
 constexpr int kRunFrames5 = 128;   // frames per run: a multiple of the 32-frame finishing segment and of FR
 
@@ -75,7 +87,7 @@ __host__ __device__ inline V5TSmem v5t_layout() {
 }
 
 template <int LOGN, int HR>
-__global__ void __launch_bounds__(kTW5 * 32, 1) stft_v5_transform_kernel(const StftArgs a, const V5Args v) {
+__global__ void V5_TATTR stft_v5_transform_kernel(const StftArgs a, const V5Args v) {
   using G = V3G<LOGN, HR>;
   constexpr int N = G::N, M = G::M, J = G::J, FR = G::FR, PK = G::PK, RR = G::RR, NEW = G::NEW, KSTR = G::KSTR,
                 PROW = G::PROW, H = G::H;
