@@ -175,15 +175,28 @@ struct WalkBlocks {
   int64_t limit;        // samples [0, limit) belong to the blocks in use
 };
 
-template <int G, bool ALIGNED, bool BS>
+// STAGED (hop a multiple of 16, aligned rows): the lanes of a warp walk ranges G hops apart, so a direct 16-byte load
+// touches 32 different 128-byte lines per instruction and the kernel is bound by the L1 tag stage (ncu: l1tex 85 %,
+// 0.15 issue slots per scheduler-cycle; 2.0 of its 2.9 ms per 64 x 300 s are tag cycles).  Here the warp fetches the next
+// 16 samples of all its 32 lanes TOGETHER -- eight cp.async instructions of four whole lines each -- into a padded
+// shared-memory tile (row stride 144 B: the lanes' 16-byte reads of their own rows are conflict free), one chunk ahead
+// of the arithmetic.  Every lane still sees its samples in the same order: results are bit-identical.
+// RT > 0 (staged form, frame = RT hops): the sums of the RT frames that contain the current hop live in a SLIDING window
+// of RT registers that every sample is added to unconditionally (slot j = the frame that started j hops ago; at the end
+// of a hop the oldest frame is finished and written, the others move up): the generic form below tests eight
+// frame-active flags per sample, 51 instructions per sample with its ALU pipe 71 % busy (ncu), this one ~20.  Each
+// frame's sum still receives its squares one by one in ascending order from 0.0 (bit-identical); the crossing counts are
+// integers, so they are taken per hop and added to the frames at the end of the hop (the frame that STARTS in a hop
+// does not count the hop's first sample: zero_crossing_rate.go:43).
+template <int G, bool ALIGNED, bool BS, bool STAGED = false, int RT = 0>
 __global__ void __launch_bounds__(128) frame_walk_multi_kernel(
     const double* __restrict__ pcm, int64_t stride, double alpha, int frame, int hop, int R, int64_t Tn, int sr,
     double* __restrict__ out, int64_t out_stride, int64_t o_energy, int64_t o_entropy, int64_t o_zcr, WalkBlocks wb) {
   const int s = blockIdx.y;
   const int64_t tw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t f0 = tw * G;
-  if (f0 >= Tn) return;
-  const int nf = (int)((Tn - f0 < G) ? (Tn - f0) : G);
+  if (!STAGED && f0 >= Tn) return;  // (staged: lanes without frames still help to load)
+  const int nf = f0 >= Tn ? 0 : (int)((Tn - f0 < G) ? (Tn - f0) : G);
   const double* __restrict__ x = pcm + (int64_t)s * stride;
   const int64_t s0 = f0 * hop;
   double sum[G];
@@ -193,14 +206,132 @@ __global__ void __launch_bounds__(128) frame_walk_multi_kernel(
     sum[g] = 0.0;
     cnt[g] = 0;
   }
-  double xprev = s0 > 0 ? x[s0 - 1] : 0.0;  // x[-1] = 0 (pre_emphasis.go:135-155)
+  double xprev = (s0 > 0 && nf > 0) ? x[s0 - 1] : 0.0;  // x[-1] = 0 (pre_emphasis.go:135-155)
   bool prev_neg = false;
-  const int nseg = nf - 1 + R;
+  const int nseg = nf > 0 ? nf - 1 + R : 0;
   // block sums (BS): bcur collects the owned samples, p_first keeps what was collected before the boundary
-  const bool last_thread = f0 + G >= Tn;
+  const bool last_thread = nf > 0 && f0 + G >= Tn;
   const int64_t next_b = BS ? (s0 / wb.hopL + 1) * wb.hopL : 0;  // first sample of the next block
   double bcur = 0.0, p_first = 0.0;
   bool flushed = false;
+  if constexpr (STAGED) {
+    constexpr int kRowD = 18;  // doubles per tile row: 16 samples + 16 bytes of padding
+    __shared__ __align__(16) double s_tile[4][2][32][kRowD];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int64_t f0w = f0 - (int64_t)lane * G;  // first frame of lane 0
+    const int cps = hop / 16;                    // chunks per segment
+    const int nseg_w = __shfl_sync(0xffffffffu, nseg, 0);  // lane 0 has the most segments
+    const int total = nseg_w * cps;
+    auto issue = [&](int q, int buf) {
+      const int sg = q / cps, c = q - sg * cps;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + (lane >> 3), col = lane & 7;
+        const int64_t f0r = f0w + (int64_t)row * G;
+        const int nfr = f0r >= Tn ? 0 : (int)((Tn - f0r < G) ? (Tn - f0r) : G);
+        if (nfr > 0 && sg < nfr - 1 + R) {
+          const double* src = x + f0r * hop + (int64_t)sg * hop + 16 * c + 2 * col;
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_tile[wrp][buf][row][2 * col]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (total > 0) issue(0, 0);
+    bool act[G];
+    int rel_b = -1;
+    bool own = false;
+    double wsum[RT > 0 ? RT : 1];
+    int wcnt[RT > 0 ? RT : 1], segc = 0, firstc = 0;
+#pragma unroll
+    for (int j = 0; j < (RT > 0 ? RT : 1); ++j) {
+      wsum[j] = 0.0;
+      wcnt[j] = 0;
+    }
+    double* __restrict__ o = out + (int64_t)s * out_stride;
+    const double dur = (double)frame / (double)sr;
+    for (int q = 0; q < total; ++q) {
+      const int sg = q / cps, c = q - sg * cps, buf = q & 1;
+      if (q + 1 < total) {
+        issue(q + 1, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncwarp();
+      if (c == 0) {
+        if (RT == 0) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) act[g] = g < nf && g <= sg && sg < g + R;
+        }
+        own = BS && (last_thread || sg < G);
+        const int64_t seg0 = s0 + (int64_t)sg * hop;
+        rel_b = (own && next_b >= seg0 && next_b < seg0 + hop) ? (int)(next_b - seg0) : -1;
+        segc = 0;
+      }
+      auto step = [&](double xv, bool first, int idx) {
+        const double y = xv - alpha * xprev;
+        xprev = xv;
+        const double sq = y * y;
+        const bool neg = (unsigned long long)__double_as_longlong(y) > 0x8000000000000000ull;
+        const int cross = (neg != prev_neg) ? 1 : 0;
+        prev_neg = neg;
+        if (BS) {
+          const bool hit = idx == rel_b;
+          p_first = hit ? bcur : p_first;
+          flushed = flushed || hit;
+          const double add = own ? sq : 0.0;
+          bcur = hit ? add : bcur + add;
+        }
+        if (RT > 0) {
+#pragma unroll
+          for (int j = 0; j < (RT > 0 ? RT : 1); ++j) wsum[j] += sq;
+          segc += cross;
+          if (first) firstc = cross;
+        } else {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (act[g]) {
+              sum[g] += sq;
+              if (!(first && sg == g)) cnt[g] += cross;
+            }
+          }
+        }
+      };
+      if (sg < nseg) {
+        const double2* __restrict__ row = reinterpret_cast<const double2*>(&s_tile[wrp][buf][lane][0]);
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = row[u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          step(v[u].x, c == 0 && u == 0, 16 * c + 2 * u);
+          step(v[u].y, false, 16 * c + 2 * u + 1);
+        }
+        if (RT > 0 && c == cps - 1) {  // end of the hop: the oldest frame of the window is complete
+#pragma unroll
+          for (int j = 0; j < (RT > 0 ? RT : 1); ++j) wcnt[j] += segc;
+          wcnt[0] -= firstc;
+          const int g = sg - (RT - 1);
+          if (g >= 0 && g < nf) {
+            const int64_t f = f0 + g;
+            const double e = sqrt(wsum[RT > 0 ? RT - 1 : 0] / (double)frame);
+            o[o_energy + f] = e;
+            if (o_entropy >= 0) o[o_entropy + f] = e > 0.0 ? -e * log(e + 1e-10) : 0.0;
+            o[o_zcr + f] = frame < 2 ? 0.0 : (double)wcnt[RT > 0 ? RT - 1 : 0] / dur;
+          }
+#pragma unroll
+          for (int j = (RT > 0 ? RT : 1) - 1; j > 0; --j) {
+            wsum[j] = wsum[j - 1];
+            wcnt[j] = wcnt[j - 1];
+          }
+          wsum[0] = 0.0;
+          wcnt[0] = 0;
+        }
+      }
+      __syncwarp();  // the buffer is rewritten two chunks later
+    }
+  } else
   for (int sg = 0; sg < nseg; ++sg) {
     bool act[G];
 #pragma unroll
@@ -271,10 +402,13 @@ __global__ void __launch_bounds__(128) frame_walk_multi_kernel(
         bcur += y * y;
       }
     }
-    double* part = wb.part + (int64_t)s * wb.part_stride + 2 * tw;
-    part[0] = flushed ? p_first : bcur;  // block s0 / hopL
-    part[1] = flushed ? bcur : 0.0;      // the block after it
+    if (nf > 0) {
+      double* part = wb.part + (int64_t)s * wb.part_stride + 2 * tw;
+      part[0] = flushed ? p_first : bcur;  // block s0 / hopL
+      part[1] = flushed ? bcur : 0.0;      // the block after it
+    }
   }
+  if (STAGED && RT > 0) return;  // the sliding form wrote every frame as it finished
   double* __restrict__ o = out + (int64_t)s * out_stride;
   const double dur = (double)frame / (double)sr;  // len(frame)/sampleRate; sr==0 -> +Inf -> zcr 0
 #pragma unroll
@@ -637,8 +771,24 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
                       wl->hop > (int64_t)(G + 1) * hop + frame && (wl->nw - 1) * wl->hop + wl->win <= n &&
                       wl->part_stride >= 2 * groups;
     if (fuse) wb = WalkBlocks{wl->part, wl->part_stride, wl->hop, (wl->nw - 1) * wl->hop + wl->win};
+    static const bool direct = std::getenv("SONAR_FRAME_WALK_DIRECT") != nullptr;  // diagnostic: per-lane 16-byte loads
+    const bool staged = aligned && !direct && hop % 16 == 0;
     prof_begin("frame_walk_kernel", st);
-    if (aligned && fuse)
+    static const bool flags = std::getenv("SONAR_FRAME_WALK_FLAGS") != nullptr;  // diagnostic: per-sample active flags
+    const bool slide = staged && !flags && frame / hop == 4;
+    if (slide && fuse)
+      frame_walk_multi_kernel<G, true, true, true, 4><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn,
+                                                                         sr, out, out_stride, o_energy, o_entropy, o_zcr, wb);
+    else if (slide)
+      frame_walk_multi_kernel<G, true, false, true, 4><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn,
+                                                                          sr, out, out_stride, o_energy, o_entropy, o_zcr, wb);
+    else if (staged && fuse)
+      frame_walk_multi_kernel<G, true, true, true><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr,
+                                                                      out, out_stride, o_energy, o_entropy, o_zcr, wb);
+    else if (staged)
+      frame_walk_multi_kernel<G, true, false, true><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr,
+                                                                       out, out_stride, o_energy, o_entropy, o_zcr, wb);
+    else if (aligned && fuse)
       frame_walk_multi_kernel<G, true, true><<<mg, 128, 0, st>>>(pcm, stride, alpha, frame, hop, frame / hop, Tn, sr, out,
                                                                 out_stride, o_energy, o_entropy, o_zcr, wb);
     else if (aligned)
