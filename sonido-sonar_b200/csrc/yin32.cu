@@ -35,7 +35,11 @@
 namespace sonar {
 namespace {
 
-constexpr int kYW = 10;                 // warps per CTA (one CTA per SM; 21 KB of shared memory per warp)
+constexpr int kYW = 8;                  // warps per CTA, one CTA per SM: TWO per scheduler.  Measured per 64 x 300 s (ms): 4 warps
+                                        // 8.46, 6 warps 10.56, 8 warps 8.01, 10 warps 8.99 -- the kernel is bound by instruction
+                                        // delivery (its loop body exceeds the 32 KB instruction cache level), a second warp per
+                                        // scheduler adds 5 %, and a scheduler left with fewer warps than its neighbours (6, 10)
+                                        // makes the whole CTA wait for the crowded ones.  21 KB of shared memory per warp.
 constexpr unsigned kFullY = 0xffffffffu;
 constexpr int kN = 1024, kHalf = 512, kHop = 512;
 constexpr int kTileRowY = 34;           // exchange tile row stride (float2)
@@ -367,63 +371,70 @@ __global__ void __launch_bounds__(kYW * 32, 1)
 
   const int64_t limit = (Tp + 1) * kHop;  // samples [0, limit) belong to the Tp frames
   const float rscale = 1.0f / 4096.0f;    // 1/4 (Hermitian split of both factors) * 1/1024 (inverse transform)
-  for (int64_t pr = (int64_t)blockIdx.x * kYW + warp; pr < total_pairs; pr += (int64_t)gridDim.x * kYW) {
+  for (int64_t base = (int64_t)blockIdx.x * kYW; base < total_pairs; base += (int64_t)gridDim.x * kYW) {
+    const int64_t pr = base + warp;
+    if (pr >= total_pairs) continue;
     const int s = (int)(pr / pairs_per_stream);
     const int64_t fa = (pr % pairs_per_stream) * 2, fb = fa + 1;
     const double* __restrict__ x = pcm + (int64_t)s * stride;
     float2 qa[16], qb[16], nyqa, nyqb;
     float e0a = 0.f, e0b = 0.f, etota = 0.f, etotb = 0.f;
     bool fina = true, finb = true;
-    // ---- frame a, then frame b: stage, forward transform, conj(U) P (one code instance, see warp_fft1024) -------
+    // ---- three passes through ONE instance of the transform (the loop body must stay near the 32 KB instruction cache
+    //      level, profiles/r02_stft_v5_ncu.md): frame a, frame b (stage, forward transform, conj(U) P), then the inverse
+    //      of Q = Q_a + i Q_b.  Frame b's pass leaves Q, conjugated for the inverse-by-forward transform, in z itself, so
+    //      nothing but qa is carried from one pass to the next.
+    float2 z[32];
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      float* pb = pbuf + c * (kN + 32);
-      float e0c, etc;
-      bool fc;
-      stage_frame(x, (fa + c) * kHop, limit, c == 0 || fb < Tp, alpha, s_hann, stage, pb, ebuf + c * (kHalf + 4), lane, &e0c,
-                  &etc, &fc);
-      float2 z[32];
+    for (int c = 0; c < 3; ++c) {
+      if (c < 2) {
+        float* pb = pbuf + c * (kN + 32);
+        float e0c, etc;
+        bool fc;
+        stage_frame(x, (fa + c) * kHop, limit, c == 0 || fb < Tp, alpha, s_hann, stage, pb, ebuf + c * (kHalf + 4), lane, &e0c,
+                    &etc, &fc);
+        if (c == 0)
+          e0a = e0c, etota = etc, fina = fc;
+        else
+          e0b = e0c, etotb = etc, finb = fc;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) z[j] = make_float2(pb[pidx(lane + 32 * j)], pb[pidx(lane + 32 * j + kHalf)]);
+        for (int j = 0; j < 16; ++j) z[j] = make_float2(pb[pidx(lane + 32 * j)], pb[pidx(lane + 32 * j + kHalf)]);
 #pragma unroll
-      for (int j = 16; j < 32; ++j) z[j] = make_float2(0.f, 0.f);
-      __syncwarp();
+        for (int j = 16; j < 32; ++j) z[j] = make_float2(0.f, 0.f);
+        __syncwarp();
+      }
       warp_fft1024(z, tile, s_tw, lane);
-      spectrum_product(z, lane, qb, &nyqb);
-      if (c == 0) {
+      if (c < 2) {
+        spectrum_product(z, lane, qb, &nyqb);
+        if (c == 0) {
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) qa[k2] = qb[k2];
-        nyqa = nyqb;
-        e0a = e0c, etota = etc, fina = fc;
+          for (int k2 = 0; k2 < 16; ++k2) qa[k2] = qb[k2];
+          nyqa = nyqb;
+        } else {
+          const int src = (32 - lane) & 31;
+          const bool lane0 = lane == 0;
+          float2 g[16];  // Q[1024 - k] = conj(Q_a[k]) + i conj(Q_b[k]), destined for the partner lane's upper registers
+#pragma unroll
+          for (int k2 = 0; k2 < 16; ++k2) {
+            const float2 a = qa[k2], b = qb[k2];
+            z[k2] = make_float2(a.x - b.y, -(a.y + b.x));      // conj(Q_a + i Q_b)
+            g[k2] = make_float2(a.x + b.y, -(b.x - a.y));      // conj(conj Q_a + i conj Q_b)
+          }
+          const float2 wn = make_float2(nyqa.x - nyqb.y, -(nyqa.y + nyqb.x));
+#pragma unroll
+          for (int r = 16; r < 32; ++r) {
+            // lanes != 0: register r <- partner's g[31 - r]; lane 0: r = 16 <- the Nyquist bin, r > 16 <- own g[32 - r]
+            const float2 give = lane0 ? (r == 16 ? wn : g[32 - r]) : g[31 - r];
+            z[r] = make_float2(__shfl_sync(kFullY, give.x, src), __shfl_sync(kFullY, give.y, src));
+          }
+        }
       } else {
-        e0b = e0c, etotb = etc, finb = fc;
-      }
-    }
-    // ---- Q = Q_a + i Q_b on all 1024 bins, conjugated for the inverse-by-forward transform --------------------
-    {
-      float2 w[32];
-      const int src = (32 - lane) & 31;
-      const bool lane0 = lane == 0;
-      float2 g[16];  // Q[1024 - k] = conj(Q_a[k]) + i conj(Q_b[k]), destined for the partner lane's upper registers
+        __syncwarp();  // every lane has its row of the tile in registers: the tile becomes r
+        // IFFT(Q) = conj(FFT(conj Q)) / N: r_a = Re, r_b = -Im; lags tau = lane + 32 k2 < 512
 #pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) {
-        const float2 a = qa[k2], b = qb[k2];
-        w[k2] = make_float2(a.x - b.y, -(a.y + b.x));      // conj(Q_a + i Q_b)
-        g[k2] = make_float2(a.x + b.y, -(b.x - a.y));      // conj(conj Q_a + i conj Q_b)
+        for (int k2 = 0; k2 < 16; ++k2)
+          *reinterpret_cast<float2*>(rbuf + 2 * ppos(lane + 32 * k2)) = make_float2(z[k2].x, -z[k2].y);
       }
-      const float2 wn = make_float2(nyqa.x - nyqb.y, -(nyqa.y + nyqb.x));
-#pragma unroll
-      for (int r = 16; r < 32; ++r) {
-        // lanes != 0: register r <- partner's g[31 - r]; lane 0: r = 16 <- the Nyquist bin, r > 16 <- own g[32 - r]
-        const float2 give = lane0 ? (r == 16 ? wn : g[32 - r]) : g[31 - r];
-        w[r] = make_float2(__shfl_sync(kFullY, give.x, src), __shfl_sync(kFullY, give.y, src));
-      }
-      warp_fft1024(w, tile, s_tw, lane);
-      __syncwarp();  // every lane has its row of the tile in registers: the tile becomes r
-      // IFFT(Q) = conj(FFT(conj Q)) / N: r_a = Re, r_b = -Im; lags tau = lane + 32 k2 < 512
-#pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2)
-        *reinterpret_cast<float2*>(rbuf + 2 * ppos(lane + 32 * k2)) = make_float2(w[k2].x, -w[k2].y);
     }
     __syncwarp();
     // ---- CMNDF, first dip, refinement; borderline frames go to the exact list ---------------------------------
