@@ -177,12 +177,22 @@ __device__ __forceinline__ void stage_frame(const double* __restrict__ x, int64_
   const float base = incl - run;  // S[32 l]
   *etot = __shfl_sync(kFullY, incl, 31);
   *e0 = __shfl_sync(kFullY, base, 16);  // S[512]
-  // E(tau) = S[tau + 512] - S[tau], tau = 32 l + k for the lanes l < 16; S[tau + 512] sits in lane l + 16
+  // E(tau) = S[tau + 512] - S[tau].  The prefix sums S[32 l + k] = base + loc[k] cross the warp through the staging buffer
+  // (its float64 samples are in registers by now; rows of 36 floats: the 128-bit stores and loads below are conflict free),
+  // then lane l forms the sixteen lags 16 l .. 16 l + 15 it will also read in pick32: 8 + 8 + 4 vector accesses per frame
+  // where one shuffle and one predicated store per lag (32 + 32, half the lanes idle) were needed before.
+  float* sbuf = reinterpret_cast<float*>(stage);
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const float s_here = base + loc[k];
-    const float s_far = __shfl_down_sync(kFullY, s_here, 16);
-    if (lane < 16) ebuf[spos(32 * lane + k)] = s_far - s_here;
+  for (int c4 = 0; c4 < 8; ++c4)
+    *reinterpret_cast<float4*>(sbuf + lane * 36 + 4 * c4) =
+        make_float4(base + loc[4 * c4], base + loc[4 * c4 + 1], base + loc[4 * c4 + 2], base + loc[4 * c4 + 3]);
+  __syncwarp();
+  const float* lo = sbuf + (lane >> 1) * 36 + (lane & 1) * 16;  // S[16 l ..]: row (16 l) / 32, column (16 l) % 32
+  const float* hi = lo + 16 * 36;                               // S[16 l + 512 ..]
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const float4 a = *reinterpret_cast<const float4*>(lo + 4 * c4), b = *reinterpret_cast<const float4*>(hi + 4 * c4);
+    *reinterpret_cast<float4*>(ebuf + spos(16 * lane + 4 * c4)) = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, b.w - a.w);
   }
   __syncwarp();
 }
