@@ -617,14 +617,17 @@ __device__ __forceinline__ double median_nonzero5(const double (&h)[5], int n) {
 // everything else — the confidence gate, the median-of-three smoothing, the derived arrays — is a pure
 // function of a three-frame window and runs one frame per lane.  Lane 0 therefore walks just the gated
 // frames of a round (ballot + find-first-set), in order, with the reference's arithmetic.
+constexpr int kTrackBatch = 4;
 __global__ void __launch_bounds__(32) yin_track_kernel(const double* __restrict__ raw, int64_t raw_stride,
                                                        int n_streams, int64_t Tp, double* __restrict__ feat,
                                                        int64_t feat_stride, int64_t o_pitch, int64_t o_conf,
                                                        int64_t o_voicing, int64_t o_hratio, int64_t o_inharm,
                                                        int64_t o_tonal, const double* __restrict__ speech_gate,
                                                        int64_t gate_stride) {
-  __shared__ double c_sm[5 + 32];  // corrected pitches: [0..4] = the five frames before this round
-  __shared__ double raw_sm[32];
+  constexpr int kB = kTrackBatch, kRound = 32 * kTrackBatch;  // frames per round: kB per lane
+  __shared__ double c_sm[5 + kRound];  // corrected pitches: [0..4] = the five frames before this round
+  __shared__ double raw_sm[kRound];
+  __shared__ unsigned todo_sm[kB];
   const int s = blockIdx.x;
   const int lane = threadIdx.x;
   const double* r = raw + (int64_t)s * raw_stride;
@@ -636,69 +639,96 @@ __global__ void __launch_bounds__(32) yin_track_kernel(const double* __restrict_
   // what the harmonic block starts from.  Pass 0 of two replays that sweep without writing anything.
   const int passes = (speech_gate && speech_gate[(int64_t)s * gate_stride] != 0.0) ? 2 : 1;
   for (int pass = 0; pass < passes; ++pass) {
-  const bool write = pass == passes - 1;
-  const int64_t hist0 = pass == 0 ? 0 : (Tp < 20 ? Tp : 20);  // history entries before the pass's first frame
-  for (int64_t base = 0; base < Tp; base += 32) {
-    const int cnt = (int)((Tp - base < 32) ? (Tp - base) : 32);
-    const int64_t i = base + lane;
-    double rawp = 0.0, conf = 0.0;
-    if (lane < cnt) {
-      rawp = r[i];
-      conf = r[Tp + i];
-    }
-    const bool gate = lane < cnt && rawp != 0.0 && conf >= 0.5;  // :782-786: below 0.5 everything is zeroed
-    raw_sm[lane] = rawp;
-    c_sm[5 + lane] = gate ? rawp : 0.0;
-    unsigned todo = __ballot_sync(0xffffffffu, gate);
-    __syncwarp();
-    if (lane == 0) {
-      while (todo) {
-        const int k = __ffs(todo) - 1;
-        todo &= todo - 1;
-        int64_t hlen = hist0 + base + k;  // history entries before this frame
-        if (hlen > 20) hlen = 20;
-        double pitch = raw_sm[k];
-        if (hlen >= 3) {  // applyOctaveCorrection :792-829 (needs >= 3 of the last five)
-          const double h[5] = {c_sm[k], c_sm[k + 1], c_sm[k + 2], c_sm[k + 3], c_sm[k + 4]};
-          const double med = median_nonzero5(h, hlen < 5 ? (int)hlen : 5);
-          const double ratios[4] = {0.5, 2.0, 1.0 / 3.0, 3.0};
+    const bool write = pass == passes - 1;
+    const int64_t hist0 = pass == 0 ? 0 : (Tp < 20 ? Tp : 20);  // history entries before the pass's first frame
+    // A round covers kRound frames (kB per lane) and its raw values are fetched one round AHEAD of the walk: the fixed
+    // cost of a round (shared-memory hand-overs around the sequential octave correction, ~900 cycles) is paid once per
+    // 128 frames instead of once per 32, and the two global loads no longer add their latency to it (0.61 -> 0.37 ms per
+    // 25,838 frames with the prefetch alone; this kernel is the tail of the fingerprint step and was 2.7 of the 8.7 ms of
+    // the one-hour streams of C3).
+    double nraw[kB], nconf[kB];
+    auto fetch = [&](int64_t b0) {
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const double expect = med * ratios[q];
-            if (fabs(pitch - expect) / expect < 0.1) {
-              if (fabs(pitch - med) > fabs(expect - med)) pitch = expect;
-              break;
+      for (int u = 0; u < kB; ++u) {
+        const int64_t i = b0 + 32 * u + lane;
+        nraw[u] = i < Tp ? r[i] : 0.0;
+        nconf[u] = i < Tp ? r[Tp + i] : 0.0;
+      }
+    };
+    fetch(0);
+    for (int64_t base = 0; base < Tp; base += kRound) {
+      const int cnt = (int)((Tp - base < kRound) ? (Tp - base) : kRound);
+      double conf[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int e = 32 * u + lane;
+        const double rawp = nraw[u];  // zero beyond the last frame
+        conf[u] = nconf[u];
+        const bool gate = e < cnt && rawp != 0.0 && conf[u] >= 0.5;  // :782-786: below 0.5 everything is zeroed
+        raw_sm[e] = rawp;
+        c_sm[5 + e] = gate ? rawp : 0.0;
+        const unsigned td = __ballot_sync(0xffffffffu, gate);
+        if (lane == 0) todo_sm[u] = td;
+      }
+      fetch(base + kRound);
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll 1  // ONE instance of the correction code: unrolled, the round was 33 KB of instructions fetched by a lone warp
+        for (int u = 0; u < kB; ++u) {
+          unsigned td = todo_sm[u];
+          while (td) {
+            const int k = 32 * u + __ffs(td) - 1;
+            td &= td - 1;
+            int64_t hlen = hist0 + base + k;  // history entries before this frame
+            if (hlen > 20) hlen = 20;
+            double pitch = raw_sm[k];
+            if (hlen >= 3) {  // applyOctaveCorrection :792-829 (needs >= 3 of the last five)
+              const double h[5] = {c_sm[k], c_sm[k + 1], c_sm[k + 2], c_sm[k + 3], c_sm[k + 4]};
+              const double med = median_nonzero5(h, hlen < 5 ? (int)hlen : 5);
+              const double ratios[4] = {0.5, 2.0, 1.0 / 3.0, 3.0};
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const double expect = med * ratios[q];
+                if (fabs(pitch - expect) / expect < 0.1) {
+                  if (fabs(pitch - med) > fabs(expect - med)) pitch = expect;
+                  break;
+                }
+              }
             }
+            c_sm[5 + k] = pitch;
           }
         }
-        c_sm[5 + k] = pitch;
       }
-    }
-    __syncwarp();
-    if (lane < cnt) {
-      const double c0 = c_sm[5 + lane], c1 = c_sm[4 + lane], c2 = c_sm[3 + lane];
-      double pitch = c0;  // applyTemporalSmoothing :905-921 on the history that already includes this frame
-      const int64_t hsize = hist0 + i + 1;  // history length including this frame (capped at 20: >= 3 either way)
-      if (hsize >= 3)
-        pitch = median_nonzero3(c2, c1, c0);
-      else if (hsize == 2)
-        pitch = 0.3 * c0 + (1 - 0.3) * c1;  // history of two: blend with the previous (unsmoothed) output
-      const double cf = conf < 0.5 ? 0.0 : conf;
-      if (write) {
-        fo[o_pitch + i] = pitch;
-        fo[o_conf + i] = cf;
-        fo[o_voicing + i] = cf;
-        fo[o_hratio + i] = cf * 10.0;               // speech.go:499
-        fo[o_inharm + i] = 1.0 - cf;                // speech.go:500
-        fo[o_tonal + i] = pitch > 0 ? pitch : 0.0;  // speech.go:503-505
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int e = 32 * u + lane;
+        if (e < cnt) {
+          const int64_t i = base + e;
+          const double c0 = c_sm[5 + e], c1 = c_sm[4 + e], c2 = c_sm[3 + e];
+          double pitch = c0;  // applyTemporalSmoothing :905-921 on the history that already includes this frame
+          const int64_t hsize = hist0 + i + 1;  // history length including this frame (capped at 20: >= 3 either way)
+          if (hsize >= 3)
+            pitch = median_nonzero3(c2, c1, c0);
+          else if (hsize == 2)
+            pitch = 0.3 * c0 + (1 - 0.3) * c1;  // history of two: blend with the previous (unsmoothed) output
+          const double cf = conf[u] < 0.5 ? 0.0 : conf[u];
+          if (write) {
+            fo[o_pitch + i] = pitch;
+            fo[o_conf + i] = cf;
+            fo[o_voicing + i] = cf;
+            fo[o_hratio + i] = cf * 10.0;               // speech.go:499
+            fo[o_inharm + i] = 1.0 - cf;                // speech.go:500
+            fo[o_tonal + i] = pitch > 0 ? pitch : 0.0;  // speech.go:503-505
+          }
+        }
       }
+      __syncwarp();
+      const double carry = (lane < 5) ? c_sm[cnt + lane] : 0.0;  // the five entries that end with this round's last frame
+      __syncwarp();
+      if (lane < 5) c_sm[lane] = carry;
+      __syncwarp();
     }
-    __syncwarp();
-    const double carry = (lane < 5) ? c_sm[cnt + lane] : 0.0;  // the five entries that end with this round's last frame
-    __syncwarp();
-    if (lane < 5) c_sm[lane] = carry;
-    __syncwarp();
-  }
   }
 }
 
