@@ -63,7 +63,9 @@ __device__ __forceinline__ double cell_get(const double* __restrict__ cells, con
 }
 
 constexpr int kRing = 2048;       // staged q / r window (power of two), doubles each
-constexpr int kRefill = 1024;     // diagonals between two refills of the register wavefront's rings
+constexpr int kWRing = 512;       // register wavefront: staged q / r window per warp (needs kWRefill + band + 10 <= kWRing)
+constexpr int kWRefill = 256;     // diagonals between two refills of the register wavefront's rings
+constexpr int kDtwWarps = 4;      // pairs (= warps) per CTA of the register wavefront
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -294,7 +296,7 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
                                                    const DtwGeom& g, double* __restrict__ cells, double* ring_q,
                                                    double* ring_r) {
   constexpr int H = NPL / 2;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int n = g.n, m = g.m, band = g.band, W = (int)g.W;
   const double inf = d_inf();
   const int kbase = NPL * lane - 1;  // offset of slot 0
@@ -315,13 +317,13 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
   }
   const int last = n + m;
   // q / r reach the rings through cp.async one refill period AHEAD of their use, so the warp never waits for
-  // a global load: the call at diagonal d first waits for the copies issued at d - kRefill (everything the
-  // diagonals [d, d + kRefill) read), then issues the elements of the following period.
+  // a global load: the call at diagonal d first waits for the copies issued at d - kWRefill (everything the
+  // diagonals [d, d + kWRefill) read), then issues the elements of the following period.
   int loaded = 0;
   auto issue = [&](int target) {
     for (int e = loaded + lane; e < target; e += 32) {
-      if (e < n) cp_async8(&ring_q[e & (kRing - 1)], q + e);
-      if (e < m) cp_async8(&ring_r[e & (kRing - 1)], r + e);
+      if (e < n) cp_async8(&ring_q[e & (kWRing - 1)], q + e);
+      if (e < m) cp_async8(&ring_r[e & (kWRing - 1)], r + e);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     loaded = target > loaded ? target : loaded;
@@ -329,7 +331,7 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
   auto refill = [&](int d) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    issue(((d + 2 * kRefill + band) >> 1) + 8);
+    issue(((d + 2 * kWRefill + band) >> 1) + 8);
   };
   // The single warp is issue-bound (one instruction every ~2 cycles), so the loop body is kept minimal: the
   // invalid slots get their +Inf through the local distance, stores are predicated (no branches), the store
@@ -373,9 +375,9 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
   };
   const int half_l = (NPL / 2) * lane;  // (NPL*lane) >> 1
   int d = 2;
-  issue(((d + kRefill + band) >> 1) + 8);
+  issue(((d + kWRefill + band) >> 1) + 8);
   refill(d);
-  int next_refill = d + kRefill;
+  int next_refill = d + kWRefill;
   // Cells of an aligned iteration (d - band even): odd slots on d are (ib + h, jb - h), even slots on d + 1 are
   // (ib + h, jb - h + 1), with ib = (d - band + NPL*lane) / 2, jb = d - ib; Q[h] = q[ib + h - 1], R[u] = r[jb - u].
   double Q[H], R[H + 1];
@@ -385,18 +387,18 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
 #pragma unroll
     for (int h = 0; h < H; ++h) {
       ok[h] = (unsigned)(d - dlo[2 * h]) <= span[2 * h];
-      Q[h] = ring_q[(ib + h - 1) & (kRing - 1)];
+      Q[h] = ring_q[(ib + h - 1) & (kWRing - 1)];
     }
 #pragma unroll
-    for (int u = 0; u <= H; ++u) R[u] = ring_r[(jb - u) & (kRing - 1)];
+    for (int u = 0; u <= H; ++u) R[u] = ring_r[(jb - u) & (kWRing - 1)];
     half_a(cells + (int64_t)d * W + half_l - 1, Q, R, ok);
     ++d;
   }
   int ib = (d - band + NPL * lane) >> 1, jb = d - ib;
 #pragma unroll
-  for (int h = 0; h < H; ++h) Q[h] = ring_q[(ib + h - 1) & (kRing - 1)];
+  for (int h = 0; h < H; ++h) Q[h] = ring_q[(ib + h - 1) & (kWRing - 1)];
 #pragma unroll
-  for (int u = 0; u <= H; ++u) R[u] = ring_r[(jb - u) & (kRing - 1)];
+  for (int u = 0; u <= H; ++u) R[u] = ring_r[(jb - u) & (kWRing - 1)];
   double* __restrict__ rowb = cells + (int64_t)d * W + half_l;  // diagonal d, odd slots; diagonal d + 1's even slots: + W - 1
   // steady state: every in-band offset has a cell on the diagonal; [sd0, sd1) in steps of two from d
   const int mn = n < m ? n : m;
@@ -405,9 +407,9 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
     constexpr bool STEADY = decltype(steady_tag)::value;
     if (d >= next_refill) {
       refill(d);
-      next_refill += kRefill;
+      next_refill += kWRefill;
     }
-    const double qn = ring_q[(ib + H - 1) & (kRing - 1)], rn = ring_r[(jb + 1) & (kRing - 1)];  // next iteration's
+    const double qn = ring_q[(ib + H - 1) & (kWRing - 1)], rn = ring_r[(jb + 1) & (kWRing - 1)];  // next iteration's
     bool okb[H], oka[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
@@ -436,20 +438,26 @@ __device__ __forceinline__ void dtw_fill_warp_body(const double* __restrict__ q,
   while (d <= last) iterate(std::false_type{});
 }
 
+// kDtwWarps pairs per CTA, one warp each (a warp per scheduler: the chains do not compete for issue slots).  A CTA per
+// pair put 32 single-warp CTAs with 32 KB of rings each on 32 SMs, and the persistent STFT kernels, whose CTAs need a
+// whole SM's shared memory, ran on the remaining 116 SMs for as long as the fill lasted (+1 ms on the STFT pair in the
+// step); eight CTAs with 8 KB of rings per warp take 8 SMs and fit beside a pitch-kernel CTA.
 template <int NPL, int STEP>
-__global__ void __launch_bounds__(32) dtw_fill_warp_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
-                                                           DtwGeom g, double* __restrict__ cells_all,
-                                                           const double* const* __restrict__ qptr,
-                                                           const double* const* __restrict__ rptr) {
-  __shared__ double ring_q[kRing], ring_r[kRing];
-  const int pair = blockIdx.x;
+__global__ void __launch_bounds__(32 * kDtwWarps) dtw_fill_warp_kernel(const double* __restrict__ qs, const double* __restrict__ rs,
+                                                                       DtwGeom g, double* __restrict__ cells_all,
+                                                                       const double* const* __restrict__ qptr,
+                                                                       const double* const* __restrict__ rptr, int n_pairs) {
+  __shared__ double rings[kDtwWarps][2][kWRing];
+  const int w = threadIdx.x >> 5;
+  const int pair = blockIdx.x * kDtwWarps + w;
+  if (pair >= n_pairs) return;  // the body synchronises warps only
   const double* __restrict__ q = qptr ? qptr[pair] : qs + (int64_t)pair * g.n;
   const double* __restrict__ r = rptr ? rptr[pair] : rs + (int64_t)pair * g.m;
   double* cells = cells_all + (int64_t)pair * g.cells;
   if (cells[g.flag_off] != 0.0)  // warp-uniform verdict of dtw_screen_kernel
-    dtw_fill_warp_body<NPL, STEP, true>(q, r, g, cells, ring_q, ring_r);
+    dtw_fill_warp_body<NPL, STEP, true>(q, r, g, cells, rings[w][0], rings[w][1]);
   else
-    dtw_fill_warp_body<NPL, STEP, false>(q, r, g, cells, ring_q, ring_r);
+    dtw_fill_warp_body<NPL, STEP, false>(q, r, g, cells, rings[w][0], rings[w][1]);
 }
 
 constexpr int kBtTile = 64;
@@ -937,13 +945,14 @@ int launch_dtw(const double* q, const double* r, int n_pairs, const DtwGeom& g, 
 #define SONAR_DTW_WARP(NPL)                                                                       \
   do {                                                                                            \
     if (step == SONAR_STEP_SYMMETRIC2)                                                            \
-      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC2><<<n_pairs, 32, 0, st>>>(q, r, g, cells, qptr, rptr);   \
+      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC2><<<wgrid, 32 * kDtwWarps, 0, st>>>(q, r, g, cells, qptr, rptr, n_pairs);   \
     else if (step == SONAR_STEP_ASYMMETRIC)                                                       \
-      dtw_fill_warp_kernel<NPL, SONAR_STEP_ASYMMETRIC><<<n_pairs, 32, 0, st>>>(q, r, g, cells, qptr, rptr);   \
+      dtw_fill_warp_kernel<NPL, SONAR_STEP_ASYMMETRIC><<<wgrid, 32 * kDtwWarps, 0, st>>>(q, r, g, cells, qptr, rptr, n_pairs);   \
     else                                                                                          \
-      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC1><<<n_pairs, 32, 0, st>>>(q, r, g, cells, qptr, rptr);   \
+      dtw_fill_warp_kernel<NPL, SONAR_STEP_SYMMETRIC1><<<wgrid, 32 * kDtwWarps, 0, st>>>(q, r, g, cells, qptr, rptr, n_pairs);   \
   } while (0)
     const int offs = 2 * g.band + 3;  // one never-valid slot on each side (see dtw_fill_warp_body)
+    const unsigned wgrid = (unsigned)((n_pairs + kDtwWarps - 1) / kDtwWarps);
     prof_begin("dtw_screen_kernel", st);
     dtw_screen_kernel<<<n_pairs, 1024, 0, st>>>(q, r, g, cells, qptr, rptr);
     prof_end();
