@@ -766,9 +766,10 @@ int launch_frame_walk(const double* pcm, int64_t n, int64_t stride, int n_stream
     const bool staged = aligned && !direct && hop % 16 == 0;
     const bool slide = staged && !flags && frame / hop == 4;
     // Frames per thread.  A thread reads G + R - 1 hops to finish G frames (R = frame / hop), so the sliding-window form,
-    // whose registers do not grow with G, takes 12: 15 hops per 12 frames instead of 11 per 8 (-9 % samples walked), and
-    // the 64 x 300 s step becomes 2.9 waves of CTAs instead of 4.4 rounded up to 5 (1.82 -> 1.5 ms).  12 is also the most
-    // the fused loudness block sums allow at 44.1 kHz (a thread's range may hold one 4,410-sample block boundary).
+    // whose registers do not grow with G, takes 12: 15 hops per 12 frames instead of 11 per 8 (-9 % samples walked;
+    // measured 1.90 -> 1.85 ms per 64 x 300 s: the kernel waits on its staged loads, long_scoreboard 1.5 warps per issue,
+    // more than on its arithmetic).  12 is also the most the fused loudness block sums allow at 44.1 kHz (a thread's range
+    // may hold one 4,410-sample block boundary).
     auto run = [&](auto g_tag) -> int {
     constexpr int G = decltype(g_tag)::value;
     const int64_t groups = (Tn + G - 1) / G;
