@@ -136,6 +136,12 @@ bool stft_v3_eligible(const FpPlan& plan, const StftArgs& a);
 int launch_stft_v3(const FpPlan& plan, StftArgs& a, cudaStream_t st);
 // fifth generation (stft_v5.cu): the same work as a transform kernel + a scan kernel, each within the 32 KB instruction cache
 int launch_stft_v5(const FpPlan& plan, StftArgs& a, cudaStream_t st);
+// SMs the persistent STFT kernels leave unclaimed for the launches that follow on the calling thread.  The pair pipeline
+// sets it to the number of CTAs its DTW fill occupies (kDtwPairsPerCta pairs each) while it enqueues a chunk's fingerprint:
+// both STFT kernels give every CTA a static share of the runs, so a CTA whose SM is held by the alignment branch starts late
+// and the launch waits for it (scripts/sm_reserve_ab.py, 32 pairs: 19.8 ms per step with 0, 18.7 with 8, 19.2 with 16).
+extern thread_local int tl_stft_sm_reserve;
+constexpr int kDtwPairsPerCta = 4;
 void stft_workspace_release(int device, cudaStream_t st);  // frees the pair's workspace of a stream about to be destroyed
 
 // ---- fingerprint sequencing shared by the host-pointer, device-resident and pipeline entry points ----------

@@ -65,7 +65,7 @@ __device__ __forceinline__ double cell_get(const double* __restrict__ cells, con
 constexpr int kRing = 2048;       // staged q / r window (power of two), doubles each
 constexpr int kWRing = 512;       // register wavefront: staged q / r window per warp (needs kWRefill + band + 10 <= kWRing)
 constexpr int kWRefill = 256;     // diagonals between two refills of the register wavefront's rings
-constexpr int kDtwWarps = 4;      // pairs (= warps) per CTA of the register wavefront
+constexpr int kDtwWarps = kDtwPairsPerCta;  // pairs (= warps) per CTA of the register wavefront (common.h)
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -163,7 +163,11 @@ int enqueue_chunk(sonar_ctx* ctx, int device, const sonar_fp_params* p, const Pa
                   const double* pcm_dev, void* d_tmp, void* d_out, cudaStream_t st, cudaStream_t st2, cudaEvent_t mid,
                   cudaEvent_t fpdone, bool exact_curve, bool feat_travel) {
   double* feat = at<double>(d_out, L.o_feat);
+  // the DTW fill of this (or the previous) chunk sits on ceil(c / kDtwPairsPerCta) SMs for several milliseconds beside the
+  // persistent STFT kernels: they leave that many SMs unclaimed (common.h)
+  tl_stft_sm_reserve = std::min((c + kDtwPairsPerCta - 1) / kDtwPairsPerCta, 16);
   int rc = enqueue_fingerprint(ctx, device, p, G.sh, pcm_dev, G.n, G.stride, 2 * c, feat, at<double>(d_tmp, L.t_fp), st, mid);
+  tl_stft_sm_reserve = 0;
   if (rc) return rc;
   SONAR_CUDA(cudaEventRecord(fpdone, st));
   SONAR_CUDA(cudaStreamWaitEvent(st2, mid, 0));

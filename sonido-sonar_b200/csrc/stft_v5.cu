@@ -655,6 +655,14 @@ int v5_launch(const FpPlan& plan, StftArgs& a, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // Both kernels are persistent, one CTA per SM with a static share of the runs: a CTA that finds its SM taken by a kernel
+  // of another stream (the alignment branch of the pair pipeline) starts late and the whole launch waits for it.  Leaving
+  // a few SMs unclaimed costs their share of the throughput and keeps the launch off that wait (tl_stft_sm_reserve, common.h).
+  {
+    const char* e = std::getenv("SONAR_STFT_SM_RESERVE");  // diagnostic override (read per launch: scripts/sm_reserve_ab.py)
+    const int reserve = e ? std::atoi(e) : tl_stft_sm_reserve;
+    if (reserve > 0) sms = std::max(sms / 2, sms - reserve);
+  }
   unsigned char* ws = nullptr;
   int rc = ws_get(dev, st, per_stream * (size_t)group, &ws);
   while (rc == SONAR_ERR_UNSUPPORTED && group > 1) {  // smaller groups of streams, more launches
@@ -683,6 +691,8 @@ int v5_launch(const FpPlan& plan, StftArgs& a, cudaStream_t st) {
 }
 
 }  // namespace
+
+thread_local int tl_stft_sm_reserve = 0;
 
 void stft_workspace_release(int device, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_ws_mu);
