@@ -648,3 +648,123 @@ def test_truncate_to_alignment_errors(oracle, capi):
         oracle.truncate_to_alignment(50000, 1000, 44100, 2.0)
     with pytest.raises(capi.SonarError, match="offset too large: need to skip 44100 samples but pcm1 only has 44100"):
         oracle.truncate_to_alignment(44100, 90000, 44100, -1.0)
+
+
+# ---------------------------------------------------------------- YIN + the detector's temporal post-pass
+
+def py_pitch_track(pcm, sr, alpha=0.97):
+    """Independent restatement, written from the Go source, of extractHarmonicFeatures (extractors/speech.go:462-509) over
+    the pre-emphasised stream (speech.go:161, filters/pre_emphasis.go:135-155): PitchDetector.DetectPitch per 1024 / 512
+    frame = preprocessFrame (pitch_detection.go:282-314) -> detectPitchYin (:349-420, sums sequential in j and tau) ->
+    parabolicInterpolation (:743-764) -> postProcessResult (:767-790: octave correction against the median of the last
+    five history entries, MinConfidence 0.5) -> updateTemporalTracking (:876-902: history of 20, median-of-three
+    smoothing on the history that already includes the frame, exponential blend while the history holds two)."""
+    y = pcm.copy()
+    y[1:] = pcm[1:] - alpha * pcm[:-1]
+    N, H, half = 1024, 512, 512
+    hann = np.array([0.5 * (1.0 - math.cos(2.0 * math.pi * i / (N - 1))) for i in range(N)])
+    T = (y.size - N) // H + 1
+    pitch_out, conf_out = np.zeros(T), np.zeros(T)
+    history, prev = [], 0.0
+    py_pitch_track.corrected = py_pitch_track.smoothed = 0
+
+    def median_nonzero(vals):
+        f = sorted(v for v in vals if v > 0)
+        if not f:
+            return 0.0
+        n = len(f)
+        return (f[n // 2 - 1] + f[n // 2]) / 2.0 if n % 2 == 0 else f[n // 2]
+
+    for t in range(T):
+        fr = y[t * H:t * H + N]
+        p = fr.copy()
+        p[1:] = fr[1:] - 0.97 * fr[:-1]
+        p = p * hann
+        # d[tau] = sum_j (p[j] - p[j + tau])^2, accumulated left to right (np.add.accumulate along j is sequential)
+        idx = np.arange(half)[None, :] + np.arange(half)[:, None]          # [tau, j] -> j + tau
+        delta = p[None, :half] - p[idx]
+        d = np.add.accumulate(delta * delta, axis=1)[:, -1]
+        cm = np.ones(half)
+        run = 0.0
+        for tau in range(1, half):
+            run += d[tau]
+            cm[tau] = d[tau] / (run / tau) if run != 0.0 else (math.nan if d[tau] == 0.0 else math.inf)
+        min_tau = -1
+        for tau in range(1, half):
+            if cm[tau] < 0.15 and tau + 1 < half and cm[tau] < cm[tau + 1]:
+                min_tau = tau
+                break
+        pitch = conf = 0.0
+        if min_tau > 0:
+            period = float(min_tau)
+            if 0 < min_tau < half - 1:
+                y1, y2, y3 = cm[min_tau - 1], cm[min_tau], cm[min_tau + 1]
+                a, b = (y1 - 2 * y2 + y3) / 2, (y3 - y1) / 2
+                if a != 0:
+                    period = min_tau + (-b / (2 * a))
+            freq = sr / period
+            if 80.0 <= freq <= 1000.0:
+                pitch, conf = freq, 1.0 - cm[min_tau]
+        # postProcessResult
+        if pitch != 0.0 and history:
+            recent = history[-5:]
+            if len(recent) >= 3:
+                med = median_nonzero(recent)
+                for ratio in (0.5, 2.0, 1.0 / 3.0, 3.0):
+                    expect = med * ratio
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        close = np.float64(abs(pitch - expect)) / np.float64(expect) < 0.1
+                    if close:
+                        if abs(pitch - med) > abs(expect - med):
+                            pitch = expect
+                            py_pitch_track.corrected += 1
+                        break
+        if conf < 0.5:
+            pitch = conf = 0.0
+        # updateTemporalTracking
+        history.append(pitch)
+        history = history[-20:]
+        out = pitch
+        if len(history) > 1:
+            recent = history[-3:]
+            out = median_nonzero(recent) if len(recent) >= 3 else 0.3 * pitch + (1 - 0.3) * prev
+        prev = out
+        py_pitch_track.smoothed += out != pitch
+        pitch_out[t], conf_out[t] = out, conf
+    return pitch_out, conf_out
+
+
+def _voiced_test_signal(sr, seconds, seed):
+    n = int(seconds * sr)
+    t = np.arange(n) / sr
+    f = 300.0 * (1.0 + 0.2 * np.sin(2 * np.pi * 0.9 * t))           # a gliding "voice"
+    ph = 2 * np.pi * np.cumsum(f) / sr
+    gate = (np.sin(2 * np.pi * 1.7 * t) > -0.4).astype(np.float64)  # voiced stretches and gaps
+    rng = np.random.default_rng(seed)
+    gate[int(0.42 * n):int(0.75 * n)] = 1.0                          # no gap around the octave jump below
+    x = 0.4 * (np.sin(ph) + 0.05 * np.sin(2 * ph)) * gate + 1e-4 * rng.standard_normal(n)
+    # an octave jump in the middle: exercises the octave correction against the history
+    j0, j1 = int(0.55 * n), int(0.62 * n)
+    x[j0:j1] = 0.4 * np.sin(2.0 * ph[j0:j1]) + 1e-4 * rng.standard_normal(j1 - j0)
+    return x
+
+
+@pytest.mark.parametrize("sr,seconds,seed", [(16000, 2.0, 1), (44100, 1.2, 2), (22050, 2.0, 5)])
+def test_yin_and_pitch_tracking_against_python_restatement(oracle, sr, seconds, seed):
+    """Raw YIN decisions, parabolic refinement, octave correction, confidence gate and the median-of-three smoothing of the
+    oracle are bit-identical to a restatement written independently from pitch_detection.go / speech.go."""
+    x = _voiced_test_signal(sr, seconds, seed)
+    fp = oracle.fingerprint(x, oracle.default_params(algo_sample_rate=sr, call_sample_rate=sr))
+    want_p, want_c = py_pitch_track(x, sr)
+    assert fp.pitch_estimate.shape == want_p.shape
+    voiced = want_c > 0
+    assert 20 <= voiced.sum() < want_p.size, "the signal must hold voiced stretches and gaps"
+    assert py_pitch_track.smoothed >= 20
+    if sr == 22050:
+        assert py_pitch_track.corrected >= 1, "this case must exercise the octave correction"
+    assert np.array_equal(fp.pitch_confidence, want_c)
+    assert np.array_equal(fp.pitch_estimate, want_p)
+    assert np.array_equal(fp.voicing_strength, want_c)            # speech.go:484: Voicing = confidence after the gate
+    assert np.array_equal(fp.harmonic_ratio, want_c * 10.0)       # :499
+    assert np.array_equal(fp.inharmonicity_ratio, 1.0 - want_c)   # :500
+    assert np.array_equal(fp.tonal_centroid, np.where(want_p > 0, want_p, 0.0))  # :503-505
