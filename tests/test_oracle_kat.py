@@ -768,3 +768,106 @@ def test_yin_and_pitch_tracking_against_python_restatement(oracle, sr, seconds, 
     assert np.array_equal(fp.harmonic_ratio, want_c * 10.0)       # :499
     assert np.array_equal(fp.inharmonicity_ratio, 1.0 - want_c)   # :500
     assert np.array_equal(fp.tonal_centroid, np.where(want_p > 0, want_p, 0.0))  # :503-505
+
+
+# ---------------------------------------------------------------- temporal feature group + loudness range
+
+def py_ste(y, frame, hop):
+    """temporal/energy.go:25-50: RMS per frame, squares summed left to right."""
+    if y.size < frame or hop <= 0 or frame <= 0:
+        return np.zeros(0)
+    T = (y.size - frame) // hop + 1
+    return np.array([math.sqrt(seq_sum(y[t * hop:t * hop + frame] ** 2) / frame) for t in range(T)])
+
+
+def py_loudness_range(y, sr):
+    """temporal/energy.go:157-225: 400 ms windows, hop = a quarter, 'loudness units', 10th..95th percentile through
+    calculatePercentileRange (whose log of a ratio of dB values returns 0 unless the 95th percentile is positive)."""
+    if y.size == 0 or sr <= 0:
+        return 0.0
+    win = int(0.4 * sr)
+    hop = win // 4 or 1
+    e = py_ste(y, win, hop)
+    if e.size == 0:
+        return 0.0
+    lv = sorted((-0.691 + 10.0 * math.log10(v * v)) if v > 0 else -70.0 for v in e)
+    lo, hi = lv[int(0.10 * (len(lv) - 1))], lv[int(0.95 * (len(lv) - 1))]
+    if lo <= 0.0:
+        lo = 1e-10
+    if hi <= 0.0:
+        return 0.0
+    return 20.0 * math.log10(hi / lo)
+
+
+def py_temporal_group(pcm, sr, frame, hop, alpha=0.97):
+    """extractTemporalFeatures (extractors/speech.go:370-408) and its helpers (:641-777), written from the Go source."""
+    y = pcm.copy()
+    y[1:] = pcm[1:] - alpha * pcm[:-1]
+    rms = py_ste(y, frame, hop)
+    out = {"rms": rms, "dynamic_range": py_loudness_range(y, sr)}
+    thr = sorted(rms)[len(rms) // 10]                                # :641-668 (the bubble sort is a sort)
+    out["silence_ratio"] = float((rms <= thr).sum()) / len(rms)
+    out["peak_amplitude"] = float(np.max(np.abs(y)))
+    out["average_amplitude"] = seq_sum(np.abs(y)) / y.size
+    der = rms[1:] - rms[:-1]                                         # energy.go:122-133
+    mean = seq_sum(der) / der.size                                   # :695-716
+    sd = math.sqrt(seq_sum((der - mean) ** 2) / der.size)
+    gate = mean + 2 * sd
+    onsets = [i for i in range(1, der.size - 1) if der[i] > der[i - 1] and der[i] > der[i + 1] and der[i] > gate]
+    out["onset_density"] = len(onsets) / (y.size / sr)
+    frame_time = hop / sr
+    attack = []
+    for o in onsets:                                                 # :718-749
+        peak, start = rms[o], o
+        j = o - 1
+        while j >= 0 and j > o - 10:
+            if rms[j] < 0.1 * peak:
+                start = j
+                break
+            j -= 1
+        attack.append(min((o - start) * frame_time, 0.1))
+    out["attack"] = np.array(attack)
+    T = (y.size - 512) // 256 + 1                                    # :751-777
+    out["envelope"] = np.array([math.sqrt(seq_sum(y[t * 256:t * 256 + 512] ** 2) / 512) for t in range(T)])
+    return out
+
+
+def test_temporal_group_against_python_restatement(oracle, capi):
+    sr = 16000
+    rng = np.random.default_rng(5)  # noise bursts with abrupt onsets over a quiet floor
+    n = 6 * sr
+    pcm = 0.02 * rng.standard_normal(n)
+    t = 0
+    while t < n:
+        on, off = int(rng.uniform(0.05, 0.2) * sr), int(rng.uniform(0.2, 0.6) * sr)
+        if t + on <= n:
+            pcm[t:t + on] += rng.uniform(0.2, 0.8) * rng.standard_normal(on)
+        t += on + off
+    kw = dict(window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=sr, call_sample_rate=sr,
+              enable=capi.FP_ENABLE_MFCC | capi.FP_ENABLE_TEMPORAL)
+    fp = oracle.fingerprint(pcm, oracle.default_params(**kw))
+    want = py_temporal_group(pcm, sr, 512, 160)
+    assert len(want["attack"]) >= 3, "the case must contain onsets"
+    assert np.array_equal(fp.rms_energy, want["rms"])
+    assert np.array_equal(fp.envelope_shape, want["envelope"])
+    assert fp.n_attack_time == len(want["attack"])
+    assert np.array_equal(fp.attack_time[:fp.n_attack_time], want["attack"])
+    assert fp.scalars["silence_ratio"] == want["silence_ratio"]
+    assert fp.scalars["peak_amplitude"] == want["peak_amplitude"]
+    assert fp.scalars["average_amplitude"] == want["average_amplitude"]
+    assert fp.scalars["onset_density"] == pytest.approx(want["onset_density"], rel=1e-15)
+    assert fp.scalars["dynamic_range"] == pytest.approx(want["dynamic_range"], rel=1e-12, abs=1e-15)
+
+
+@pytest.mark.parametrize("gain,sr", [(0.05, 44100), (40.0, 16000), (25.0, 44100)])
+def test_loudness_range_against_python_restatement(oracle, synth, gain, sr):
+    """Loud inputs reach positive 'loudness units' (the only way calculatePercentileRange returns a non-zero range)."""
+    rng = np.random.default_rng(int(gain) + 1)
+    n = int(4.0 * sr)
+    x = gain * rng.standard_normal(n) * (0.2 + np.abs(np.sin(np.arange(n) * 2 * np.pi / (1.3 * sr))))
+    fp = oracle.fingerprint(x, oracle.default_params(algo_sample_rate=sr, call_sample_rate=sr))
+    y = x.copy()
+    y[1:] = x[1:] - 0.97 * x[:-1]
+    want = py_loudness_range(y, sr)
+    assert (want > 0.0) == (gain > 1.0), "a quiet input has no positive loudness unit, a loud one has"
+    assert fp.loudness_range == pytest.approx(want, rel=1e-12, abs=1e-15)
