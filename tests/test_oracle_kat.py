@@ -871,3 +871,72 @@ def test_loudness_range_against_python_restatement(oracle, synth, gain, sr):
     want = py_loudness_range(y, sr)
     assert (want > 0.0) == (gain > 1.0), "a quiet input has no positive loudness unit, a loud one has"
     assert fp.loudness_range == pytest.approx(want, rel=1e-12, abs=1e-15)
+
+
+# ---------------------------------------------------------------- AlignmentAnalyzer.alignWithDTW scalars
+
+def py_dtw_scalars(pq, pr, pc, distance, n, m, sr):
+    """algorithms/stats/alignment.go:129-148 and its helpers :380-643, written from the Go source."""
+    L = len(pq)
+
+    def mean_cost():
+        return seq_sum(np.asarray(pc, dtype=np.float64)) / L if L else 0.0
+
+    def cost_consistency():
+        if L <= 1:
+            return 0.0
+        w = max(min(5, L // 4), 2)
+        sm = np.empty(L)
+        for i in range(L):
+            lo, hi = max(0, i - w // 2), min(L - 1, i + w // 2)
+            sm[i] = seq_sum(np.asarray(pc[lo:hi + 1], dtype=np.float64)) / (hi - lo + 1)
+        mu = seq_sum(sm) / L
+        if mu <= 1e-10:
+            return 1.0
+        sd = math.sqrt(seq_sum((sm - mu) ** 2) / L)
+        return 1.0 / (1.0 + sd / mu)
+
+    def diagonal_bias():
+        if L <= 1:
+            return 1.0
+        diag = sum(1 for i in range(1, L) if pq[i] - pq[i - 1] > 0 and pr[i] - pr[i - 1] > 0)
+        return 1.0 / (1.0 + math.exp(-10.0 * (diag / (L - 1) - 0.3)))
+
+    def changes():
+        return sum(1 for i in range(2, L) if (pq[i] - pq[i - 1], pr[i] - pr[i - 1]) != (pq[i - 1] - pq[i - 2], pr[i - 1] - pr[i - 2]))
+
+    def smoothness():
+        return 1.0 if L <= 2 else max(0.0, 1.0 - changes() / (L - 1))
+
+    def quality():
+        if L == 0:
+            return 0.0
+        eff = min(1.0, max(float(n), float(m)) / L)
+        return min(1.0, max(0.0, 0.3 * eff + 0.3 * diagonal_bias() + 0.2 * smoothness() + 0.2 * cost_consistency()))
+
+    avg_len = (n + m) / 2.0
+    nd = distance / avg_len
+    similarity = min(1.0, max(0.0, 0.5 * (1.0 / (1.0 + nd)) + 0.3 * quality() + 0.2 * (1.0 / (1.0 + mean_cost()))))
+    eff = min(1.0, max(float(n), float(m)) / L)
+    confidence = min(1.0, max(0.0, 0.4 * math.exp(-nd * 2.0) + 0.25 * eff + 0.2 * cost_consistency() + 0.15 * diagonal_bias()))
+    s = sum(int(b) - int(a) for a, b in zip(pq, pr))
+    offset = int(s / L) if L else 0                                   # Go integer division truncates toward zero
+    stability = 0.0 if L < 3 else max(0.0, 1.0 - changes() / (L - 1))
+    return dict(similarity=similarity, confidence=confidence, offset=offset, offset_seconds=offset / sr,
+                alignment_quality=quality(), stability=stability)
+
+
+@pytest.mark.parametrize("n,m,band,seed", [(300, 280, 40, 1), (64, 64, 0, 2), (500, 430, 90, 3), (2, 2, 0, 4)])
+def test_dtw_scalars_against_python_restatement(oracle, n, m, band, seed):
+    rng = np.random.default_rng(seed)
+    base = np.cumsum(rng.standard_normal(max(n, m) + 50))
+    q = base[:n] + 0.05 * rng.standard_normal(n)
+    r = np.interp(np.linspace(0, n - 1, m) + 6.0 * np.sin(np.linspace(0, 5, m)), np.arange(base.size), base)
+    r = r + 0.05 * rng.standard_normal(m)
+    res = oracle.dtw(q, r, band=band)
+    ar = oracle.align_dtw_scalars(res, n, m, 16000)
+    want = py_dtw_scalars(res["path_query"], res["path_ref"], res["path_cost"], res["distance"], n, m, 16000)
+    assert ar.offset == want["offset"]
+    assert ar.offset_seconds == want["offset_seconds"]
+    for k in ("similarity", "confidence", "alignment_quality", "stability"):
+        assert getattr(ar, k) == pytest.approx(want[k], rel=1e-12, abs=1e-15), k
