@@ -940,3 +940,98 @@ def test_dtw_scalars_against_python_restatement(oracle, n, m, band, seed):
     assert ar.offset_seconds == want["offset_seconds"]
     for k in ("similarity", "confidence", "alignment_quality", "stability"):
         assert getattr(ar, k) == pytest.approx(want[k], rel=1e-12, abs=1e-15), k
+
+
+# ---------------------------------------------------------------- FingerprintComparator.Compare
+
+def py_compare(a, b, weights, ct_a=0, ct_b=0, content_filter=False, spectral=True, harmonic=True, temporal=False):
+    """fingerprint/comparison.go:133-194 (Compare), :266-341 (calculateFeatureSimilarity), :345-402 (compareMFCC = cosine of
+    the per-coefficient mean / sample-std vector), :646-770 (spectral / temporal / harmonic groups), :772-882 (helpers),
+    :886-889 (overall = feature similarity), :1011-1037 (confidence), written from the Go source; gonum's stat.Mean /
+    stat.Variance / floats.Dot / floats.Norm restated as their definitions (unbiased variance, Euclidean norm)."""
+    def cos(u, v):
+        u, v = np.asarray(u, dtype=np.float64), np.asarray(v, dtype=np.float64)
+        if u.size != v.size or u.size == 0:
+            return 0.0
+        nu, nv = math.sqrt(float(u @ u)), math.sqrt(float(v @ v))
+        return 0.0 if nu == 0 or nv == 0 else float(u @ v) / (nu * nv)
+
+    def seqstats(s1, s2):
+        if len(s1) == 0 or len(s2) == 0:
+            return 0.0
+        return cos([np.mean(s1), np.std(s1, ddof=1)], [np.mean(s2), np.std(s2, ddof=1)])
+
+    def scalar(v1, v2):
+        if v1 == 0 and v2 == 0:
+            return 1.0
+        mx = max(abs(v1), abs(v2))
+        return 1.0 if mx == 0 else max(0.0, 1.0 - abs(v1 - v2) / mx)
+
+    match = ct_a == ct_b
+    if content_filter and not match:
+        return dict(overall=0.0, feature=0.0, confidence=0.25, match=match, n=0, dist={})
+    sims, ws, dist = [], [], {}
+    w = dict(zip(("mfcc", "spectral", "chroma", "temporal", "speech", "harmonic", "energy"), weights))
+    if len(a["mfcc"]) and len(b["mfcc"]):
+        st = lambda m: np.concatenate([m.mean(0), m.std(0, ddof=1)])
+        s = cos(st(a["mfcc"]), st(b["mfcc"]))
+        sims.append(s); ws.append(w["mfcc"]); dist["mfcc"] = 1.0 - s
+    if spectral:
+        parts = [seqstats(a[k], b[k]) for k in ("spectral_centroid", "spectral_rolloff", "spectral_flux") if len(a[k]) and len(b[k])]
+        s = float(np.mean(parts)) if parts else 0.0
+        sims.append(s); ws.append(w["spectral"]); dist["spectral"] = 1.0 - s if parts else 1.0
+    if temporal:
+        parts = []
+        if a["dynamic_range"] > 0 and b["dynamic_range"] > 0:
+            parts.append(scalar(a["dynamic_range"], b["dynamic_range"]))
+        parts.append(scalar(a["silence_ratio"], b["silence_ratio"]))
+        if a["onset_density"] > 0 and b["onset_density"] > 0:
+            parts.append(scalar(a["onset_density"], b["onset_density"]))
+        if len(a["rms_energy"]) and len(b["rms_energy"]):
+            parts.append(seqstats(a["rms_energy"], b["rms_energy"]))
+        s = float(np.mean(parts))
+        sims.append(s); ws.append(w["temporal"]); dist["temporal"] = 1.0 - s
+    if harmonic:
+        parts = [seqstats(a[k], b[k]) for k in ("harmonic_ratio", "pitch_estimate") if len(a[k]) and len(b[k])]
+        s = float(np.mean(parts)) if parts else 0.0
+        sims.append(s); ws.append(w["harmonic"]); dist["harmonic"] = 1.0 - s if parts else 1.0
+    feat = float(np.dot(sims, ws) / np.sum(ws))
+    conf = 0.5 + (0.3 if feat > 0.8 else 0.2 if feat > 0.6 else 0.0) + (0.1 if match else 0.0) + 0.05 * len(dist)
+    return dict(overall=feat, feature=feat, confidence=max(0.0, min(1.0, conf)), match=match, n=len(dist), dist=dist)
+
+
+def _cmp_inputs(fp):
+    d = {k: fp.arrays[k] for k in ("mfcc", "spectral_centroid", "spectral_rolloff", "spectral_flux", "harmonic_ratio",
+                                   "pitch_estimate")}
+    if "rms_energy" in fp.arrays:
+        d["rms_energy"] = fp.arrays["rms_energy"]
+        for k in ("dynamic_range", "silence_ratio", "onset_density"):
+            d[k] = fp.scalars[k]
+    return d
+
+
+@pytest.mark.parametrize("temporal,harmonic,ct_b,content_filter", [(False, True, 0, False), (True, True, 0, False),
+                                                                   (True, False, 2, False), (False, True, 2, True)])
+def test_compare_against_python_restatement(oracle, capi, synth, temporal, harmonic, ct_b, content_filter):
+    sr = 16000
+    kw = dict(window_size=512, hop_size=160, energy_frame=512, energy_hop=160, algo_sample_rate=sr, call_sample_rate=sr,
+              enable=capi.FP_ENABLE_MFCC | (capi.FP_ENABLE_TEMPORAL if temporal else 0))
+    rng = np.random.default_rng(11)
+    xa = _voiced_test_signal(sr, 2.0, 1) + 0.05 * rng.standard_normal(2 * sr) * (np.arange(2 * sr) % 4000 < 900)
+    xb = 0.7 * synth.speech_band_noise(2.5) + 0.3 * _voiced_test_signal(sr, 2.5, 7)
+    fa, fb = oracle.fingerprint(xa, oracle.default_params(**kw)), oracle.fingerprint(xb, oracle.default_params(**kw))
+    weights = [0.35, 0.25, 0.10, 0.20, 0.10, 0.10, 0.15]  # comparison.go:1092-1103 (default content type)
+    ca, _ka = oracle.cmp_features(fa, content_type=0, harmonic=harmonic, temporal=temporal)
+    cb, _kb = oracle.cmp_features(fb, content_type=ct_b, harmonic=harmonic, temporal=temporal)
+    got = oracle.compare(ca, cb, weights, content_filter=content_filter)
+    want = py_compare(_cmp_inputs(fa), _cmp_inputs(fb), weights, 0, ct_b, content_filter, True, harmonic, temporal)
+    assert bool(got.content_type_match) == want["match"]
+    assert got.confidence == pytest.approx(want["confidence"], abs=1e-12)
+    assert got.overall_similarity == pytest.approx(want["overall"], rel=1e-10, abs=1e-12)
+    if content_filter and not want["match"]:
+        return
+    assert 0.05 < want["overall"] < 0.999, "the two fingerprints must differ"
+    assert got.feature_similarity == pytest.approx(want["feature"], rel=1e-10)
+    assert got.n_features == want["n"]
+    for k, v in want["dist"].items():
+        assert getattr(got, "dist_" + k) == pytest.approx(v, rel=1e-9, abs=1e-12), k
